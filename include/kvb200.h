@@ -1,0 +1,310 @@
+/* kvb200.h — C ABI of libkvb200.so, the B200-native elastic KV-cache hot path.
+ *
+ * This is the drop-in boundary for the reference's `kvcached.vmm_ops` extension
+ * (csrc/torch_bindings.cpp:182-258) and for the bookkeeping its Python
+ * `KVCacheManager` performs on the host (kvcached/kv_cache_manager.py:58-506).
+ * Plain pointers, sizes and integer status codes only: no torch types, no C++
+ * types, no exceptions, no abort().  The Python package `kvcached_b200` binds
+ * these with ctypes and re-creates the reference's Python names on top
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns an int status unless stated: 0 = KVB_OK, <0 = error;
+ *     kvb_last_error() returns the message of the last error on the calling thread.
+ *   - "insufficient space" is not an error: alloc-type entry points report it per
+ *     request with KVB_ST_NONE (the reference returns None, kv_cache_manager.py:262-266).
+ *   - block ids / page ids cross the ABI as int64_t, like the reference's
+ *     std::vector<int64_t> / List[int].
+ *   - all bookkeeping state lives in device memory; host code only launches the
+ *     sm_100a kernels and runs the CUDA driver VMM loop the kernels ask for.
+ *   - thread safety: one mutex per manager / per VMM group; every entry point sets
+ *     the CUDA device itself, so it may be called from foreign threads.
+ */
+#ifndef KVB200_H_
+#define KVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVB_OK 0
+#define KVB_ERR_INVALID (-1)   /* bad argument / bad configuration            */
+#define KVB_ERR_CUDA (-2)      /* a CUDA runtime or driver call failed         */
+#define KVB_ERR_STATE (-3)     /* not initialised / tensors not created / ...  */
+#define KVB_ERR_NOMEM (-4)     /* host or device allocation failed             */
+#define KVB_ERR_OVERFLOW (-5)  /* caller buffer too small                      */
+
+/* per-request status written by the bookkeeping kernel */
+#define KVB_ST_OK 1
+#define KVB_ST_FALSE 0          /* resize()/try_to_reserve() returned False    */
+#define KVB_ST_NONE (-1)        /* alloc() -> None: available_size() < need    */
+#define KVB_ST_NO_PAGES (-2)    /* reference raises RuntimeError("No free pages left"), page_allocator.cpp:200-207 */
+#define KVB_ST_ASSERT (-3)      /* reference AssertionError: reserved blocks present at resize, kv_cache_manager.py:394 */
+#define KVB_ST_NULL_BLOCK (-4)  /* null block could not be reserved at index 0, kv_cache_manager.py:239-243 */
+#define KVB_ST_CAPACITY (-5)    /* resize beyond the virtual range created at init (the reference would alias page ids) */
+
+const char *kvb_last_error(void);
+/* ABI version of the loaded library (bumped on any signature change). */
+int kvb_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Virtual KV tensors and the batched VMM engine
+ *    replaces csrc/allocator.cpp (FTensorAllocator), csrc/ftensor.cpp (FTensor),
+ *    csrc/page.cpp (GPUPage) and the free functions of csrc/torch_bindings.cpp:20-60.
+ * ------------------------------------------------------------------------------------------ */
+
+/* init_kvcached(dev_str, page_size, contiguous_layout) — torch_bindings.cpp:20-24, allocator.cpp:72-99.
+ * page_size 0 = default 2 MiB; must be a multiple of 2 MiB (the reference abort()s, we return KVB_ERR_INVALID).
+ * Re-initialising drops every existing group, like the reference. */
+int kvb_init(int device_index, int64_t page_size, int contiguous_layout);
+/* shutdown_kvcached() — torch_bindings.cpp:26-29 */
+int kvb_shutdown(void);
+int kvb_is_initialized(void);
+int64_t kvb_page_size(void);
+int kvb_contiguous_layout(void);
+
+/* create_kv_tensors(size, dtype_size, dev, num_layers, num_kv_buffers, group_id, unified_pool)
+ * — torch_bindings.cpp:31-40, allocator.cpp:121-154, :277-296.
+ * `size_per_layer` = bytes of one layer's K and V together (rounded up to the page size).
+ * contiguous layout: ONE range of size_per_layer*num_layers bytes whose compound page is
+ *   page_size*num_layers*num_kv_buffers; per-layer layout: num_layers ranges.
+ * Writes the device base address and byte size of every range (1 or num_layers entries)
+ * and returns the number of ranges (>0) or an error (<0).  The whole range is readable and
+ * writable at once: unmapped pages alias one shared zero page (ftensor.cpp:160-176). */
+int kvb_create_kv_tensors(int64_t group_id, int64_t size_per_layer, int64_t num_layers,
+                          int64_t num_kv_buffers, int unified_pool,
+                          uint64_t *out_ptrs, int64_t *out_bytes, int cap);
+/* kv_tensors_created(group_id) — torch_bindings.cpp:42-46; returns 1/0 */
+int kvb_kv_tensors_created(int64_t group_id);
+
+/* map_to_kv_tensors / unmap_from_kv_tensors(offsets, group_id) — torch_bindings.cpp:48-60,
+ * allocator.cpp:161-257.  offsets are the reference's byte offsets
+ * (page_id*page_size*(L*nKV if contiguous else 1), page_allocator.cpp:619-631).
+ * One call runs the whole cuMemUnmap/cuMemMap/cuMemSetAccess loop over all layers' ranges with
+ * pooled physical handles.  Mapping an already mapped page / unmapping an unmapped one is
+ * tolerated (ftensor.cpp:104-107, :124-127).  Returns 1 (True), 0 (tensors not created) or <0. */
+int kvb_map_to_kv_tensors(int64_t group_id, const int64_t *offsets, int64_t n);
+int kvb_unmap_from_kv_tensors(int64_t group_id, const int64_t *offsets, int64_t n);
+/* same, addressed by page id (what the device bookkeeping emits) */
+int kvb_map_pages(int64_t group_id, const int64_t *page_ids, int64_t n);
+int kvb_unmap_pages(int64_t group_id, const int64_t *page_ids, int64_t n);
+/* events[i] = page_id*2 + is_unmap, applied in order (the bookkeeping kernel's event log,
+ * and the payload rank 0 broadcasts to the other tensor-parallel ranks). */
+int kvb_apply_page_events(int64_t group_id, const int64_t *events, int64_t n);
+
+/* physical-handle pool (no cuMemCreate / cuMemRelease on the hot path; page.cpp:10-25 creates and
+ * releases one handle per map).  `max_cached` handles are kept after unmap, the rest released;
+ * kvb_vmm_pool_prefill creates up to n handles ahead of demand. */
+int kvb_vmm_pool_config(int64_t group_id, int64_t max_cached);
+int kvb_vmm_pool_prefill(int64_t group_id, int64_t n);
+/* stats[0..7] = mapped pages, pooled handles, handles created, handles released, map calls,
+ * unmap calls, bytes mapped, compound page bytes */
+int kvb_vmm_stats(int64_t group_id, int64_t *stats8);
+/* sorted ids of the currently mapped pages; returns the count or KVB_ERR_OVERFLOW */
+int64_t kvb_vmm_mapped_pages(int64_t group_id, int64_t *out, int64_t cap);
+/* get_avail_physical_pages() arithmetic — page_allocator.cpp:442-455:
+ * max(free - total*(1-gpu_utilization), 0) / page_size / num_layers / num_kv_buffers, plus the
+ * handles parked in the pool (their memory is already ours). */
+int64_t kvb_vmm_avail_physical_pages(int64_t group_id, int64_t num_layers, int64_t num_kv_buffers,
+                                     double gpu_utilization);
+/* raw-driver control loop for the map/unmap latency metric (cf. benchmarks/bench_vmm/bench_vmm.cpp:139-228):
+ * maps and unmaps `n_pages` pre-created handles `iters` times over a private range and writes
+ * per-iteration microseconds.  compound=1 uses the group's compound page size, else page_size. */
+int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int compound,
+                        double *map_us, double *unmap_us);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Device-resident block manager
+ *    replaces the host bookkeeping of kvcached/kv_cache_manager.py:58-506 and
+ *    csrc/page_allocator.cpp:40-100, :103-460, :471-498, :619-709.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kvb_mgr kvb_mgr;
+
+typedef struct kvb_mgr_config {
+  int64_t num_blocks;          /* KVCacheManager(num_blocks, ...)           kv_cache_manager.py:60 */
+  int64_t block_size;          /* tokens per block                                              */
+  int64_t cell_size;           /* bytes of one token's K (or V) in one layer                    */
+  int64_t num_layers;
+  int64_t num_kv_buffers;      /* 2 = K+V, 1 = MLA                                              */
+  int64_t page_size;           /* 0 = kvb_page_size() / 2 MiB                                   */
+  int64_t group_id;
+  int64_t min_reserved_pages;  /* <0 = env KVCACHED_MIN_RESERVED_PAGES or 5  page_allocator.cpp:24-37 */
+  int64_t max_reserved_pages;  /* <0 = env KVCACHED_MAX_RESERVED_PAGES or 10 */
+  int32_t reserve_null_block;
+  int32_t async_sched;         /* synchronise the device before unmapping    page_allocator.cpp:671-673 */
+  int32_t contiguous_layout;   /* <0 = kvb_contiguous_layout()                                  */
+  int32_t attach_vmm;          /* 1 = apply the kernel's map/unmap events to the group's tensors;
+                                  0 = bookkeeping only (events are still logged)               */
+  int32_t device_index;        /* <0 = device of kvb_init, else cudaGetDevice                   */
+  int32_t world_size;          /* >1: events are also exported for the TP broadcast             */
+  double gpu_utilization;      /* <=0 = env KVCACHED_GPU_UTILIZATION or 0.95                    */
+} kvb_mgr_config;
+
+/* one request of a batched step */
+typedef struct kvb_op {
+  int32_t kind;   /* KVB_OP_* */
+  int32_t n;      /* ALLOC/TRY_RESERVE: blocks wanted; FREE_IDS: number of ids; FREE_REF: number of refs */
+  int64_t arg;    /* FREE_IDS: offset into the id pool; FREE_REF: offset into the ref pool (in refs);
+                     RESIZE: new size in bytes */
+} kvb_op;
+
+#define KVB_OP_ALLOC 1          /* KVCacheManager.alloc          kv_cache_manager.py:246-304 */
+#define KVB_OP_FREE_IDS 2       /* KVCacheManager.free           kv_cache_manager.py:307-360 */
+#define KVB_OP_FREE_REF 3       /* free(concat of earlier results' slices), ids never leave the device */
+#define KVB_OP_RESIZE 4         /* KVCacheManager.resize         kv_cache_manager.py:381-401 */
+#define KVB_OP_TRIM 5           /* KVCacheManager.trim           kv_cache_manager.py:404-409 */
+#define KVB_OP_TRY_RESERVE 6    /* KVCacheManager.try_to_reserve kv_cache_manager.py:363-372 */
+#define KVB_OP_FREE_RESERVED 7  /* KVCacheManager.free_reserved  kv_cache_manager.py:375-378 */
+#define KVB_OP_AVAIL 8          /* KVCacheManager.available_size kv_cache_manager.py:412-423 */
+#define KVB_OP_CLEAR 9          /* KVCacheManager.clear          kv_cache_manager.py:444-489 */
+#define KVB_OP_ALLOC_PAGE 10    /* PageAllocator.alloc_page      page_allocator.cpp:161-237  */
+#define KVB_OP_FREE_PAGES 11    /* PageAllocator.free_pages      page_allocator.cpp:264-310  */
+#define KVB_OP_PA_RESIZE 12     /* PageAllocator.resize          page_allocator.cpp:312-401  */
+#define KVB_OP_RESET_ORDER 13   /* PageAllocator.reset_free_page_order page_allocator.cpp:703-709 */
+
+/* a slice of an earlier request's result: ids = result(op)[lo:hi] (Python slice semantics, clipped) */
+typedef struct kvb_ref {
+  int32_t op;  /* index of the earlier ALLOC request (absolute index in the resident trace, or index
+                  inside the current step for kvb_mgr_step) */
+  int32_t lo;
+  int32_t hi;
+} kvb_ref;
+
+/* result of one request */
+typedef struct kvb_res {
+  int32_t status;  /* KVB_ST_*                                               */
+  int32_t n;       /* ids produced (ALLOC) / ids consumed (FREE)              */
+  int64_t off;     /* offset of the first id in the id output buffer          */
+  int64_t avail;   /* available_size() right after the request                */
+} kvb_res;
+
+/* counters of the device state as of the last completed launch */
+typedef struct kvb_mgr_stats {
+  int64_t num_free_pages, num_inuse_pages, num_reserved_pages, num_total_pages;
+  int64_t num_avail_blocks, num_reserved_blocks, in_shrink, target_num_blocks;
+  int64_t num_avail_pages, num_full_pages, num_mapped_pages, has_null_block;
+  int64_t blocks_per_page, block_mem_size, page_size, mem_size;
+  int64_t bad_frees, unknown_page_frees, launches, events;
+} kvb_mgr_stats;
+
+/* KVCacheManager.__init__ + _post_init — kv_cache_manager.py:60-243.  Returns NULL on error
+ * (block larger than page -> KVCachedConfigError, :104-116). */
+kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg);
+int kvb_mgr_destroy(kvb_mgr *m);
+
+/* ---- batched fast path: one scheduler step = one kernel launch ----------------------------
+ * Runs `n_ops` requests with exactly the results N sequential reference calls would give.
+ * `ids` is the pool FREE_IDS requests index, `refs` the pool FREE_REF requests index (refs name
+ * requests of THIS call).  Results: res[i] for every request, block ids of all ALLOC requests
+ * concatenated into out_ids (res[i].off/res[i].n locate them).  All buffers are HOST memory;
+ * the call copies in, launches, copies out, then applies the kernel's page map/unmap list to
+ * the group's virtual tensors (cuMemMap loop) before returning.  Returns the number of ids
+ * written to out_ids, or <0. */
+int64_t kvb_mgr_step(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
+                     const kvb_ref *refs, int64_t n_refs, kvb_res *res, int64_t *out_ids, int64_t out_cap);
+
+/* ---- single-request entry points (the reference's method set) ---------------------------- */
+/* alloc(n): returns n (ids in out), KVB_ST_NONE, KVB_ST_NO_PAGES, or <= KVB_ERR_* - 100 */
+int64_t kvb_mgr_alloc(kvb_mgr *m, int64_t n, int64_t *out, int64_t cap);
+int kvb_mgr_free(kvb_mgr *m, const int64_t *ids, int64_t n);
+int kvb_mgr_resize(kvb_mgr *m, int64_t new_mem_size);      /* 1 True, 0 False, KVB_ST_ASSERT */
+int kvb_mgr_trim(kvb_mgr *m);
+int kvb_mgr_try_to_reserve(kvb_mgr *m, int64_t n);         /* 1 / 0 / KVB_ST_NO_PAGES */
+int kvb_mgr_free_reserved(kvb_mgr *m);
+int kvb_mgr_clear(kvb_mgr *m);
+/* available_size(): host arithmetic on the counters the last launch published + live physical
+ * memory, no launch (kv_cache_manager.py:412-423, page_allocator.cpp:442-455). */
+int64_t kvb_mgr_available_size(kvb_mgr *m);
+int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *out);
+/* parity/test hooks: override the physical-page budget (<0 = live cudaMemGetInfo) */
+int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n);
+
+/* ---- resident traces: requests and results stay in HBM ------------------------------------
+ * Upload a whole trace once; then run ranges of it.  FREE_REF refs name absolute request indices.
+ * kvb_mgr_trace_run launches one kernel per step range [step_begin, step_end) given by
+ * step_offsets (n_steps+1 request indices) without any host round trip in between; page
+ * events accumulate on the device and are applied (if attach_vmm) when the call returns. */
+int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
+                         const kvb_ref *refs, int64_t n_refs, const int64_t *step_offsets, int64_t n_steps,
+                         int64_t out_capacity);
+int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_end, int steps_per_launch,
+                      float *device_ms, int64_t *n_launches);
+int kvb_mgr_trace_results(kvb_mgr *m, kvb_res *res, int64_t n_ops, int64_t *out_ids, int64_t out_cap,
+                          int64_t *n_out);
+int kvb_mgr_trace_reset_cursor(kvb_mgr *m);
+
+/* ---- state inspection (tests, debugging, the consistency audit) ---------------------------- */
+/* which: 0 free_page_list, 1 reserved_page_list, 2 reclaimed_page_list, 3 avail_pages (insertion
+ * order), 4 full_pages (ascending), 5 reserved_blocks, 6 mapped pages per the bookkeeping (ascending) */
+int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_t cap);
+int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t page_id, int64_t *out, int64_t cap);
+/* drains the ordered page event log (page*2 + is_unmap) accumulated since the last drain */
+int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap);
+/* full-bitmap audit kernel (coalesced uint4 sweep + popc): recounts used blocks per page from the
+ * bitmap and checks them against the per-page counters.  out4 = {used blocks, in-use pages,
+ * fully-free in-use pages, mismatching pages}.  device_ms (optional) = kernel time. */
+int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms);
+/* device pointer + word count of the used-block bitmap (tests, external sweeps) */
+int kvb_mgr_bitmap(kvb_mgr *m, uint64_t *dev_ptr, int64_t *n_words32);
+
+/* ---- tensor parallel: rank-consistent page mapping ----------------------------------------
+ * After a step, rank 0's page events sit in a fixed device buffer
+ * [seq, n, e0 .. e(n-1), 0 ...] of kvb_tp_buffer_words() int64 words.  The host side broadcasts
+ * that buffer with ONE NCCL broadcast (torch.distributed) and every other rank calls
+ * kvb_tp_apply on its copy.  Replaces kvcached/tp_ipc_util.py:96-267. */
+int64_t kvb_tp_buffer_words(void);
+int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst_device_ptr, void *stream);
+int kvb_tp_apply(int64_t group_id, uint64_t src_device_ptr, void *stream, int64_t *seq_out, int64_t *n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Page arithmetic helpers — InternalPage statics, csrc/page_allocator.cpp:87-100, :457-498
+ * ------------------------------------------------------------------------------------------ */
+void kvb_page_block_range(int64_t page_id, int64_t page_size, int64_t block_mem_size, int64_t *start,
+                          int64_t *end);
+int64_t kvb_page_num_blocks(int64_t page_size, int64_t block_mem_size);
+int64_t kvb_page_id_of_block(int64_t block_id, int64_t block_mem_size, int64_t page_size);
+/* group_indices_by_page on the DEVICE (same kernel code path free() uses): writes the distinct
+ * pages in the reference's dict order, the number of ids of each, and the ids regrouped by page
+ * (input order inside a page).  Returns the number of distinct pages. */
+int64_t kvb_group_indices_by_page(kvb_mgr *m, const int64_t *ids, int64_t n, int64_t *pages_out,
+                                  int64_t *counts_out, int64_t *grouped_out);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Fused paged KV scatter / gather (sm_100a, 128-bit accesses)
+ *    The reference has no such kernel; it defines the address layout the engines' kernels write
+ *    through (integration/vllm/interfaces.py:281-298, integration/sglang/interfaces.py:132-173).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct kvb_kv_layout {
+  uint64_t base;           /* device address of layer 0, K                         */
+  int64_t stride_block;    /* bytes between consecutive blocks                      */
+  int64_t stride_token;    /* bytes between consecutive tokens inside a block       */
+  int64_t stride_layer;    /* bytes between layers                                  */
+  int64_t stride_kv;       /* bytes between K and V of one layer                    */
+  int64_t cell_bytes;      /* contiguous bytes of one token's K (or V) in one layer */
+  int32_t block_size;      /* tokens per block                                      */
+  int32_t num_layers;
+  int32_t num_kv;          /* 2 = K and V, 1 = MLA                                  */
+  int32_t pad_;
+} kvb_kv_layout;
+
+/* src layout: [num_kv][num_layers][T][cell_bytes] contiguous (k_src = kv 0, v_src = kv 1; v may be 0
+ * when num_kv == 1).  slots[T] are token slots (block = slot / block_size).  layer_begin/layer_end
+ * select the layers one launch covers (0, num_layers = fused all-layer launch).
+ * Pointers are DEVICE addresses; `stream` is a cudaStream_t (NULL = legacy default stream). */
+int kvb_kv_scatter(const kvb_kv_layout *lay, uint64_t slots_dev, int64_t T, uint64_t k_src, uint64_t v_src,
+                   int32_t layer_begin, int32_t layer_end, void *stream);
+int kvb_kv_gather(const kvb_kv_layout *lay, uint64_t slots_dev, int64_t T, uint64_t k_dst, uint64_t v_dst,
+                  int32_t layer_begin, int32_t layer_end, void *stream);
+/* host-buffer convenience used by the end-to-end path: copies slots and K/V from pinned or pageable
+ * host memory, scatters, and (gather) copies back. */
+int kvb_kv_scatter_host(const kvb_kv_layout *lay, const int64_t *slots, int64_t T, const void *k_src,
+                        const void *v_src);
+int kvb_kv_gather_host(const kvb_kv_layout *lay, const int64_t *slots, int64_t T, void *k_dst, void *v_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVB200_H_ */

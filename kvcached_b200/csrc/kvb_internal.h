@@ -1,0 +1,115 @@
+// kvb_internal.h — structures shared by the sm_100a bookkeeping kernels and their host launcher.
+// Not part of the ABI (include/kvb200.h is).
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/kvb200.h"
+
+namespace kvb {
+
+// Scalars of the device-resident manager state (int64 each).  They restate the scalar members of
+// the reference's PageAllocator (csrc/inc/page_allocator.hpp:138-148) and KVCacheManager
+// (kvcached/kv_cache_manager.py:171-179).
+enum Sc : int {
+  SC_NFREE = 0,     // num_free_pages_
+  SC_NTOTAL,        // num_total_pages_
+  SC_NAB,           // num_avail_blocks
+  SC_INSHRINK,      // in_shrink
+  SC_TARGET,        // target_num_blocks (-1 = None)
+  SC_RB_HEAD,       // reserved_blocks ring: head index
+  SC_NRB,           // len(reserved_blocks)
+  SC_FL_HEAD,       // free_page_list_ ring
+  SC_FL_SIZE,
+  SC_RL_HEAD,       // reserved_page_list_ ring
+  SC_RL_SIZE,
+  SC_CL_HEAD,       // reclaimed_page_list_ ring
+  SC_CL_SIZE,
+  SC_AP_TAIL,       // avail_pages insertion-order stack: one past the last entry
+  SC_NAVAILPG,      // len(avail_pages)
+  SC_NFULLPG,       // len(full_pages)
+  SC_NMAPPED,       // pages with a physical mapping (in use + reserved)
+  SC_HAS_NULL,      // null block held
+  SC_OUT_CURSOR,    // next free position of the id output arena (resident traces)
+  SC_NEV,           // entries in the page event log
+  SC_BAD_FREES,     // ids ignored by free(): not allocated / duplicate / out of range
+  SC_UNKNOWN_FREES, // pages named by free() that are not in use (the reference logs and skips)
+  SC_PHYS,          // physical page budget of the running launch
+  SC_LAUNCHES,
+  SC_COUNT = 32
+};
+
+enum : int { PG_NONE = 0, PG_AVAIL = 1, PG_FULL = 2 };
+
+// Everything the kernels need to find the state; passed by value (constant bank).
+struct DevState {
+  int64_t P;            // page size in bytes
+  int64_t B;            // block_mem_size = block_size * cell_size
+  int32_t bpp;          // P / B  (InternalPage::get_num_blocks)
+  int32_t exact;        // B divides P: page p holds exactly blocks [p*bpp, (p+1)*bpp)
+  int64_t num_blocks;
+  int32_t max_pages;    // pages of the virtual range created at init (capacity of every page array)
+  int32_t q_mask;       // page deque capacity - 1 (power of two)
+  int32_t rb_mask;      // reserved-block ring capacity - 1
+  int32_t ap_cap;       // avail stack capacity
+  int32_t min_reserved, max_reserved;
+  int32_t ev_cap;
+  int32_t n_primes;
+  int64_t *sc;          // [SC_COUNT]
+  int32_t *fl, *rl, *cl;        // page deques (ring buffers)
+  int32_t *ap;                  // avail_pages in insertion order, -1 = tombstone
+  int32_t *pg_state, *pg_cnt, *pg_head, *pg_pos, *pg_mapped;
+  int32_t *pg_first, *pg_slot;  // scratch of free(): first index naming the page, its slot
+  uint32_t *ring;               // [max_pages][bpp] per-page FIFO of free block offsets
+  uint32_t *bitmap;             // bit per block: 1 = allocated
+  int64_t *rb;                  // reserved_blocks ring
+  int64_t *fids;                // scratch: ids of the running free()
+  int32_t *fpage;               // scratch: their pages
+  int32_t *g_dist, *g_ord, *g_cnt, *g_next, *g_bkt, *g_ptf;  // large-call fallbacks of the smem tables
+  int32_t g_bkt_cap;
+  int64_t f_cap;                // capacity of fids / fpage
+  int64_t *ev;                  // page event log: page*2 + is_unmap
+  const uint64_t *primes;       // libstdc++ __prime_list
+};
+
+// What one launch publishes for the host (written last; pinned host or device memory).
+struct Summary {
+  int64_t seq;
+  int64_t ops_done;       // requests completed by this launch
+  int64_t out_used;       // ids written to the output buffer by this launch (step mode) / arena cursor
+  int64_t n_events;       // events appended by this launch
+  int64_t ev_begin;       // index of this launch's first event in the device log
+  int64_t sc[SC_COUNT];
+  int64_t ev_inline_n;
+  int64_t ev_inline[256];
+};
+
+struct LaunchArgs {
+  const kvb_op *ops;      // request array
+  int32_t op_begin, op_end;
+  const int64_t *ids;     // FREE_IDS pool
+  const kvb_ref *refs;    // FREE_REF pool
+  kvb_res *res;           // results, indexed like ops
+  int64_t *out_ids;       // id output buffer / arena
+  int64_t out_cap;
+  int64_t phys_free;      // get_avail_physical_pages() at launch time
+  Summary *summary;
+  int64_t seq;
+  int32_t arena_mode;     // 0: output cursor and event log restart at 0; 1: both continue (resident traces);
+                          // 2: cursor continues, event log restarts (relaunch of a partially done step)
+  int32_t group_only;     // 1: requests are FREE_IDS probes for kvb_group_indices_by_page (state untouched)
+  int64_t *grp_pages, *grp_counts, *grp_ids;   // outputs of group_only
+};
+
+constexpr int kStepThreads = 512;
+
+size_t step_kernel_smem_bytes();
+// launches (host side, defined in kvb_kernels.cu)
+int launch_step(const DevState &st, const LaunchArgs &a, void *stream);
+int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream);
+int launch_audit(const DevState &st, int64_t *d_out4, void *stream);
+int launch_dump_avail(const DevState &st, int64_t *d_out, int64_t *d_n, void *stream);
+int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, void *k, void *v, int32_t l0,
+                   int32_t l1, int gather, void *stream);
+
+}  // namespace kvb

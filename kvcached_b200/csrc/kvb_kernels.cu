@@ -1,0 +1,1466 @@
+// kvb_kernels.cu — hand-written sm_100a kernels of the elastic KV-cache hot path.
+//
+//   kvb_step_kernel   one CTA replays a batch of alloc / free / resize / ... requests against the
+//                     device-resident block<->page state with exactly the results N sequential calls
+//                     of the reference KVCacheManager would give (kvcached/kv_cache_manager.py:246-506,
+//                     csrc/page_allocator.cpp:40-100, :161-460, :471-498).
+//   kvb_audit_kernel  grid-wide coalesced uint4 sweep of the used-block bitmap (+popc) that recounts
+//                     every page and flags fully-free pages.
+//   kvb_kv_copy_kernel fused paged KV scatter / gather through the mapped virtual range, 128-bit
+//                     accesses, all layers and K/V in one launch.
+//
+// State design (DevState, kvb_internal.h).  The reference keeps, on the host, a std::vector FIFO per
+// page, two Python dicts (avail_pages in insertion order, full_pages) and three std::deque page lists.
+// Here:  per page a ring of free block offsets + count + head (the FIFO), a used-block bitmap (1 bit
+// per block; membership, double-free rejection, popc audits), page state words, the avail_pages
+// insertion order as an append-only stack with tombstones (popitem() = last live entry), and the
+// three page lists as ring buffers.  Order, not just set membership, is what makes results bit-exact
+// (SURVEY.md Appendix A), so every structure that decides an order is carried explicitly.
+//
+// Why one CTA: requests of a step are sequentially dependent by definition (request i sees the state
+// request i-1 left).  Parallelism is taken INSIDE a request or a run of requests:
+//   * a run of consecutive alloc() requests consumes one deterministic stream of free blocks
+//     (reserved blocks, then avail pages newest-first, then fresh pages); thread 0 walks pages and
+//     cuts the stream into segments, all warps then emit ids / bitmap bits / ring inits in parallel;
+//   * free(ids): all threads classify ids (page arithmetic, bitmap test-and-clear), find the distinct
+//     pages in first-appearance order (atomicMin + __ballot_sync/__popc compaction), one lane replays
+//     libstdc++'s unordered_map insertion policy to get the reference's dict order while a second warp
+//     computes per-page FIFO ranks with __match_any_sync, then all threads apply per-page updates
+//     (empty-page detection, avail stack re-insertion) with ballot/popc prefix sums.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdint>
+
+#include "kvb_internal.h"
+
+namespace kvb {
+
+namespace {
+
+constexpr int NT = kStepThreads;
+constexpr int NW = NT / 32;
+constexpr int OPS_CHUNK = 256;   // requests staged in shared memory at a time
+constexpr int SEG_CAP = 1024;    // stream segments per generation round
+constexpr int FRESH_CAP = 512;   // fresh pages per generation round
+constexpr int APW = 256;         // prefetched window of the avail stack
+constexpr int NEWPG_W = 64;      // prefetched window of upcoming fresh page ids
+constexpr int HT_D_CAP = 2048;   // distinct pages per free() handled in shared memory
+constexpr int HT_NB_CAP = 4099;  // hash buckets handled in shared memory
+constexpr int EV_INLINE = 256;
+
+enum : int { SEG_RB = 0, SEG_RING = 1, SEG_FRESH = 2 };
+
+struct Seg {
+  int32_t out_rel;   // offset of the segment's first id, relative to the round's output base
+  int32_t page;      // page id (RING/FRESH)
+  int32_t base;      // RB: ring index into rb; RING: ring position; FRESH: block offset inside the page
+  int32_t len_kind;  // len | kind << 28
+};
+
+// Resumable state of the alloc-run walk (thread 0 only).
+struct AllocSim {
+  int32_t op;          // next request of the run
+  int32_t req_active;  // a request is half done (round ran out of segment slots)
+  int64_t req_rem;     // blocks the active request still needs
+  int64_t req_off;     // output offset of the active request's first id
+  int64_t req_n;
+  int32_t ap_top;      // avail stack: one past the entry under inspection
+  int32_t ap_tail0;    // stack tail when the run started (window origin)
+  int32_t cur_p;       // page being consumed (-1 none)
+  int32_t cur_cnt;     // free blocks left in it
+  int32_t cur_head;    // ring position / fresh offset of its next free block
+  int32_t cur_fresh;   // 1: page taken in this run, ring not materialised yet
+  int32_t cur_idx;     // its stack index (-1: not on the stack yet)
+  int32_t newpg_j;     // fresh pages taken so far in this run
+  int32_t rl_size0;    // reserved_page_list size when the run started
+  int32_t nseg, nfresh;
+  int32_t done;
+  int32_t failed;      // request hit "No free pages left"
+  int64_t out_pos;     // stream position (absolute in the output buffer)
+  int64_t round_base;  // output position where this round started
+};
+
+struct Smem {
+  int64_t sc[SC_COUNT];
+  int64_t acc[8];
+  kvb_op ops[OPS_CHUNK];
+  Seg segs[SEG_CAP];
+  int2 fresh[FRESH_CAP];
+  int32_t apw[APW], apcnt[APW], aphead[APW];
+  int32_t newpg[NEWPG_W];
+  int32_t ht_key[HT_D_CAP], ht_next[HT_D_CAP], ht_ord[HT_D_CAP], ht_cnt[HT_D_CAP];
+  int32_t ht_bkt[HT_NB_CAP + 1];
+  int32_t wtot[NW], wtot2[NW];
+  int32_t misc[16];
+  int64_t tmp64[NT];
+  AllocSim sim;
+};
+
+enum : int { MI_D = 0, MI_NB0, MI_E, MI_USE_G, MI_STOP, MI_BASE_A, MI_BASE_B, MI_N, MI_BAD, MI_UNK, MI_K };
+
+// ------------------------------------------------------------------------------------ page arithmetic
+// InternalPage::get_block_range / get_num_blocks, csrc/page_allocator.cpp:87-100
+__device__ __forceinline__ int64_t pg_start(const DevState &c, int p) {
+  return c.exact ? (int64_t)p * c.bpp : ((int64_t)p * c.P + c.B - 1) / c.B;
+}
+__device__ __forceinline__ int pg_nblk(const DevState &c, int p) {
+  if (c.exact) return c.bpp;
+  int64_t s = ((int64_t)p * c.P + c.B - 1) / c.B;
+  int64_t e = ((int64_t)(p + 1) * c.P) / c.B;
+  return (int)(e - s);
+}
+// PageAllocator::get_page_id, csrc/page_allocator.cpp:457-460
+__device__ __forceinline__ int64_t blk_page(const DevState &c, int64_t id) {
+  if (c.exact) return (id < INT_MAX) ? (int64_t)((int32_t)id / c.bpp) : id / c.bpp;
+  return (id * c.B) / c.P;
+}
+
+// KVCacheManager.available_size, kv_cache_manager.py:412-423
+__device__ __forceinline__ int64_t avail_size(const DevState &c, const int64_t *sc) {
+  int64_t a = sc[SC_NAB] + sc[SC_NRB];
+  if (sc[SC_INSHRINK]) return a;
+  int64_t phys = (sc[SC_PHYS] > 0 ? sc[SC_PHYS] : 0) + sc[SC_RL_SIZE];
+  int64_t fp = sc[SC_NFREE] < phys ? sc[SC_NFREE] : phys;
+  return a + fp * c.bpp;
+}
+// KVCacheManager._get_num_alloced_blocks, kv_cache_manager.py:493-506
+__device__ __forceinline__ int64_t alloced_blocks(const DevState &c, const int64_t *sc) {
+  return sc[SC_NFULLPG] * c.bpp + sc[SC_NAVAILPG] * c.bpp - sc[SC_NAB] + sc[SC_NRB];
+}
+
+// ------------------------------------------------------------------------------------ thread-0 helpers
+__device__ __forceinline__ void ev_push(const DevState &c, int64_t *sc, int page, int unmap) {
+  int64_t n = sc[SC_NEV];
+  if (n < c.ev_cap) c.ev[n] = (int64_t)page * 2 + unmap;
+  sc[SC_NEV] = n + 1;
+  c.pg_mapped[page] = unmap ? 0 : 1;
+  sc[SC_NMAPPED] += unmap ? -1 : 1;
+  sc[SC_PHYS] += unmap ? 1 : -1;
+}
+__device__ __forceinline__ void dq_push_back(int32_t *q, int mask, int64_t *sc, int ih, int is, int v) {
+  q[(int)((sc[ih] + sc[is]) & mask)] = v;
+  sc[is] += 1;
+}
+__device__ __forceinline__ int dq_pop_front(int32_t *q, int mask, int64_t *sc, int ih, int is) {
+  int v = q[(int)(sc[ih] & mask)];
+  sc[ih] = (sc[ih] + 1) & mask;
+  sc[is] -= 1;
+  return v;
+}
+__device__ __forceinline__ int dq_pop_back(int32_t *q, int mask, int64_t *sc, int ih, int is) {
+  sc[is] -= 1;
+  return q[(int)((sc[ih] + sc[is]) & mask)];
+}
+
+// PageAllocator::resize, csrc/page_allocator.cpp:312-401 (thread 0; rare)
+__device__ int pa_resize(const DevState &c, int64_t *sc, int64_t new_mem_size, int *capacity_err) {
+  int64_t new_pages = new_mem_size / c.P;
+  int64_t total = sc[SC_NTOTAL];
+  if (new_pages < total - sc[SC_NFREE]) return 0;
+  if (new_pages == total) return 1;
+  if (new_pages > total) {
+    int64_t expand = new_pages - total;
+    int64_t reuse = sc[SC_CL_SIZE] < expand ? sc[SC_CL_SIZE] : expand;
+    if (expand - reuse > 0) {
+      // The reference would append ids total..new-1 here, which alias live pages after a shrink
+      // (page_allocator.cpp:343-346) and lie beyond the virtual range created at init.
+      if (capacity_err) *capacity_err = 1;
+      return 0;
+    }
+    for (int64_t i = 0; i < reuse; ++i) {
+      int p = dq_pop_front(c.cl, c.q_mask, sc, SC_CL_HEAD, SC_CL_SIZE);
+      dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+    }
+    sc[SC_NFREE] += reuse;
+    sc[SC_NTOTAL] = new_pages;
+    return 1;
+  }
+  int64_t reclaim = total - new_pages;
+  if (sc[SC_FL_SIZE] < reclaim) {
+    if (sc[SC_RL_SIZE] == 0) return 0;
+    while (sc[SC_RL_SIZE] > 0) {   // reserved pages are unmapped and appended to the free list
+      int p = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
+      ev_push(c, sc, p, 1);
+      dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+    }
+    if (sc[SC_FL_SIZE] < reclaim) return 0;
+  }
+  for (int64_t i = 0; i < reclaim; ++i) {
+    int p = dq_pop_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE);
+    dq_push_back(c.cl, c.q_mask, sc, SC_CL_HEAD, SC_CL_SIZE, p);
+  }
+  sc[SC_NFREE] -= reclaim;
+  sc[SC_NTOTAL] = new_pages;
+  return 1;
+}
+
+// PageAllocator::trim, csrc/page_allocator.cpp:403-427 (thread 0)
+__device__ void pa_trim(const DevState &c, int64_t *sc) {
+  while (sc[SC_RL_SIZE] > 0) {
+    int p = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
+    ev_push(c, sc, p, 1);
+    dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+  }
+}
+
+// ------------------------------------------------------------------------------------ block-wide scans
+// Ordered exclusive prefix of a per-thread flag over the CTA: __ballot_sync + __popc inside a warp,
+// warp totals through shared memory.  Returns the exclusive rank; *total receives the CTA total.
+__device__ __forceinline__ int block_rank(bool flag, int32_t *wtot, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned m = __ballot_sync(0xffffffffu, flag);
+  int r = __popc(m & ((1u << lane) - 1u));
+  if (lane == 0) wtot[w] = __popc(m);
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    int t = wtot[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + r;
+}
+// Ordered exclusive prefix sum of a per-thread int over the CTA (warp shuffles + shared memory).
+__device__ __forceinline__ int block_exscan(int v, int32_t *wtot, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wtot[w] = x;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    int t = wtot[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + x - v;
+}
+
+// ------------------------------------------------------------------------------------ libstdc++ policy
+// std::__detail::_Prime_rehash_policy::_M_next_bkt (libstdc++ 13, hashtable_c++0x.cc) with the
+// library's own __prime_list uploaded at init.
+__device__ int next_bkt(const DevState &c, int64_t n) {
+  const unsigned char fast[14] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13};
+  if (n < 14) return n == 0 ? 1 : fast[n];
+  int lo = 6, hi = c.n_primes - 1;   // lower_bound over [__prime_list + 6, last)
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (c.primes[mid] < (uint64_t)n) lo = mid + 1; else hi = mid;
+  }
+  return (int)c.primes[lo];
+}
+
+// Replays std::unordered_map<int64_t, ...>::operator[] for keys[0..D) (distinct, first-appearance
+// order) after reserve(n_ids / bpp + 1) and returns the container's iteration order as slot indices:
+// _M_insert_bucket_begin / _M_rehash_aux of libstdc++'s _Hashtable with unique keys, identity hash,
+// max_load_factor 1 (csrc/page_allocator.cpp:471-498 builds exactly this map; pybind11 walks it).
+// bkt[b] holds the node BEFORE bucket b's first node: -1 empty, -2 the before-begin sentinel.
+__device__ void ht_order(const DevState &c, const int32_t *keys, int D, int nb, int32_t *next, int32_t *bkt,
+                         int32_t *ord) {
+  int head = -1;
+  for (int d = 0; d < D; ++d) {
+    int k = keys[d];
+    if (d + 1 > nb) {   // _M_need_rehash: n_elt + 1 > _M_next_resize (= nb at load factor 1)
+      int64_t want = (int64_t)d + 2;
+      if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+      int nb2 = next_bkt(c, want);
+      for (int b = 0; b < nb2; ++b) bkt[b] = -1;
+      int p = head, bbegin = 0;
+      head = -1;
+      while (p >= 0) {   // _M_rehash_aux(unique keys)
+        int nx = next[p];
+        int b = keys[p] % nb2;
+        if (bkt[b] == -1) {
+          next[p] = head;
+          head = p;
+          bkt[b] = -2;
+          if (next[p] >= 0) bkt[bbegin] = p;
+          bbegin = b;
+        } else {
+          int prev = bkt[b];
+          if (prev == -2) { next[p] = head; head = p; }
+          else { next[p] = next[prev]; next[prev] = p; }
+        }
+        p = nx;
+      }
+      nb = nb2;
+    }
+    int b = k % nb;
+    int prev = bkt[b];
+    if (prev != -1) {   // bucket not empty: insert after its before-node
+      if (prev == -2) { next[d] = head; head = d; }
+      else { next[d] = next[prev]; next[prev] = d; }
+    } else {            // empty bucket: new node becomes the global head
+      next[d] = head;
+      head = d;
+      if (next[d] >= 0) bkt[keys[next[d]] % nb] = d;
+      bkt[b] = -2;
+    }
+  }
+  int i = 0;
+  for (int p = head; p >= 0; p = next[p]) ord[i++] = p;
+}
+// bucket count the table ends with (decides shared vs global tables before the replay)
+__device__ int ht_final_buckets(const DevState &c, int D, int nb0) {
+  int nb = nb0;
+  for (int d = 0; d < D; ++d) {
+    if (d + 1 > nb) {
+      int64_t want = (int64_t)d + 2;
+      if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+      nb = next_bkt(c, want);
+      if (nb >= D) break;
+    }
+  }
+  return nb;
+}
+
+// ==================================================================================== alloc run
+// Thread 0: walk requests [sim.op, run_end) and cut the free-block stream into segments
+// (kv_cache_manager.py:250-304 for every request, in order).
+__device__ void alloc_walk(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int run_end,
+                           int to_reserved) {
+  AllocSim &m = s.sim;
+  int64_t *sc = s.sc;
+  m.nseg = 0;
+  m.nfresh = 0;
+  m.round_base = m.out_pos;
+  while (true) {
+    if (!m.req_active) {
+      if (m.op >= run_end) { m.done = 1; break; }
+      if (m.nseg >= SEG_CAP - 2) goto round_full;
+      const kvb_op &o = s.ops[m.op - chunk_base];
+      int64_t need = o.n;
+      kvb_res r;
+      if (avail_size(c, sc) < need || need < 0) {   // -> None, state unchanged
+        r.status = to_reserved ? KVB_ST_FALSE : KVB_ST_NONE;
+        r.n = 0;
+        r.off = m.out_pos;
+        r.avail = avail_size(c, sc);
+        a.res[m.op] = r;
+        m.op++;
+        continue;
+      }
+      if (!to_reserved && m.out_pos + need > a.out_cap) {   // output buffer exhausted: stop before this request
+        s.misc[MI_STOP] = 1;
+        m.done = 1;
+        break;
+      }
+      m.req_active = 1;
+      m.req_rem = need;
+      m.req_off = m.out_pos;
+      m.req_n = need;
+      m.failed = 0;
+      // reserved blocks first (:272-277)
+      int64_t take = sc[SC_NRB] < need ? sc[SC_NRB] : need;
+      if (take > 0) {
+        Seg g;
+        g.out_rel = (int32_t)(m.out_pos - m.round_base);
+        g.page = -1;
+        g.base = (int32_t)sc[SC_RB_HEAD];
+        g.len_kind = (int32_t)take | (SEG_RB << 28);
+        s.segs[m.nseg++] = g;
+        sc[SC_RB_HEAD] = (sc[SC_RB_HEAD] + take) & c.rb_mask;
+        sc[SC_NRB] -= take;
+        m.out_pos += take;
+        m.req_rem -= take;
+      }
+    }
+    // page loop (:279-302)
+    while (m.req_rem > 0) {
+      if (m.nseg >= SEG_CAP - 1 || m.nfresh >= FRESH_CAP) goto round_full;
+      if (m.cur_p < 0) {
+        // avail_pages.popitem(): last live entry of the stack
+        int i = m.ap_top - 1;
+        int found = -1;
+        while (i >= 0) {
+          int k = m.ap_tail0 - 1 - i;
+          int e = (k < APW) ? s.apw[k] : c.ap[i];
+          if (e >= 0) { found = e; break; }
+          --i;
+        }
+        if (found >= 0) {
+          int k = m.ap_tail0 - 1 - i;
+          m.cur_p = found;
+          m.cur_cnt = (k < APW) ? s.apcnt[k] : c.pg_cnt[found];
+          m.cur_head = (k < APW) ? s.aphead[k] : c.pg_head[found];
+          m.cur_fresh = 0;
+          m.cur_idx = i;
+          m.ap_top = i + 1;
+        } else {
+          m.ap_top = 0;
+          // PageAllocator::alloc_page (page_allocator.cpp:161-237): reserved list first, then free list
+          int j = m.newpg_j;
+          int p;
+          int from_reserved = sc[SC_RL_SIZE] > 0;
+          if (!from_reserved && sc[SC_FL_SIZE] <= 0) {   // "No free pages left"
+            m.failed = 1;
+            break;
+          }
+          if (from_reserved) {
+            p = (j < NEWPG_W) ? s.newpg[j] : c.rl[(int)(sc[SC_RL_HEAD] & c.q_mask)];
+            sc[SC_RL_HEAD] = (sc[SC_RL_HEAD] + 1) & c.q_mask;
+            sc[SC_RL_SIZE] -= 1;
+          } else {
+            p = (j < NEWPG_W) ? s.newpg[j] : c.fl[(int)(sc[SC_FL_HEAD] & c.q_mask)];
+            sc[SC_FL_HEAD] = (sc[SC_FL_HEAD] + 1) & c.q_mask;
+            sc[SC_FL_SIZE] -= 1;
+            ev_push(c, sc, p, 0);
+          }
+          m.newpg_j = j + 1;
+          sc[SC_NFREE] -= 1;
+          int nb = pg_nblk(c, p);
+          c.pg_head[p] = 0;
+          if (nb <= 0) {   // page holds no whole block: parked in full_pages (:287-289)
+            c.pg_state[p] = PG_FULL;
+            c.pg_cnt[p] = 0;
+            sc[SC_NFULLPG] += 1;
+            continue;
+          }
+          sc[SC_NAB] += nb;
+          s.fresh[m.nfresh++] = make_int2(p, nb);
+          m.cur_p = p;
+          m.cur_cnt = nb;
+          m.cur_head = 0;
+          m.cur_fresh = 1;
+          m.cur_idx = -1;
+        }
+      }
+      int t = (int)(m.cur_cnt < m.req_rem ? m.cur_cnt : m.req_rem);
+      Seg g;
+      g.out_rel = (int32_t)(m.out_pos - m.round_base);
+      g.page = m.cur_p;
+      g.base = m.cur_head;
+      g.len_kind = t | ((m.cur_fresh ? SEG_FRESH : SEG_RING) << 28);
+      s.segs[m.nseg++] = g;
+      m.cur_cnt -= t;
+      m.cur_head += t;
+      if (!m.cur_fresh && m.cur_head >= c.bpp) m.cur_head -= c.bpp;
+      sc[SC_NAB] -= t;
+      m.out_pos += t;
+      m.req_rem -= t;
+      if (m.cur_cnt == 0) {   // page.full() -> full_pages
+        int p = m.cur_p;
+        c.pg_state[p] = PG_FULL;
+        c.pg_cnt[p] = 0;
+        c.pg_head[p] = m.cur_fresh ? 0 : m.cur_head;
+        sc[SC_NFULLPG] += 1;
+        if (m.cur_idx >= 0) { sc[SC_NAVAILPG] -= 1; m.ap_top = m.cur_idx; }
+        m.cur_p = -1;
+      }
+    }
+    {
+      // request finished (or failed)
+      kvb_res r;
+      r.status = m.failed ? KVB_ST_NO_PAGES : KVB_ST_OK;
+      r.n = m.failed ? 0 : (int32_t)m.req_n;
+      r.off = m.req_off;
+      r.avail = avail_size(c, sc);
+      a.res[m.op] = r;
+      m.req_active = 0;
+      m.req_rem = 0;
+      m.op++;
+    }
+  }
+round_full:
+  if (m.done) {
+    // run over: the page under consumption goes back to avail_pages as the newest entry
+    if (m.cur_p >= 0) {
+      int p = m.cur_p;
+      c.pg_cnt[p] = m.cur_cnt;
+      if (m.cur_fresh) {
+        // ring of a fresh page is materialised as the identity; its head is the consumed prefix
+        c.pg_head[p] = m.cur_head;
+        c.pg_state[p] = PG_AVAIL;
+        c.ap[m.ap_top] = p;
+        c.pg_pos[p] = m.ap_top;
+        m.ap_top += 1;
+        sc[SC_NAVAILPG] += 1;
+      } else {
+        c.pg_head[p] = m.cur_head;
+      }
+      m.cur_p = -1;
+    }
+    sc[SC_AP_TAIL] = m.ap_top;
+  }
+}
+
+// All threads: materialise the round — fresh-page rings, output ids, bitmap bits.
+__device__ void alloc_emit(const DevState &c, Smem &s, const LaunchArgs &a, int64_t *dst, int64_t dst_mask) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const AllocSim &m = s.sim;
+  // fresh pages: ring[p][t] = t (InternalPage::init, page_allocator.cpp:44-53)
+  for (int f = w; f < m.nfresh; f += NW) {
+    int2 pg = s.fresh[f];
+    uint32_t *r = c.ring + (size_t)pg.x * c.bpp;
+    for (int t = lane; t < pg.y; t += 32) r[t] = (uint32_t)t;
+  }
+  for (int g = w; g < m.nseg; g += NW) {
+    Seg sg = s.segs[g];
+    int kind = sg.len_kind >> 28, len = sg.len_kind & 0x0fffffff;
+    int64_t o = m.round_base + sg.out_rel;
+    if (kind == SEG_RB) {
+      for (int t = lane; t < len; t += 32) {
+        int64_t id = c.rb[(sg.base + t) & c.rb_mask];
+        if (dst_mask) dst[(o + t) & dst_mask] = id; else dst[o + t] = id;
+      }
+    } else {
+      int64_t start = pg_start(c, sg.page);
+      const uint32_t *r = c.ring + (size_t)sg.page * c.bpp;
+      for (int t = lane; t < len; t += 32) {
+        int64_t id;
+        if (kind == SEG_FRESH) {
+          id = start + sg.base + t;
+        } else {
+          int pos = sg.base + t;
+          if (pos >= c.bpp) pos -= c.bpp;
+          id = start + r[pos];
+        }
+        if (dst_mask) dst[(o + t) & dst_mask] = id; else dst[o + t] = id;
+        atomicOr(&c.bitmap[id >> 5], 1u << (id & 31));
+      }
+    }
+  }
+}
+
+// A run of consecutive ALLOC requests [op0, run_end) (all inside the staged chunk), or one
+// TRY_RESERVE request (to_reserved = 1, ids appended to reserved_blocks instead of the output).
+__device__ void alloc_run(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end,
+                          int to_reserved) {
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+  // prefetch the top of the avail stack and the next fresh page ids
+  {
+    int tail = (int)sc[SC_AP_TAIL];
+    if (tid < APW) {
+      int i = tail - 1 - tid;
+      int e = (i >= 0) ? c.ap[i] : -1;
+      s.apw[tid] = e;
+      if (e >= 0) { s.apcnt[tid] = c.pg_cnt[e]; s.aphead[tid] = c.pg_head[e]; }
+    }
+    if (tid >= NT - NEWPG_W) {
+      int j = tid - (NT - NEWPG_W);
+      int rls = (int)sc[SC_RL_SIZE], fls = (int)sc[SC_FL_SIZE];
+      int v = -1;
+      if (j < rls) v = c.rl[(int)((sc[SC_RL_HEAD] + j) & c.q_mask)];
+      else if (j - rls < fls) v = c.fl[(int)((sc[SC_FL_HEAD] + (j - rls)) & c.q_mask)];
+      s.newpg[j] = v;
+    }
+    if (tid == 0) {
+      AllocSim &m = s.sim;
+      m.op = op0;
+      m.req_active = 0;
+      m.req_rem = 0;
+      m.ap_top = tail;
+      m.ap_tail0 = tail;
+      m.cur_p = -1;
+      m.newpg_j = 0;
+      m.done = 0;
+      m.failed = 0;
+      if (to_reserved) {
+        // ids go to the back of the reserved_blocks ring
+        m.out_pos = sc[SC_RB_HEAD] + sc[SC_NRB];
+      } else {
+        m.out_pos = sc[SC_OUT_CURSOR];
+      }
+    }
+  }
+  __syncthreads();
+  // NOTE on newpg: entry j of the window is the j-th page alloc_page() will hand out in this run
+  // (all of the reserved list, then the free list): nothing pushes to either list during a run.
+  while (true) {
+    if (tid == 0) alloc_walk(c, s, a, chunk_base, run_end, to_reserved);
+    __syncthreads();
+    if (to_reserved) alloc_emit(c, s, a, c.rb, (int64_t)c.rb_mask);
+    else alloc_emit(c, s, a, a.out_ids, 0);
+    int done = s.sim.done;
+    __syncthreads();
+    if (done) break;
+  }
+  if (tid == 0) {
+    if (to_reserved) {
+      // try_to_reserve: reserved_blocks.extend(result) (:371); alloc() consumed the old front first
+      const kvb_res &r = a.res[op0];
+      if (r.status == KVB_ST_OK) sc[SC_NRB] += r.n;
+    } else {
+      sc[SC_OUT_CURSOR] = s.sim.out_pos;
+    }
+  }
+  __syncthreads();
+}
+
+// ==================================================================================== free
+// Compact the avail stack (drop tombstones, keep order) when it has grown past max_pages.
+__device__ void ap_compact(const DevState &c, Smem &s) {
+  int tail = (int)s.sc[SC_AP_TAIL];
+  if (tail <= c.max_pages) return;   // uniform
+  int base = 0;
+  for (int i0 = 0; i0 < tail; i0 += NT) {
+    int i = i0 + threadIdx.x;
+    int e = (i < tail) ? c.ap[i] : -1;
+    int tot;
+    int r = block_rank(e >= 0, s.wtot, &tot);
+    // all reads of this chunk happened before block_rank's barriers; writes land at or below i
+    if (e >= 0) { c.ap[base + r] = e; c.pg_pos[e] = base + r; }
+    base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s.sc[SC_AP_TAIL] = base;
+  __syncthreads();
+}
+
+// free(ids) for the n ids already gathered in c.fids (kv_cache_manager.py:307-360).
+// `n_decl` is len(indices) as the reference sees it (sizes the unordered_map reserve()).
+// group_only: no state change; writes the grouping (pages, counts, ids) for kvb_group_indices_by_page.
+__device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n, int group_only) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int64_t *sc = s.sc;
+  if (n <= 0) return;
+  if (!group_only) ap_compact(c, s);
+  if (tid == 0) { s.misc[MI_BAD] = 0; s.misc[MI_UNK] = 0; }
+  for (int i = tid; i < HT_D_CAP; i += NT) s.ht_cnt[i] = 0;
+  __syncthreads();
+
+  // ---- F0: classify ids: page arithmetic + bitmap test-and-clear (a block must be allocated) -----
+  int bad = 0;
+  for (int j = tid; j < n; j += NT) {
+    int64_t id = c.fids[j];
+    int32_t pg = INT_MIN;
+    if (id >= 0 && id < c.num_blocks) {
+      int64_t p64 = blk_page(c, id);
+      if (p64 < c.max_pages) {
+        int p = (int)p64;
+        bool ok = true;
+        if (!c.exact && !group_only) {   // a block straddling the page edge is never handed out
+          int64_t st = pg_start(c, p);
+          ok = id >= st && id < st + pg_nblk(c, p);
+        }
+        if (ok && !group_only) {
+          uint32_t bit = 1u << (id & 31);
+          uint32_t old = atomicAnd(&c.bitmap[id >> 5], ~bit);
+          ok = (old & bit) != 0;
+        }
+        pg = ok ? p : ~p;   // ~p: page takes part in the dict order, the id is ignored
+      }
+    }
+    if (pg < 0) bad++;
+    c.fpage[j] = pg;
+  }
+  if (bad) atomicAdd(&s.misc[MI_BAD], bad);
+  __syncthreads();
+
+  // ---- F1: first index naming each page (only run heads can be first) ---------------------------
+  for (int j = tid; j < n; j += NT) {
+    int32_t pg = c.fpage[j];
+    if (pg == INT_MIN) continue;
+    int p = pg < 0 ? ~pg : pg;
+    bool head = true;
+    if (j > 0) {
+      int32_t q = c.fpage[j - 1];
+      if (q != INT_MIN && (q < 0 ? ~q : q) == p) head = false;
+    }
+    if (head) atomicMin(&c.pg_first[p], j);
+  }
+  __syncthreads();
+
+  // ---- F2: distinct pages in first-appearance order (ballot/popc compaction) -------------------
+  int D = 0;
+  for (int j0 = 0; j0 < n; j0 += NT) {
+    int j = j0 + tid;
+    int p = -1;
+    bool first = false;
+    if (j < n) {
+      int32_t pg = c.fpage[j];
+      if (pg != INT_MIN) {
+        p = pg < 0 ? ~pg : pg;
+        first = (c.pg_first[p] == j);
+      }
+    }
+    int tot;
+    int r = block_rank(first, s.wtot, &tot);
+    if (first) {
+      int d = D + r;
+      c.pg_slot[p] = d;
+      if (d < HT_D_CAP) s.ht_key[d] = p;
+      c.g_dist[d] = p;
+      c.g_cnt[d] = 0;
+    }
+    D += tot;
+  }
+  __syncthreads();
+
+  // ---- F3: dict order (one lane) || per-page FIFO ranks (one warp) --------------------------------
+  // groups.reserve(n / bpp + 1): csrc/page_allocator.cpp:477
+  int nb0 = next_bkt(c, (int64_t)n / c.bpp + 1);
+  int nbf = ht_final_buckets(c, D, nb0);
+  const bool use_g = (D > HT_D_CAP) || (nbf > HT_NB_CAP);
+  int32_t *keys = use_g ? c.g_dist : s.ht_key;
+  int32_t *nxt = use_g ? c.g_next : s.ht_next;
+  int32_t *bkt = use_g ? c.g_bkt : s.ht_bkt;
+  int32_t *ord = use_g ? c.g_ord : s.ht_ord;
+  int32_t *cnt = use_g ? c.g_cnt : s.ht_cnt;
+  if (w == 0) {
+    for (int b = lane; b < nb0; b += 32) bkt[b] = -1;
+    __syncwarp();
+    if (lane == 0) ht_order(c, keys, D, nb0, nxt, bkt, ord);
+  } else if (w == 1) {
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      int j = j0 + lane;
+      int32_t pg = (j < n) ? c.fpage[j] : INT_MIN;
+      int slot = (pg >= 0) ? c.pg_slot[pg] : -1 - lane;   // distinct negatives: no grouping
+      unsigned mask = __match_any_sync(0xffffffffu, slot);
+      int r = __popc(mask & ((1u << lane) - 1u));
+      int basecnt = 0;
+      if (slot >= 0) basecnt = cnt[slot];
+      __syncwarp();
+      if (slot >= 0 && r == 0) cnt[slot] = basecnt + __popc(mask);
+      __syncwarp();
+      if (slot >= 0) {
+        int rank = basecnt + r;
+        if (group_only) {
+          c.fpage[j] = rank;   // reuse as rank store; the page is recoverable from the id
+        } else {
+          int p = pg;
+          int pos = c.pg_head[p] + c.pg_cnt[p] + rank;   // InternalPage::free_batch appends (:69-73)
+          pos %= c.bpp;
+          c.ring[(size_t)p * c.bpp + pos] = (uint32_t)(c.fids[j] - pg_start(c, p));
+        }
+      } else if (group_only && j < n) {
+        c.fpage[j] = -1;
+      }
+    }
+  }
+  __syncthreads();
+
+  if (group_only) {
+    // pages in dict order, their id counts, ids regrouped by page
+    int run = 0;
+    for (int d0 = 0; d0 < D; d0 += NT) {
+      int d = d0 + tid;
+      int slot = (d < D) ? ord[d] : 0;
+      int cn = (d < D) ? cnt[slot] : 0;
+      int tot;
+      int ex = block_exscan(cn, s.wtot, &tot);
+      if (d < D) {
+        a.grp_pages[d] = keys[slot];
+        a.grp_counts[d] = cn;
+        c.g_ptf[slot] = run + ex;   // output offset of the slot's first id
+      }
+      run += tot;
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += NT) {
+      int rank = c.fpage[j];
+      if (rank < 0) continue;
+      int64_t id = c.fids[j];
+      int p = (int)blk_page(c, id);
+      a.grp_ids[c.g_ptf[c.pg_slot[p]] + rank] = id;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += NT) c.pg_first[keys[d]] = INT_MAX;
+    if (tid == 0) s.misc[MI_D] = D;
+    __syncthreads();
+    return;
+  }
+
+  // ---- F4: per-page update in dict order (:322-349) -----------------------------------------------
+  if (tid == 0) { s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; s.acc[3] = 0; }
+  __syncthreads();
+  int tail = (int)sc[SC_AP_TAIL];
+  int E = 0;
+  for (int d0 = 0; d0 < D; d0 += NT) {
+    int d = d0 + tid;
+    bool live = false, empty = false;
+    int p = -1, add = 0, st = PG_NONE, newc = 0;
+    if (d < D) {
+      int slot = ord[d];
+      p = keys[slot];
+      add = cnt[slot];
+      st = c.pg_state[p];
+      c.pg_first[p] = INT_MAX;   // reset scratch
+      if (st == PG_NONE) {
+        atomicAdd(&s.misc[MI_UNK], 1);   // page not in avail_pages / full_pages: logged and skipped
+      } else if (add > 0) {
+        live = true;
+        newc = c.pg_cnt[p] + add;
+        empty = (newc == pg_nblk(c, p));   // InternalPage::empty (:75-77)
+      }
+    }
+    int totS, totE;
+    int rs = block_rank(live && !empty, s.wtot, &totS);
+    int re = block_rank(live && empty, s.wtot2, &totE);
+    if (live) {
+      if (st == PG_AVAIL) c.ap[c.pg_pos[p]] = -1;   // avail_pages.pop(page_id)
+      long long dnab = add;
+      if (empty) {
+        c.g_ptf[E + re] = p;
+        c.pg_state[p] = PG_NONE;
+        c.pg_cnt[p] = 0;
+        dnab -= newc;
+      } else {
+        c.ap[tail + rs] = p;            // avail_pages[page_id] = page (newest)
+        c.pg_pos[p] = tail + rs;
+        c.pg_state[p] = PG_AVAIL;
+        c.pg_cnt[p] = newc;
+      }
+      atomicAdd((unsigned long long *)&s.acc[0], (unsigned long long)dnab);
+      int dav = (empty ? 0 : 1) - (st == PG_AVAIL ? 1 : 0);
+      int dfu = -(st == PG_FULL ? 1 : 0);
+      if (dav) atomicAdd((unsigned long long *)&s.acc[1], (unsigned long long)(long long)dav);
+      if (dfu) atomicAdd((unsigned long long *)&s.acc[2], (unsigned long long)(long long)dfu);
+    }
+    tail += totS;
+    E += totE;
+  }
+  __syncthreads();
+
+  // ---- F5: PageAllocator::free_pages(pages_to_free) (page_allocator.cpp:264-310) --------------------
+  int rl_size = (int)sc[SC_RL_SIZE], fl_size = (int)sc[SC_FL_SIZE];
+  int room = c.max_reserved - rl_size;
+  int k = room > 0 ? (room < E ? room : E) : 0;
+  int64_t nev0 = sc[SC_NEV];
+  for (int i = tid; i < E; i += NT) {
+    int p = c.g_ptf[i];
+    if (i < k) {
+      c.rl[(int)((sc[SC_RL_HEAD] + rl_size + i) & c.q_mask)] = p;   // stays mapped
+    } else {
+      int u = i - k;
+      c.fl[(int)((sc[SC_FL_HEAD] + fl_size + u) & c.q_mask)] = p;
+      if (nev0 + u < c.ev_cap) c.ev[nev0 + u] = (int64_t)p * 2 + 1;
+      c.pg_mapped[p] = 0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sc[SC_NAB] += s.acc[0];
+    sc[SC_NAVAILPG] += s.acc[1];
+    sc[SC_NFULLPG] += s.acc[2];
+    sc[SC_AP_TAIL] = tail;
+    sc[SC_NFREE] += E;
+    sc[SC_RL_SIZE] += k;
+    sc[SC_FL_SIZE] += E - k;
+    sc[SC_NEV] += E - k;
+    sc[SC_NMAPPED] -= E - k;
+    sc[SC_PHYS] += E - k;
+    sc[SC_BAD_FREES] += s.misc[MI_BAD];
+    sc[SC_UNKNOWN_FREES] += s.misc[MI_UNK];
+    // pending shrink completes once usage is under the target (:354-360); resize result ignored
+    if (sc[SC_INSHRINK] && alloced_blocks(c, sc) <= sc[SC_TARGET]) {
+      pa_resize(c, sc, sc[SC_TARGET] * c.B, nullptr);
+      sc[SC_INSHRINK] = 0;
+      sc[SC_TARGET] = -1;
+    }
+  }
+  __syncthreads();
+}
+
+// Gather the ids of a FREE_REF request into c.fids: concat of result(op)[lo:hi] of earlier requests.
+// Returns the id count (uniform).
+__device__ int gather_refs(const DevState &c, Smem &s, const LaunchArgs &a, int64_t ref_off, int nrefs) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int total = 0;
+  int64_t *r_src = s.tmp64;     // staged (source offset, length, destination) of one chunk of refs
+  int32_t *r_len = s.ht_next;   // borrowed shared arrays (free_core has not started)
+  int32_t *r_dst = s.ht_ord;
+  for (int r0 = 0; r0 < nrefs; r0 += NT) {
+    int r = r0 + tid;
+    int len = 0;
+    int64_t src = 0;
+    if (r < nrefs) {
+      kvb_ref rf = a.refs[ref_off + r];
+      kvb_res rs = a.res[rf.op];
+      int n = rs.status == KVB_ST_OK ? rs.n : 0;
+      int lo = rf.lo < 0 ? (rf.lo + n < 0 ? 0 : rf.lo + n) : (rf.lo > n ? n : rf.lo);
+      int hi = rf.hi < 0 ? (rf.hi + n < 0 ? 0 : rf.hi + n) : (rf.hi > n ? n : rf.hi);
+      len = hi > lo ? hi - lo : 0;
+      src = rs.off + lo;
+    }
+    int tot;
+    int ex = block_exscan(len, s.wtot, &tot);
+    r_src[tid] = src;
+    r_len[tid] = len;
+    r_dst[tid] = total + ex;
+    __syncthreads();
+    int nr = nrefs - r0 < NT ? nrefs - r0 : NT;
+    for (int q = w; q < nr; q += NW) {   // one warp copies one ref's ids
+      int64_t so = r_src[q];
+      int ln = r_len[q], dp = r_dst[q];
+      for (int t = lane; t < ln; t += 32)
+        if (dp + t < c.f_cap) c.fids[dp + t] = a.out_ids[so + t];
+    }
+    total += tot;
+    __syncthreads();
+  }
+  return total;
+}
+
+// ==================================================================================== clear
+// KVCacheManager.clear (kv_cache_manager.py:444-489; semantics SURVEY A.7): everything released,
+// reserved pages trimmed, free list sorted ascending, counters zeroed.  The null block is
+// re-reserved by the caller through the alloc path.
+__device__ void clear_all(const DevState &c, Smem &s) {
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+  // membership of the new free list = old free list + reserved list + every in-use page.
+  // pg_slot is borrowed as the membership flag.
+  for (int p = tid; p < c.max_pages; p += NT) c.pg_slot[p] = (c.pg_state[p] != PG_NONE) ? 1 : 0;
+  __syncthreads();
+  int fls = (int)sc[SC_FL_SIZE], rls = (int)sc[SC_RL_SIZE];
+  for (int i = tid; i < fls; i += NT) c.pg_slot[c.fl[(int)((sc[SC_FL_HEAD] + i) & c.q_mask)]] = 1;
+  for (int i = tid; i < rls; i += NT) c.pg_slot[c.rl[(int)((sc[SC_RL_HEAD] + i) & c.q_mask)]] = 1;
+  __syncthreads();
+  // unmap events for every mapped page (in-use pages beyond the reserved cap + the trimmed reserve)
+  int nev = (int)sc[SC_NEV];
+  int base = 0, evn = 0;
+  for (int p0 = 0; p0 < c.max_pages; p0 += NT) {
+    int p = p0 + tid;
+    bool in = (p < c.max_pages) && c.pg_slot[p];
+    bool mp = (p < c.max_pages) && c.pg_mapped[p];
+    int tot, totm;
+    int r = block_rank(in, s.wtot, &tot);
+    int rm = block_rank(mp, s.wtot2, &totm);
+    if (in) c.fl[base + r] = p;   // reset_free_page_order: ascending (page_allocator.cpp:703-709)
+    if (mp) {
+      if (nev + evn + rm < c.ev_cap) c.ev[nev + evn + rm] = (int64_t)p * 2 + 1;
+      c.pg_mapped[p] = 0;
+    }
+    if (p < c.max_pages) {
+      c.pg_state[p] = PG_NONE;
+      c.pg_cnt[p] = 0;
+      c.pg_head[p] = 0;
+    }
+    base += tot;
+    evn += totm;
+  }
+  __syncthreads();
+  int64_t nwords = (c.num_blocks + 31) / 32;
+  for (int64_t i = tid; i < nwords; i += NT) c.bitmap[i] = 0;
+  if (tid == 0) {
+    sc[SC_FL_HEAD] = 0;
+    sc[SC_FL_SIZE] = base;
+    sc[SC_RL_HEAD] = 0;
+    sc[SC_RL_SIZE] = 0;
+    sc[SC_NFREE] = base;
+    sc[SC_NAB] = 0;
+    sc[SC_INSHRINK] = 0;
+    sc[SC_TARGET] = -1;
+    sc[SC_RB_HEAD] = 0;
+    sc[SC_NRB] = 0;
+    sc[SC_AP_TAIL] = 0;
+    sc[SC_NAVAILPG] = 0;
+    sc[SC_NFULLPG] = 0;
+    sc[SC_NEV] += evn;
+    sc[SC_PHYS] += evn;
+    sc[SC_NMAPPED] -= evn;
+    sc[SC_HAS_NULL] = 0;
+  }
+  __syncthreads();
+}
+
+}  // namespace
+
+// ==================================================================================== the step kernel
+__global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+
+  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
+  if (tid < 16) s.misc[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    sc[SC_PHYS] = a.phys_free;
+    sc[SC_LAUNCHES] += 1;
+    if (a.arena_mode == 0) sc[SC_OUT_CURSOR] = 0;
+    if (a.arena_mode != 1) sc[SC_NEV] = 0;
+  }
+  __syncthreads();
+  const int64_t ev_begin = sc[SC_NEV];
+  const int64_t out_begin = sc[SC_OUT_CURSOR];
+
+  int op = a.op_begin;
+  while (op < a.op_end && !s.misc[MI_STOP]) {
+    const int chunk_base = op;
+    const int chunk_n = (a.op_end - op) < OPS_CHUNK ? (a.op_end - op) : OPS_CHUNK;
+    if (tid < chunk_n) s.ops[tid] = a.ops[chunk_base + tid];
+    __syncthreads();
+    while (op < chunk_base + chunk_n && !s.misc[MI_STOP]) {
+      const kvb_op o = s.ops[op - chunk_base];
+      if (a.arena_mode != 1 && sc[SC_NEV] + 2 * (int64_t)c.max_pages + 8 > c.ev_cap) {   // event log nearly full: hand back to the host
+        if (tid == 0) s.misc[MI_STOP] = 1;
+        __syncthreads();
+        break;
+      }
+      if (a.group_only) {
+        for (int j = tid; j < o.n; j += NT) c.fids[j] = a.ids[o.arg + j];
+        __syncthreads();
+        free_core(c, s, a, o.n, 1);
+        if (tid == 0) { kvb_res r; r.status = KVB_ST_OK; r.n = s.misc[MI_D]; r.off = 0; r.avail = 0; a.res[op] = r; }
+        op++;
+        continue;
+      }
+      switch (o.kind) {
+        case KVB_OP_ALLOC: {
+          int e = op + 1;
+          while (e < chunk_base + chunk_n && s.ops[e - chunk_base].kind == KVB_OP_ALLOC) ++e;
+          alloc_run(c, s, a, chunk_base, op, e, 0);
+          op = s.sim.op;   // == e unless the output buffer ran out
+          break;
+        }
+        case KVB_OP_TRY_RESERVE: {
+          alloc_run(c, s, a, chunk_base, op, op + 1, 1);
+          op++;
+          break;
+        }
+        case KVB_OP_FREE_IDS:
+        case KVB_OP_FREE_REF:
+        case KVB_OP_FREE_RESERVED: {
+          int n = 0;
+          if (o.kind == KVB_OP_FREE_IDS) {
+            n = o.n;
+            for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j];
+          } else if (o.kind == KVB_OP_FREE_REF) {
+            n = gather_refs(c, s, a, o.arg, o.n);
+          } else {
+            n = (int)sc[SC_NRB];
+            for (int j = tid; j < n; j += NT) c.fids[j] = c.rb[(int)((sc[SC_RB_HEAD] + j) & c.rb_mask)];
+          }
+          __syncthreads();
+          const bool too_many = n > c.f_cap;   // more ids than blocks exist: cannot be a valid call
+          if (!too_many) free_core(c, s, a, n, 0);
+          if (tid == 0) {
+            if (o.kind == KVB_OP_FREE_RESERVED) { sc[SC_NRB] = 0; sc[SC_RB_HEAD] = 0; }
+            kvb_res r; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_RESIZE: {   // KVCacheManager.resize, kv_cache_manager.py:381-401
+          if (tid == 0) {
+            kvb_res r; r.n = 0; r.off = 0;
+            int cap_err = 0;
+            if (pa_resize(c, sc, o.arg, &cap_err)) {
+              if (sc[SC_INSHRINK]) { sc[SC_INSHRINK] = 0; sc[SC_TARGET] = -1; }
+              r.status = KVB_ST_OK;
+            } else if (cap_err) {
+              r.status = KVB_ST_CAPACITY;
+            } else if (sc[SC_NRB] > 0) {
+              r.status = KVB_ST_ASSERT;
+            } else {
+              sc[SC_INSHRINK] = 1;
+              sc[SC_TARGET] = o.arg / c.B;
+              r.status = KVB_ST_FALSE;
+            }
+            r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_PA_RESIZE: {
+          if (tid == 0) {
+            kvb_res r; r.n = 0; r.off = 0;
+            int cap_err = 0;
+            r.status = pa_resize(c, sc, o.arg, &cap_err) ? KVB_ST_OK : (cap_err ? KVB_ST_CAPACITY : KVB_ST_FALSE);
+            r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_TRIM: {
+          if (tid == 0) {
+            pa_trim(c, sc);
+            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_AVAIL: {
+          if (tid == 0) {
+            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          op++;
+          break;
+        }
+        case KVB_OP_CLEAR: {
+          // free_reserved(); free_pages(all); trim(); reset_free_page_order(); counters = 0
+          clear_all(c, s);
+          if (tid == 0) {
+            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_ALLOC_PAGE: {   // PageAllocator::alloc_page, page_allocator.cpp:161-237
+          if (tid == 0) {
+            kvb_res r; r.n = 0; r.off = -1;
+            if (sc[SC_RL_SIZE] > 0) {
+              r.off = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
+              sc[SC_NFREE] -= 1;
+              r.status = KVB_ST_OK;
+            } else if (sc[SC_FL_SIZE] > 0) {
+              int p = dq_pop_front(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE);
+              sc[SC_NFREE] -= 1;
+              ev_push(c, sc, p, 0);
+              r.off = p;
+              r.status = KVB_ST_OK;
+            } else {
+              r.status = KVB_ST_NO_PAGES;
+            }
+            if (r.status == KVB_ST_OK) {   // the page is held by the caller: account it as full
+              c.pg_state[(int)r.off] = PG_FULL;
+              c.pg_cnt[(int)r.off] = 0;
+              sc[SC_NFULLPG] += 1;
+            }
+            r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_FREE_PAGES: {   // PageAllocator::free_pages, page_allocator.cpp:264-310
+          if (tid == 0) {
+            int done = 0;
+            for (int i = 0; i < o.n; ++i) {
+              int64_t p64 = a.ids[o.arg + i];
+              if (p64 < 0 || p64 >= c.max_pages) continue;
+              int p = (int)p64;
+              if (c.pg_state[p] == PG_NONE) continue;
+              sc[SC_NFULLPG] -= (c.pg_state[p] == PG_FULL);
+              sc[SC_NAVAILPG] -= (c.pg_state[p] == PG_AVAIL);
+              c.pg_state[p] = PG_NONE;
+              sc[SC_NFREE] += 1;
+              if (sc[SC_RL_SIZE] < c.max_reserved) {
+                dq_push_back(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE, p);
+              } else {
+                ev_push(c, sc, p, 1);
+                dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+              }
+              done++;
+            }
+            kvb_res r; r.status = KVB_ST_OK; r.n = done; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        default: {
+          if (tid == 0) { kvb_res r; r.status = KVB_ERR_INVALID; r.n = 0; r.off = 0; r.avail = 0; a.res[op] = r; }
+          op++;
+          break;
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+
+  // publish
+  __syncthreads();
+  if (tid < SC_COUNT) c.sc[tid] = sc[tid];
+  Summary *sm = a.summary;
+  if (sm) {
+    int64_t nev = sc[SC_NEV] - ev_begin;
+    int64_t nin = nev < EV_INLINE ? nev : EV_INLINE;
+    for (int i = tid; i < nin; i += NT) sm->ev_inline[i] = c.ev[ev_begin + i];
+    if (tid < SC_COUNT) sm->sc[tid] = sc[tid];
+    __syncthreads();
+    if (tid == 0) {
+      sm->ops_done = op - a.op_begin;
+      sm->out_used = sc[SC_OUT_CURSOR] - out_begin;
+      sm->n_events = nev;
+      sm->ev_begin = ev_begin;
+      sm->ev_inline_n = nin;
+      __threadfence_system();
+      sm->seq = a.seq;   // written last: the host may poll it
+    }
+  }
+}
+
+// ==================================================================================== init
+// Initial state: free_page_list = 0..N-1 (page_allocator.cpp:121-124), everything else empty.
+__global__ void kvb_init_state_kernel(DevState c, int64_t num_total_pages) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = i; p < c.max_pages; p += stride) {
+    c.pg_state[p] = PG_NONE;
+    c.pg_cnt[p] = 0;
+    c.pg_head[p] = 0;
+    c.pg_pos[p] = -1;
+    c.pg_mapped[p] = 0;
+    c.pg_first[p] = INT_MAX;
+    c.pg_slot[p] = 0;
+    if (p < num_total_pages) c.fl[p] = (int32_t)p;
+  }
+  const int64_t nwords = (c.num_blocks + 31) / 32;
+  for (int64_t wd = i; wd < nwords + 4; wd += stride) c.bitmap[wd] = 0;
+  if (i < SC_COUNT) {
+    int64_t v = 0;
+    if (i == SC_NFREE || i == SC_NTOTAL || i == SC_FL_SIZE) v = num_total_pages;
+    if (i == SC_TARGET) v = -1;
+    c.sc[i] = v;
+  }
+}
+
+// ==================================================================================== audit sweep
+// Recount every page from the used-block bitmap with coalesced 128-bit loads + popc and compare with
+// the per-page counters; also counts in-use pages whose blocks are all free ("reclaimable").
+// out4 = {used blocks, in-use pages, fully-free in-use pages, mismatching pages}
+//   mode 0  bpp in {32, 64, 128}: a thread's uint4 (128 blocks) covers 128/bpp whole pages
+//   mode 1  bpp = 128 * g, g a power of two <= 32: g adjacent lanes hold one page, shuffle-reduce
+//   mode 2  anything else (blocks straddling page edges, odd sizes): one warp per page, masked words
+__device__ __forceinline__ void audit_page(const DevState &c, int64_t p, unsigned used_p, unsigned long long &used,
+                                           unsigned long long &inuse, unsigned long long &empties,
+                                           unsigned long long &bad) {
+  int st = c.pg_state[p];
+  used += used_p;
+  if (st != PG_NONE) {
+    inuse++;
+    if (used_p == 0) empties++;
+    if ((int)used_p != pg_nblk(c, (int)p) - c.pg_cnt[p]) bad++;
+  } else if (used_p != 0) {
+    bad++;
+  }
+}
+
+__global__ void __launch_bounds__(256) kvb_audit_kernel(DevState c, int64_t *out4, int mode) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long used = 0, inuse = 0, empties = 0, bad = 0;
+  if (mode == 0) {
+    const int ppv = 128 / c.bpp;          // pages per uint4: 4, 2 or 1
+    const int wpp = c.bpp / 32;           // words per page: 1, 2 or 4
+    const int64_t nvec = ((int64_t)c.max_pages + ppv - 1) / ppv;
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
+    for (int64_t q = gtid; q < nvec; q += gthreads) {
+      uint4 v = b4[q];
+      unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < ppv) {
+          int64_t p = q * ppv + k;
+          if (p < c.max_pages) {
+            unsigned u = 0;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              if (x < wpp) u += __popc(wd[k * wpp + x]);
+            audit_page(c, p, u, used, inuse, empties, bad);
+          }
+        }
+      }
+    }
+  } else if (mode == 1) {
+    const int g = c.bpp / 128;
+    const int64_t nvec = (int64_t)c.max_pages * g;
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
+    const int64_t span = (nvec + gthreads - 1) / gthreads;
+    for (int64_t it = 0; it < span; ++it) {   // uniform trip count: shuffles need the whole warp
+      int64_t q = it * gthreads + gtid;
+      unsigned u = 0;
+      if (q < nvec) {
+        uint4 v = b4[q];
+        u = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      }
+      for (int d = 1; d < g; d <<= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
+      if (q < nvec && (q % g) == 0) audit_page(c, q / g, u, used, inuse, empties, bad);
+    }
+  } else {
+    const int64_t warp = gtid >> 5, nwarps = gthreads >> 5;
+    for (int64_t p = warp; p < c.max_pages; p += nwarps) {
+      int64_t start = pg_start(c, (int)p);
+      int64_t end = start + pg_nblk(c, (int)p);
+      unsigned u = 0;
+      for (int64_t wd = (start >> 5) + lane; wd <= ((end - 1) >> 5) && end > start; wd += 32) {
+        unsigned x = c.bitmap[wd];
+        int64_t lo = wd << 5;
+        if (lo < start) x &= ~0u << (start - lo);
+        if (lo + 32 > end) x &= ~0u >> (lo + 32 - end);
+        u += __popc(x);
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
+      if (lane == 0) audit_page(c, p, u, used, inuse, empties, bad);
+    }
+  }
+  // warp-level reduction, one atomic per warp and counter
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    used += __shfl_xor_sync(0xffffffffu, used, d);
+    inuse += __shfl_xor_sync(0xffffffffu, inuse, d);
+    empties += __shfl_xor_sync(0xffffffffu, empties, d);
+    bad += __shfl_xor_sync(0xffffffffu, bad, d);
+  }
+  if (lane == 0) {
+    if (used) atomicAdd((unsigned long long *)&out4[0], used);
+    if (inuse) atomicAdd((unsigned long long *)&out4[1], inuse);
+    if (empties) atomicAdd((unsigned long long *)&out4[2], empties);
+    if (bad) atomicAdd((unsigned long long *)&out4[3], bad);
+  }
+}
+
+// Dump avail_pages in insertion order (tests): skips tombstones.
+__global__ void kvb_dump_avail_kernel(DevState c, int64_t *out, int64_t *n_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int tail = (int)c.sc[SC_AP_TAIL];
+    int64_t n = 0;
+    for (int i = 0; i < tail; ++i) {
+      int e = c.ap[i];
+      if (e >= 0) out[n++] = e;
+    }
+    *n_out = n;
+  }
+}
+
+// ==================================================================================== KV scatter / gather
+// One warp moves one token's K (or V) cell of one layer: cell_bytes contiguous bytes between the
+// dense source [kv][layer][T][cell] and the paged destination
+//   base + block*stride_block + in_block*stride_token + layer*stride_layer + kv*stride_kv
+// (kvcached/integration/vllm/interfaces.py:281-298, integration/sglang/interfaces.py:132-173).
+// Every lane keeps UNROLL independent 16-byte loads in flight before the first store; loads bypass
+// L1 (streaming, no reuse) and stores are full 128-byte lines.  Grid = persistent CTAs, a multiple
+// of the SM count; work items are (token, layer, kv) cells, token-fastest inside a layer so that a
+// CTA's concurrent source reads are contiguous.
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// `g` lanes (a power of two, chosen by the launcher so that a lane moves ~4 vectors) serve one cell;
+// a warp serves 32/g cells at once, so small cells (TP shards, 256 B) keep every lane busy.
+template <int GATHER>
+__global__ void __launch_bounds__(256) kvb_kv_copy_kernel(kvb_kv_layout lay, const int64_t *__restrict__ slots,
+                                                          int64_t T, unsigned char *kbuf, unsigned char *vbuf,
+                                                          int32_t l0, int32_t l1, int32_t g) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (g - 1);            // lane inside its group
+  const int cpw = 32 / g;                   // cells per warp
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nl = l1 - l0;
+  const int64_t cells = T * nl * lay.num_kv;
+  const int vec = (int)(lay.cell_bytes >> 4);   // 16-byte vectors per cell
+  for (int64_t it = warp * cpw + lane / g; it < cells; it += nwarps * cpw) {
+    // it = (kv * nl + layer) * T + token
+    int64_t tok = it % T;
+    int64_t rest = it / T;
+    int layer = (int)(rest % nl);
+    int kv = (int)(rest / nl);
+    int64_t slot = slots[tok];
+    int64_t blk = slot / lay.block_size;
+    int inb = (int)(slot - blk * lay.block_size);
+    unsigned char *paged = reinterpret_cast<unsigned char *>(lay.base) + blk * lay.stride_block +
+                           inb * lay.stride_token + (int64_t)(l0 + layer) * lay.stride_layer + kv * lay.stride_kv;
+    unsigned char *dense = (kv ? vbuf : kbuf) + ((int64_t)layer * T + tok) * lay.cell_bytes;
+    const uint4 *src = reinterpret_cast<const uint4 *>(GATHER ? paged : dense);
+    uint4 *dst = reinterpret_cast<uint4 *>(GATHER ? dense : paged);
+    int v = gl;
+    for (; v + 3 * g < vec; v += 4 * g) {
+      uint4 a0 = ld_stream(src + v), a1 = ld_stream(src + v + g), a2 = ld_stream(src + v + 2 * g),
+            a3 = ld_stream(src + v + 3 * g);
+      st_stream(dst + v, a0);
+      st_stream(dst + v + g, a1);
+      st_stream(dst + v + 2 * g, a2);
+      st_stream(dst + v + 3 * g, a3);
+    }
+    for (; v < vec; v += g) st_stream(dst + v, ld_stream(src + v));
+  }
+}
+
+// ==================================================================================== host launchers
+size_t step_kernel_smem_bytes() { return sizeof(Smem); }
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kvb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  kvb_step_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
+  return (int)cudaGetLastError();
+}
+
+int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream) {
+  kvb_init_state_kernel<<<sm_count(), 256, 0, (cudaStream_t)stream>>>(st, num_total_pages);
+  return (int)cudaGetLastError();
+}
+
+int launch_audit(const DevState &st, int64_t *d_out4, void *stream) {
+  cudaError_t e = cudaMemsetAsync(d_out4, 0, 4 * sizeof(int64_t), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  int mode = 2;
+  if (st.exact && (st.bpp == 32 || st.bpp == 64 || st.bpp == 128)) mode = 0;
+  else if (st.exact && st.bpp % 128 == 0 && st.bpp / 128 <= 32 && ((st.bpp / 128) & (st.bpp / 128 - 1)) == 0) mode = 1;
+  kvb_audit_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(st, d_out4, mode);
+  return (int)cudaGetLastError();
+}
+
+int launch_dump_avail(const DevState &st, int64_t *d_out, int64_t *d_n, void *stream) {
+  kvb_dump_avail_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(st, d_out, d_n);
+  return (int)cudaGetLastError();
+}
+
+int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, void *k, void *v, int32_t l0,
+                   int32_t l1, int gather, void *stream) {
+  if (T <= 0 || l1 <= l0) return 0;
+  int64_t cells = T * (int64_t)(l1 - l0) * lay.num_kv;
+  int vec = (int)(lay.cell_bytes >> 4);
+  int g = 32;                        // lanes per cell: largest power of two with >= 4 vectors per lane
+  while (g > 1 && g * 4 > vec) g >>= 1;
+  int64_t want = (cells * g + 255) / 256;
+  int64_t grid = (int64_t)sm_count() * 8;   // persistent: 8 resident CTAs of 256 threads per SM
+  if (want < grid) grid = want;
+  if (gather)
+    kvb_kv_copy_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,
+                                                                            (unsigned char *)v, l0, l1, g);
+  else
+    kvb_kv_copy_kernel<0><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,
+                                                                            (unsigned char *)v, l0, l1, g);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace kvb

@@ -1,0 +1,809 @@
+// kvb_manager.cpp — host side of the device-resident block manager: owns the device state, packs
+// request batches, launches the sm_100a step kernel, reads results back and hands the kernel's
+// page map/unmap list to the VMM engine.  No bookkeeping decisions are taken here: every block id,
+// page id and counter comes from the kernel (kvb_kernels.cu).  There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "kvb_internal.h"
+#include "kvb_vmm.h"
+
+using namespace kvb;
+
+// libstdc++'s own bucket-count table (src/shared/hashtable-aux.cc, exported as
+// _ZNSt8__detail12__prime_listE): uploaded to the device so that the kernel's replay of
+// std::unordered_map's rehash policy uses the very numbers the reference's container uses.
+namespace std { namespace __detail { extern const unsigned long __prime_list[]; } }
+
+#define CUDA_TRY(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      set_error("%s failed: %s at %s:%d", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return KVB_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+namespace {
+constexpr int kNumPrimes = 256 + 48;   // entries of libstdc++'s __prime_list before the sentinel (64-bit)
+
+int64_t env_i64(const char *name, int64_t dflt) {
+  const char *e = getenv(name);
+  if (!e || !*e) return dflt;
+  return atoll(e);
+}
+double env_f64(const char *name, double dflt) {
+  const char *e = getenv(name);
+  if (!e || !*e) return dflt;
+  return atof(e);
+}
+int64_t pow2_ge(int64_t v) {
+  int64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+}  // namespace
+
+struct kvb_mgr {
+  kvb_mgr_config cfg{};
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  DevState st{};
+  unsigned char *d_block = nullptr;   // one allocation carved into the state arrays
+  size_t d_block_bytes = 0;
+  std::mutex mu;
+
+  int64_t P = 0, B = 0, bpp = 0, mem_size = 0, max_pages = 0, f_cap = 0;
+  double gpu_util = 0.95;
+
+  // step I/O (pinned host <-> device mirrors)
+  unsigned char *h_in = nullptr, *d_in = nullptr;
+  size_t in_cap = 0;
+  unsigned char *h_out = nullptr, *d_out = nullptr;
+  size_t out_cap_bytes = 0;
+  Summary last{};
+  int64_t seq = 0;
+  int64_t launches = 0;
+  int64_t phys_override = -1;
+  int has_null = 0;
+  int64_t total_events = 0;
+  std::vector<int64_t> pending_events;
+  int64_t *d_scratch = nullptr;   // small device scratch (audit counters, dump sizes)
+  int64_t *d_dump = nullptr;
+  int64_t dump_cap = 0;
+
+  // resident trace
+  kvb_op *t_ops = nullptr;
+  int64_t *t_ids = nullptr;
+  kvb_ref *t_refs = nullptr;
+  kvb_res *t_res = nullptr;
+  int64_t *t_out = nullptr;
+  int64_t t_out_cap = 0, t_nops = 0;
+  Summary *t_sum = nullptr;   // device
+  std::vector<int64_t> t_steps;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int ensure_io(kvb_mgr *m, size_t in_bytes, size_t out_bytes) {
+  if (in_bytes > m->in_cap) {
+    size_t cap = std::max<size_t>(align_up(in_bytes * 2, 4096), 1 << 16);
+    if (m->h_in) cudaFreeHost(m->h_in);
+    if (m->d_in) cudaFree(m->d_in);
+    m->h_in = m->d_in = nullptr;
+    CUDA_TRY(cudaHostAlloc((void **)&m->h_in, cap, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc((void **)&m->d_in, cap));
+    m->in_cap = cap;
+  }
+  if (out_bytes > m->out_cap_bytes) {
+    size_t cap = std::max<size_t>(align_up(out_bytes * 2, 4096), 1 << 16);
+    if (m->h_out) cudaFreeHost(m->h_out);
+    if (m->d_out) cudaFree(m->d_out);
+    m->h_out = m->d_out = nullptr;
+    CUDA_TRY(cudaHostAlloc((void **)&m->h_out, cap, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc((void **)&m->d_out, cap));
+    m->out_cap_bytes = cap;
+  }
+  return 0;
+}
+
+// PageAllocator::get_avail_physical_pages, csrc/page_allocator.cpp:442-455
+int64_t phys_free_pages(kvb_mgr *m) {
+  if (m->phys_override >= 0) return m->phys_override;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  double headroom = (double)tot * (1.0 - m->gpu_util);
+  double avail = (double)fr - headroom;
+  if (avail < 0) avail = 0;   // the reference's size_t subtraction wraps here; we clamp
+  int64_t pages = (int64_t)((size_t)avail / (size_t)m->P / (size_t)m->cfg.num_layers / (size_t)m->cfg.num_kv_buffers);
+  if (m->cfg.attach_vmm) {
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g) pages += g->pooled_pages();   // pooled handles are memory we already hold
+  }
+  return pages;
+}
+
+int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n) {
+  if (n <= 0) return 0;
+  m->total_events += n;
+  if (m->pending_events.size() > (1u << 22)) m->pending_events.clear();
+  m->pending_events.insert(m->pending_events.end(), ev, ev + n);
+  if (!m->cfg.attach_vmm) return 0;
+  VmmGroup *g = vmm_group(m->cfg.group_id, false);
+  if (!g || !g->created()) {
+    set_error("page events produced but the KV tensors of group %ld are not created", (long)m->cfg.group_id);
+    return KVB_ERR_STATE;
+  }
+  if (m->cfg.async_sched) {
+    // the engine may still have kernels in flight on pages about to be unmapped (page_allocator.cpp:671-673)
+    bool any_unmap = false;
+    for (int64_t i = 0; i < n; ++i) any_unmap |= (ev[i] & 1);
+    if (any_unmap) cudaDeviceSynchronize();
+  }
+  std::lock_guard<std::mutex> lk(g->mu);
+  int rc = g->apply_events(ev, n);
+  return rc < 0 ? rc : 0;
+}
+
+// One launch over requests [op_begin, op_end) of a device-resident request array.
+int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int64_t *d_ids, const kvb_ref *d_refs,
+           kvb_res *d_res, int64_t *d_outids, int64_t out_cap, Summary *d_sum, int arena_mode, int group_only,
+           int64_t *grp_pages = nullptr, int64_t *grp_counts = nullptr, int64_t *grp_ids = nullptr) {
+  LaunchArgs a{};
+  a.ops = d_ops;
+  a.op_begin = op_begin;
+  a.op_end = op_end;
+  a.ids = d_ids;
+  a.refs = d_refs;
+  a.res = d_res;
+  a.out_ids = d_outids;
+  a.out_cap = out_cap;
+  a.phys_free = phys_free_pages(m);
+  a.summary = d_sum;
+  a.seq = ++m->seq;
+  a.arena_mode = arena_mode;
+  a.group_only = group_only;
+  a.grp_pages = grp_pages;
+  a.grp_counts = grp_counts;
+  a.grp_ids = grp_ids;
+  int rc = launch_step(m->st, a, m->stream);
+  if (rc != 0) {
+    set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    return KVB_ERR_CUDA;
+  }
+  m->launches++;
+  return 0;
+}
+
+}  // namespace
+
+// ============================================================================================ create
+extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
+  if (!cfg) { set_error("null config"); return nullptr; }
+  auto *m = new kvb_mgr();
+  m->cfg = *cfg;
+  kvb_mgr_config &c = m->cfg;
+  if (c.page_size <= 0) c.page_size = vmm_initialized() ? vmm_page_size() : (2 << 20);
+  if (c.contiguous_layout < 0) c.contiguous_layout = vmm_initialized() ? (int)vmm_contiguous() : 1;
+  if (c.num_kv_buffers <= 0) c.num_kv_buffers = 2;
+  if (c.min_reserved_pages < 0) c.min_reserved_pages = env_i64("KVCACHED_MIN_RESERVED_PAGES", 5);
+  if (c.max_reserved_pages < 0) c.max_reserved_pages = env_i64("KVCACHED_MAX_RESERVED_PAGES", 10);
+  m->gpu_util = c.gpu_utilization > 0 ? c.gpu_utilization : env_f64("KVCACHED_GPU_UTILIZATION", 0.95);
+  m->P = c.page_size;
+  m->B = c.block_size * c.cell_size;
+  if (c.num_blocks <= 0 || c.block_size <= 0 || c.cell_size <= 0 || c.num_layers <= 0) {
+    set_error("KVCacheManager: num_blocks, block_size, cell_size, num_layers must be positive");
+    delete m;
+    return nullptr;
+  }
+  if (m->B > m->P) {   // KVCachedConfigError, kv_cache_manager.py:104-116
+    set_error("Block memory size (%ld bytes = block_size %ld x cell_size %ld) exceeds page size (%ld bytes). "
+              "Set KVCACHED_PAGE_SIZE_MB to at least %ld.",
+              (long)m->B, (long)c.block_size, (long)c.cell_size, (long)m->P,
+              (long)(((m->B + (2 << 20) - 1) / (2 << 20)) * 2));
+    delete m;
+    return nullptr;
+  }
+  m->bpp = m->P / m->B;
+  m->mem_size = c.num_blocks * m->B;            // kv_cache_manager.py:118
+  m->max_pages = m->mem_size / m->P;            // page_allocator.cpp:115-116
+  if (m->max_pages <= 0 || m->max_pages > (1 << 28) || c.num_blocks > (int64_t)1 << 31) {
+    set_error("KVCacheManager: pool of %ld pages / %ld blocks is outside the supported range", (long)m->max_pages,
+              (long)c.num_blocks);
+    delete m;
+    return nullptr;
+  }
+  m->dev = c.device_index >= 0 ? c.device_index : (vmm_initialized() ? vmm_device() : 0);
+  auto fail = [&](const char *what) -> kvb_mgr * {
+    if (what) set_error("%s: %s", what, cudaGetErrorString(cudaGetLastError()));
+    kvb_mgr_destroy(m);
+    return nullptr;
+  };
+  if (cudaSetDevice(m->dev) != cudaSuccess) return fail("cudaSetDevice");
+  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess) return fail("cudaEventCreate");
+
+  // ---- carve the device state --------------------------------------------------------------------
+  DevState &s = m->st;
+  s.P = m->P;
+  s.B = m->B;
+  s.bpp = (int32_t)m->bpp;
+  s.exact = (m->P % m->B == 0) ? 1 : 0;
+  s.num_blocks = c.num_blocks;
+  s.max_pages = (int32_t)m->max_pages;
+  int64_t qcap = pow2_ge(m->max_pages + 2);
+  s.q_mask = (int32_t)(qcap - 1);
+  int64_t rbcap = pow2_ge(2 * c.num_blocks + 4);
+  s.rb_mask = (int32_t)(rbcap - 1);
+  s.ap_cap = (int32_t)(2 * m->max_pages + 8);
+  s.min_reserved = (int32_t)std::min<int64_t>(m->max_pages, c.min_reserved_pages);   // page_allocator.cpp:117-118
+  s.max_reserved = (int32_t)std::min<int64_t>(m->max_pages, c.max_reserved_pages);
+  s.ev_cap = (int32_t)std::max<int64_t>(1 << 20, 4 * m->max_pages + 64);
+  s.n_primes = kNumPrimes;
+  m->f_cap = c.num_blocks + 1024;
+  s.f_cap = m->f_cap;
+  int64_t bkt_cap = 3 * std::max<int64_t>(2 * m->max_pages, m->f_cap / m->bpp + 1) + 64;
+  s.g_bkt_cap = (int32_t)bkt_cap;
+  int64_t nwords = (c.num_blocks + 31) / 32;
+
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  size_t o_sc = carve(SC_COUNT * 8), o_fl = carve(qcap * 4), o_rl = carve(qcap * 4), o_cl = carve(qcap * 4);
+  size_t o_ap = carve((size_t)s.ap_cap * 4);
+  size_t o_pg[7];
+  for (auto &o : o_pg) o = carve((size_t)m->max_pages * 4);
+  size_t o_ring = carve((size_t)m->max_pages * m->bpp * 4);
+  size_t o_bm = carve((size_t)(nwords + 8) * 4);
+  size_t o_rb = carve((size_t)rbcap * 8);
+  size_t o_fids = carve((size_t)m->f_cap * 8), o_fpage = carve((size_t)m->f_cap * 4);
+  size_t o_g[5];
+  for (auto &o : o_g) o = carve((size_t)m->max_pages * 4);
+  size_t o_bkt = carve((size_t)bkt_cap * 4);
+  size_t o_ev = carve((size_t)s.ev_cap * 8);
+  size_t o_pr = carve((size_t)kNumPrimes * 8);
+  m->d_block_bytes = off;
+  if (cudaMalloc((void **)&m->d_block, off) != cudaSuccess) return fail("cudaMalloc(state)");
+  unsigned char *b = m->d_block;
+  s.sc = (int64_t *)(b + o_sc);
+  s.fl = (int32_t *)(b + o_fl);
+  s.rl = (int32_t *)(b + o_rl);
+  s.cl = (int32_t *)(b + o_cl);
+  s.ap = (int32_t *)(b + o_ap);
+  s.pg_state = (int32_t *)(b + o_pg[0]);
+  s.pg_cnt = (int32_t *)(b + o_pg[1]);
+  s.pg_head = (int32_t *)(b + o_pg[2]);
+  s.pg_pos = (int32_t *)(b + o_pg[3]);
+  s.pg_mapped = (int32_t *)(b + o_pg[4]);
+  s.pg_first = (int32_t *)(b + o_pg[5]);
+  s.pg_slot = (int32_t *)(b + o_pg[6]);
+  s.ring = (uint32_t *)(b + o_ring);
+  s.bitmap = (uint32_t *)(b + o_bm);
+  s.rb = (int64_t *)(b + o_rb);
+  s.fids = (int64_t *)(b + o_fids);
+  s.fpage = (int32_t *)(b + o_fpage);
+  s.g_dist = (int32_t *)(b + o_g[0]);
+  s.g_ord = (int32_t *)(b + o_g[1]);
+  s.g_cnt = (int32_t *)(b + o_g[2]);
+  s.g_next = (int32_t *)(b + o_g[3]);
+  s.g_ptf = (int32_t *)(b + o_g[4]);
+  s.g_bkt = (int32_t *)(b + o_bkt);
+  s.ev = (int64_t *)(b + o_ev);
+  s.primes = (const uint64_t *)(b + o_pr);
+  static_assert(sizeof(unsigned long) == sizeof(uint64_t), "LP64 expected");
+  if (cudaMemcpy((void *)s.primes, std::__detail::__prime_list, kNumPrimes * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("cudaMemcpy(primes)");
+  if (cudaMalloc((void **)&m->d_scratch, 64 * 8) != cudaSuccess) return fail("cudaMalloc(scratch)");
+  if (cudaMalloc((void **)&m->t_sum, sizeof(Summary)) != cudaSuccess) return fail("cudaMalloc(summary)");
+
+  int rc = launch_init_state(s, m->max_pages, m->stream);
+  if (rc != 0 || cudaStreamSynchronize(m->stream) != cudaSuccess) return fail("init kernel");
+  // summary cache = initial state
+  memset(&m->last, 0, sizeof(m->last));
+  m->last.sc[SC_NFREE] = m->last.sc[SC_NTOTAL] = m->last.sc[SC_FL_SIZE] = m->max_pages;
+  m->last.sc[SC_TARGET] = -1;
+
+  // _post_init: reserve the null block (kv_cache_manager.py:233-243)
+  if (c.reserve_null_block) {
+    int64_t id = -1;
+    int64_t r = kvb_mgr_alloc(m, 1, &id, 1);
+    if (r != 1 || id != 0) {
+      set_error("Failed to reserve null block at index 0 (got rc=%ld id=%ld)", (long)r, (long)id);
+      kvb_mgr_destroy(m);
+      return nullptr;
+    }
+    m->has_null = 1;
+  }
+  return m;
+}
+
+extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
+  if (!m) return 0;
+  cudaSetDevice(m->dev);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->d_block) cudaFree(m->d_block);
+  if (m->h_in) cudaFreeHost(m->h_in);
+  if (m->d_in) cudaFree(m->d_in);
+  if (m->h_out) cudaFreeHost(m->h_out);
+  if (m->d_out) cudaFree(m->d_out);
+  if (m->d_scratch) cudaFree(m->d_scratch);
+  if (m->d_dump) cudaFree(m->d_dump);
+  if (m->t_ops) cudaFree(m->t_ops);
+  if (m->t_ids) cudaFree(m->t_ids);
+  if (m->t_refs) cudaFree(m->t_refs);
+  if (m->t_res) cudaFree(m->t_res);
+  if (m->t_out) cudaFree(m->t_out);
+  if (m->t_sum) cudaFree(m->t_sum);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  cudaGetLastError();
+  delete m;
+  return 0;
+}
+
+// ============================================================================================ step
+// Layout of the step buffers:
+//   in : [ops n_ops*16][ids n_ids*8][refs n_refs*12, padded]
+//   out: [Summary][res n_ops*24][ids out_cap*8]
+static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
+                           const kvb_ref *refs, int64_t n_refs, kvb_res *res, int64_t *out_ids, int64_t out_cap) {
+  if (n_ops <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(m->dev));
+  int64_t need_out = 0;
+  for (int64_t i = 0; i < n_ops; ++i) {
+    if (ops[i].kind == KVB_OP_ALLOC && ops[i].n > 0) need_out += ops[i].n;
+    if (ops[i].kind == KVB_OP_FREE_IDS || ops[i].kind == KVB_OP_FREE_PAGES) {
+      if (ops[i].n < 0 || ops[i].arg < 0 || ops[i].arg + ops[i].n > n_ids) { set_error("free request %ld indexes outside the id pool", (long)i); return KVB_ERR_INVALID; }
+      if (ops[i].n > m->f_cap) { set_error("free of %d ids exceeds the pool's block count", ops[i].n); return KVB_ERR_INVALID; }
+    }
+    if (ops[i].kind == KVB_OP_FREE_REF) {
+      if (ops[i].n < 0 || ops[i].arg < 0 || ops[i].arg + ops[i].n > n_refs) { set_error("free request %ld indexes outside the ref pool", (long)i); return KVB_ERR_INVALID; }
+      for (int64_t r = ops[i].arg; r < ops[i].arg + ops[i].n; ++r)
+        if (refs[r].op < 0 || refs[r].op >= i) { set_error("free request %ld refers to request %d that does not precede it", (long)i, refs[r].op); return KVB_ERR_INVALID; }
+    }
+  }
+  if (need_out > out_cap) { set_error("out_ids capacity %ld < %ld ids requested", (long)out_cap, (long)need_out); return KVB_ERR_OVERFLOW; }
+  size_t b_ops = (size_t)n_ops * sizeof(kvb_op), b_ids = (size_t)n_ids * 8, b_refs = align_up((size_t)n_refs * sizeof(kvb_ref), 8);
+  size_t in_bytes = b_ops + b_ids + b_refs;
+  size_t b_res = (size_t)n_ops * sizeof(kvb_res);
+  size_t o_res = align_up(sizeof(Summary), 16), o_ids = o_res + align_up(b_res, 16);
+  size_t out_bytes = o_ids + (size_t)need_out * 8;
+  int rc = ensure_io(m, in_bytes, out_bytes);
+  if (rc) return rc;
+  memcpy(m->h_in, ops, b_ops);
+  if (n_ids) memcpy(m->h_in + b_ops, ids, b_ids);
+  if (n_refs) memcpy(m->h_in + b_ops + b_ids, refs, (size_t)n_refs * sizeof(kvb_ref));
+  CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in, in_bytes, cudaMemcpyHostToDevice, m->stream));
+  const kvb_op *d_ops = (const kvb_op *)m->d_in;
+  const int64_t *d_ids = (const int64_t *)(m->d_in + b_ops);
+  const kvb_ref *d_refs = (const kvb_ref *)(m->d_in + b_ops + b_ids);
+  Summary *d_sum = (Summary *)m->d_out;
+  kvb_res *d_res = (kvb_res *)(m->d_out + o_res);
+  int64_t *d_outids = (int64_t *)(m->d_out + o_ids);
+
+  int64_t done = 0;
+  bool first = true;
+  while (done < n_ops) {
+    rc = launch(m, d_ops, (int)done, (int)n_ops, d_ids, d_refs, d_res, d_outids, need_out, d_sum, first ? 0 : 2, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(m->h_out, m->d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const Summary *hs = (const Summary *)m->h_out;
+    m->last = *hs;
+    // page map/unmap list of this launch -> VMM engine
+    if (hs->n_events > 0) {
+      if (hs->n_events <= hs->ev_inline_n) {
+        rc = apply_events(m, hs->ev_inline, hs->n_events);
+      } else {
+        std::vector<int64_t> ev((size_t)hs->n_events);
+        CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev + hs->ev_begin, (size_t)hs->n_events * 8, cudaMemcpyDeviceToHost));
+        rc = apply_events(m, ev.data(), hs->n_events);
+      }
+      if (rc) return rc;
+    }
+    if (hs->ops_done <= 0) { set_error("step kernel made no progress at request %ld", (long)done); return KVB_ERR_STATE; }
+    done += hs->ops_done;
+    first = false;
+  }
+  memcpy(res, m->h_out + o_res, b_res);
+  const Summary *hs = (const Summary *)m->h_out;
+  int64_t used = hs->sc[SC_OUT_CURSOR];
+  if (used > 0) memcpy(out_ids, m->h_out + o_ids, (size_t)used * 8);
+  return used;
+}
+
+extern "C" int64_t kvb_mgr_step(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
+                                const kvb_ref *refs, int64_t n_refs, kvb_res *res, int64_t *out_ids,
+                                int64_t out_cap) {
+  if (!m || (n_ops > 0 && (!ops || !res))) { set_error("kvb_mgr_step: null argument"); return KVB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  return step_locked(m, ops, n_ops, ids, n_ids, refs, n_refs, res, out_ids, out_cap);
+}
+
+// ---- single-request wrappers ---------------------------------------------------------------------------
+static int one_op(kvb_mgr *m, int kind, int32_t n, int64_t arg, const int64_t *ids, int64_t n_ids, kvb_res *r,
+                  int64_t *out, int64_t cap) {
+  kvb_op o{kind, n, arg};
+  std::lock_guard<std::mutex> lk(m->mu);
+  int64_t rc = step_locked(m, &o, 1, ids, n_ids, nullptr, 0, r, out, cap);
+  return rc < 0 ? (int)rc : 0;
+}
+
+extern "C" int64_t kvb_mgr_alloc(kvb_mgr *m, int64_t n, int64_t *out, int64_t cap) {
+  if (!m || n < 0 || n > INT32_MAX) { set_error("kvb_mgr_alloc: bad argument"); return KVB_ERR_INVALID - 100; }
+  kvb_res r{};
+  int rc = one_op(m, KVB_OP_ALLOC, (int32_t)n, 0, nullptr, 0, &r, out, cap);
+  if (rc) return rc - 100;
+  if (r.status == KVB_ST_OK) return r.n;
+  return r.status;
+}
+extern "C" int kvb_mgr_free(kvb_mgr *m, const int64_t *ids, int64_t n) {
+  if (!m || n < 0 || (n > 0 && !ids)) { set_error("kvb_mgr_free: bad argument"); return KVB_ERR_INVALID; }
+  if (n == 0) return 0;   // kv_cache_manager.py:310-311
+  kvb_res r{};
+  return one_op(m, KVB_OP_FREE_IDS, (int32_t)n, 0, ids, n, &r, nullptr, 0);
+}
+extern "C" int kvb_mgr_resize(kvb_mgr *m, int64_t new_mem_size) {
+  if (!m || new_mem_size <= 0) { set_error("new_mem_size must be positive"); return KVB_ERR_INVALID; }
+  kvb_res r{};
+  int rc = one_op(m, KVB_OP_RESIZE, 0, new_mem_size, nullptr, 0, &r, nullptr, 0);
+  return rc ? rc - 100 : r.status;
+}
+extern "C" int kvb_mgr_trim(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  kvb_res r{};
+  return one_op(m, KVB_OP_TRIM, 0, 0, nullptr, 0, &r, nullptr, 0);
+}
+extern "C" int kvb_mgr_try_to_reserve(kvb_mgr *m, int64_t n) {
+  if (!m || n < 0 || n > INT32_MAX) return KVB_ERR_INVALID - 100;
+  kvb_res r{};
+  int rc = one_op(m, KVB_OP_TRY_RESERVE, (int32_t)n, 0, nullptr, 0, &r, nullptr, 0);
+  return rc ? rc - 100 : r.status;
+}
+extern "C" int kvb_mgr_free_reserved(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  kvb_res r{};
+  return one_op(m, KVB_OP_FREE_RESERVED, 0, 0, nullptr, 0, &r, nullptr, 0);
+}
+extern "C" int kvb_mgr_clear(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  kvb_op ops[2] = {{KVB_OP_CLEAR, 0, 0}, {KVB_OP_ALLOC, 1, 0}};
+  kvb_res r[2]{};
+  int64_t id = -1;
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->has_null = 0;
+  int64_t rc = step_locked(m, ops, m->cfg.reserve_null_block ? 2 : 1, nullptr, 0, nullptr, 0, r, &id, 1);
+  if (rc < 0) return (int)rc;
+  if (m->cfg.reserve_null_block) {
+    if (r[1].status != KVB_ST_OK || id != 0) { set_error("Failed to reserve null block at index 0"); return KVB_ST_NULL_BLOCK; }
+    m->has_null = 1;
+  }
+  return 0;
+}
+
+extern "C" int64_t kvb_mgr_available_size(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  const int64_t *sc = m->last.sc;
+  int64_t a = sc[SC_NAB] + sc[SC_NRB];
+  if (sc[SC_INSHRINK]) return a;
+  cudaSetDevice(m->dev);
+  int64_t phys = phys_free_pages(m) + sc[SC_RL_SIZE];
+  return a + std::min(sc[SC_NFREE], phys) * m->bpp;
+}
+
+extern "C" int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *o) {
+  if (!m || !o) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  const int64_t *sc = m->last.sc;
+  o->num_free_pages = sc[SC_NFREE];
+  o->num_total_pages = sc[SC_NTOTAL];
+  o->num_inuse_pages = sc[SC_NTOTAL] - sc[SC_NFREE];
+  o->num_reserved_pages = sc[SC_RL_SIZE];
+  o->num_avail_blocks = sc[SC_NAB];
+  o->num_reserved_blocks = sc[SC_NRB];
+  o->in_shrink = sc[SC_INSHRINK];
+  o->target_num_blocks = sc[SC_TARGET];
+  o->num_avail_pages = sc[SC_NAVAILPG];
+  o->num_full_pages = sc[SC_NFULLPG];
+  o->num_mapped_pages = sc[SC_NMAPPED];
+  o->has_null_block = m->has_null;
+  o->blocks_per_page = m->bpp;
+  o->block_mem_size = m->B;
+  o->page_size = m->P;
+  o->mem_size = m->mem_size;
+  o->bad_frees = sc[SC_BAD_FREES];
+  o->unknown_page_frees = sc[SC_UNKNOWN_FREES];
+  o->launches = m->launches;
+  o->events = m->total_events;
+  return 0;
+}
+
+extern "C" int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->phys_override = n;
+  return 0;
+}
+
+// ============================================================================================ resident traces
+extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
+                                    const kvb_ref *refs, int64_t n_refs, const int64_t *step_offsets, int64_t n_steps,
+                                    int64_t out_capacity) {
+  if (!m || !ops || n_ops <= 0 || !step_offsets || n_steps <= 0) { set_error("trace_upload: bad argument"); return KVB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  for (void *p : {(void *)m->t_ops, (void *)m->t_ids, (void *)m->t_refs, (void *)m->t_res, (void *)m->t_out})
+    if (p) cudaFree(p);
+  m->t_ops = nullptr; m->t_ids = nullptr; m->t_refs = nullptr; m->t_res = nullptr; m->t_out = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&m->t_ops, (size_t)n_ops * sizeof(kvb_op)));
+  CUDA_TRY(cudaMalloc((void **)&m->t_ids, std::max<size_t>((size_t)n_ids * 8, 8)));
+  CUDA_TRY(cudaMalloc((void **)&m->t_refs, std::max<size_t>((size_t)n_refs * sizeof(kvb_ref), 16)));
+  CUDA_TRY(cudaMalloc((void **)&m->t_res, (size_t)n_ops * sizeof(kvb_res)));
+  CUDA_TRY(cudaMalloc((void **)&m->t_out, std::max<size_t>((size_t)out_capacity * 8, 8)));
+  CUDA_TRY(cudaMemcpy(m->t_ops, ops, (size_t)n_ops * sizeof(kvb_op), cudaMemcpyHostToDevice));
+  if (n_ids) CUDA_TRY(cudaMemcpy(m->t_ids, ids, (size_t)n_ids * 8, cudaMemcpyHostToDevice));
+  if (n_refs) CUDA_TRY(cudaMemcpy(m->t_refs, refs, (size_t)n_refs * sizeof(kvb_ref), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(m->t_res, 0, (size_t)n_ops * sizeof(kvb_res)));
+  m->t_out_cap = out_capacity;
+  m->t_nops = n_ops;
+  m->t_steps.assign(step_offsets, step_offsets + n_steps + 1);
+  if (m->t_steps.front() != 0 || m->t_steps.back() != n_ops) { set_error("trace_upload: step_offsets must span [0, n_ops]"); return KVB_ERR_INVALID; }
+  return 0;
+}
+
+extern "C" int kvb_mgr_trace_reset_cursor(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_OUT_CURSOR, 0, 8, m->stream));
+  CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_end, int steps_per_launch,
+                                 float *device_ms, int64_t *n_launches) {
+  if (!m || !m->t_ops) { set_error("trace_run: no trace uploaded"); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  int64_t n_steps = (int64_t)m->t_steps.size() - 1;
+  if (step_begin < 0 || step_end > n_steps || step_begin > step_end) { set_error("trace_run: bad step range"); return KVB_ERR_INVALID; }
+  if (steps_per_launch <= 0) steps_per_launch = 1;
+  CUDA_TRY(cudaSetDevice(m->dev));
+  int64_t launches0 = m->launches;
+  // events of the whole range accumulate in the device log
+  CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
+  CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
+    int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
+    int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
+    if (oe == ob) continue;
+    int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, m->ev0, m->ev1));
+  if (n_launches) *n_launches = m->launches - launches0;
+  if (m->launches == launches0) return 0;
+  CUDA_TRY(cudaMemcpy(&m->last, m->t_sum, sizeof(Summary), cudaMemcpyDeviceToHost));
+  int64_t nev = m->last.sc[SC_NEV];
+  if (nev > m->st.ev_cap) { set_error("trace_run: page event log overflow (%ld > %d)", (long)nev, m->st.ev_cap); return KVB_ERR_OVERFLOW; }
+  if (m->last.sc[SC_OUT_CURSOR] > m->t_out_cap) { set_error("trace_run: id arena overflow"); return KVB_ERR_OVERFLOW; }
+  if (nev > 0) {
+    std::vector<int64_t> ev((size_t)nev);
+    CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev, (size_t)nev * 8, cudaMemcpyDeviceToHost));
+    int rc = apply_events(m, ev.data(), nev);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int kvb_mgr_trace_results(kvb_mgr *m, kvb_res *res, int64_t n_ops, int64_t *out_ids, int64_t out_cap,
+                                     int64_t *n_out) {
+  if (!m || !m->t_ops) { set_error("trace_results: no trace uploaded"); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  if (n_ops > m->t_nops) n_ops = m->t_nops;
+  if (res && n_ops > 0) CUDA_TRY(cudaMemcpy(res, m->t_res, (size_t)n_ops * sizeof(kvb_res), cudaMemcpyDeviceToHost));
+  int64_t cur = 0;
+  CUDA_TRY(cudaMemcpy(&cur, m->st.sc + SC_OUT_CURSOR, 8, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = cur;
+  if (out_ids) {
+    if (cur > out_cap) { set_error("trace_results: out_cap %ld < %ld", (long)out_cap, (long)cur); return KVB_ERR_OVERFLOW; }
+    if (cur > 0) CUDA_TRY(cudaMemcpy(out_ids, m->t_out, (size_t)cur * 8, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ============================================================================================ inspection
+static int ensure_dump(kvb_mgr *m, int64_t n) {
+  if (n <= m->dump_cap) return 0;
+  if (m->d_dump) cudaFree(m->d_dump);
+  m->d_dump = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&m->d_dump, (size_t)n * 8));
+  m->dump_cap = n;
+  return 0;
+}
+
+extern "C" int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_t cap) {
+  if (!m || !out) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  int64_t sc[SC_COUNT];
+  CUDA_TRY(cudaMemcpy(sc, m->st.sc, sizeof(sc), cudaMemcpyDeviceToHost));
+  std::vector<int64_t> v;
+  if (which >= 0 && which <= 2) {
+    const int32_t *q = which == 0 ? m->st.fl : which == 1 ? m->st.rl : m->st.cl;
+    int64_t head = sc[which == 0 ? SC_FL_HEAD : which == 1 ? SC_RL_HEAD : SC_CL_HEAD];
+    int64_t size = sc[which == 0 ? SC_FL_SIZE : which == 1 ? SC_RL_SIZE : SC_CL_SIZE];
+    std::vector<int32_t> h((size_t)m->st.q_mask + 1);
+    CUDA_TRY(cudaMemcpy(h.data(), q, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < size; ++i) v.push_back(h[(size_t)((head + i) & m->st.q_mask)]);
+  } else if (which == 3) {
+    int rc = ensure_dump(m, m->max_pages + 1);
+    if (rc) return rc;
+    if (launch_dump_avail(m->st, m->d_dump, m->d_scratch, m->stream) != 0) { set_error("dump kernel launch failed"); return KVB_ERR_CUDA; }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    int64_t n = 0;
+    CUDA_TRY(cudaMemcpy(&n, m->d_scratch, 8, cudaMemcpyDeviceToHost));
+    v.resize((size_t)n);
+    if (n) CUDA_TRY(cudaMemcpy(v.data(), m->d_dump, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  } else if (which == 4 || which == 6) {
+    std::vector<int32_t> h((size_t)m->max_pages);
+    CUDA_TRY(cudaMemcpy(h.data(), which == 4 ? m->st.pg_state : m->st.pg_mapped, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < m->max_pages; ++p)
+      if (which == 4 ? h[(size_t)p] == PG_FULL : h[(size_t)p] != 0) v.push_back(p);
+  } else if (which == 5) {
+    int64_t head = sc[SC_RB_HEAD], size = sc[SC_NRB];
+    std::vector<int64_t> h((size_t)size);
+    for (int64_t i = 0; i < size; ++i)
+      CUDA_TRY(cudaMemcpy(&h[(size_t)i], m->st.rb + ((head + i) & m->st.rb_mask), 8, cudaMemcpyDeviceToHost));
+    v = h;
+  } else {
+    set_error("dump_list: unknown list %d", which);
+    return KVB_ERR_INVALID;
+  }
+  if ((int64_t)v.size() > cap) return KVB_ERR_OVERFLOW;
+  if (!v.empty()) memcpy(out, v.data(), v.size() * 8);
+  return (int64_t)v.size();
+}
+
+extern "C" int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t p, int64_t *out, int64_t cap) {
+  if (!m || p < 0 || p >= m->max_pages) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  int32_t st = 0, cnt = 0, head = 0;
+  CUDA_TRY(cudaMemcpy(&st, m->st.pg_state + p, 4, cudaMemcpyDeviceToHost));
+  if (st == PG_NONE) return -1;
+  CUDA_TRY(cudaMemcpy(&cnt, m->st.pg_cnt + p, 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&head, m->st.pg_head + p, 4, cudaMemcpyDeviceToHost));
+  if (cnt > cap) return KVB_ERR_OVERFLOW;
+  std::vector<uint32_t> ring((size_t)m->bpp);
+  CUDA_TRY(cudaMemcpy(ring.data(), m->st.ring + (size_t)p * m->bpp, ring.size() * 4, cudaMemcpyDeviceToHost));
+  int64_t start = (p * m->P + m->B - 1) / m->B;
+  for (int i = 0; i < cnt; ++i) out[i] = start + ring[(size_t)((head + i) % m->bpp)];
+  return cnt;
+}
+
+extern "C" int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  int64_t n = (int64_t)m->pending_events.size();
+  if (n > cap) return KVB_ERR_OVERFLOW;
+  if (n) memcpy(out, m->pending_events.data(), (size_t)n * 8);
+  m->pending_events.clear();
+  return n;
+}
+
+extern "C" int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms) {
+  if (!m || !out4) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  if (launch_audit(m->st, m->d_scratch + 8, m->stream) != 0) { set_error("audit kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return KVB_ERR_CUDA; }
+  CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, m->ev0, m->ev1));
+  CUDA_TRY(cudaMemcpy(out4, m->d_scratch + 8, 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int kvb_mgr_bitmap(kvb_mgr *m, uint64_t *dev_ptr, int64_t *n_words32) {
+  if (!m) return KVB_ERR_INVALID;
+  if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)m->st.bitmap;
+  if (n_words32) *n_words32 = (m->cfg.num_blocks + 31) / 32;
+  return 0;
+}
+
+// group_indices_by_page through the same device code path free() uses (state untouched)
+extern "C" int64_t kvb_group_indices_by_page(kvb_mgr *m, const int64_t *ids, int64_t n, int64_t *pages_out,
+                                             int64_t *counts_out, int64_t *grouped_out) {
+  if (!m || n < 0 || (n > 0 && (!ids || !pages_out || !counts_out || !grouped_out))) return KVB_ERR_INVALID;
+  if (n == 0) return 0;
+  if (n > m->f_cap) { set_error("group_indices_by_page: %ld ids exceed the pool's block count", (long)n); return KVB_ERR_INVALID; }
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  kvb_op op{KVB_OP_FREE_IDS, (int32_t)n, 0};
+  size_t b_ops = sizeof(kvb_op), b_ids = (size_t)n * 8;
+  size_t o_res = align_up(sizeof(Summary), 16), o_pg = o_res + 64, o_ct = o_pg + b_ids, o_gr = o_ct + b_ids;
+  int rc = ensure_io(m, b_ops + b_ids, o_gr + b_ids);
+  if (rc) return rc;
+  memcpy(m->h_in, &op, b_ops);
+  memcpy(m->h_in + b_ops, ids, b_ids);
+  CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in, b_ops + b_ids, cudaMemcpyHostToDevice, m->stream));
+  rc = launch(m, (const kvb_op *)m->d_in, 0, 1, (const int64_t *)(m->d_in + b_ops), nullptr, (kvb_res *)(m->d_out + o_res),
+              nullptr, 0, (Summary *)m->d_out, 2, 1, (int64_t *)(m->d_out + o_pg), (int64_t *)(m->d_out + o_ct),
+              (int64_t *)(m->d_out + o_gr));
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(m->h_out, m->d_out, o_gr + b_ids, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  const kvb_res *r = (const kvb_res *)(m->h_out + o_res);
+  int64_t D = r->n;
+  memcpy(pages_out, m->h_out + o_pg, (size_t)D * 8);
+  memcpy(counts_out, m->h_out + o_ct, (size_t)D * 8);
+  memcpy(grouped_out, m->h_out + o_gr, b_ids);
+  return D;
+}
+
+// ============================================================================================ TP export
+// [seq, n, e0 .. e(n-1)] in a fixed-size int64 device buffer: the payload of the one NCCL broadcast
+// that replaces kvcached/tp_ipc_util.py's per-rank socket round trips.
+static constexpr int64_t kTpWords = 2 + 1022;
+extern "C" int64_t kvb_tp_buffer_words(void) { return kTpWords; }
+
+extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
+  if (!m || !dst) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  CUDA_TRY(cudaSetDevice(m->dev));
+  int64_t n = (int64_t)m->pending_events.size();
+  if (n > kTpWords - 2) { set_error("tp_export: %ld page events exceed the broadcast buffer (%ld)", (long)n, (long)(kTpWords - 2)); return KVB_ERR_OVERFLOW; }
+  size_t bytes = (size_t)(2 + n) * 8;
+  int rc = ensure_io(m, bytes, 0);
+  if (rc) return rc;
+  int64_t *h = (int64_t *)m->h_in;
+  h[0] = m->seq;
+  h[1] = n;
+  if (n) memcpy(h + 2, m->pending_events.data(), (size_t)n * 8);
+  m->pending_events.clear();
+  CUDA_TRY(cudaMemcpyAsync((void *)(uintptr_t)dst, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_t *seq_out, int64_t *n_out) {
+  if (!src) return KVB_ERR_INVALID;
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g || !g->created()) { set_error("tp_apply: KV tensors of group %ld are not created", (long)group_id); return KVB_ERR_STATE; }
+  int64_t hdr[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(hdr, (const void *)(uintptr_t)src, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (seq_out) *seq_out = hdr[0];
+  if (n_out) *n_out = hdr[1];
+  if (hdr[1] < 0 || hdr[1] > kTpWords - 2) { set_error("tp_apply: corrupt header n=%ld", (long)hdr[1]); return KVB_ERR_INVALID; }
+  if (hdr[1] == 0) return 0;
+  std::vector<int64_t> ev((size_t)hdr[1]);
+  CUDA_TRY(cudaMemcpy(ev.data(), (const void *)(uintptr_t)(src + 16), (size_t)hdr[1] * 8, cudaMemcpyDeviceToHost));
+  std::lock_guard<std::mutex> lk(g->mu);
+  int rc = g->apply_events(ev.data(), hdr[1]);
+  return rc < 0 ? rc : 0;
+}

@@ -1,0 +1,452 @@
+// kvb_vmm.cpp — see kvb_vmm.h.
+#include "kvb_vmm.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+namespace kvb {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  const char *lvl = getenv("KVCACHED_LOG_LEVEL");
+  if (lvl && (lvl[0] == 'D' || lvl[0] == 'd')) fprintf(stderr, "[kvb200] %s\n", g_err);
+}
+const char *get_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------ driver
+static Driver g_drv;
+static std::once_flag g_drv_once;
+
+template <typename F>
+static bool resolve(const char *name, F *out) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return false;
+  *out = reinterpret_cast<F>(fn);
+  return true;
+}
+
+const Driver *driver() {
+  std::call_once(g_drv_once, [] {
+    bool ok = true;
+    ok &= resolve("cuMemAddressReserve", &g_drv.MemAddressReserve);
+    ok &= resolve("cuMemAddressFree", &g_drv.MemAddressFree);
+    ok &= resolve("cuMemCreate", &g_drv.MemCreate);
+    ok &= resolve("cuMemRelease", &g_drv.MemRelease);
+    ok &= resolve("cuMemMap", &g_drv.MemMap);
+    ok &= resolve("cuMemUnmap", &g_drv.MemUnmap);
+    ok &= resolve("cuMemSetAccess", &g_drv.MemSetAccess);
+    ok &= resolve("cuMemGetAllocationGranularity", &g_drv.MemGetAllocationGranularity);
+    ok &= resolve("cuGetErrorString", &g_drv.GetErrorString);
+    g_drv.ok = ok;
+  });
+  if (!g_drv.ok) {
+    cudaGetLastError();
+    set_error("CUDA driver entry points unavailable (no driver / no GPU)");
+    return nullptr;
+  }
+  return &g_drv;
+}
+
+static const char *cu_str(CUresult r) {
+  const char *s = nullptr;
+  if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+  return s ? s : "unknown CUresult";
+}
+#define CU_TRY(call)                                                         \
+  do {                                                                       \
+    CUresult r_ = (call);                                                    \
+    if (r_ != CUDA_SUCCESS) {                                                \
+      set_error("%s failed: %s (%d) at %s:%d", #call, cu_str(r_), (int)r_, __FILE__, __LINE__); \
+      return KVB_ERR_CUDA_;                                                  \
+    }                                                                        \
+  } while (0)
+static constexpr int KVB_ERR_CUDA_ = -2;
+static constexpr int KVB_ERR_INVALID_ = -1;
+static constexpr int KVB_ERR_STATE_ = -3;
+
+// The reference reserves at 0x1f0_0000_0000 + running offset (ftensor.cpp:26-47, constants.hpp).  We
+// hint at a different window so both libraries can live in one process.
+static constexpr uint64_t kVaHint = 0x2f0000000000ull;
+static std::atomic<size_t> g_va_off{0};
+
+// ------------------------------------------------------------------------------------------ group
+VmmGroup::~VmmGroup() {
+  const Driver *d = g_drv.ok ? &g_drv : nullptr;
+  if (!d) return;
+  cudaSetDevice(dev_);
+  for (auto &r : ranges_) {
+    if (!r.base) continue;
+    d->MemUnmap(r.base, r.bytes);          // tolerate stale mappings at teardown (ftensor.cpp:78-98)
+    d->MemAddressFree(r.base, r.bytes);
+  }
+  for (auto h : handles_)
+    if (h) d->MemRelease(h);
+  for (auto h : pool_) d->MemRelease(h);
+  if (have_zero_) d->MemRelease(zero_);
+}
+
+int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv, bool unified) {
+  const Driver *d = driver();
+  if (!d) return KVB_ERR_CUDA_;
+  if (created_) {
+    if (num_layers != L_) { set_error("create_kv_tensors: num_layers changed (%ld -> %ld)", (long)L_, (long)num_layers); return KVB_ERR_INVALID_; }
+    return (int)ranges_.size();
+  }
+  if (size_per_layer <= 0 || num_layers <= 0 || num_kv <= 0) { set_error("create_kv_tensors: bad sizes"); return KVB_ERR_INVALID_; }
+  if (cudaSetDevice(dev_) != cudaSuccess || cudaFree(0) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", dev_); return KVB_ERR_CUDA_; }
+  // allocator.cpp:130-136: round the per-layer size up to the page size
+  size_t aligned = ((size_t)size_per_layer + P_ - 1) / P_ * P_;
+  L_ = num_layers;
+  nkv_ = num_kv;
+  unified_ = unified;
+  size_per_layer_ = aligned;
+
+  memset(&prop_, 0, sizeof(prop_));
+  prop_.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop_.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop_.location.id = dev_;
+  access_.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  access_.location.id = dev_;
+  access_.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  size_t gran = 0;
+  CU_TRY(d->MemGetAllocationGranularity(&gran, &prop_, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
+  if (gran == 0 || P_ % gran != 0) { set_error("page size %zu is not a multiple of the VMM granularity %zu", P_, gran); return KVB_ERR_INVALID_; }
+
+  if (contiguous_) {
+    unit_ = P_ * (size_t)num_layers * (size_t)num_kv;   // compound page, allocator.cpp:139-142
+    n_sub_ = 1;
+    size_t total = aligned * (size_t)num_layers;
+    n_pages_ = (int64_t)(total / unit_);
+    ranges_.resize(1);
+    ranges_[0].bytes = total;
+  } else {
+    unit_ = P_;
+    if (unified) {
+      n_sub_ = (int)num_layers;
+      n_pages_ = (int64_t)(aligned / P_);
+    } else {
+      if (aligned % (2 * P_) != 0) { set_error("per-layer size %zu must be a multiple of 2 * page size (allocator.cpp:46-52)", aligned); return KVB_ERR_INVALID_; }
+      n_sub_ = (int)num_layers * 2;
+      n_pages_ = (int64_t)(aligned / 2 / P_);
+    }
+    ranges_.resize((size_t)num_layers);
+    for (auto &r : ranges_) r.bytes = aligned;
+  }
+  // reserve VA (ftensor.cpp:26-47)
+  for (auto &r : ranges_) {
+    size_t off = g_va_off.fetch_add(r.bytes);
+    CU_TRY(d->MemAddressReserve(&r.base, r.bytes, 2u << 20, (CUdeviceptr)(kVaHint + off), 0));
+  }
+  // one zero page backs every unmapped page (ftensor.cpp:160-176).  Map per unit, grant access once
+  // per range instead of once per page.
+  CU_TRY(d->MemCreate(&zero_, unit_, &prop_, 0));
+  have_zero_ = true;
+  n_created_++;
+  for (auto &r : ranges_) {
+    for (size_t off = 0; off + unit_ <= r.bytes; off += unit_) CU_TRY(d->MemMap(r.base + off, unit_, 0, zero_, 0));
+    size_t covered = r.bytes / unit_ * unit_;
+    if (covered) CU_TRY(d->MemSetAccess(r.base, covered, &access_, 1));
+  }
+  // the zero page must read as zeros
+  if (cudaMemset((void *)ranges_[0].base, 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("zero page memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return KVB_ERR_CUDA_;
+  }
+  handles_.assign((size_t)n_pages_ * n_sub_, 0);
+  mapped_.assign((size_t)n_pages_, 0);
+  if (pool_cap_ == 0) {
+    const char *e = getenv("KVB200_HANDLE_POOL_PAGES");
+    pool_cap_ = (e ? atoll(e) : 16) * n_sub_;
+  }
+  created_ = true;
+  return (int)ranges_.size();
+}
+
+CUdeviceptr VmmGroup::sub_addr(int64_t p, int sub) const {
+  if (contiguous_) return ranges_[0].base + (size_t)p * unit_;
+  if (unified_) return ranges_[(size_t)sub].base + (size_t)p * P_;
+  int l = sub >> 1, kv = sub & 1;   // K at off, V at off + size/2 (allocator.cpp:46-52, :178-207)
+  return ranges_[(size_t)l].base + (size_t)kv * (size_per_layer_ / 2) + (size_t)p * P_;
+}
+
+int VmmGroup::get_handle(CUmemGenericAllocationHandle *h) {
+  if (!pool_.empty()) {
+    *h = pool_.back();
+    pool_.pop_back();
+    return 0;
+  }
+  CU_TRY(g_drv.MemCreate(h, unit_, &prop_, 0));
+  n_created_++;
+  return 0;
+}
+void VmmGroup::put_handle(CUmemGenericAllocationHandle h) {
+  if ((int64_t)pool_.size() < pool_cap_) {
+    pool_.push_back(h);
+  } else {
+    g_drv.MemRelease(h);
+    n_released_++;
+  }
+}
+
+// FTensor::map (ftensor.cpp:100-118) for every layer / K / V range of page p, SetAccess deferred.
+int VmmGroup::map_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched) {
+  if (p < 0 || p >= n_pages_) { set_error("map: page %ld out of range [0, %ld)", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
+  if (mapped_[(size_t)p]) return 0;   // "already mapped" is tolerated (allocator.cpp:174-177)
+  for (int s = 0; s < n_sub_; ++s) {
+    CUdeviceptr a = sub_addr(p, s);
+    CUmemGenericAllocationHandle h;
+    int rc = get_handle(&h);
+    if (rc) return rc;
+    CU_TRY(g_drv.MemUnmap(a, unit_));
+    CU_TRY(g_drv.MemMap(a, unit_, 0, h, 0));
+    handles_[(size_t)p * n_sub_ + s] = h;
+    touched.emplace_back(a, unit_);
+  }
+  mapped_[(size_t)p] = 1;
+  n_mapped_++;
+  return 0;
+}
+
+// FTensor::unmap (ftensor.cpp:120-140): back to the zero page, handle to the pool.
+int VmmGroup::unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched) {
+  if (p < 0 || p >= n_pages_) { set_error("unmap: page %ld out of range [0, %ld)", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
+  if (!mapped_[(size_t)p]) return 0;
+  for (int s = 0; s < n_sub_; ++s) {
+    CUdeviceptr a = sub_addr(p, s);
+    CU_TRY(g_drv.MemUnmap(a, unit_));
+    CU_TRY(g_drv.MemMap(a, unit_, 0, zero_, 0));
+    put_handle(handles_[(size_t)p * n_sub_ + s]);
+    handles_[(size_t)p * n_sub_ + s] = 0;
+    touched.emplace_back(a, unit_);
+  }
+  mapped_[(size_t)p] = 0;
+  n_mapped_--;
+  return 0;
+}
+
+// One cuMemSetAccess per run of adjacent units.
+int VmmGroup::set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &t) {
+  if (t.empty()) return 0;
+  if (t.size() > 1) std::sort(t.begin(), t.end());
+  size_t i = 0;
+  while (i < t.size()) {
+    CUdeviceptr a = t[i].first;
+    size_t len = t[i].second;
+    size_t j = i + 1;
+    while (j < t.size() && t[j].first == a + len) { len += t[j].second; ++j; }
+    CU_TRY(g_drv.MemSetAccess(a, len, &access_, 1));
+    i = j;
+  }
+  t.clear();
+  return 0;
+}
+
+int VmmGroup::map_pages(const int64_t *ids, int64_t n) {
+  if (!created_) return 0;
+  if (!driver()) return KVB_ERR_CUDA_;
+  cudaSetDevice(dev_);
+  std::vector<std::pair<CUdeviceptr, size_t>> touched;
+  touched.reserve((size_t)n * n_sub_);
+  int rc = 0;
+  for (int64_t i = 0; i < n && !rc; ++i) rc = map_one(ids[i], touched);
+  int rc2 = set_access_merged(touched);
+  n_map_calls_++;
+  return rc ? rc : (rc2 ? rc2 : 1);
+}
+
+int VmmGroup::unmap_pages(const int64_t *ids, int64_t n) {
+  if (!created_) return 0;
+  if (!driver()) return KVB_ERR_CUDA_;
+  cudaSetDevice(dev_);
+  std::vector<std::pair<CUdeviceptr, size_t>> touched;
+  touched.reserve((size_t)n * n_sub_);
+  int rc = 0;
+  for (int64_t i = 0; i < n && !rc; ++i) rc = unmap_one(ids[i], touched);
+  int rc2 = set_access_merged(touched);
+  n_unmap_calls_++;
+  return rc ? rc : (rc2 ? rc2 : 1);
+}
+
+int VmmGroup::apply_events(const int64_t *ev, int64_t n) {
+  if (!created_) return 0;
+  if (n <= 0) return 1;
+  if (!driver()) return KVB_ERR_CUDA_;
+  cudaSetDevice(dev_);
+  std::vector<std::pair<CUdeviceptr, size_t>> touched;
+  int rc = 0;
+  // Events are applied in order; SetAccess is flushed whenever a page is touched twice so that a
+  // later unmap never meets a mapping without access rights (harmless, but keeps the loop simple).
+  std::vector<int64_t> seen;
+  for (int64_t i = 0; i < n && !rc; ++i) {
+    int64_t p = ev[i] >> 1;
+    bool un = ev[i] & 1;
+    if (std::find(seen.begin(), seen.end(), p) != seen.end()) {
+      rc = set_access_merged(touched);
+      seen.clear();
+      if (rc) break;
+    }
+    seen.push_back(p);
+    rc = un ? unmap_one(p, touched) : map_one(p, touched);
+  }
+  int rc2 = set_access_merged(touched);
+  n_map_calls_++;
+  return rc ? rc : (rc2 ? rc2 : 1);
+}
+
+void VmmGroup::pool_config(int64_t max_cached_pages) {
+  pool_cap_ = max_cached_pages * n_sub_;
+  while ((int64_t)pool_.size() > pool_cap_ && g_drv.ok) {
+    g_drv.MemRelease(pool_.back());
+    pool_.pop_back();
+    n_released_++;
+  }
+}
+int VmmGroup::pool_prefill(int64_t n_pages) {
+  if (!created_) { set_error("pool_prefill: tensors not created"); return KVB_ERR_STATE_; }
+  if (!driver()) return KVB_ERR_CUDA_;
+  cudaSetDevice(dev_);
+  int64_t want = std::min<int64_t>(n_pages * n_sub_, pool_cap_);
+  while ((int64_t)pool_.size() < want) {
+    CUmemGenericAllocationHandle h;
+    CU_TRY(g_drv.MemCreate(&h, unit_, &prop_, 0));
+    n_created_++;
+    pool_.push_back(h);
+  }
+  return 0;
+}
+int64_t VmmGroup::pooled_pages() { return n_sub_ ? (int64_t)pool_.size() / n_sub_ : 0; }
+
+void VmmGroup::stats(int64_t *s) {
+  s[0] = n_mapped_;
+  s[1] = (int64_t)pool_.size();
+  s[2] = n_created_;
+  s[3] = n_released_;
+  s[4] = n_map_calls_;
+  s[5] = n_unmap_calls_;
+  s[6] = n_mapped_ * (int64_t)unit_ * n_sub_;
+  s[7] = (int64_t)unit_ * n_sub_;
+}
+int64_t VmmGroup::mapped_pages(int64_t *out, int64_t cap) {
+  int64_t n = 0;
+  for (int64_t p = 0; p < n_pages_; ++p)
+    if (mapped_[(size_t)p]) {
+      if (n >= cap) return -5;
+      out[n++] = p;
+    }
+  return n;
+}
+
+// Raw-driver control for the map/unmap latency metric: the same three driver calls per unit as
+// map_one / unmap_one on pre-created handles over a private range, nothing else in the loop
+// (cf. the reference's benchmarks/bench_vmm/bench_vmm.cpp:139-228).
+int VmmGroup::raw_control(int64_t n_pages, int64_t iters, double *map_us, double *unmap_us) {
+  const Driver *d = driver();
+  if (!d) return KVB_ERR_CUDA_;
+  if (!created_) { set_error("raw_control: tensors not created"); return KVB_ERR_STATE_; }
+  cudaSetDevice(dev_);
+  size_t n_units = (size_t)n_pages * n_sub_;
+  size_t bytes = n_units * unit_;
+  CUdeviceptr base = 0;
+  CU_TRY(d->MemAddressReserve(&base, bytes, 2u << 20, 0, 0));
+  std::vector<CUmemGenericAllocationHandle> hs(n_units);
+  for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit_, &prop_, 0));
+  for (size_t u = 0; u < n_units; ++u) CU_TRY(d->MemMap(base + u * unit_, unit_, 0, zero_, 0));
+  CU_TRY(d->MemSetAccess(base, bytes, &access_, 1));
+  using clk = std::chrono::steady_clock;
+  for (int64_t it = 0; it < iters; ++it) {
+    auto t0 = clk::now();
+    for (size_t u = 0; u < n_units; ++u) {
+      CUdeviceptr a = base + u * unit_;
+      CU_TRY(d->MemUnmap(a, unit_));
+      CU_TRY(d->MemMap(a, unit_, 0, hs[u], 0));
+      CU_TRY(d->MemSetAccess(a, unit_, &access_, 1));
+    }
+    auto t1 = clk::now();
+    for (size_t u = 0; u < n_units; ++u) {
+      CUdeviceptr a = base + u * unit_;
+      CU_TRY(d->MemUnmap(a, unit_));
+      CU_TRY(d->MemMap(a, unit_, 0, zero_, 0));
+      CU_TRY(d->MemSetAccess(a, unit_, &access_, 1));
+    }
+    auto t2 = clk::now();
+    map_us[it] = std::chrono::duration<double, std::micro>(t1 - t0).count();
+    unmap_us[it] = std::chrono::duration<double, std::micro>(t2 - t1).count();
+  }
+  d->MemUnmap(base, bytes);
+  d->MemAddressFree(base, bytes);
+  for (auto h : hs) d->MemRelease(h);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ registry
+struct Registry {
+  std::mutex mu;
+  bool inited = false;
+  int dev = 0;
+  int64_t page_size = 2 << 20;
+  bool contiguous = true;
+  std::map<int64_t, std::unique_ptr<VmmGroup>> groups;
+};
+static Registry &reg() {
+  static Registry r;
+  return r;
+}
+
+int vmm_init(int dev, int64_t page_size, bool contiguous) {
+  Registry &r = reg();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (page_size == 0) page_size = 2 << 20;
+  if (page_size < 0 || page_size % (2 << 20) != 0) {   // the reference abort()s (allocator.cpp:84-90)
+    set_error("Invalid page size: %ld, must be a multiple of 2MB (2097152 bytes)", (long)page_size);
+    return KVB_ERR_INVALID_;
+  }
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  }
+  r.groups.clear();   // re-initialising drops existing allocators (allocator.cpp:75-78)
+  r.inited = true;
+  r.dev = dev;
+  r.page_size = page_size;
+  r.contiguous = contiguous;
+  return 0;
+}
+int vmm_shutdown() {
+  Registry &r = reg();
+  std::lock_guard<std::mutex> lk(r.mu);
+  r.groups.clear();
+  r.inited = false;
+  return 0;
+}
+bool vmm_initialized() { return reg().inited; }
+int64_t vmm_page_size() { return reg().page_size; }
+bool vmm_contiguous() { return reg().contiguous; }
+int vmm_device() { return reg().dev; }
+VmmGroup *vmm_group(int64_t group_id, bool create_if_missing) {
+  Registry &r = reg();
+  std::lock_guard<std::mutex> lk(r.mu);
+  if (!r.inited) { set_error("kvb_init() must be called first"); return nullptr; }
+  auto it = r.groups.find(group_id);
+  if (it != r.groups.end()) return it->second.get();
+  if (!create_if_missing) return nullptr;
+  auto g = std::make_unique<VmmGroup>(r.dev, (size_t)r.page_size, r.contiguous);   // lazily, allocator.cpp:101-114
+  VmmGroup *p = g.get();
+  r.groups[group_id] = std::move(g);
+  return p;
+}
+
+}  // namespace kvb

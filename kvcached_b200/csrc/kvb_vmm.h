@@ -1,0 +1,110 @@
+// kvb_vmm.h — batched CUDA VMM engine: reserved VA ranges of every layer's K/V tensor, one shared
+// zero page, pooled physical handles, and the cuMemUnmap / cuMemMap / cuMemSetAccess loop.
+// Replaces csrc/allocator.cpp (FTensorAllocator), csrc/ftensor.cpp (FTensor), csrc/page.cpp (GPUPage)
+// and csrc/inc/gpu_vmm.hpp of the reference.  Host-only C++.
+#pragma once
+
+#include <cuda.h>
+
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace kvb {
+
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+// CUDA driver entry points, resolved at first use through cudaGetDriverEntryPoint so that the
+// library itself has no link-time dependency on libcuda.so.1 (it must load on driver-less boxes).
+struct Driver {
+  CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+  bool ok = false;
+};
+const Driver *driver();   // nullptr (and error set) when no driver is available
+
+struct VmmRange {
+  CUdeviceptr base = 0;
+  size_t bytes = 0;
+};
+
+class VmmGroup {
+ public:
+  VmmGroup(int dev, size_t page_size, bool contiguous) : dev_(dev), P_(page_size), contiguous_(contiguous) {}
+  ~VmmGroup();
+
+  // FTensorAllocator::create_kv_tensors, allocator.cpp:121-154
+  int create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv, bool unified);
+  bool created() const { return created_; }
+  const std::vector<VmmRange> &ranges() const { return ranges_; }
+
+  // page-id addressed batch ops (each runs the whole driver loop over all layers' ranges)
+  int map_pages(const int64_t *ids, int64_t n);
+  int unmap_pages(const int64_t *ids, int64_t n);
+  int apply_events(const int64_t *events, int64_t n);   // page*2 + is_unmap, in order
+  // reference byte offsets (page_allocator.cpp:619-631) -> page ids
+  int64_t offset_to_page(int64_t off) const { return off / (int64_t)(contiguous_ ? unit_ : P_); }
+
+  void pool_config(int64_t max_cached);
+  int pool_prefill(int64_t n_pages);
+  void stats(int64_t *s8);
+  int64_t mapped_pages(int64_t *out, int64_t cap);
+  int64_t pooled_pages();
+  int64_t num_pages() const { return n_pages_; }
+  size_t unit() const { return unit_; }
+  int64_t num_layers() const { return L_; }
+  int64_t num_kv() const { return nkv_; }
+  int raw_control(int64_t n_pages, int64_t iters, double *map_us, double *unmap_us);
+
+  std::mutex mu;
+
+ private:
+  int map_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched);
+  int unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched);
+  int set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &touched);
+  CUdeviceptr sub_addr(int64_t p, int sub) const;
+  int get_handle(CUmemGenericAllocationHandle *h);
+  void put_handle(CUmemGenericAllocationHandle h);
+
+  int dev_;
+  size_t P_;
+  bool contiguous_;
+  bool unified_ = false;
+  bool created_ = false;
+  int64_t L_ = 0, nkv_ = 0;
+  size_t size_per_layer_ = 0;
+  size_t unit_ = 0;       // bytes of one physical handle: compound page (contiguous) or page
+  int n_sub_ = 1;         // handles per page id
+  int64_t n_pages_ = 0;
+  std::vector<VmmRange> ranges_;
+  CUmemGenericAllocationHandle zero_ = 0;
+  bool have_zero_ = false;
+  std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
+  std::vector<uint8_t> mapped_;
+  std::vector<CUmemGenericAllocationHandle> pool_;
+  int64_t pool_cap_ = 0;
+  CUmemAllocationProp prop_{};
+  CUmemAccessDesc access_{};
+  int64_t n_mapped_ = 0, n_created_ = 0, n_released_ = 0, n_map_calls_ = 0, n_unmap_calls_ = 0;
+};
+
+// process-global registry (FTensorAllocator::init / global_allocator / shutdown, allocator.cpp:72-119)
+int vmm_init(int dev, int64_t page_size, bool contiguous);
+int vmm_shutdown();
+bool vmm_initialized();
+int64_t vmm_page_size();
+bool vmm_contiguous();
+int vmm_device();
+VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
+
+}  // namespace kvb
