@@ -116,6 +116,11 @@ int64_t kvb_vmm_avail_physical_pages(int64_t group_id, int64_t num_layers, int64
 int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int compound,
                         double *map_us, double *unmap_us);
 
+/* per-call driver costs in microseconds (measurement aid, cf. benchmarks/bench_vmm/bench_vmm.cpp):
+ * out8 = {cuMemCreate, cuMemMap, cuMemSetAccess per unit, cuMemSetAccess whole range (one call),
+ *         cuMemUnmap per unit, cuMemUnmap whole range (one call), cuMemRelease, unmap+map+setaccess per unit} */
+int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t iters, double *out8);
+
 /* ------------------------------------------------------------------------------------------
  * 2. Device-resident block manager
  *    replaces the host bookkeeping of kvcached/kv_cache_manager.py:58-506 and

@@ -119,7 +119,7 @@ int64_t kvb_vmm_avail_physical_pages(int64_t group_id, int64_t num_layers, int64
     const char *e = getenv("KVCACHED_GPU_UTILIZATION");
     gpu_utilization = e && *e ? atof(e) : 0.95;
   }
-  if (vmm_initialized()) cudaSetDevice(vmm_device());
+  if (vmm_initialized()) ensure_device(vmm_device());
   size_t fr = 0, tot = 0;
   CUDA_TRY(cudaMemGetInfo(&fr, &tot));
   double avail = (double)fr - (double)tot * (1.0 - gpu_utilization);
@@ -136,6 +136,11 @@ int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int co
   if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
   std::lock_guard<std::mutex> lk(g->mu);
   return g->raw_control(n_pages, iters, map_us, unmap_us);
+}
+
+int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t iters, double *out8) {
+  if (unit_bytes <= 0 || unit_bytes % (2 << 20) || n_units <= 0 || iters <= 0 || !out8) { set_error("vmm_probe: bad argument"); return KVB_ERR_INVALID; }
+  return vmm_probe(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, n_units, iters, out8);
 }
 
 // ------------------------------------------------------------------------------------------ page helpers

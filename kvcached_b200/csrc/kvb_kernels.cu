@@ -638,7 +638,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     int32_t pg = INT_MIN;
     if (id >= 0 && id < c.num_blocks) {
       int64_t p64 = blk_page(c, id);
-      if (p64 < c.max_pages) {
+      if (p64 <= c.max_pages) {   // page max_pages can be named (tail of a non-page-aligned pool); it is never in use
         int p = (int)p64;
         bool ok = true;
         if (!c.exact && !group_only) {   // a block straddling the page edge is never handed out
@@ -908,24 +908,24 @@ __device__ int gather_refs(const DevState &c, Smem &s, const LaunchArgs &a, int6
 // KVCacheManager.clear (kv_cache_manager.py:444-489; semantics SURVEY A.7): everything released,
 // reserved pages trimmed, free list sorted ascending, counters zeroed.  The null block is
 // re-reserved by the caller through the alloc path.
-__device__ void clear_all(const DevState &c, Smem &s) {
+__device__ void clear_all(const DevState &c, Smem &s, int order_only) {
   const int tid = threadIdx.x;
   int64_t *sc = s.sc;
-  // membership of the new free list = old free list + reserved list + every in-use page.
-  // pg_slot is borrowed as the membership flag.
-  for (int p = tid; p < c.max_pages; p += NT) c.pg_slot[p] = (c.pg_state[p] != PG_NONE) ? 1 : 0;
+  // membership of the new free list = old free list (+ reserved list + every in-use page for clear()).
+  // pg_slot is borrowed as the membership flag.  order_only = PageAllocator::reset_free_page_order.
+  for (int p = tid; p < c.max_pages; p += NT) c.pg_slot[p] = (!order_only && c.pg_state[p] != PG_NONE) ? 1 : 0;
   __syncthreads();
-  int fls = (int)sc[SC_FL_SIZE], rls = (int)sc[SC_RL_SIZE];
+  int fls = (int)sc[SC_FL_SIZE], rls = order_only ? 0 : (int)sc[SC_RL_SIZE];
   for (int i = tid; i < fls; i += NT) c.pg_slot[c.fl[(int)((sc[SC_FL_HEAD] + i) & c.q_mask)]] = 1;
   for (int i = tid; i < rls; i += NT) c.pg_slot[c.rl[(int)((sc[SC_RL_HEAD] + i) & c.q_mask)]] = 1;
   __syncthreads();
-  // unmap events for every mapped page (in-use pages beyond the reserved cap + the trimmed reserve)
+  // unmap events for every mapped page (in-use pages + the trimmed reserve), ascending
   int nev = (int)sc[SC_NEV];
   int base = 0, evn = 0;
   for (int p0 = 0; p0 < c.max_pages; p0 += NT) {
     int p = p0 + tid;
     bool in = (p < c.max_pages) && c.pg_slot[p];
-    bool mp = (p < c.max_pages) && c.pg_mapped[p];
+    bool mp = !order_only && (p < c.max_pages) && c.pg_mapped[p];
     int tot, totm;
     int r = block_rank(in, s.wtot, &tot);
     int rm = block_rank(mp, s.wtot2, &totm);
@@ -934,7 +934,7 @@ __device__ void clear_all(const DevState &c, Smem &s) {
       if (nev + evn + rm < c.ev_cap) c.ev[nev + evn + rm] = (int64_t)p * 2 + 1;
       c.pg_mapped[p] = 0;
     }
-    if (p < c.max_pages) {
+    if (!order_only && p < c.max_pages) {
       c.pg_state[p] = PG_NONE;
       c.pg_cnt[p] = 0;
       c.pg_head[p] = 0;
@@ -943,6 +943,11 @@ __device__ void clear_all(const DevState &c, Smem &s) {
     evn += totm;
   }
   __syncthreads();
+  if (order_only) {
+    if (tid == 0) { sc[SC_FL_HEAD] = 0; sc[SC_FL_SIZE] = base; }
+    __syncthreads();
+    return;
+  }
   int64_t nwords = (c.num_blocks + 31) / 32;
   for (int64_t i = tid; i < nwords; i += NT) c.bitmap[i] = 0;
   if (tid == 0) {
@@ -1103,7 +1108,17 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         }
         case KVB_OP_CLEAR: {
           // free_reserved(); free_pages(all); trim(); reset_free_page_order(); counters = 0
-          clear_all(c, s);
+          clear_all(c, s, 0);
+          if (tid == 0) {
+            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_RESET_ORDER: {
+          clear_all(c, s, 1);
           if (tid == 0) {
             kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
@@ -1205,7 +1220,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
 __global__ void kvb_init_state_kernel(DevState c, int64_t num_total_pages) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t p = i; p < c.max_pages; p += stride) {
+  for (int64_t p = i; p <= c.max_pages; p += stride) {
     c.pg_state[p] = PG_NONE;
     c.pg_cnt[p] = 0;
     c.pg_head[p] = 0;

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,9 @@ int64_t pow2_ge(int64_t v) {
   return p;
 }
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 }  // namespace
 
 struct kvb_mgr {
@@ -74,6 +78,9 @@ struct kvb_mgr {
   int64_t seq = 0;
   int64_t launches = 0;
   int64_t phys_override = -1;
+  int64_t phys_cached = -1;        // last live get_avail_physical_pages() (cudaMemGetInfo costs ~100 us here)
+  double phys_time_us = 0;
+  double phys_refresh_us = 1000;
   int has_null = 0;
   int64_t total_events = 0;
   std::vector<int64_t> pending_events;
@@ -120,6 +127,11 @@ int ensure_io(kvb_mgr *m, size_t in_bytes, size_t out_bytes) {
 // PageAllocator::get_avail_physical_pages, csrc/page_allocator.cpp:442-455
 int64_t phys_free_pages(kvb_mgr *m) {
   if (m->phys_override >= 0) return m->phys_override;
+  // live like the reference, but at most once per refresh interval; our own map/unmap activity
+  // invalidates the cached value (apply_events), other tenants' activity is seen within the interval.
+  double now = now_us();
+  if (m->phys_cached >= 0 && now - m->phys_time_us < m->phys_refresh_us) return m->phys_cached;
+  m->phys_time_us = now;
   size_t fr = 0, tot = 0;
   if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
     cudaGetLastError();
@@ -133,6 +145,7 @@ int64_t phys_free_pages(kvb_mgr *m) {
     VmmGroup *g = vmm_group(m->cfg.group_id, false);
     if (g) pages += g->pooled_pages();   // pooled handles are memory we already hold
   }
+  m->phys_cached = pages;
   return pages;
 }
 
@@ -155,6 +168,7 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n) {
   }
   std::lock_guard<std::mutex> lk(g->mu);
   int rc = g->apply_events(ev, n);
+  m->phys_cached = -1;   // physical memory just changed hands
   return rc < 0 ? rc : 0;
 }
 
@@ -201,6 +215,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   if (c.num_kv_buffers <= 0) c.num_kv_buffers = 2;
   if (c.min_reserved_pages < 0) c.min_reserved_pages = env_i64("KVCACHED_MIN_RESERVED_PAGES", 5);
   if (c.max_reserved_pages < 0) c.max_reserved_pages = env_i64("KVCACHED_MAX_RESERVED_PAGES", 10);
+  m->phys_refresh_us = env_f64("KVB200_MEMINFO_REFRESH_US", 1000);
   m->gpu_util = c.gpu_utilization > 0 ? c.gpu_utilization : env_f64("KVCACHED_GPU_UTILIZATION", 0.95);
   m->P = c.page_size;
   m->B = c.block_size * c.cell_size;
@@ -268,13 +283,14 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   size_t o_sc = carve(SC_COUNT * 8), o_fl = carve(qcap * 4), o_rl = carve(qcap * 4), o_cl = carve(qcap * 4);
   size_t o_ap = carve((size_t)s.ap_cap * 4);
   size_t o_pg[7];
-  for (auto &o : o_pg) o = carve((size_t)m->max_pages * 4);
+  const size_t cap_pages = (size_t)m->max_pages + 1;   // ids < num_blocks can name page max_pages (never in use)
+  for (auto &o : o_pg) o = carve(cap_pages * 4);
   size_t o_ring = carve((size_t)m->max_pages * m->bpp * 4);
   size_t o_bm = carve((size_t)(nwords + 8) * 4);
   size_t o_rb = carve((size_t)rbcap * 8);
   size_t o_fids = carve((size_t)m->f_cap * 8), o_fpage = carve((size_t)m->f_cap * 4);
   size_t o_g[5];
-  for (auto &o : o_g) o = carve((size_t)m->max_pages * 4);
+  for (auto &o : o_g) o = carve(cap_pages * 4);
   size_t o_bkt = carve((size_t)bkt_cap * 4);
   size_t o_ev = carve((size_t)s.ev_cap * 8);
   size_t o_pr = carve((size_t)kNumPrimes * 8);
@@ -365,7 +381,7 @@ extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
 static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
                            const kvb_ref *refs, int64_t n_refs, kvb_res *res, int64_t *out_ids, int64_t out_cap) {
   if (n_ops <= 0) return 0;
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   int64_t need_out = 0;
   for (int64_t i = 0; i < n_ops; ++i) {
     if (ops[i].kind == KVB_OP_ALLOC && ops[i].n > 0) need_out += ops[i].n;
@@ -504,7 +520,7 @@ extern "C" int64_t kvb_mgr_available_size(kvb_mgr *m) {
   const int64_t *sc = m->last.sc;
   int64_t a = sc[SC_NAB] + sc[SC_NRB];
   if (sc[SC_INSHRINK]) return a;
-  cudaSetDevice(m->dev);
+  ensure_device(m->dev);
   int64_t phys = phys_free_pages(m) + sc[SC_RL_SIZE];
   return a + std::min(sc[SC_NFREE], phys) * m->bpp;
 }
@@ -549,7 +565,7 @@ extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops
                                     int64_t out_capacity) {
   if (!m || !ops || n_ops <= 0 || !step_offsets || n_steps <= 0) { set_error("trace_upload: bad argument"); return KVB_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   for (void *p : {(void *)m->t_ops, (void *)m->t_ids, (void *)m->t_refs, (void *)m->t_res, (void *)m->t_out})
     if (p) cudaFree(p);
   m->t_ops = nullptr; m->t_ids = nullptr; m->t_refs = nullptr; m->t_res = nullptr; m->t_out = nullptr;
@@ -572,7 +588,7 @@ extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops
 extern "C" int kvb_mgr_trace_reset_cursor(kvb_mgr *m) {
   if (!m) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_OUT_CURSOR, 0, 8, m->stream));
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -586,7 +602,7 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
   int64_t n_steps = (int64_t)m->t_steps.size() - 1;
   if (step_begin < 0 || step_end > n_steps || step_begin > step_end) { set_error("trace_run: bad step range"); return KVB_ERR_INVALID; }
   if (steps_per_launch <= 0) steps_per_launch = 1;
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   int64_t launches0 = m->launches;
   // events of the whole range accumulate in the device log
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
@@ -620,7 +636,7 @@ extern "C" int kvb_mgr_trace_results(kvb_mgr *m, kvb_res *res, int64_t n_ops, in
                                      int64_t *n_out) {
   if (!m || !m->t_ops) { set_error("trace_results: no trace uploaded"); return KVB_ERR_STATE; }
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   if (n_ops > m->t_nops) n_ops = m->t_nops;
   if (res && n_ops > 0) CUDA_TRY(cudaMemcpy(res, m->t_res, (size_t)n_ops * sizeof(kvb_res), cudaMemcpyDeviceToHost));
   int64_t cur = 0;
@@ -646,7 +662,7 @@ static int ensure_dump(kvb_mgr *m, int64_t n) {
 extern "C" int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_t cap) {
   if (!m || !out) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   int64_t sc[SC_COUNT];
   CUDA_TRY(cudaMemcpy(sc, m->st.sc, sizeof(sc), cudaMemcpyDeviceToHost));
@@ -690,7 +706,7 @@ extern "C" int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_
 extern "C" int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t p, int64_t *out, int64_t cap) {
   if (!m || p < 0 || p >= m->max_pages) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   int32_t st = 0, cnt = 0, head = 0;
   CUDA_TRY(cudaMemcpy(&st, m->st.pg_state + p, 4, cudaMemcpyDeviceToHost));
@@ -718,7 +734,7 @@ extern "C" int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap) {
 extern "C" int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms) {
   if (!m || !out4) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
   if (launch_audit(m->st, m->d_scratch + 8, m->stream) != 0) { set_error("audit kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
@@ -742,7 +758,7 @@ extern "C" int64_t kvb_group_indices_by_page(kvb_mgr *m, const int64_t *ids, int
   if (n == 0) return 0;
   if (n > m->f_cap) { set_error("group_indices_by_page: %ld ids exceed the pool's block count", (long)n); return KVB_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   kvb_op op{KVB_OP_FREE_IDS, (int32_t)n, 0};
   size_t b_ops = sizeof(kvb_op), b_ids = (size_t)n * 8;
   size_t o_res = align_up(sizeof(Summary), 16), o_pg = o_res + 64, o_ct = o_pg + b_ids, o_gr = o_ct + b_ids;
@@ -774,7 +790,7 @@ extern "C" int64_t kvb_tp_buffer_words(void) { return kTpWords; }
 extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
   if (!m || !dst) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
-  CUDA_TRY(cudaSetDevice(m->dev));
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   int64_t n = (int64_t)m->pending_events.size();
   if (n > kTpWords - 2) { set_error("tp_export: %ld page events exceed the broadcast buffer (%ld)", (long)n, (long)(kTpWords - 2)); return KVB_ERR_OVERFLOW; }
   size_t bytes = (size_t)(2 + n) * 8;

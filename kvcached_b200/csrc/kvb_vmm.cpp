@@ -89,10 +89,9 @@ VmmGroup::~VmmGroup() {
   const Driver *d = g_drv.ok ? &g_drv : nullptr;
   if (!d) return;
   cudaSetDevice(dev_);
-  for (auto &r : ranges_) {
-    if (!r.base) continue;
-    d->MemUnmap(r.base, r.bytes);          // tolerate stale mappings at teardown (ftensor.cpp:78-98)
-    d->MemAddressFree(r.base, r.bytes);
+  if (va_base_) {
+    d->MemUnmap(va_base_, va_bytes_);      // tolerate stale mappings at teardown (ftensor.cpp:78-98)
+    d->MemAddressFree(va_base_, va_bytes_);
   }
   for (auto h : handles_)
     if (h) d->MemRelease(h);
@@ -147,10 +146,15 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     ranges_.resize((size_t)num_layers);
     for (auto &r : ranges_) r.bytes = aligned;
   }
-  // reserve VA (ftensor.cpp:26-47)
-  for (auto &r : ranges_) {
-    size_t off = g_va_off.fetch_add(r.bytes);
-    CU_TRY(d->MemAddressReserve(&r.base, r.bytes, 2u << 20, (CUdeviceptr)(kVaHint + off), 0));
+  // reserve VA (ftensor.cpp:26-47).  ONE reservation for all layers: per-layer ranges sit back to back,
+  // so the scatter/gather kernel addresses every layer with a constant stride.
+  va_bytes_ = 0;
+  for (auto &r : ranges_) va_bytes_ += r.bytes;
+  {
+    size_t off = g_va_off.fetch_add(va_bytes_);
+    CU_TRY(d->MemAddressReserve(&va_base_, va_bytes_, 2u << 20, (CUdeviceptr)(kVaHint + off), 0));
+    size_t o = 0;
+    for (auto &r : ranges_) { r.base = va_base_ + o; o += r.bytes; }
   }
   // one zero page backs every unmapped page (ftensor.cpp:160-176).  Map per unit, grant access once
   // per range instead of once per page.
@@ -259,7 +263,7 @@ int VmmGroup::set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &t) 
 int VmmGroup::map_pages(const int64_t *ids, int64_t n) {
   if (!created_) return 0;
   if (!driver()) return KVB_ERR_CUDA_;
-  cudaSetDevice(dev_);
+  ensure_device(dev_);
   std::vector<std::pair<CUdeviceptr, size_t>> touched;
   touched.reserve((size_t)n * n_sub_);
   int rc = 0;
@@ -272,7 +276,7 @@ int VmmGroup::map_pages(const int64_t *ids, int64_t n) {
 int VmmGroup::unmap_pages(const int64_t *ids, int64_t n) {
   if (!created_) return 0;
   if (!driver()) return KVB_ERR_CUDA_;
-  cudaSetDevice(dev_);
+  ensure_device(dev_);
   std::vector<std::pair<CUdeviceptr, size_t>> touched;
   touched.reserve((size_t)n * n_sub_);
   int rc = 0;
@@ -286,7 +290,7 @@ int VmmGroup::apply_events(const int64_t *ev, int64_t n) {
   if (!created_) return 0;
   if (n <= 0) return 1;
   if (!driver()) return KVB_ERR_CUDA_;
-  cudaSetDevice(dev_);
+  ensure_device(dev_);
   std::vector<std::pair<CUdeviceptr, size_t>> touched;
   int rc = 0;
   // Events are applied in order; SetAccess is flushed whenever a page is touched twice so that a
@@ -393,6 +397,67 @@ int VmmGroup::raw_control(int64_t n_pages, int64_t iters, double *map_us, double
   return 0;
 }
 
+// Per-call driver costs (microseconds, averaged): out[0] cuMemCreate, [1] cuMemMap, [2] cuMemSetAccess per
+// unit, [3] cuMemSetAccess over the whole range (one call), [4] cuMemUnmap per unit, [5] cuMemUnmap of the
+// whole range (one call), [6] cuMemRelease, [7] remap cycle per unit (unmap + map + setaccess on a mapped unit)
+int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out) {
+  const Driver *d = driver();
+  if (!d) return KVB_ERR_CUDA_;
+  ensure_device(dev);
+  cudaFree(0);
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  size_t bytes = unit * (size_t)n;
+  CUdeviceptr base = 0;
+  CU_TRY(d->MemAddressReserve(&base, bytes, 2u << 20, 0, 0));
+  std::vector<CUmemGenericAllocationHandle> hs((size_t)n);
+  using clk = std::chrono::steady_clock;
+  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  for (int64_t it = 0; it < iters; ++it) {
+    auto t0 = clk::now();
+    for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
+    auto t1 = clk::now();
+    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
+    auto t2 = clk::now();
+    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemSetAccess(base + u * unit, unit, &acc, 1));
+    auto t3 = clk::now();
+    for (int64_t u = 0; u < n; ++u) {   // remap cycle on live units
+      CU_TRY(d->MemUnmap(base + u * unit, unit));
+      CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
+      CU_TRY(d->MemSetAccess(base + u * unit, unit, &acc, 1));
+    }
+    auto t4 = clk::now();
+    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemUnmap(base + u * unit, unit));
+    auto t5 = clk::now();
+    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
+    auto t6 = clk::now();
+    CU_TRY(d->MemSetAccess(base, bytes, &acc, 1));
+    auto t7 = clk::now();
+    CU_TRY(d->MemUnmap(base, bytes));
+    auto t8 = clk::now();
+    for (auto h : hs) CU_TRY(d->MemRelease(h));
+    auto t9 = clk::now();
+    out[0] += us(t0, t1) / n;
+    out[1] += (us(t1, t2) + us(t5, t6)) / (2 * n);
+    out[2] += us(t2, t3) / n;
+    out[3] += us(t6, t7);
+    out[4] += us(t4, t5) / n;
+    out[5] += us(t7, t8);
+    out[6] += us(t8, t9) / n;
+    out[7] += us(t3, t4) / n;
+  }
+  for (int k = 0; k < 8; ++k) out[k] /= (double)iters;
+  d->MemAddressFree(base, bytes);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ registry
 struct Registry {
   std::mutex mu;
@@ -436,6 +501,12 @@ bool vmm_initialized() { return reg().inited; }
 int64_t vmm_page_size() { return reg().page_size; }
 bool vmm_contiguous() { return reg().contiguous; }
 int vmm_device() { return reg().dev; }
+int ensure_device(int dev) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == dev) return 0;
+  return cudaSetDevice(dev) == cudaSuccess ? 0 : -2;
+}
+
 VmmGroup *vmm_group(int64_t group_id, bool create_if_missing) {
   Registry &r = reg();
   std::lock_guard<std::mutex> lk(r.mu);

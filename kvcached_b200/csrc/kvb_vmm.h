@@ -87,6 +87,8 @@ class VmmGroup {
   int n_sub_ = 1;         // handles per page id
   int64_t n_pages_ = 0;
   std::vector<VmmRange> ranges_;
+  CUdeviceptr va_base_ = 0;
+  size_t va_bytes_ = 0;
   CUmemGenericAllocationHandle zero_ = 0;
   bool have_zero_ = false;
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
@@ -106,5 +108,9 @@ int64_t vmm_page_size();
 bool vmm_contiguous();
 int vmm_device();
 VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
+// cudaSetDevice only when the calling thread is on another device (cudaSetDevice itself costs tens of
+// microseconds on this stack; cudaGetDevice does not)
+int ensure_device(int dev);
+int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out8);
 
 }  // namespace kvb

@@ -1,0 +1,183 @@
+"""The VMM engine and the KV scatter/gather kernels on a real device, through the C ABI.
+
+Mirrors the reference's own GPU tests: tests/test_kvcache_manager.py (alloc/free conservation, trim,
+reserve) and tests/test_paged_allocator_aliasing.py (unmapped pages alias the zero page; data written
+through distinct physical pages reads back exactly).  KV contents: bit-exact against torch indexing
+through the same virtual tensor (the reference publishes no scatter kernel — SURVEY §8(c))."""
+import numpy as np
+import pytest
+
+from kvcached_b200 import _lib, kv_ops, vmm_ops
+from kvcached_b200 import trace as T
+from kvcached_b200.kv_cache_manager import KVCacheManager
+
+pytestmark = pytest.mark.gpu
+
+PAGE = 2 << 20
+
+
+@pytest.fixture()
+def kvcached_fixture():
+    """tests/test_kvcache_manager.py:43-85 of the reference, scaled to 4 layers."""
+    import torch
+    torch.cuda.init()
+    vmm_ops.init_kvcached("cuda:0", PAGE, True)
+    L, blocks, bs, H, D = 4, 4096, 16, 8, 64
+    cell = H * D * 2
+    per_layer = blocks * bs * cell * 2           # K and V
+    (flat,) = vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", L)
+    mgr = KVCacheManager(blocks, bs, cell, L)
+    yield dict(mgr=mgr, flat=flat, L=L, blocks=blocks, bs=bs, cell=cell, H=H, D=D)
+    mgr.close()
+    vmm_ops.shutdown_kvcached()
+
+
+def test_alloc_free_conservation_trim_reserve(kvcached_fixture):
+    m = kvcached_fixture["mgr"]
+    a0 = m.available_size()
+    ids = m.alloc(256)
+    assert ids is not None and len(ids) == 256 and m.available_size() == a0 - 256
+    assert sorted(vmm_ops.mapped_pages()) == m.mapped_pages()
+    m.free(ids)
+    assert m.available_size() == a0
+    assert m.alloc(a0 + 1) is None
+    m.trim()
+    assert m.page_allocator.get_num_reserved_pages() == 0 and vmm_ops.mapped_pages() == []
+    assert m.try_to_reserve(512) and len(m.reserved_blocks) == 512
+    m.free_reserved()
+    assert m.reserved_blocks == [] and m.available_size() == a0
+
+
+def test_unmapped_pages_alias_zero_page_and_mapped_pages_hold_data(kvcached_fixture):
+    import torch
+    f = kvcached_fixture
+    m, flat, L, bs, cell = f["mgr"], f["flat"], f["L"], f["bs"], f["cell"]
+    # layout: [num_blocks, L, 2, block, cell/2] int16 (vllm contiguous)
+    kv = flat.view(torch.int16).view(f["blocks"], L, 2, bs, cell // 2)
+    # nothing mapped: writes land in the shared zero page and alias across pages
+    kv[0, 0, 0, 0, 0] = 7
+    torch.cuda.synchronize()
+    bpp = PAGE // (bs * cell)
+    assert int(kv[bpp, 0, 0, 0, 0]) == 7      # same offset inside another (unmapped) page aliases
+    kv[0, 0, 0, 0, 0] = 0
+    ids = m.alloc(3 * bpp)                     # three physical pages
+    assert ids == list(range(3 * bpp))
+    for p in range(3):
+        kv[p * bpp, :, :, 0, 0] = 100 + p
+    torch.cuda.synchronize()
+    for p in range(3):
+        assert torch.all(kv[p * bpp, :, :, 0, 0] == 100 + p)
+    assert int(kv[3 * bpp, 0, 0, 0, 0]) == 0   # still the zero page
+    m.free(ids)
+    m.trim()
+    torch.cuda.synchronize()
+    assert int(kv[0, 0, 0, 0, 0]) == 0         # unmapped again: reads the zero page
+
+
+def test_map_unmap_by_offsets_is_idempotent(kvcached_fixture):
+    f = kvcached_fixture
+    per = PAGE * f["L"] * 2
+    assert vmm_ops.map_to_kv_tensors([0, 3 * per])
+    assert vmm_ops.map_to_kv_tensors([3 * per])          # double map tolerated
+    assert vmm_ops.mapped_pages() == [0, 3]
+    assert vmm_ops.unmap_from_kv_tensors([0, 3 * per, 5 * per])   # unmapping an unmapped page tolerated
+    assert vmm_ops.mapped_pages() == []
+    st = vmm_ops.vmm_stats()
+    assert st["pooled_handles"] == 2 and st["handles_created"] >= 3   # zero page + 2, parked in the pool
+
+
+@pytest.mark.parametrize("layout", ["vllm_contig", "sglang_contig", "per_layer", "mla"])
+@pytest.mark.parametrize("T_tokens", [1, 37, 4096])
+def test_kv_scatter_gather_bit_exact(layout, T_tokens):
+    import torch
+    torch.cuda.init()
+    contiguous = layout != "per_layer"
+    vmm_ops.init_kvcached("cuda:0", PAGE, contiguous)
+    try:
+        L, bs, blocks = 4, 16, 2048
+        nkv = 1 if layout == "mla" else 2
+        cell = 576 * 2 if layout == "mla" else 8 * 128 * 2
+        if layout == "sglang_contig":
+            bs = 1
+            blocks = 2048 * 16
+        blk_bytes = bs * cell
+        per_layer = -(-blocks * blk_bytes * nkv // (2 * PAGE)) * 2 * PAGE
+        ranges = vmm_ops.create_kv_tensors_raw(per_layer, L, nkv)
+        tens = vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", L, nkv)
+        m = KVCacheManager(blocks, bs, cell, L, num_kv_buffers=nkv)
+        need_blocks = -(-T_tokens // bs) + 3
+        ids = np.asarray(m.alloc(need_blocks), dtype=np.int64)
+        rng = np.random.default_rng(T_tokens)
+        all_slots = (ids[:, None] * bs + np.arange(bs)[None, :]).reshape(-1)
+        slots_np = rng.choice(all_slots, size=T_tokens, replace=False)
+        slots = torch.from_numpy(slots_np).cuda()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        k_src = torch.randint(-32768, 32767, (L, T_tokens, cell // 2), dtype=torch.int16, device="cuda", generator=g)
+        v_src = torch.randint(-32768, 32767, (L, T_tokens, cell // 2), dtype=torch.int16, device="cuda", generator=g) \
+            if nkv == 2 else None
+        base = ranges[0][0]
+        if layout in ("vllm_contig", "mla"):
+            lay = kv_ops.layout_vllm_contiguous(base, L, bs, cell, nkv)
+            view = tens[0].view(torch.int16).view(-1, L, nkv, bs, cell // 2)
+
+            def ref_write(kv_i, l, src):
+                view[slots // bs, l, kv_i, slots % bs] = src
+            def ref_read(kv_i, l):
+                return view[slots // bs, l, kv_i, slots % bs]
+        elif layout == "sglang_contig":
+            lay = kv_ops.layout_sglang_contiguous(base, L, cell, nkv)
+            view = tens[0].view(torch.int16).view(-1, L, nkv, cell // 2)
+
+            def ref_write(kv_i, l, src):
+                view[slots, l, kv_i] = src
+            def ref_read(kv_i, l):
+                return view[slots, l, kv_i]
+        else:
+            assert all(ranges[i + 1][0] - ranges[i][0] == ranges[0][1] for i in range(L - 1))
+            lay = kv_ops.layout_per_layer(base, ranges[0][1], per_layer, L, bs, cell, nkv)
+            views = [t.view(torch.int16).view(2, -1, cell // 2) for t in tens]
+
+            def ref_write(kv_i, l, src):
+                views[l][kv_i, slots] = src
+            def ref_read(kv_i, l):
+                return views[l][kv_i, slots]
+        # 1. scatter with the kernel, read back with torch indexing
+        kv_ops.kv_scatter(lay, slots, k_src, v_src)
+        torch.cuda.synchronize()
+        for l in range(L):
+            assert torch.equal(ref_read(0, l), k_src[l])
+            if nkv == 2:
+                assert torch.equal(ref_read(1, l), v_src[l])
+        # 2. write with torch indexing, gather with the kernel
+        k2 = k_src.flip(1).contiguous()
+        v2 = v_src.flip(1).contiguous() if nkv == 2 else None
+        for l in range(L):
+            ref_write(0, l, k2[l])
+            if nkv == 2:
+                ref_write(1, l, v2[l])
+        k_out = torch.empty_like(k_src)
+        v_out = torch.empty_like(k_src) if nkv == 2 else None
+        kv_ops.kv_gather(lay, slots, k_out, v_out)
+        torch.cuda.synchronize()
+        assert torch.equal(k_out, k2)
+        if nkv == 2:
+            assert torch.equal(v_out, v2)
+        # 3. per-layer launch range == fused launch
+        k_out.zero_()
+        for l in range(L):
+            kv_ops.kv_gather(lay, slots, k_out[l:l + 1], None if v_out is None else v_out[l:l + 1], l, l + 1)
+        torch.cuda.synchronize()
+        assert torch.equal(k_out, k2)
+        m.close()
+    finally:
+        vmm_ops.shutdown_kvcached()
+
+
+def test_raw_control_and_pool(kvcached_fixture):
+    lib = _lib.load()
+    n, iters = 4, 5
+    a = np.zeros(iters)
+    b = np.zeros(iters)
+    rc = lib.kvb_vmm_raw_control(0, n, iters, 1, a.ctypes.data_as(_lib.p_f64), b.ctypes.data_as(_lib.p_f64))
+    assert rc == 0, _lib.last_error()
+    assert (a > 0).all() and (b > 0).all()
