@@ -49,6 +49,8 @@ extern "C" {
 const char *kvb_last_error(void);
 /* ABI version of the loaded library (bumped on any signature change). */
 int kvb_abi_version(void);
+/* kernels this library launched since it was loaded (bookkeeping steps, audits, KV scatter/gather) */
+int64_t kvb_total_launches(void);
 
 /* ------------------------------------------------------------------------------------------
  * 1. Virtual KV tensors and the batched VMM engine
@@ -103,6 +105,9 @@ int kvb_vmm_pool_prefill(int64_t group_id, int64_t n);
 /* stats[0..7] = mapped pages, pooled handles, handles created, handles released, map calls,
  * unmap calls, bytes mapped, compound page bytes */
 int kvb_vmm_stats(int64_t group_id, int64_t *stats8);
+/* wall time attribution of the driver loop: out10 = microseconds spent in {cuMemCreate, cuMemRelease, cuMemUnmap,
+ * cuMemMap, cuMemSetAccess} followed by the five call counts */
+int kvb_vmm_timing(int64_t group_id, double *out10);
 /* sorted ids of the currently mapped pages; returns the count or KVB_ERR_OVERFLOW */
 int64_t kvb_vmm_mapped_pages(int64_t group_id, int64_t *out, int64_t cap);
 /* get_avail_physical_pages() arithmetic — page_allocator.cpp:442-455:
@@ -120,6 +125,10 @@ int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int co
  * out8 = {cuMemCreate, cuMemMap, cuMemSetAccess per unit, cuMemSetAccess whole range (one call),
  *         cuMemUnmap per unit, cuMemUnmap whole range (one call), cuMemRelease, unmap+map+setaccess per unit} */
 int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t iters, double *out8);
+/* map/unmap cycle cost against M live zero-page mappings: mode bit0 = one cuMemSetAccess over the whole range
+ * at init instead of one per unit, bit1 = cycle units of a separate small reservation.
+ * out3 = {us per map cycle, us per unmap cycle, init ms} */
+int kvb_vmm_probe2(int device_index, int64_t unit_bytes, int64_t m_units, int mode, int64_t iters, double *out3);
 
 /* ------------------------------------------------------------------------------------------
  * 2. Device-resident block manager
@@ -193,6 +202,7 @@ typedef struct kvb_mgr_stats {
   int64_t num_avail_pages, num_full_pages, num_mapped_pages, has_null_block;
   int64_t blocks_per_page, block_mem_size, page_size, mem_size;
   int64_t bad_frees, unknown_page_frees, launches, events;
+  int64_t h2d_bytes, d2h_bytes;   /* bytes kvb_mgr_step copied host->device / device->host so far */
 } kvb_mgr_stats;
 
 /* KVCacheManager.__init__ + _post_init — kv_cache_manager.py:60-243.  Returns NULL on error

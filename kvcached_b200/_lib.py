@@ -42,7 +42,7 @@ class MgrStats(C.Structure):           # kvb_mgr_stats
         "num_avail_blocks", "num_reserved_blocks", "in_shrink", "target_num_blocks",
         "num_avail_pages", "num_full_pages", "num_mapped_pages", "has_null_block",
         "blocks_per_page", "block_mem_size", "page_size", "mem_size",
-        "bad_frees", "unknown_page_frees", "launches", "events")]
+        "bad_frees", "unknown_page_frees", "launches", "events", "h2d_bytes", "d2h_bytes")]
 
 
 class KvLayout(C.Structure):           # kvb_kv_layout
@@ -59,6 +59,7 @@ ST_OK, ST_FALSE, ST_NONE, ST_NO_PAGES, ST_ASSERT, ST_NULL_BLOCK, ST_CAPACITY = 1
 SIGNATURES = {
     "kvb_last_error": (C.c_char_p, []),
     "kvb_abi_version": (C.c_int, []),
+    "kvb_total_launches": (i64, []),
     "kvb_init": (C.c_int, [C.c_int, i64, C.c_int]),
     "kvb_shutdown": (C.c_int, []),
     "kvb_is_initialized": (C.c_int, []),
@@ -74,10 +75,12 @@ SIGNATURES = {
     "kvb_vmm_pool_config": (C.c_int, [i64, i64]),
     "kvb_vmm_pool_prefill": (C.c_int, [i64, i64]),
     "kvb_vmm_stats": (C.c_int, [i64, p_i64]),
+    "kvb_vmm_timing": (C.c_int, [i64, p_f64]),
     "kvb_vmm_mapped_pages": (i64, [i64, p_i64, i64]),
     "kvb_vmm_avail_physical_pages": (i64, [i64, i64, i64, f64]),
     "kvb_vmm_raw_control": (C.c_int, [i64, i64, i64, C.c_int, p_f64, p_f64]),
     "kvb_vmm_probe": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
+    "kvb_vmm_probe2": (C.c_int, [C.c_int, i64, i64, C.c_int, i64, p_f64]),
     "kvb_mgr_create": (C.c_void_p, [C.POINTER(MgrConfig)]),
     "kvb_mgr_destroy": (C.c_int, [C.c_void_p]),
     "kvb_mgr_step": (i64, [C.c_void_p, C.POINTER(Op), i64, p_i64, i64, C.POINTER(Ref), i64, C.POINTER(Res), p_i64, i64]),

@@ -3,6 +3,7 @@
 // the KV scatter / gather launchers.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -12,6 +13,7 @@
 #include "kvb_vmm.h"
 
 using namespace kvb;
+namespace kvb { extern std::atomic<int64_t> g_total_launches; }
 
 #define CUDA_TRY(call)                                                                     \
   do {                                                                                     \
@@ -106,6 +108,13 @@ int kvb_vmm_stats(int64_t group_id, int64_t *stats8) {
   g->stats(stats8);
   return 0;
 }
+int kvb_vmm_timing(int64_t group_id, double *out10) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->timing(out10);
+  return 0;
+}
 int64_t kvb_vmm_mapped_pages(int64_t group_id, int64_t *out, int64_t cap) {
   VmmGroup *g = vmm_group(group_id, false);
   if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
@@ -143,6 +152,11 @@ int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t
   return vmm_probe(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, n_units, iters, out8);
 }
 
+int kvb_vmm_probe2(int device_index, int64_t unit_bytes, int64_t m_units, int mode, int64_t iters, double *out3) {
+  if (unit_bytes <= 0 || unit_bytes % (2 << 20) || m_units < 16 || iters <= 0 || !out3) { set_error("vmm_probe2: bad argument"); return KVB_ERR_INVALID; }
+  return vmm_probe2(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, m_units, mode, iters, out3);
+}
+
 // ------------------------------------------------------------------------------------------ page helpers
 // InternalPage::get_block_range / get_num_blocks / PageAllocator::get_page_id (page_allocator.cpp:87-100, :457-460)
 void kvb_page_block_range(int64_t page_id, int64_t page_size, int64_t bms, int64_t *start, int64_t *end) {
@@ -169,6 +183,7 @@ int kvb_kv_scatter(const kvb_kv_layout *lay, uint64_t slots_dev, int64_t T, uint
   if (T < 0 || !slots_dev || !k_src || (lay->num_kv == 2 && !v_src)) { set_error("kv_scatter: null buffer"); return KVB_ERR_INVALID; }
   int e = launch_kv_copy(*lay, (const int64_t *)(uintptr_t)slots_dev, T, (void *)(uintptr_t)k_src, (void *)(uintptr_t)v_src,
                          l0, l1, 0, stream);
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
   if (e) { set_error("kv_scatter launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KVB_ERR_CUDA; }
   return 0;
 }
@@ -179,6 +194,7 @@ int kvb_kv_gather(const kvb_kv_layout *lay, uint64_t slots_dev, int64_t T, uint6
   if (T < 0 || !slots_dev || !k_dst || (lay->num_kv == 2 && !v_dst)) { set_error("kv_gather: null buffer"); return KVB_ERR_INVALID; }
   int e = launch_kv_copy(*lay, (const int64_t *)(uintptr_t)slots_dev, T, (void *)(uintptr_t)k_dst, (void *)(uintptr_t)v_dst,
                          l0, l1, 1, stream);
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
   if (e) { set_error("kv_gather launch failed: %s", cudaGetErrorString((cudaError_t)e)); return KVB_ERR_CUDA; }
   return 0;
 }
@@ -215,6 +231,7 @@ static int kv_host(const kvb_kv_layout *lay, const int64_t *slots, int64_t T, vo
     if (d_v) KV_TRY(cudaMemcpyAsync(d_v, v, per, cudaMemcpyHostToDevice, st));
   }
   int e = launch_kv_copy(*lay, d_slots, T, d_k, d_v, 0, lay->num_layers, gather, st);
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
   if (e) { set_error("kv copy launch failed: %s", cudaGetErrorString((cudaError_t)e)); cleanup(); return KVB_ERR_CUDA; }
   if (gather) {
     KV_TRY(cudaMemcpyAsync(k, d_k, per, cudaMemcpyDeviceToHost, st));

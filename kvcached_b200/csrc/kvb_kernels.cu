@@ -48,6 +48,7 @@ constexpr int NEWPG_W = 64;      // prefetched window of upcoming fresh page ids
 constexpr int HT_D_CAP = 2048;   // distinct pages per free() handled in shared memory
 constexpr int HT_NB_CAP = 4099;  // hash buckets handled in shared memory
 constexpr int EV_INLINE = 256;
+constexpr int PRIMES_SM = 128;   // __prime_list[0..127] reaches 2^17; larger bucket counts read the global table
 
 enum : int { SEG_RB = 0, SEG_RING = 1, SEG_FRESH = 2 };
 
@@ -89,6 +90,8 @@ struct Smem {
   int2 fresh[FRESH_CAP];
   int32_t apw[APW], apcnt[APW], aphead[APW];
   int32_t newpg[NEWPG_W];
+  int32_t cpage[APW], ccnt[APW], chead[APW], csidx[APW], ccum[APW];   // live window entries, newest first
+  uint32_t primes32[PRIMES_SM];                                        // head of libstdc++'s __prime_list
   int32_t ht_key[HT_D_CAP], ht_next[HT_D_CAP], ht_ord[HT_D_CAP], ht_cnt[HT_D_CAP];
   int32_t ht_bkt[HT_NB_CAP + 1];
   int32_t wtot[NW], wtot2[NW];
@@ -250,9 +253,17 @@ __device__ __forceinline__ int block_exscan(int v, int32_t *wtot, int *total) {
 // ------------------------------------------------------------------------------------ libstdc++ policy
 // std::__detail::_Prime_rehash_policy::_M_next_bkt (libstdc++ 13, hashtable_c++0x.cc) with the
 // library's own __prime_list uploaded at init.
-__device__ int next_bkt(const DevState &c, int64_t n) {
-  const unsigned char fast[14] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13};
-  if (n < 14) return n == 0 ? 1 : fast[n];
+__device__ int next_bkt(const DevState &c, const uint32_t *primes32, int64_t n) {
+  // __fast_bkt[] = {2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13}, one nibble per entry
+  if (n < 14) return n == 0 ? 1 : (int)((0x22235577BBBBDDull >> (4 * (13 - n))) & 15);
+  if ((uint64_t)n <= primes32[PRIMES_SM - 1]) {
+    int lo = 6, hi = PRIMES_SM - 1;   // lower_bound over [__prime_list + 6, ...)
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (primes32[mid] < (uint32_t)n) lo = mid + 1; else hi = mid;
+    }
+    return (int)primes32[lo];
+  }
   int lo = 6, hi = c.n_primes - 1;   // lower_bound over [__prime_list + 6, last)
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -266,61 +277,117 @@ __device__ int next_bkt(const DevState &c, int64_t n) {
 // _M_insert_bucket_begin / _M_rehash_aux of libstdc++'s _Hashtable with unique keys, identity hash,
 // max_load_factor 1 (csrc/page_allocator.cpp:471-498 builds exactly this map; pybind11 walks it).
 // bkt[b] holds the node BEFORE bucket b's first node: -1 empty, -2 the before-begin sentinel.
-__device__ void ht_order(const DevState &c, const int32_t *keys, int D, int nb, int32_t *next, int32_t *bkt,
-                         int32_t *ord) {
+// Sequential (one lane); used when a call names more than 32 distinct pages.
+__device__ __forceinline__ void ht_order_seq(const DevState &c, const uint32_t *primes32, const int32_t *keys, int D,
+                                             int nb, int32_t *next, int32_t *bkt, int32_t *ord) {
   int head = -1;
   for (int d = 0; d < D; ++d) {
-    int k = keys[d];
+    unsigned k = (unsigned)keys[d];
     if (d + 1 > nb) {   // _M_need_rehash: n_elt + 1 > _M_next_resize (= nb at load factor 1)
       int64_t want = (int64_t)d + 2;
       if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-      int nb2 = next_bkt(c, want);
-      for (int b = 0; b < nb2; ++b) bkt[b] = -1;
+      unsigned nb2 = (unsigned)next_bkt(c, primes32, want);
+      for (unsigned b = 0; b < nb2; ++b) bkt[b] = -1;
       int p = head, bbegin = 0;
       head = -1;
       while (p >= 0) {   // _M_rehash_aux(unique keys)
         int nx = next[p];
-        int b = keys[p] % nb2;
-        if (bkt[b] == -1) {
+        int b = (int)((unsigned)keys[p] % nb2);
+        int prev = bkt[b];
+        if (prev == -1) {
           next[p] = head;
+          if (head >= 0) bkt[bbegin] = p;
           head = p;
           bkt[b] = -2;
-          if (next[p] >= 0) bkt[bbegin] = p;
           bbegin = b;
+        } else if (prev == -2) {
+          next[p] = head;
+          head = p;
         } else {
-          int prev = bkt[b];
-          if (prev == -2) { next[p] = head; head = p; }
-          else { next[p] = next[prev]; next[prev] = p; }
+          next[p] = next[prev];
+          next[prev] = p;
         }
         p = nx;
       }
-      nb = nb2;
+      nb = (int)nb2;
     }
-    int b = k % nb;
+    int b = (int)(k % (unsigned)nb);
     int prev = bkt[b];
-    if (prev != -1) {   // bucket not empty: insert after its before-node
-      if (prev == -2) { next[d] = head; head = d; }
-      else { next[d] = next[prev]; next[prev] = d; }
-    } else {            // empty bucket: new node becomes the global head
+    if (prev == -1) {            // empty bucket: new node becomes the global head
+      next[d] = head;
+      if (head >= 0) bkt[(unsigned)keys[head] % (unsigned)nb] = d;
+      head = d;
+      bkt[b] = -2;
+    } else if (prev == -2) {     // bucket starts at the list head: insert after before-begin
       next[d] = head;
       head = d;
-      if (next[d] >= 0) bkt[keys[next[d]] % nb] = d;
-      bkt[b] = -2;
+    } else {                     // insert after the bucket's before-node
+      next[d] = next[prev];
+      next[prev] = d;
     }
   }
   int i = 0;
   for (int p = head; p >= 0; p = next[p]) ord[i++] = p;
 }
-// bucket count the table ends with (decides shared vs global tables before the replay)
-__device__ int ht_final_buckets(const DevState &c, int D, int nb0) {
-  int nb = nb0;
-  for (int d = 0; d < D; ++d) {
-    if (d + 1 > nb) {
-      int64_t want = (int64_t)d + 2;
-      if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-      nb = next_bkt(c, want);
-      if (nb >= D) break;
+
+// The same order for D <= 32 without any pointer chasing, one warp, keys in registers.
+// Between two rehashes the container obeys one rule: a key joins the FRONT of its bucket's run, and a key
+// of a new bucket becomes the list head.  So a phase (all keys placed under one bucket count nb, in
+// sequence S) ends as: bucket runs ordered by LAST-first-appearance first, and inside a run the later key
+// first — i.e. S sorted by (first position of my bucket in S, my position in S), both descending.  A rehash
+// re-places the current list front to back under the new nb, which is the same rule applied to S = current
+// order; keys inserted afterwards simply extend S.  Lane l holds the key at position l of S.
+__device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t *primes32, const int32_t *keys,
+                                              int D, int nb, int32_t *ord) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  // cur_slot = slot index of the key at S position `lane` (valid for lane < placed)
+  int cur_slot = lane;
+  unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
+  int placed = 0;   // keys already in the container
+  while (true) {
+    // keys inserted under this bucket count: until the container holds nb keys (then the next insert rehashes)
+    int upto = D < nb ? D : nb;
+    // S = [current order of `placed` keys] ++ [slots placed .. upto-1 in insertion order]
+    // lanes >= placed and < upto take their insertion slot
+    if (lane >= placed && lane < upto) { cur_slot = lane; cur_key = (unsigned)keys[lane]; }
+    const bool in = lane < upto;
+    unsigned b = in ? cur_key % (unsigned)nb : 0xffffffffu - lane;
+    unsigned grp = __match_any_sync(0xffffffffu, b);
+    int gfirst = __ffs(grp) - 1;                        // first position of my bucket in S
+    int later_in_grp = __popc(grp & ~lt & ~(1u << lane));
+    // keys whose bucket first appears after mine come before me
+    int before = 0;
+    for (int v = 0; v < upto; ++v) {
+      unsigned m = __ballot_sync(0xffffffffu, in && gfirst > v);
+      if (v == gfirst) before = __popc(m);
     }
+    int newpos = before + later_in_grp;
+    // permute: the key at new position p comes from the lane whose newpos == p
+    int src = 0;
+    for (int p = 0; p < upto; ++p) {
+      unsigned m = __ballot_sync(0xffffffffu, in && newpos == p);
+      if (lane == p) src = __ffs(m) - 1;
+    }
+    int ns = __shfl_sync(0xffffffffu, cur_slot, src);
+    unsigned nk = __shfl_sync(0xffffffffu, cur_key, src);
+    if (in) { cur_slot = ns; cur_key = nk; }
+    placed = upto;
+    if (placed >= D) break;
+    int64_t want = (int64_t)placed + 2;                 // _M_need_rehash -> _M_next_bkt(max(n+1+1, 2*nb))
+    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+    nb = next_bkt(c, primes32, want);
+  }
+  if (lane < D) ord[lane] = cur_slot;
+}
+
+// bucket count the table ends with (decides shared vs global tables before the replay)
+__device__ int ht_final_buckets(const DevState &c, const uint32_t *primes32, int D, int nb0) {
+  int nb = nb0;
+  while (D > nb) {
+    int64_t want = (int64_t)nb + 2;
+    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+    nb = next_bkt(c, primes32, want);
   }
   return nb;
 }
@@ -533,6 +600,176 @@ __device__ void alloc_emit(const DevState &c, Smem &s, const LaunchArgs &a, int6
   }
 }
 
+// Fast path of an alloc run: every request succeeds and the free-block stream is a pure function of the
+// state at the start of the run, so nothing has to be walked in sequence:
+//   * request i takes stream positions [off_i, off_i + n_i), off = exclusive prefix sum of the sizes;
+//   * the stream is [reserved_blocks][avail pages newest first, each page's FIFO][fresh pages, whole];
+//   * in an exact geometry (block size divides page size) available_size() drops by exactly one per
+//     block taken, across page boundaries too, so request i sees available_size() = A0 - off_i and the
+//     run cannot fail iff A0 >= total.
+// Preconditions (else the caller takes the sequential walk, which is the general restatement):
+// exact geometry, not shrinking, <= NT requests, A0 >= total, the avail pages needed sit in the
+// prefetched window, at most NEWPG_W fresh pages.  Returns 1 if the run was handled (uniform).
+__device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int64_t *sc = s.sc;
+  const int R = run_end - op0;
+  if (!c.exact || sc[SC_INSHRINK] || R > NT) return 0;
+  const int tail = (int)sc[SC_AP_TAIL];
+  const int rls = (int)sc[SC_RL_SIZE], fls = (int)sc[SC_FL_SIZE];
+  // ---- sizes -> offsets; prefetch the top of the avail stack and the upcoming fresh pages ----
+  int n_i = 0;
+  if (tid < R) n_i = s.ops[op0 - chunk_base + tid].n;
+  int e = -1, ecnt = 0, ehead = 0;
+  if (tid < APW) {
+    int i = tail - 1 - tid;
+    e = (i >= 0) ? c.ap[i] : -1;
+    if (e >= 0) { ecnt = c.pg_cnt[e]; ehead = c.pg_head[e]; }
+  }
+  if (tid >= NT - NEWPG_W) {
+    int j = tid - (NT - NEWPG_W);
+    int v = -1;
+    if (j < rls) v = c.rl[(int)((sc[SC_RL_HEAD] + j) & c.q_mask)];
+    else if (j - rls < fls) v = c.fl[(int)((sc[SC_FL_HEAD] + (j - rls)) & c.q_mask)];
+    s.newpg[j] = v;
+  }
+  const bool neg = __syncthreads_or(n_i < 0 || n_i > (1 << 21));   // odd sizes take the general walk
+  int T;
+  const int off_i = block_exscan(n_i, s.wtot, &T);
+  int nlive;
+  const int li = block_rank(e >= 0, s.wtot2, &nlive);        // position among live entries, newest first
+  int sum_av;
+  const int cum = block_exscan(e >= 0 ? ecnt : 0, s.wtot, &sum_av);
+  if (e >= 0) {
+    s.cpage[li] = e;
+    s.ccnt[li] = ecnt;
+    s.chead[li] = ehead;
+    s.csidx[li] = tail - 1 - tid;
+    s.ccum[li] = cum;
+  }
+  const int64_t A0 = avail_size(c, sc);
+  const int64_t cursor = sc[SC_OUT_CURSOR];
+  const int nrb = (int)sc[SC_NRB];
+  const int take_rb = nrb < T ? nrb : T;
+  const int rem1 = T - take_rb;
+  const int take_av = rem1 < sum_av ? rem1 : sum_av;
+  const int rem2 = rem1 - take_av;                           // blocks that come from fresh pages
+  const int F = (rem2 + c.bpp - 1) / c.bpp;
+  const bool ok = !neg && A0 >= T && cursor + T <= a.out_cap && (rem2 == 0 || tail <= APW) && F <= NEWPG_W &&
+                  F <= rls + fls;
+  __syncthreads();                                           // compact window visible (or nothing touched yet)
+  if (!ok) return 0;
+  const int from_rl = F < rls ? F : rls;                      // alloc_page(): reserved list first, then free list
+  const int from_fl = F - from_rl;
+  const int last_used = F ? rem2 - (F - 1) * c.bpp : 0;       // blocks taken from the last fresh page
+  const int64_t nev0 = sc[SC_NEV];
+  // ---- emit ids (all warps): warp-strided over stream positions ----
+  const int64_t rbh = sc[SC_RB_HEAD];
+  for (int j = tid; j < T; j += NT) {
+    int64_t id;
+    if (j < take_rb) {
+      id = c.rb[(int)((rbh + j) & c.rb_mask)];
+    } else {
+      int j1 = j - take_rb;
+      if (j1 < take_av) {
+        int lo = 0, hi = nlive - 1;                           // last live entry with ccum <= j1
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (s.ccum[mid] <= j1) lo = mid; else hi = mid - 1;
+        }
+        int pg = s.cpage[lo];
+        int pos = s.chead[lo] + (j1 - s.ccum[lo]);
+        if (pos >= c.bpp) pos -= c.bpp;
+        id = (int64_t)pg * c.bpp + c.ring[(size_t)pg * c.bpp + pos];
+      } else {
+        int j2 = j1 - take_av;
+        int q = j2 / c.bpp;
+        id = (int64_t)s.newpg[q] * c.bpp + (j2 - q * c.bpp);
+      }
+      atomicOr(&c.bitmap[id >> 5], 1u << (id & 31));
+    }
+    a.out_ids[cursor + j] = id;
+  }
+  // ---- per-request results ----
+  if (tid < R) {
+    kvb_res r;
+    r.status = KVB_ST_OK;
+    r.n = n_i;
+    r.off = cursor + off_i;
+    r.avail = A0 - off_i - n_i;
+    a.res[op0 + tid] = r;
+  }
+  // ---- page state: consumed / partly consumed avail pages ----
+  int n_full_av = 0;   // uniform: live entries entirely consumed
+  {
+    int lo = 0, hi = nlive;                                   // first live entry NOT entirely consumed
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (s.ccum[mid] + s.ccnt[mid] <= take_av) lo = mid + 1; else hi = mid;
+    }
+    n_full_av = lo;
+  }
+  if (tid < nlive) {
+    int pg = s.cpage[tid], cn = s.ccnt[tid], cm = s.ccum[tid];
+    if (tid < n_full_av) {
+      int h = s.chead[tid] + cn;
+      c.pg_state[pg] = PG_FULL;
+      c.pg_cnt[pg] = 0;
+      c.pg_head[pg] = h >= c.bpp ? h - c.bpp : h;
+    } else if (cm < take_av) {                                 // the one page left partly consumed
+      int used = take_av - cm;
+      int h = s.chead[tid] + used;
+      c.pg_cnt[pg] = cn - used;
+      c.pg_head[pg] = h >= c.bpp ? h - c.bpp : h;
+    }
+  }
+  // ---- fresh pages: one warp per page ----
+  for (int q = w; q < F; q += NW) {
+    int pg = s.newpg[q];
+    bool partial = (q == F - 1) && last_used < c.bpp;
+    if (lane == 0) {
+      c.pg_state[pg] = partial ? PG_AVAIL : PG_FULL;
+      c.pg_cnt[pg] = partial ? c.bpp - last_used : 0;
+      c.pg_head[pg] = partial ? last_used : 0;
+      if (q >= from_rl) {                                      // came off the free list: needs a mapping
+        int64_t k = nev0 + (q - from_rl);
+        if (k < c.ev_cap) c.ev[k] = (int64_t)pg * 2;
+        c.pg_mapped[pg] = 1;
+      }
+      if (partial) { c.ap[0] = pg; c.pg_pos[pg] = 0; }         // the stack is empty when fresh pages are taken
+    }
+    if (partial) {                                             // InternalPage::init: FIFO = identity
+      uint32_t *r = c.ring + (size_t)pg * c.bpp;
+      for (int t = lane; t < c.bpp; t += 32) r[t] = (uint32_t)t;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const bool fresh_partial = F > 0 && last_used < c.bpp;
+    sc[SC_RB_HEAD] = (rbh + take_rb) & c.rb_mask;
+    sc[SC_NRB] -= take_rb;
+    sc[SC_NAB] += (int64_t)F * c.bpp - rem2 - take_av;
+    sc[SC_NAVAILPG] += (fresh_partial ? 1 : 0) - n_full_av;
+    sc[SC_NFULLPG] += n_full_av + F - (fresh_partial ? 1 : 0);
+    sc[SC_NFREE] -= F;
+    sc[SC_RL_HEAD] = (sc[SC_RL_HEAD] + from_rl) & c.q_mask;
+    sc[SC_RL_SIZE] -= from_rl;
+    sc[SC_FL_HEAD] = (sc[SC_FL_HEAD] + from_fl) & c.q_mask;
+    sc[SC_FL_SIZE] -= from_fl;
+    sc[SC_NEV] += from_fl;
+    sc[SC_NMAPPED] += from_fl;
+    sc[SC_PHYS] -= from_fl;
+    sc[SC_OUT_CURSOR] = cursor + T;
+    int new_tail;
+    if (F > 0) new_tail = fresh_partial ? 1 : 0;
+    else if (n_full_av < nlive) new_tail = s.csidx[n_full_av] + 1;   // newest surviving entry
+    else new_tail = tail > APW ? tail - APW : 0;                     // whole window consumed (or empty)
+    sc[SC_AP_TAIL] = new_tail;
+  }
+  __syncthreads();
+  return 1;
+}
+
 // A run of consecutive ALLOC requests [op0, run_end) (all inside the staged chunk), or one
 // TRY_RESERVE request (to_reserved = 1, ids appended to reserved_blocks instead of the output).
 __device__ void alloc_run(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end,
@@ -701,18 +938,23 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
 
   // ---- F3: dict order (one lane) || per-page FIFO ranks (one warp) --------------------------------
   // groups.reserve(n / bpp + 1): csrc/page_allocator.cpp:477
-  int nb0 = next_bkt(c, (int64_t)n / c.bpp + 1);
-  int nbf = ht_final_buckets(c, D, nb0);
-  const bool use_g = (D > HT_D_CAP) || (nbf > HT_NB_CAP);
+  int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
+  const bool use_g = (D > HT_D_CAP) || (D > 32 && ht_final_buckets(c, s.primes32, D, nb0) > HT_NB_CAP);
   int32_t *keys = use_g ? c.g_dist : s.ht_key;
-  int32_t *nxt = use_g ? c.g_next : s.ht_next;
-  int32_t *bkt = use_g ? c.g_bkt : s.ht_bkt;
   int32_t *ord = use_g ? c.g_ord : s.ht_ord;
   int32_t *cnt = use_g ? c.g_cnt : s.ht_cnt;
   if (w == 0) {
-    for (int b = lane; b < nb0; b += 32) bkt[b] = -1;
-    __syncwarp();
-    if (lane == 0) ht_order(c, keys, D, nb0, nxt, bkt, ord);
+    if (D <= 32) {
+      ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord);           // registers + warp votes
+    } else if (!use_g) {
+      for (int b = lane; b < nb0; b += 32) s.ht_bkt[b] = -1;
+      __syncwarp();
+      if (lane == 0) ht_order_seq(c, s.primes32, s.ht_key, D, nb0, s.ht_next, s.ht_bkt, s.ht_ord);
+    } else {
+      for (int b = lane; b < nb0; b += 32) c.g_bkt[b] = -1;
+      __syncwarp();
+      if (lane == 0) ht_order_seq(c, s.primes32, c.g_dist, D, nb0, c.g_next, c.g_bkt, c.g_ord);
+    }
   } else if (w == 1) {
     for (int j0 = 0; j0 < n; j0 += 32) {
       int j = j0 + lane;
@@ -983,6 +1225,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
 
   if (tid < SC_COUNT) sc[tid] = c.sc[tid];
   if (tid < 16) s.misc[tid] = 0;
+  if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
   __syncthreads();
   if (tid == 0) {
     sc[SC_PHYS] = a.phys_free;
@@ -1017,10 +1260,20 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
       }
       switch (o.kind) {
         case KVB_OP_ALLOC: {
-          int e = op + 1;
-          while (e < chunk_base + chunk_n && s.ops[e - chunk_base].kind == KVB_OP_ALLOC) ++e;
-          alloc_run(c, s, a, chunk_base, op, e, 0);
-          op = s.sim.op;   // == e unless the output buffer ran out
+          // end of the run of consecutive ALLOC requests inside the staged chunk
+          if (tid == 0) s.misc[MI_K] = chunk_base + chunk_n;
+          __syncthreads();
+          for (int q = op + 1 + tid; q < chunk_base + chunk_n; q += NT)
+            if (s.ops[q - chunk_base].kind != KVB_OP_ALLOC) { atomicMin(&s.misc[MI_K], q); break; }
+          __syncthreads();
+          int e = s.misc[MI_K];
+          if (e - op > NT) e = op + NT;
+          if (alloc_run_fast(c, s, a, chunk_base, op, e)) {
+            op = e;
+          } else {
+            alloc_run(c, s, a, chunk_base, op, e, 0);
+            op = s.sim.op;   // == e unless the output buffer ran out
+          }
           break;
         }
         case KVB_OP_TRY_RESERVE: {

@@ -33,6 +33,8 @@ namespace std { namespace __detail { extern const unsigned long __prime_list[]; 
     }                                                                                      \
   } while (0)
 
+namespace kvb { std::atomic<int64_t> g_total_launches{0}; }
+
 namespace {
 constexpr int kNumPrimes = 256 + 48;   // entries of libstdc++'s __prime_list before the sentinel (64-bit)
 
@@ -83,6 +85,7 @@ struct kvb_mgr {
   double phys_refresh_us = 1000;
   int has_null = 0;
   int64_t total_events = 0;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes the step path copied over PCIe (the e2e accounting)
   std::vector<int64_t> pending_events;
   int64_t *d_scratch = nullptr;   // small device scratch (audit counters, dump sizes)
   int64_t *d_dump = nullptr;
@@ -199,6 +202,7 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
     return KVB_ERR_CUDA;
   }
   m->launches++;
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
 
@@ -407,6 +411,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
   if (n_ids) memcpy(m->h_in + b_ops, ids, b_ids);
   if (n_refs) memcpy(m->h_in + b_ops + b_ids, refs, (size_t)n_refs * sizeof(kvb_ref));
   CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in, in_bytes, cudaMemcpyHostToDevice, m->stream));
+  m->h2d_bytes += (int64_t)in_bytes;
   const kvb_op *d_ops = (const kvb_op *)m->d_in;
   const int64_t *d_ids = (const int64_t *)(m->d_in + b_ops);
   const kvb_ref *d_refs = (const kvb_ref *)(m->d_in + b_ops + b_ids);
@@ -420,6 +425,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     rc = launch(m, d_ops, (int)done, (int)n_ops, d_ids, d_refs, d_res, d_outids, need_out, d_sum, first ? 0 : 2, 0);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(m->h_out, m->d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+    m->d2h_bytes += (int64_t)out_bytes;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     const Summary *hs = (const Summary *)m->h_out;
     m->last = *hs;
@@ -549,6 +555,8 @@ extern "C" int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *o) {
   o->unknown_page_frees = sc[SC_UNKNOWN_FREES];
   o->launches = m->launches;
   o->events = m->total_events;
+  o->h2d_bytes = m->h2d_bytes;
+  o->d2h_bytes = m->d2h_bytes;
   return 0;
 }
 
@@ -736,6 +744,7 @@ extern "C" int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms) {
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
   if (launch_audit(m->st, m->d_scratch + 8, m->stream) != 0) { set_error("audit kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return KVB_ERR_CUDA; }
   CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -823,3 +832,6 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   int rc = g->apply_events(ev.data(), hdr[1]);
   return rc < 0 ? rc : 0;
 }
+
+// kernels launched by this library since load (bookkeeping steps, audits, KV scatter/gather)
+extern "C" int64_t kvb_total_launches(void) { return g_total_launches.load(); }

@@ -75,6 +75,18 @@ static const char *cu_str(CUresult r) {
       return KVB_ERR_CUDA_;                                                  \
     }                                                                        \
   } while (0)
+// driver call with wall-time attribution (slot: 0 create, 1 release, 2 unmap, 3 map, 4 setaccess)
+#define CU_TIMED(slot, call)                                                 \
+  do {                                                                       \
+    auto t0_ = std::chrono::steady_clock::now();                             \
+    CUresult r_ = (call);                                                    \
+    t_us_[slot] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0_).count(); \
+    t_n_[slot] += 1;                                                         \
+    if (r_ != CUDA_SUCCESS) {                                                \
+      set_error("%s failed: %s (%d) at %s:%d", #call, cu_str(r_), (int)r_, __FILE__, __LINE__); \
+      return KVB_ERR_CUDA_;                                                  \
+    }                                                                        \
+  } while (0)
 static constexpr int KVB_ERR_CUDA_ = -2;
 static constexpr int KVB_ERR_INVALID_ = -1;
 static constexpr int KVB_ERR_STATE_ = -3;
@@ -162,9 +174,10 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   have_zero_ = true;
   n_created_++;
   for (auto &r : ranges_) {
-    for (size_t off = 0; off + unit_ <= r.bytes; off += unit_) CU_TRY(d->MemMap(r.base + off, unit_, 0, zero_, 0));
-    size_t covered = r.bytes / unit_ * unit_;
-    if (covered) CU_TRY(d->MemSetAccess(r.base, covered, &access_, 1));
+    for (size_t off = 0; off + unit_ <= r.bytes; off += unit_) {
+      CU_TRY(d->MemMap(r.base + off, unit_, 0, zero_, 0));
+      CU_TRY(d->MemSetAccess(r.base + off, unit_, &access_, 1));
+    }
   }
   // the zero page must read as zeros
   if (cudaMemset((void *)ranges_[0].base, 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
@@ -173,9 +186,19 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   }
   handles_.assign((size_t)n_pages_ * n_sub_, 0);
   mapped_.assign((size_t)n_pages_, 0);
-  if (pool_cap_ == 0) {
+  if (pool_cap_pages_ < 0) {
+    // Physical handles are recycled, not released: on this driver every cuMemCreate / cuMemRelease cycle
+    // makes later cuMemUnmap / cuMemSetAccess calls slower (tools/probe_e2e.py: 0.6 ms -> 8 ms per unmap
+    // after three replays of churn).  Default cap: a quarter of the device's pages; trim()-style release
+    // through kvb_vmm_pool_config(group, n).
     const char *e = getenv("KVB200_HANDLE_POOL_PAGES");
-    pool_cap_ = (e ? atoll(e) : 16) * n_sub_;
+    int64_t pages = e ? atoll(e) : -1;
+    if (pages < 0) {
+      size_t fr = 0, tot = 0;
+      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); tot = (size_t)180 << 30; }
+      pages = (int64_t)(tot / 4 / (unit_ * (size_t)n_sub_));
+    }
+    pool_cap_pages_ = pages;
   }
   created_ = true;
   return (int)ranges_.size();
@@ -194,15 +217,18 @@ int VmmGroup::get_handle(CUmemGenericAllocationHandle *h) {
     pool_.pop_back();
     return 0;
   }
-  CU_TRY(g_drv.MemCreate(h, unit_, &prop_, 0));
+  CU_TIMED(0, g_drv.MemCreate(h, unit_, &prop_, 0));
   n_created_++;
   return 0;
 }
 void VmmGroup::put_handle(CUmemGenericAllocationHandle h) {
-  if ((int64_t)pool_.size() < pool_cap_) {
+  if ((int64_t)pool_.size() < pool_cap_pages_ * n_sub_) {
     pool_.push_back(h);
   } else {
+    auto t0 = std::chrono::steady_clock::now();
     g_drv.MemRelease(h);
+    t_us_[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    t_n_[1] += 1;
     n_released_++;
   }
 }
@@ -216,8 +242,8 @@ int VmmGroup::map_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &to
     CUmemGenericAllocationHandle h;
     int rc = get_handle(&h);
     if (rc) return rc;
-    CU_TRY(g_drv.MemUnmap(a, unit_));
-    CU_TRY(g_drv.MemMap(a, unit_, 0, h, 0));
+    CU_TIMED(2, g_drv.MemUnmap(a, unit_));
+    CU_TIMED(3, g_drv.MemMap(a, unit_, 0, h, 0));
     handles_[(size_t)p * n_sub_ + s] = h;
     touched.emplace_back(a, unit_);
   }
@@ -232,8 +258,8 @@ int VmmGroup::unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &
   if (!mapped_[(size_t)p]) return 0;
   for (int s = 0; s < n_sub_; ++s) {
     CUdeviceptr a = sub_addr(p, s);
-    CU_TRY(g_drv.MemUnmap(a, unit_));
-    CU_TRY(g_drv.MemMap(a, unit_, 0, zero_, 0));
+    CU_TIMED(2, g_drv.MemUnmap(a, unit_));
+    CU_TIMED(3, g_drv.MemMap(a, unit_, 0, zero_, 0));
     put_handle(handles_[(size_t)p * n_sub_ + s]);
     handles_[(size_t)p * n_sub_ + s] = 0;
     touched.emplace_back(a, unit_);
@@ -243,19 +269,11 @@ int VmmGroup::unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &
   return 0;
 }
 
-// One cuMemSetAccess per run of adjacent units.
+// cuMemSetAccess for every unit touched by a batch.  One call per unit: on this driver (580.x, B200) a
+// single call spanning several mappings is slower than the per-unit calls it replaces (8 units: 4.8 ms
+// against 8 x 0.19 ms, tools/probe_vmm.py), so adjacent units are deliberately NOT merged.
 int VmmGroup::set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &t) {
-  if (t.empty()) return 0;
-  if (t.size() > 1) std::sort(t.begin(), t.end());
-  size_t i = 0;
-  while (i < t.size()) {
-    CUdeviceptr a = t[i].first;
-    size_t len = t[i].second;
-    size_t j = i + 1;
-    while (j < t.size() && t[j].first == a + len) { len += t[j].second; ++j; }
-    CU_TRY(g_drv.MemSetAccess(a, len, &access_, 1));
-    i = j;
-  }
+  for (auto &u : t) CU_TIMED(4, g_drv.MemSetAccess(u.first, u.second, &access_, 1));
   t.clear();
   return 0;
 }
@@ -313,8 +331,8 @@ int VmmGroup::apply_events(const int64_t *ev, int64_t n) {
 }
 
 void VmmGroup::pool_config(int64_t max_cached_pages) {
-  pool_cap_ = max_cached_pages * n_sub_;
-  while ((int64_t)pool_.size() > pool_cap_ && g_drv.ok) {
+  pool_cap_pages_ = max_cached_pages;
+  while ((int64_t)pool_.size() > pool_cap_pages_ * n_sub_ && g_drv.ok) {
     g_drv.MemRelease(pool_.back());
     pool_.pop_back();
     n_released_++;
@@ -324,7 +342,7 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
   if (!created_) { set_error("pool_prefill: tensors not created"); return KVB_ERR_STATE_; }
   if (!driver()) return KVB_ERR_CUDA_;
   cudaSetDevice(dev_);
-  int64_t want = std::min<int64_t>(n_pages * n_sub_, pool_cap_);
+  int64_t want = std::min<int64_t>(n_pages, pool_cap_pages_) * n_sub_;
   while ((int64_t)pool_.size() < want) {
     CUmemGenericAllocationHandle h;
     CU_TRY(g_drv.MemCreate(&h, unit_, &prop_, 0));
@@ -334,6 +352,10 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
   return 0;
 }
 int64_t VmmGroup::pooled_pages() { return n_sub_ ? (int64_t)pool_.size() / n_sub_ : 0; }
+
+void VmmGroup::timing(double *out10) {
+  for (int i = 0; i < 5; ++i) { out10[i] = t_us_[i]; out10[5 + i] = (double)t_n_[i]; }
+}
 
 void VmmGroup::stats(int64_t *s) {
   s[0] = n_mapped_;
@@ -455,6 +477,79 @@ int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out) {
   }
   for (int k = 0; k < 8; ++k) out[k] /= (double)iters;
   d->MemAddressFree(base, bytes);
+  return 0;
+}
+
+// How do map/unmap cycles scale with the number of live mappings?  A reservation of M units is backed by
+// one zero handle (SetAccess per unit, or one call over the whole range when mode&1); 8 target units —
+// inside it, or in a separate 16-unit reservation when mode&2 — are then cycled zero->handle->zero.
+// out[0] = us per map cycle (unmap+map+setaccess), out[1] = us per unmap cycle, out[2] = init ms.
+int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out) {
+  const Driver *d = driver();
+  if (!d) return KVB_ERR_CUDA_;
+  ensure_device(dev);
+  cudaFree(0);
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  using clk = std::chrono::steady_clock;
+  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  CUdeviceptr big = 0, small = 0;
+  CUmemGenericAllocationHandle zero;
+  CU_TRY(d->MemCreate(&zero, unit, &prop, 0));
+  auto t0 = clk::now();
+  CU_TRY(d->MemAddressReserve(&big, unit * (size_t)M, 2u << 20, 0, 0));
+  for (int64_t u = 0; u < M; ++u) {
+    CU_TRY(d->MemMap(big + u * unit, unit, 0, zero, 0));
+    if (!(mode & 1)) CU_TRY(d->MemSetAccess(big + u * unit, unit, &acc, 1));
+  }
+  if (mode & 1) CU_TRY(d->MemSetAccess(big, unit * (size_t)M, &acc, 1));
+  auto t1 = clk::now();
+  out[2] = us(t0, t1) / 1e3;
+  const int K = 8;
+  CUdeviceptr tgt[K];
+  if (mode & 2) {
+    CU_TRY(d->MemAddressReserve(&small, unit * 16, 2u << 20, 0, 0));
+    for (int u = 0; u < 16; ++u) {
+      CU_TRY(d->MemMap(small + u * unit, unit, 0, zero, 0));
+      CU_TRY(d->MemSetAccess(small + u * unit, unit, &acc, 1));
+    }
+    for (int k = 0; k < K; ++k) tgt[k] = small + (size_t)(2 * k) * unit;
+  } else {
+    for (int k = 0; k < K; ++k) tgt[k] = big + (size_t)((M / K) * k) * unit;
+  }
+  CUmemGenericAllocationHandle hs[K];
+  for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
+  double tm = 0, tu = 0;
+  for (int64_t it = 0; it < iters; ++it) {
+    auto a = clk::now();
+    for (int k = 0; k < K; ++k) {
+      CU_TRY(d->MemUnmap(tgt[k], unit));
+      CU_TRY(d->MemMap(tgt[k], unit, 0, hs[k], 0));
+      CU_TRY(d->MemSetAccess(tgt[k], unit, &acc, 1));
+    }
+    auto b = clk::now();
+    for (int k = 0; k < K; ++k) {
+      CU_TRY(d->MemUnmap(tgt[k], unit));
+      CU_TRY(d->MemMap(tgt[k], unit, 0, zero, 0));
+      CU_TRY(d->MemSetAccess(tgt[k], unit, &acc, 1));
+    }
+    auto c = clk::now();
+    tm += us(a, b) / K;
+    tu += us(b, c) / K;
+  }
+  out[0] = tm / iters;
+  out[1] = tu / iters;
+  d->MemUnmap(big, unit * (size_t)M);
+  d->MemAddressFree(big, unit * (size_t)M);
+  if (small) { d->MemUnmap(small, unit * 16); d->MemAddressFree(small, unit * 16); }
+  for (auto h : hs) d->MemRelease(h);
+  d->MemRelease(zero);
   return 0;
 }
 

@@ -58,6 +58,7 @@ class VmmGroup {
   void pool_config(int64_t max_cached);
   int pool_prefill(int64_t n_pages);
   void stats(int64_t *s8);
+  void timing(double *out10);   // us spent in / calls of {create, release, unmap, map, setaccess}
   int64_t mapped_pages(int64_t *out, int64_t cap);
   int64_t pooled_pages();
   int64_t num_pages() const { return n_pages_; }
@@ -94,9 +95,11 @@ class VmmGroup {
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
   std::vector<uint8_t> mapped_;
   std::vector<CUmemGenericAllocationHandle> pool_;
-  int64_t pool_cap_ = 0;
+  int64_t pool_cap_pages_ = -1;   // pages' worth of handles kept after unmap; -1 = default chosen in create()
   CUmemAllocationProp prop_{};
   CUmemAccessDesc access_{};
+  double t_us_[5] = {0, 0, 0, 0, 0};
+  int64_t t_n_[5] = {0, 0, 0, 0, 0};
   int64_t n_mapped_ = 0, n_created_ = 0, n_released_ = 0, n_map_calls_ = 0, n_unmap_calls_ = 0;
 };
 
@@ -112,5 +115,6 @@ VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
 // microseconds on this stack; cudaGetDevice does not)
 int ensure_device(int dev);
 int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out8);
+int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out3);
 
 }  // namespace kvb

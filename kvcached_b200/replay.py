@@ -282,7 +282,7 @@ class HostStepPlan:
             self.steps.append((b, ops, frees, fixed_ids, alloc_local, int(ops["n"][alloc_local].sum())))
 
 
-def replay_host_steps(mgr: KVCacheManager, plan: HostStepPlan, keep_results: bool = True):
+def replay_host_steps(mgr: KVCacheManager, plan: HostStepPlan, keep_results: bool = True, after_step=None):
     """One kvb_mgr_step per scheduler step with host buffers in and out.  Returns (res_all, held) where
     held[req] is the host copy of request req's ids (None for failed / non-alloc requests)."""
     ct = plan.ct
@@ -316,6 +316,8 @@ def replay_host_steps(mgr: KVCacheManager, plan: HostStepPlan, keep_results: boo
         for j in alloc_local:
             r = res[j]
             held[b + j] = out[r["off"]:r["off"] + r["n"]] if r["status"] == ST_OK else None
+        if after_step is not None:
+            after_step()
     return res_all, held
 
 

@@ -105,6 +105,17 @@ def vmm_stats(group_id: int = 0) -> Dict[str, int]:
     return dict(zip(keys, s.tolist()))
 
 
+def vmm_timing(group_id: int = 0) -> Dict[str, float]:
+    t = np.zeros(10)
+    _lib.check(_lib.load().kvb_vmm_timing(group_id, t.ctypes.data_as(_lib.p_f64)))
+    names = ["create", "release", "unmap", "map", "setaccess"]
+    out = {}
+    for i, n in enumerate(names):
+        out[n + "_ms"] = float(t[i]) / 1e3
+        out[n + "_calls"] = int(t[5 + i])
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # InternalPage — csrc/page_allocator.cpp:40-100.  A host-side value object in the reference too (a
 # page id plus its FIFO of free block ids); the device manager keeps the same FIFO in HBM, this class

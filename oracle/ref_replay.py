@@ -37,7 +37,7 @@ def _ids(r):
     return r if isinstance(r, list) else []
 
 
-def run(trace: dict, device: str = "cpu", timing_only: bool = False) -> dict:
+def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: int = 1) -> dict:
     cfg = trace["config"]
     os.environ["KVCACHED_PAGE_PREALLOC_ENABLED"] = "true" if cfg.get("prealloc", False) else "false"
     os.environ["KVCACHED_CONTIGUOUS_LAYOUT"] = "true" if cfg.get("contiguous", True) else "false"
@@ -111,6 +111,22 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False) -> dict:
             "mapped": sorted(mapped),
         }
 
+    elapsed_all = []
+    for _rep in range(max(1, repeats)):
+        results, records, n_calls, n_blocks, elapsed = _one_pass(trace, mgr, snap, timing_only)
+        elapsed_all.append(elapsed)
+    out = {"elapsed_s": elapsed_all[-1], "elapsed_all_s": elapsed_all, "n_calls": n_calls, "n_blocks": n_blocks,
+           "null_block": mgr.null_block, "nproc": os.cpu_count(), "device": device,
+           "prealloc": bool(cfg.get("prealloc", False))}
+    if not timing_only:
+        out["records"] = records
+    else:
+        out["final"] = {"avail": mgr.available_size()}
+    vmm_ops.shutdown_kvcached()
+    return out
+
+
+def _one_pass(trace, mgr, snap, timing_only):
     results: list = []
     records: list = []
     n_calls = 0
@@ -160,14 +176,7 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False) -> dict:
         if not timing_only:
             records.append({"r": r, **snap()})
     elapsed = time.perf_counter() - t0
-    out = {"elapsed_s": elapsed, "n_calls": n_calls, "n_blocks": n_blocks,
-           "null_block": mgr.null_block}
-    if not timing_only:
-        out["records"] = records
-    else:
-        out["final"] = {"avail": mgr.available_size()}
-    vmm_ops.shutdown_kvcached()
-    return out
+    return results, records, n_calls, n_blocks, elapsed
 
 
 if __name__ == "__main__":
@@ -178,6 +187,11 @@ if __name__ == "__main__":
         args.remove(device)
     with open(args[0]) as f:
         trace = json.load(f)
-    out = run(trace, device=device, timing_only="--time" in sys.argv)
+    repeats = 1
+    if "--repeat" in sys.argv:
+        r = sys.argv[sys.argv.index("--repeat") + 1]
+        args.remove(r)
+        repeats = int(r)
+    out = run(trace, device=device, timing_only="--time" in sys.argv, repeats=repeats)
     with open(args[1], "w") as f:
         json.dump(out, f)
