@@ -128,6 +128,9 @@ int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t
 /* map/unmap cycle cost against M live zero-page mappings: mode bit0 = one cuMemSetAccess over the whole range
  * at init instead of one per unit, bit1 = cycle units of a separate small reservation.
  * out3 = {us per map cycle, us per unmap cycle, init ms} */
+/* cycle cost against M live physical mappings: inside the same reservation / in a separate one / in one placed
+ * directly behind it.  out7 = {same_map, same_unmap, separate_map, separate_unmap, adjacent_map, adjacent_unmap, adjacent?} */
+int kvb_vmm_probe3(int device_index, int64_t unit_bytes, int64_t m_units, int64_t iters, double *out7);
 int kvb_vmm_probe2(int device_index, int64_t unit_bytes, int64_t m_units, int mode, int64_t iters, double *out3);
 
 /* ------------------------------------------------------------------------------------------

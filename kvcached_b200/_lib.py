@@ -80,6 +80,7 @@ SIGNATURES = {
     "kvb_vmm_avail_physical_pages": (i64, [i64, i64, i64, f64]),
     "kvb_vmm_raw_control": (C.c_int, [i64, i64, i64, C.c_int, p_f64, p_f64]),
     "kvb_vmm_probe": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
+    "kvb_vmm_probe3": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
     "kvb_vmm_probe2": (C.c_int, [C.c_int, i64, i64, C.c_int, i64, p_f64]),
     "kvb_mgr_create": (C.c_void_p, [C.POINTER(MgrConfig)]),
     "kvb_mgr_destroy": (C.c_int, [C.c_void_p]),

@@ -157,6 +157,11 @@ int kvb_vmm_probe2(int device_index, int64_t unit_bytes, int64_t m_units, int mo
   return vmm_probe2(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, m_units, mode, iters, out3);
 }
 
+int kvb_vmm_probe3(int device_index, int64_t unit_bytes, int64_t m_units, int64_t iters, double *out7) {
+  if (unit_bytes <= 0 || unit_bytes % (2 << 20) || m_units < 0 || iters <= 0 || !out7) { set_error("vmm_probe3: bad argument"); return KVB_ERR_INVALID; }
+  return vmm_probe3(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, m_units, iters, out7);
+}
+
 // ------------------------------------------------------------------------------------------ page helpers
 // InternalPage::get_block_range / get_num_blocks / PageAllocator::get_page_id (page_allocator.cpp:87-100, :457-460)
 void kvb_page_block_range(int64_t page_id, int64_t page_size, int64_t bms, int64_t *start, int64_t *end) {

@@ -1455,6 +1455,16 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
     int64_t nin = nev < EV_INLINE ? nev : EV_INLINE;
     for (int i = tid; i < nin; i += NT) sm->ev_inline[i] = c.ev[ev_begin + i];
     if (tid < SC_COUNT) sm->sc[tid] = sc[tid];
+    if (a.host_res) {
+      // zero-copy step: results go straight to the caller's pinned host buffers over PCIe; the
+      // summary's sequence number (written last, after a system-scope fence) is what the host polls.
+      const kvb_res *dr = a.res + a.op_begin;
+      kvb_res *hr = a.host_res + a.op_begin;
+      for (int i = tid; i < op - a.op_begin; i += NT) hr[i] = dr[i];
+      const int64_t o0 = out_begin, o1 = sc[SC_OUT_CURSOR];
+      for (int64_t i = o0 + tid; i < o1; i += NT) a.host_out[i] = a.out_ids[i];
+      __threadfence_system();
+    }
     __syncthreads();
     if (tid == 0) {
       sm->ops_done = op - a.op_begin;

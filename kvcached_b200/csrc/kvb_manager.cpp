@@ -86,6 +86,7 @@ struct kvb_mgr {
   int has_null = 0;
   int64_t total_events = 0;
   int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes the step path copied over PCIe (the e2e accounting)
+  bool zero_copy = true;   // step I/O: the kernel reads/writes the pinned host buffers itself (KVB200_STEP_IO=copy disables)
   std::vector<int64_t> pending_events;
   int64_t *d_scratch = nullptr;   // small device scratch (audit counters, dump sizes)
   int64_t *d_dump = nullptr;
@@ -142,12 +143,24 @@ int64_t phys_free_pages(kvb_mgr *m) {
   }
   double headroom = (double)tot * (1.0 - m->gpu_util);
   double avail = (double)fr - headroom;
-  if (avail < 0) avail = 0;   // the reference's size_t subtraction wraps here; we clamp (SURVEY A.5)
-  int64_t pages = (int64_t)((size_t)avail / (size_t)m->P / (size_t)m->cfg.num_layers / (size_t)m->cfg.num_kv_buffers);
+  size_t page_all = (size_t)m->P * (size_t)m->cfg.num_layers * (size_t)m->cfg.num_kv_buffers;
   if (m->cfg.attach_vmm) {
     VmmGroup *g = vmm_group(m->cfg.group_id, false);
-    if (g) pages += g->pooled_pages();   // pooled handles are memory we already hold
+    if (g) {
+      std::lock_guard<std::mutex> lk(g->mu);
+      if (avail < 0 && g->pooled_pages() > 0) {
+        // somebody else needs the memory: the handle pool shrinks until the headroom is restored
+        int64_t give = (int64_t)((-avail + (double)page_all - 1) / (double)page_all);
+        avail += (double)g->pool_release(give) * (double)page_all;
+      }
+      if (avail < 0) avail = 0;
+      int64_t pages = (int64_t)((size_t)avail / page_all) + g->pooled_pages();   // pooled handles are memory we hold
+      m->phys_cached = pages;
+      return pages;
+    }
   }
+  if (avail < 0) avail = 0;   // the reference's size_t subtraction wraps here; we clamp (SURVEY A.5)
+  int64_t pages = (int64_t)((size_t)avail / page_all);
   m->phys_cached = pages;
   return pages;
 }
@@ -178,7 +191,8 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n) {
 // One launch over requests [op_begin, op_end) of a device-resident request array.
 int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int64_t *d_ids, const kvb_ref *d_refs,
            kvb_res *d_res, int64_t *d_outids, int64_t out_cap, Summary *d_sum, int arena_mode, int group_only,
-           int64_t *grp_pages = nullptr, int64_t *grp_counts = nullptr, int64_t *grp_ids = nullptr) {
+           int64_t *grp_pages = nullptr, int64_t *grp_counts = nullptr, int64_t *grp_ids = nullptr,
+           kvb_res *host_res = nullptr, int64_t *host_out = nullptr) {
   LaunchArgs a{};
   a.ops = d_ops;
   a.op_begin = op_begin;
@@ -196,6 +210,8 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
   a.grp_pages = grp_pages;
   a.grp_counts = grp_counts;
   a.grp_ids = grp_ids;
+  a.host_res = host_res;
+  a.host_out = host_out;
   int rc = launch_step(m->st, a, m->stream);
   if (rc != 0) {
     set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -220,6 +236,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   if (c.min_reserved_pages < 0) c.min_reserved_pages = env_i64("KVCACHED_MIN_RESERVED_PAGES", 5);
   if (c.max_reserved_pages < 0) c.max_reserved_pages = env_i64("KVCACHED_MAX_RESERVED_PAGES", 10);
   m->phys_refresh_us = env_f64("KVB200_MEMINFO_REFRESH_US", 1000);
+  { const char *io = getenv("KVB200_STEP_IO"); m->zero_copy = !(io && strcmp(io, "copy") == 0); }
   m->gpu_util = c.gpu_utilization > 0 ? c.gpu_utilization : env_f64("KVCACHED_GPU_UTILIZATION", 0.95);
   m->P = c.page_size;
   m->B = c.block_size * c.cell_size;
@@ -410,25 +427,54 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
   memcpy(m->h_in, ops, b_ops);
   if (n_ids) memcpy(m->h_in + b_ops, ids, b_ids);
   if (n_refs) memcpy(m->h_in + b_ops + b_ids, refs, (size_t)n_refs * sizeof(kvb_ref));
-  CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in, in_bytes, cudaMemcpyHostToDevice, m->stream));
+  const bool zc = m->zero_copy;
+  // copy mode: one H2D copy in, one D2H copy out.  zero-copy mode: the kernel reads the pinned input
+  // buffer over PCIe itself and writes results + summary straight into the pinned output buffer; the
+  // host polls the summary's sequence number instead of synchronising the stream.
+  const unsigned char *in_base = zc ? m->h_in : m->d_in;
+  if (!zc) CUDA_TRY(cudaMemcpyAsync(m->d_in, m->h_in, in_bytes, cudaMemcpyHostToDevice, m->stream));
   m->h2d_bytes += (int64_t)in_bytes;
-  const kvb_op *d_ops = (const kvb_op *)m->d_in;
-  const int64_t *d_ids = (const int64_t *)(m->d_in + b_ops);
-  const kvb_ref *d_refs = (const kvb_ref *)(m->d_in + b_ops + b_ids);
-  Summary *d_sum = (Summary *)m->d_out;
+  const kvb_op *d_ops = (const kvb_op *)in_base;
+  const int64_t *d_ids = (const int64_t *)(in_base + b_ops);
+  const kvb_ref *d_refs = (const kvb_ref *)(in_base + b_ops + b_ids);
+  Summary *d_sum = zc ? (Summary *)m->h_out : (Summary *)m->d_out;
   kvb_res *d_res = (kvb_res *)(m->d_out + o_res);
   int64_t *d_outids = (int64_t *)(m->d_out + o_ids);
+  kvb_res *h_res = (kvb_res *)(m->h_out + o_res);
+  int64_t *h_outids = (int64_t *)(m->h_out + o_ids);
 
   int64_t done = 0;
   bool first = true;
   while (done < n_ops) {
-    rc = launch(m, d_ops, (int)done, (int)n_ops, d_ids, d_refs, d_res, d_outids, need_out, d_sum, first ? 0 : 2, 0);
+    volatile int64_t *vseq = &((Summary *)m->h_out)->seq;
+    if (zc) *vseq = 0;
+    rc = launch(m, d_ops, (int)done, (int)n_ops, d_ids, d_refs, d_res, d_outids, need_out, d_sum, first ? 0 : 2, 0,
+                nullptr, nullptr, nullptr, zc ? h_res : nullptr, zc ? h_outids : nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(m->h_out, m->d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
-    m->d2h_bytes += (int64_t)out_bytes;
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (zc) {
+      const int64_t want = m->seq;
+      uint64_t spins = 0;
+      while (*vseq != want) {
+        if ((++spins & 0x3ff) == 0) {   // every ~1k polls make sure the kernel is still alive
+          cudaError_t q = cudaStreamQuery(m->stream);
+          if (q == cudaSuccess) {
+            if (*vseq == want) break;
+            CUDA_TRY(cudaStreamSynchronize(m->stream));
+            if (*vseq != want) { set_error("step kernel finished without publishing its summary"); return KVB_ERR_STATE; }
+            break;
+          }
+          if (q != cudaErrorNotReady) { set_error("step kernel failed: %s", cudaGetErrorString(q)); return KVB_ERR_CUDA; }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(m->h_out, m->d_out, out_bytes, cudaMemcpyDeviceToHost, m->stream));
+      CUDA_TRY(cudaStreamSynchronize(m->stream));
+    }
     const Summary *hs = (const Summary *)m->h_out;
     m->last = *hs;
+    m->d2h_bytes += zc ? (int64_t)(40 * 8 + hs->ev_inline_n * 8 + hs->ops_done * (int64_t)sizeof(kvb_res) + hs->out_used * 8)
+                       : (int64_t)out_bytes;
     // page map/unmap list of this launch -> VMM engine
     if (hs->n_events > 0) {
       if (hs->n_events <= hs->ev_inline_n) {

@@ -189,15 +189,12 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   if (pool_cap_pages_ < 0) {
     // Physical handles are recycled, not released: on this driver every cuMemCreate / cuMemRelease cycle
     // makes later cuMemUnmap / cuMemSetAccess calls slower (tools/probe_e2e.py: 0.6 ms -> 8 ms per unmap
-    // after three replays of churn).  Default cap: a quarter of the device's pages; trim()-style release
-    // through kvb_vmm_pool_config(group, n).
+    // after three replays of churn).  Default: keep every handle; the manager hands memory back as soon as
+    // the device's free memory drops under the utilisation headroom (pool_release, driven by the same
+    // cudaMemGetInfo poll available_size() needs) and on kvb_vmm_pool_config(group, n).
     const char *e = getenv("KVB200_HANDLE_POOL_PAGES");
     int64_t pages = e ? atoll(e) : -1;
-    if (pages < 0) {
-      size_t fr = 0, tot = 0;
-      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); tot = (size_t)180 << 30; }
-      pages = (int64_t)(tot / 4 / (unit_ * (size_t)n_sub_));
-    }
+    if (pages < 0) pages = n_pages_;   // recycle everything; memory goes back on pressure (pool_release) or trim
     pool_cap_pages_ = pages;
   }
   created_ = true;
@@ -352,6 +349,16 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
   return 0;
 }
 int64_t VmmGroup::pooled_pages() { return n_sub_ ? (int64_t)pool_.size() / n_sub_ : 0; }
+int64_t VmmGroup::pool_release(int64_t n_pages) {
+  int64_t n = 0;
+  while (n < n_pages * n_sub_ && !pool_.empty() && g_drv.ok) {
+    g_drv.MemRelease(pool_.back());
+    pool_.pop_back();
+    n_released_++;
+    n++;
+  }
+  return n_sub_ ? n / n_sub_ : 0;
+}
 
 void VmmGroup::timing(double *out10) {
   for (int i = 0; i < 5; ++i) { out10[i] = t_us_[i]; out10[5 + i] = (double)t_n_[i]; }
@@ -548,6 +555,87 @@ int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double 
   d->MemUnmap(big, unit * (size_t)M);
   d->MemAddressFree(big, unit * (size_t)M);
   if (small) { d->MemUnmap(small, unit * 16); d->MemAddressFree(small, unit * 16); }
+  for (auto h : hs) d->MemRelease(h);
+  d->MemRelease(zero);
+  return 0;
+}
+
+// Does a map/unmap cycle get slower with the number of live PHYSICAL mappings, and is that per
+// reservation?  M distinct handles are mapped into one big reservation; 8 target units are cycled
+// (a) inside it, (b) in a separate small reservation, (c) in a small reservation placed directly behind
+// the big one at a fixed address.  out = {a_map, a_unmap, b_map, b_unmap, c_map, c_unmap, c_adjacent(0/1)}
+int vmm_probe3(int dev, size_t unit, int64_t M, int64_t iters, double *out) {
+  const Driver *d = driver();
+  if (!d) return KVB_ERR_CUDA_;
+  ensure_device(dev);
+  cudaFree(0);
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  using clk = std::chrono::steady_clock;
+  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const int K = 8;
+  const CUdeviceptr hint = 0x3f0000000000ull;
+  CUdeviceptr big = 0, sep = 0, adj = 0;
+  size_t big_bytes = unit * (size_t)(M + 16);
+  CU_TRY(d->MemAddressReserve(&big, big_bytes, 2u << 20, hint, 0));
+  CU_TRY(d->MemAddressReserve(&adj, unit * 16, 2u << 20, big + big_bytes, 0));
+  CU_TRY(d->MemAddressReserve(&sep, unit * 16, 2u << 20, 0, 0));
+  out[6] = (adj == big + big_bytes) ? 1.0 : 0.0;
+  CUmemGenericAllocationHandle zero;
+  CU_TRY(d->MemCreate(&zero, unit, &prop, 0));
+  std::vector<CUmemGenericAllocationHandle> bg((size_t)M), hs(K);
+  for (auto &h : bg) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
+  for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
+  for (int64_t u = 0; u < M; ++u) {
+    CU_TRY(d->MemMap(big + u * unit, unit, 0, bg[(size_t)u], 0));
+    CU_TRY(d->MemSetAccess(big + u * unit, unit, &acc, 1));
+  }
+  for (int u = 0; u < 16; ++u) {
+    CU_TRY(d->MemMap(big + (M + u) * unit, unit, 0, zero, 0));
+    CU_TRY(d->MemSetAccess(big + (M + u) * unit, unit, &acc, 1));
+    CU_TRY(d->MemMap(sep + u * unit, unit, 0, zero, 0));
+    CU_TRY(d->MemSetAccess(sep + u * unit, unit, &acc, 1));
+    CU_TRY(d->MemMap(adj + u * unit, unit, 0, zero, 0));
+    CU_TRY(d->MemSetAccess(adj + u * unit, unit, &acc, 1));
+  }
+  CUdeviceptr bases[3] = {big + (size_t)M * unit, sep, adj};
+  for (int v = 0; v < 3; ++v) {
+    double tm = 0, tu = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+      auto a = clk::now();
+      for (int k = 0; k < K; ++k) {
+        CUdeviceptr t = bases[v] + (size_t)(2 * k) * unit;
+        CU_TRY(d->MemUnmap(t, unit));
+        CU_TRY(d->MemMap(t, unit, 0, hs[k], 0));
+        CU_TRY(d->MemSetAccess(t, unit, &acc, 1));
+      }
+      auto b = clk::now();
+      for (int k = 0; k < K; ++k) {
+        CUdeviceptr t = bases[v] + (size_t)(2 * k) * unit;
+        CU_TRY(d->MemUnmap(t, unit));
+        CU_TRY(d->MemMap(t, unit, 0, zero, 0));
+        CU_TRY(d->MemSetAccess(t, unit, &acc, 1));
+      }
+      auto c2 = clk::now();
+      tm += us(a, b) / K;
+      tu += us(b, c2) / K;
+    }
+    out[2 * v] = tm / iters;
+    out[2 * v + 1] = tu / iters;
+  }
+  d->MemUnmap(big, big_bytes);
+  d->MemUnmap(sep, unit * 16);
+  d->MemUnmap(adj, unit * 16);
+  d->MemAddressFree(big, big_bytes);
+  d->MemAddressFree(sep, unit * 16);
+  d->MemAddressFree(adj, unit * 16);
+  for (auto h : bg) d->MemRelease(h);
   for (auto h : hs) d->MemRelease(h);
   d->MemRelease(zero);
   return 0;

@@ -61,6 +61,7 @@ class VmmGroup {
   void timing(double *out10);   // us spent in / calls of {create, release, unmap, map, setaccess}
   int64_t mapped_pages(int64_t *out, int64_t cap);
   int64_t pooled_pages();
+  int64_t pool_release(int64_t n_pages);   // give pooled physical memory back to the device
   int64_t num_pages() const { return n_pages_; }
   size_t unit() const { return unit_; }
   int64_t num_layers() const { return L_; }
@@ -115,6 +116,7 @@ VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
 // microseconds on this stack; cudaGetDevice does not)
 int ensure_device(int dev);
 int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out8);
+int vmm_probe3(int dev, size_t unit, int64_t M, int64_t iters, double *out7);
 int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out3);
 
 }  // namespace kvb

@@ -243,8 +243,10 @@ def replay_resident(mgr: KVCacheManager, trace: dict, steps_per_launch: int = 1)
 
 # ----------------------------------------------------------------------------------------- host steps
 class HostStepPlan:
-    """Per-step request templates for replay_host_steps, prepared once outside any timed region:
-    request kinds/sizes and, for every free, which earlier results it concatenates."""
+    """Per-launch request templates for replay_host_steps, prepared once outside any timed region:
+    request kinds/sizes and, for every free, which slices of earlier results it concatenates.  The
+    run-time side is vectorised numpy (the host keeps allocated ids in one arena + start/len per request,
+    the way an engine keeps block tables), so the Python driver costs a few numpy calls per launch."""
 
     def __init__(self, ct: CompiledTrace):
         self.ct = ct
@@ -267,19 +269,46 @@ class HostStepPlan:
             if e <= b:
                 continue
             ops = ct.ops[b:e].copy()
-            frees = []          # (local index, [(req, lo, hi), ...]) for FREE_REF; converted to FREE_IDS at run time
-            fixed_ids = []      # (local index, ids array) for FREE_IDS taken from the trace itself
+            free_local, ref_q, ref_lo, ref_hi, owner_start = [], [], [], [], []
+            fixed = []          # (position in the free list, ids) for FREE_IDS taken from the trace itself
             for j in range(e - b):
                 k = int(ops["kind"][j])
                 if k == OP_FREE_REF:
                     a, n = int(ops["arg"][j]), int(ops["n"][j])
-                    frees.append((j, [(int(r["op"]), int(r["lo"]), int(r["hi"])) for r in ct.refs[a:a + n]]))
+                    if n == 0:
+                        ops["kind"][j] = OP_FREE_IDS
+                        ops["n"][j] = 0
+                        continue
+                    owner_start.append(len(ref_q))
+                    free_local.append(j)
+                    ref_q.extend(int(x) for x in ct.refs["op"][a:a + n])
+                    ref_lo.extend(int(x) for x in ct.refs["lo"][a:a + n])
+                    ref_hi.extend(int(x) for x in ct.refs["hi"][a:a + n])
                     ops["kind"][j] = OP_FREE_IDS
                 elif k == OP_FREE_IDS:
                     a, n = int(ops["arg"][j]), int(ops["n"][j])
-                    fixed_ids.append((j, ct.ids[a:a + n]))
+                    fixed.append((j, ct.ids[a:a + n].copy()))
             alloc_local = np.nonzero(ops["kind"] == OP_ALLOC)[0]
-            self.steps.append((b, ops, frees, fixed_ids, alloc_local, int(ops["n"][alloc_local].sum())))
+            self.steps.append(dict(
+                b=b, ops=ops, free_local=np.array(free_local, dtype=np.int64),
+                ref_q=np.array(ref_q, dtype=np.int64), ref_lo=np.array(ref_lo, dtype=np.int64),
+                ref_hi=np.array(ref_hi, dtype=np.int64), owner_start=np.array(owner_start, dtype=np.int64),
+                fixed=fixed, alloc_local=alloc_local, alloc_global=alloc_local + b,
+                need=int(ops["n"][alloc_local].sum())))
+
+
+class HeldIds:
+    """Host copy of every request's allocated ids: one arena + (start, len) per request."""
+
+    def __init__(self, n_req: int, capacity: int):
+        self.arena = np.empty(max(capacity, 1), dtype=np.int64)
+        self.start = np.zeros(n_req, dtype=np.int64)
+        self.len = np.zeros(n_req, dtype=np.int64)
+        self.ok = np.zeros(n_req, dtype=bool)
+        self.cur = 0
+
+    def __getitem__(self, q: int):
+        return self.arena[self.start[q]:self.start[q] + self.len[q]] if self.ok[q] else None
 
 
 def replay_host_steps(mgr: KVCacheManager, plan: HostStepPlan, keep_results: bool = True, after_step=None):
@@ -287,35 +316,53 @@ def replay_host_steps(mgr: KVCacheManager, plan: HostStepPlan, keep_results: boo
     held[req] is the host copy of request req's ids (None for failed / non-alloc requests)."""
     ct = plan.ct
     n = ct.ops.shape[0]
-    held: List[Optional[np.ndarray]] = [None] * n
+    held = HeldIds(n, ct.alloc_blocks + 16)
+    arena, h_start, h_len = held.arena, held.start, held.len
     res_all = np.empty(n, dtype=RES_DTYPE) if keep_results else None
-    empty = np.empty(0, dtype=np.int64)
-    for b, ops, frees, fixed_ids, alloc_local, need in plan.steps:
+    for st in plan.steps:
+        ops = st["ops"]
+        ids = None
         pieces = []
         pos = 0
-        for j, refs in frees:
-            m0 = pos
-            for q, lo, hi in refs:
-                h = held[q]
-                if h is not None:
-                    p = h[lo:hi]
-                    if p.size:
-                        pieces.append(p)
-                        pos += p.size
-            ops["arg"][j] = m0
-            ops["n"][j] = pos - m0
-        for j, arr in fixed_ids:
+        if st["ref_q"].size:
+            q = st["ref_q"]
+            ln = h_len[q]
+            lo = np.minimum(st["ref_lo"], ln)
+            cnt = np.minimum(st["ref_hi"], ln) - lo
+            np.maximum(cnt, 0, out=cnt)
+            csum = np.cumsum(cnt)
+            total = int(csum[-1])
+            if total:
+                idx = np.repeat(h_start[q] + lo - (csum - cnt), cnt) + np.arange(total, dtype=np.int64)
+                pieces.append(arena[idx])
+            per_free = np.add.reduceat(cnt, st["owner_start"])
+            # reduceat quirk: an empty trailing group cannot occur (every owner has >= 1 ref)
+            ops["n"][st["free_local"]] = per_free
+            ops["arg"][st["free_local"]] = np.cumsum(per_free) - per_free
+            pos = total
+        for j, arr in st["fixed"]:
             ops["arg"][j] = pos
             ops["n"][j] = arr.size
             pieces.append(arr)
             pos += arr.size
-        ids = np.concatenate(pieces) if pieces else empty
-        res, out = mgr.run_ops(ops, ids if pos else None, None, need)
+        if pos:
+            ids = pieces[0] if len(pieces) == 1 else np.concatenate(pieces)
+        res, out = mgr.run_ops(ops, ids, None, st["need"])
+        b = st["b"]
         if keep_results:
             res_all[b:b + ops.shape[0]] = res
-        for j in alloc_local:
-            r = res[j]
-            held[b + j] = out[r["off"]:r["off"] + r["n"]] if r["status"] == ST_OK else None
+        al = st["alloc_local"]
+        if al.size:
+            r = res[al]
+            ok = r["status"] == ST_OK
+            ag = st["alloc_global"]
+            cur = held.cur
+            if out.size:
+                arena[cur:cur + out.size] = out
+            h_start[ag] = cur + r["off"]
+            h_len[ag] = np.where(ok, r["n"], 0)
+            held.ok[ag] = ok
+            held.cur = cur + out.size
         if after_step is not None:
             after_step()
     return res_all, held

@@ -192,7 +192,7 @@ class PageAllocator:
         self._ipc_cb: Optional[Callable] = None
         # one block per page: the block manager's page lists ARE the page allocator
         lib = _lib.load()
-        attach = bool(lib.kvb_is_initialized() and lib.kvb_kv_tensors_created(group_id))
+        attach = bool(lib.kvb_is_initialized())   # tensors may not exist yet: the manager waits for them (post-init)
         self._m = KVCacheManager(mem_size_per_layer // page_size, 1, page_size, num_layers, world_size, pp_rank,
                                  async_sched, False, num_kv_buffers, group_id, page_size=page_size,
                                  attach_vmm=attach)
