@@ -179,7 +179,7 @@ def pctl(xs, q):
 def ours_main(args, rank: int, world: int, local_rank: int):
     import numpy as np
     import torch
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = args.steps, max(args.warmup, 1)   # default 3; fewer only for profiling runs, never for reported numbers
     dist = None
     if world > 1:
         import torch.distributed as dist

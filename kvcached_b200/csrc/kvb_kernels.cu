@@ -338,40 +338,38 @@ __device__ __forceinline__ void ht_order_seq(const DevState &c, const uint32_t *
 // re-places the current list front to back under the new nb, which is the same rule applied to S = current
 // order; keys inserted afterwards simply extend S.  Lane l holds the key at position l of S.
 __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t *primes32, const int32_t *keys,
-                                              int D, int nb, int32_t *ord) {
+                                              int D, int nb, int32_t *ord, int32_t *scratch64) {
   const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  // cur_slot = slot index of the key at S position `lane` (valid for lane < placed)
+  const unsigned gt = ~((2u << lane) - 1u);   // lanes above mine
+  // cur_slot / cur_key = slot index and key of the element at S position `lane` (valid for lane < placed)
   int cur_slot = lane;
   unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
   int placed = 0;   // keys already in the container
   while (true) {
-    // keys inserted under this bucket count: until the container holds nb keys (then the next insert rehashes)
-    int upto = D < nb ? D : nb;
+    // keys inserted under this bucket count: until the container holds nb keys (the next insert rehashes)
+    const int upto = D < nb ? D : nb;
     // S = [current order of `placed` keys] ++ [slots placed .. upto-1 in insertion order]
-    // lanes >= placed and < upto take their insertion slot
     if (lane >= placed && lane < upto) { cur_slot = lane; cur_key = (unsigned)keys[lane]; }
     const bool in = lane < upto;
-    unsigned b = in ? cur_key % (unsigned)nb : 0xffffffffu - lane;
-    unsigned grp = __match_any_sync(0xffffffffu, b);
-    int gfirst = __ffs(grp) - 1;                        // first position of my bucket in S
-    int later_in_grp = __popc(grp & ~lt & ~(1u << lane));
-    // keys whose bucket first appears after mine come before me
-    int before = 0;
-    for (int v = 0; v < upto; ++v) {
-      unsigned m = __ballot_sync(0xffffffffu, in && gfirst > v);
-      if (v == gfirst) before = __popc(m);
+    const unsigned b = in ? cur_key % (unsigned)nb : 0xffffffffu - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    const int gfirst = __ffs(grp) - 1;                  // first position of my bucket in S
+    const int later_in_grp = __popc(grp & gt);
+    // keys whose bucket first appears after mine come before me: suffix sum of run sizes over run leaders
+    int suf = (in && gfirst == lane) ? __popc(grp) : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int y = __shfl_down_sync(0xffffffffu, suf, d);
+      if (lane + d < 32) suf += y;
     }
-    int newpos = before + later_in_grp;
-    // permute: the key at new position p comes from the lane whose newpos == p
-    int src = 0;
-    for (int p = 0; p < upto; ++p) {
-      unsigned m = __ballot_sync(0xffffffffu, in && newpos == p);
-      if (lane == p) src = __ffs(m) - 1;
-    }
-    int ns = __shfl_sync(0xffffffffu, cur_slot, src);
-    unsigned nk = __shfl_sync(0xffffffffu, cur_key, src);
-    if (in) { cur_slot = ns; cur_key = nk; }
+    int before = __shfl_sync(0xffffffffu, suf, (gfirst + 1) & 31);
+    if (gfirst == 31) before = 0;
+    const int newpos = before + later_in_grp;
+    // permute through shared memory: position p takes the element whose newpos == p
+    if (in) { scratch64[newpos] = cur_slot; scratch64[32 + newpos] = (int)cur_key; }
+    __syncwarp();
+    if (in) { cur_slot = scratch64[lane]; cur_key = (unsigned)scratch64[32 + lane]; }
+    __syncwarp();
     placed = upto;
     if (placed >= D) break;
     int64_t want = (int64_t)placed + 2;                 // _M_need_rehash -> _M_next_bkt(max(n+1+1, 2*nb))
@@ -945,7 +943,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
   int32_t *cnt = use_g ? c.g_cnt : s.ht_cnt;
   if (w == 0) {
     if (D <= 32) {
-      ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord);           // registers + warp votes
+      ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);   // registers + warp votes
     } else if (!use_g) {
       for (int b = lane; b < nb0; b += 32) s.ht_bkt[b] = -1;
       __syncwarp();

@@ -11,15 +11,17 @@ from kvcached_b200.kv_cache_manager import KVCacheManager
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 torch.cuda.init()
 if which in ("step", "both"):
-    cfg = T.make_config("llama8b", 16384)
-    tr = T.decode_trace(cfg, 512, seed=0)
+    nreq = int(os.environ.get("NCU_REQ", "512"))
+    cfg = T.make_config("llama8b", 91520 if nreq >= 4096 else 16384)
+    tr = T.decode_trace(cfg, nreq, seed=0)
     ct = R.compile_trace(tr)
     m = R.manager_from_config(cfg, attach_vmm=False); m.set_phys_free_pages(1 << 40)
     R.upload(m, ct)
+    spl = int(os.environ.get("NCU_SPL", str(1 << 20)))     # steps per launch: 1 = one launch per scheduler step
     for _ in range(2):
         _lib.load().kvb_mgr_trace_reset_cursor(m._h)
-        ms, nl = R.run_resident(m, ct, steps_per_launch=1 << 20)
-    print("step kernel: ops", ct.n_calls, "steps", ct.step_offsets.size - 1, "ms", ms)
+        ms, nl = R.run_resident(m, ct, steps_per_launch=spl)
+    print("step kernel: ops", ct.n_calls, "steps", ct.step_offsets.size - 1, "launches", nl, "ms", ms)
     m.close()
 if which in ("kv", "both"):
     PAGE = 2 << 20
