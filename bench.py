@@ -40,6 +40,9 @@ NUM_BLOCKS_TP = 65536       # Llama-3.3-70B TP pool (BASELINE configs[4]): 80 la
 N_REQUESTS = 4096
 PAGE = 2 << 20
 SCATTER_T = 65536           # tokens per fused all-layer scatter launch (16 GiB of traffic > L2)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE kvb_kv_copy_kernel<scatter> launch at exactly this shape
+# (T = 65 536 tokens, 32 layers, cell 2048 B), ncu --set full, profiles/r1_kv_copy_T65536_full.csv
+SCATTER_TRAFFIC_NCU = 8_592_656_000 + 8_543_728_000
 
 
 def workload_config(world: int) -> dict:
@@ -274,6 +277,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             R.replay_host_steps(mgr, plan, keep_results=False)
         else:
             TP.replay_host_steps_tp(tp, mgr, plan, rank)
+        vmm_ops.fence()             # every queued unmap is applied inside the timed region
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
@@ -402,7 +406,10 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     roofline = {"kernel": "kvb_kv_copy_kernel<scatter> (fused 32-layer paged KV scatter, T=65536 tokens)",
                 "bound": "hbm", "achieved": kv["scatter"]["gbs_per_gpu"], "peak": peak, "unit": "GB/s",
-                "frac": kv["scatter"]["gbs_per_gpu"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kv["scatter"]["gbs_per_gpu"] / peak,
+                "traffic": SCATTER_TRAFFIC_NCU if (world == 1 and Tn == SCATTER_T) else None,
+                "traffic_source": "ncu --set full dram bytes of one launch at this shape (profiles/r1_kv_copy_T65536_full.csv)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "step_kernel": {"us_per_scheduler_step": 1e3 * res_ms_total / K / n_sched_steps,
                                 "note": "kvb_step_kernel is one latency-bound CTA over L2-resident state "
@@ -416,7 +423,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_total / K, "scheduler_steps": len(plan.steps),
                         "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"]},
-                        "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True"},
+                        "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
+                               "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
+                               "timed region"},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "map_unmap": map_unmap, "kv_scatter": kv,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),

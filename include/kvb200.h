@@ -97,6 +97,19 @@ int kvb_unmap_pages(int64_t group_id, const int64_t *page_ids, int64_t n);
  * and the payload rank 0 broadcasts to the other tensor-parallel ranks). */
 int kvb_apply_page_events(int64_t group_id, const int64_t *events, int64_t n);
 
+/* ---- asynchronous VMM engine --------------------------------------------------------------------
+ * Events change the WANTED state of a page; the group's single VMM thread reconciles the physical
+ * state with it, maps before unmaps; an event that meets its own page's pending opposite cancels it
+ * (no driver call).  kvb_mgr_step / kvb_tp_apply enqueue the kernel's list and wait for the maps only;
+ * kvb_vmm_fence waits for everything (unmaps included).  Replaces what the reference's prealloc
+ * thread does for map latency (page_allocator.cpp:524-617) without touching the bookkeeping.
+ * KVB200_VMM_ASYNC=0 (or kvb_vmm_set_async(group, 0)): no thread, every call settles before returning. */
+int kvb_vmm_enqueue_page_events(int64_t group_id, const int64_t *events, int64_t n);
+int kvb_vmm_wait_maps(int64_t group_id);
+int kvb_vmm_fence(int64_t group_id);
+int kvb_vmm_set_async(int64_t group_id, int on);
+int64_t kvb_vmm_pending_unmaps(int64_t group_id);
+
 /* physical-handle pool (no cuMemCreate / cuMemRelease on the hot path; page.cpp:10-25 creates and
  * releases one handle per map).  `max_cached` handles are kept after unmap, the rest released;
  * kvb_vmm_pool_prefill creates up to n handles ahead of demand. */

@@ -72,6 +72,11 @@ SIGNATURES = {
     "kvb_map_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_unmap_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_apply_page_events": (C.c_int, [i64, p_i64, i64]),
+    "kvb_vmm_enqueue_page_events": (C.c_int, [i64, p_i64, i64]),
+    "kvb_vmm_wait_maps": (C.c_int, [i64]),
+    "kvb_vmm_fence": (C.c_int, [i64]),
+    "kvb_vmm_set_async": (C.c_int, [i64, C.c_int]),
+    "kvb_vmm_pending_unmaps": (i64, [i64]),
     "kvb_vmm_pool_config": (C.c_int, [i64, i64]),
     "kvb_vmm_pool_prefill": (C.c_int, [i64, i64]),
     "kvb_vmm_stats": (C.c_int, [i64, p_i64]),

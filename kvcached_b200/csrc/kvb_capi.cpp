@@ -88,6 +88,36 @@ int kvb_apply_page_events(int64_t group_id, const int64_t *events, int64_t n) {
   std::lock_guard<std::mutex> lk(g->mu);
   return g->apply_events(events, n);
 }
+int kvb_vmm_enqueue_page_events(int64_t group_id, const int64_t *events, int64_t n) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  return g->enqueue_events(events, n);
+}
+int kvb_vmm_wait_maps(int64_t group_id) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  return g->wait_maps();
+}
+int kvb_vmm_fence(int64_t group_id) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  return g->fence();
+}
+int kvb_vmm_set_async(int64_t group_id, int on) {
+  VmmGroup *g = vmm_group(group_id, true);
+  if (!g) return KVB_ERR_STATE;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_async(on != 0);
+  return 0;
+}
+int64_t kvb_vmm_pending_unmaps(int64_t group_id) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  return g->pending_unmaps();
+}
 int kvb_vmm_pool_config(int64_t group_id, int64_t max_cached) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;

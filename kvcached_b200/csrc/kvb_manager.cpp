@@ -165,7 +165,7 @@ int64_t phys_free_pages(kvb_mgr *m) {
   return pages;
 }
 
-int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n) {
+int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n, bool settle = false) {
   if (n <= 0) return 0;
   m->total_events += n;
   if (m->pending_events.size() > (1u << 22)) m->pending_events.clear();
@@ -176,14 +176,13 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n) {
     set_error("page events produced but the KV tensors of group %ld are not created", (long)m->cfg.group_id);
     return KVB_ERR_STATE;
   }
-  if (m->cfg.async_sched) {
-    // the engine may still have kernels in flight on pages about to be unmapped (page_allocator.cpp:671-673)
-    bool any_unmap = false;
-    for (int64_t i = 0; i < n; ++i) any_unmap |= (ev[i] & 1);
-    if (any_unmap) cudaDeviceSynchronize();
-  }
+  // Maps must be in place before the step's block ids are handed out; unmaps drain behind the scheduler
+  // on the group's VMM thread (KVB200_VMM_ASYNC=0: everything settles here).  With async_sched the VMM
+  // thread synchronises the device before each unmap (page_allocator.cpp:671-673).
   std::lock_guard<std::mutex> lk(g->mu);
-  int rc = g->apply_events(ev, n);
+  g->set_sync_before_unmap(m->cfg.async_sched != 0);
+  int rc = g->enqueue_events(ev, n);
+  if (rc >= 0) rc = (g->async() && !settle) ? g->wait_maps() : g->fence();
   m->phys_cached = -1;   // physical memory just changed hands
   return rc < 0 ? rc : 0;
 }
@@ -374,6 +373,10 @@ extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
   if (!m) return 0;
   cudaSetDevice(m->dev);
   if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->cfg.attach_vmm && vmm_initialized()) {
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g && g->created()) g->fence();
+  }
   if (m->d_block) cudaFree(m->d_block);
   if (m->h_in) cudaFreeHost(m->h_in);
   if (m->d_in) cudaFree(m->d_in);
@@ -416,6 +419,11 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
         if (refs[r].op < 0 || refs[r].op >= i) { set_error("free request %ld refers to request %d that does not precede it", (long)i, refs[r].op); return KVB_ERR_INVALID; }
     }
   }
+  // trim / clear / resize hand memory back on purpose: their unmaps settle before the call returns
+  bool settle = false;
+  for (int64_t i = 0; i < n_ops; ++i)
+    settle |= ops[i].kind == KVB_OP_TRIM || ops[i].kind == KVB_OP_CLEAR || ops[i].kind == KVB_OP_RESIZE ||
+              ops[i].kind == KVB_OP_PA_RESIZE;
   if (need_out > out_cap) { set_error("out_ids capacity %ld < %ld ids requested", (long)out_cap, (long)need_out); return KVB_ERR_OVERFLOW; }
   size_t b_ops = (size_t)n_ops * sizeof(kvb_op), b_ids = (size_t)n_ids * 8, b_refs = align_up((size_t)n_refs * sizeof(kvb_ref), 8);
   size_t in_bytes = b_ops + b_ids + b_refs;
@@ -478,17 +486,25 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     // page map/unmap list of this launch -> VMM engine
     if (hs->n_events > 0) {
       if (hs->n_events <= hs->ev_inline_n) {
-        rc = apply_events(m, hs->ev_inline, hs->n_events);
+        rc = apply_events(m, hs->ev_inline, hs->n_events, settle);
       } else {
         std::vector<int64_t> ev((size_t)hs->n_events);
         CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev + hs->ev_begin, (size_t)hs->n_events * 8, cudaMemcpyDeviceToHost));
-        rc = apply_events(m, ev.data(), hs->n_events);
+        rc = apply_events(m, ev.data(), hs->n_events, settle);
       }
       if (rc) return rc;
     }
     if (hs->ops_done <= 0) { set_error("step kernel made no progress at request %ld", (long)done); return KVB_ERR_STATE; }
     done += hs->ops_done;
     first = false;
+  }
+  if (settle && m->cfg.attach_vmm) {   // also when this step produced no events of its own: earlier frees may be queued
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g && g->created()) {
+      std::lock_guard<std::mutex> lk(g->mu);
+      rc = g->fence();
+      if (rc) return rc;
+    }
   }
   memcpy(res, m->h_out + o_res, b_res);
   const Summary *hs = (const Summary *)m->h_out;
@@ -875,7 +891,8 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   std::vector<int64_t> ev((size_t)hdr[1]);
   CUDA_TRY(cudaMemcpy(ev.data(), (const void *)(uintptr_t)(src + 16), (size_t)hdr[1] * 8, cudaMemcpyDeviceToHost));
   std::lock_guard<std::mutex> lk(g->mu);
-  int rc = g->apply_events(ev.data(), hdr[1]);
+  int rc = g->enqueue_events(ev.data(), hdr[1]);
+  if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
   return rc < 0 ? rc : 0;
 }
 

@@ -75,18 +75,6 @@ static const char *cu_str(CUresult r) {
       return KVB_ERR_CUDA_;                                                  \
     }                                                                        \
   } while (0)
-// driver call with wall-time attribution (slot: 0 create, 1 release, 2 unmap, 3 map, 4 setaccess)
-#define CU_TIMED(slot, call)                                                 \
-  do {                                                                       \
-    auto t0_ = std::chrono::steady_clock::now();                             \
-    CUresult r_ = (call);                                                    \
-    t_us_[slot] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0_).count(); \
-    t_n_[slot] += 1;                                                         \
-    if (r_ != CUDA_SUCCESS) {                                                \
-      set_error("%s failed: %s (%d) at %s:%d", #call, cu_str(r_), (int)r_, __FILE__, __LINE__); \
-      return KVB_ERR_CUDA_;                                                  \
-    }                                                                        \
-  } while (0)
 static constexpr int KVB_ERR_CUDA_ = -2;
 static constexpr int KVB_ERR_INVALID_ = -1;
 static constexpr int KVB_ERR_STATE_ = -3;
@@ -98,6 +86,7 @@ static std::atomic<size_t> g_va_off{0};
 
 // ------------------------------------------------------------------------------------------ group
 VmmGroup::~VmmGroup() {
+  stop_worker();   // drains what is queued, then exits
   const Driver *d = g_drv.ok ? &g_drv : nullptr;
   if (!d) return;
   cudaSetDevice(dev_);
@@ -186,6 +175,12 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   }
   handles_.assign((size_t)n_pages_ * n_sub_, 0);
   mapped_.assign((size_t)n_pages_, 0);
+  want_.assign((size_t)n_pages_, 0);
+  {
+    // KVB200_VMM_ASYNC=0: the calling thread runs the driver loop itself and every call returns settled
+    const char *e = getenv("KVB200_VMM_ASYNC");
+    async_ = !(e && e[0] == '0');
+  }
   if (pool_cap_pages_ < 0) {
     // Physical handles are recycled, not released: on this driver every cuMemCreate / cuMemRelease cycle
     // makes later cuMemUnmap / cuMemSetAccess calls slower (tools/probe_e2e.py: 0.6 ms -> 8 ms per unmap
@@ -208,126 +203,276 @@ CUdeviceptr VmmGroup::sub_addr(int64_t p, int sub) const {
   return ranges_[(size_t)l].base + (size_t)kv * (size_per_layer_ / 2) + (size_t)p * P_;
 }
 
-int VmmGroup::get_handle(CUmemGenericAllocationHandle *h) {
-  if (!pool_.empty()) {
-    *h = pool_.back();
-    pool_.pop_back();
-    return 0;
+// ------------------------------------------------------------------------------------------ engine
+// FTensor::map (ftensor.cpp:100-118) / FTensor::unmap (:120-140) for every layer / K / V range of one page.
+// Driver calls run with the engine lock RELEASED; the page is marked in flight so nobody else touches it.
+// One cuMemSetAccess per unit: on this driver (580.x, B200) a single call spanning several mappings costs
+// more than the per-unit calls it replaces (tools/vmm_stall2.cu: R=4 -> 4x, R=16 -> 67x per call), so
+// adjacent units are deliberately NOT merged.
+#define CU_TIMED_L(slot, call)                                               \
+  if (!rc) {                                                                 \
+    auto t0_ = std::chrono::steady_clock::now();                             \
+    CUresult r_ = (call);                                                    \
+    tt[slot] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0_).count(); \
+    tn[slot] += 1;                                                           \
+    if (r_ != CUDA_SUCCESS) {                                                \
+      snprintf(emsg, sizeof(emsg), "%s failed: %s (%d) at %s:%d", #call, cu_str(r_), (int)r_, __FILE__, __LINE__); \
+      rc = KVB_ERR_CUDA_;                                                    \
+    }                                                                        \
   }
-  CU_TIMED(0, g_drv.MemCreate(h, unit_, &prop_, 0));
-  n_created_++;
-  return 0;
+
+void VmmGroup::set_want(int64_t p, bool v) {
+  bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
+  if (w == v) return;
+  need_map_ -= (w && !ph);
+  need_unmap_ -= (!w && ph);
+  want_[(size_t)p] = v;
+  need_map_ += (v && !ph);
+  need_unmap_ += (!v && ph);
 }
-void VmmGroup::put_handle(CUmemGenericAllocationHandle h) {
-  if ((int64_t)pool_.size() < pool_cap_pages_ * n_sub_) {
-    pool_.push_back(h);
+void VmmGroup::set_phys(int64_t p, bool v) {
+  bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
+  if (ph == v) return;
+  need_map_ -= (w && !ph);
+  need_unmap_ -= (!w && ph);
+  mapped_[(size_t)p] = v;
+  n_mapped_ += v ? 1 : -1;
+  need_map_ += (w && !v);
+  need_unmap_ += (!w && v);
+}
+
+int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
+  // handles for a map come from the pool (under the lock); cuMemCreate only when it is empty
+  std::vector<CUmemGenericAllocationHandle> hs((size_t)n_sub_, 0);
+  int need_create = 0;
+  if (to_mapped) {
+    for (int s = 0; s < n_sub_; ++s) {
+      if (!pool_.empty()) { hs[(size_t)s] = pool_.back(); pool_.pop_back(); } else need_create++;
+    }
   } else {
-    auto t0 = std::chrono::steady_clock::now();
-    g_drv.MemRelease(h);
-    t_us_[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    t_n_[1] += 1;
-    n_released_++;
+    for (int s = 0; s < n_sub_; ++s) hs[(size_t)s] = handles_[(size_t)p * n_sub_ + s];
   }
-}
-
-// FTensor::map (ftensor.cpp:100-118) for every layer / K / V range of page p, SetAccess deferred.
-int VmmGroup::map_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched) {
-  if (p < 0 || p >= n_pages_) { set_error("map: page %ld out of range [0, %ld)", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
-  if (mapped_[(size_t)p]) return 0;   // "already mapped" is tolerated (allocator.cpp:174-177)
-  for (int s = 0; s < n_sub_; ++s) {
+  inflight_ = p;
+  inflight_to_mapped_ = to_mapped;
+  const bool sync_first = !to_mapped && sync_before_unmap_;
+  lk.unlock();
+  double tt[5] = {0, 0, 0, 0, 0};
+  int64_t tn[5] = {0, 0, 0, 0, 0};
+  char emsg[384] = "";
+  int rc = 0, created = 0;
+  ensure_device(dev_);
+  // the engine may still have kernels in flight on pages about to be unmapped (page_allocator.cpp:671-673)
+  if (sync_first) cudaDeviceSynchronize();
+  if (to_mapped) {
+    for (int s = 0; s < n_sub_ && !rc; ++s)
+      if (!hs[(size_t)s]) {
+        CU_TIMED_L(0, g_drv.MemCreate(&hs[(size_t)s], unit_, &prop_, 0));
+        if (!rc) created++; else hs[(size_t)s] = 0;
+      }
+  }
+  for (int s = 0; s < n_sub_ && !rc; ++s) {
     CUdeviceptr a = sub_addr(p, s);
-    CUmemGenericAllocationHandle h;
-    int rc = get_handle(&h);
-    if (rc) return rc;
-    CU_TIMED(2, g_drv.MemUnmap(a, unit_));
-    CU_TIMED(3, g_drv.MemMap(a, unit_, 0, h, 0));
-    handles_[(size_t)p * n_sub_ + s] = h;
-    touched.emplace_back(a, unit_);
+    CU_TIMED_L(2, g_drv.MemUnmap(a, unit_));
+    CU_TIMED_L(3, g_drv.MemMap(a, unit_, 0, to_mapped ? hs[(size_t)s] : zero_, 0));
+    CU_TIMED_L(4, g_drv.MemSetAccess(a, unit_, &access_, 1));
   }
-  mapped_[(size_t)p] = 1;
-  n_mapped_++;
+  lk.lock();
+  inflight_ = -1;
+  for (int i = 0; i < 5; ++i) { t_us_[i] += tt[i]; t_n_[i] += tn[i]; }
+  n_created_ += created;
+  if (rc) {
+    if (!werr_) { werr_ = rc; werr_msg_ = emsg; }
+    // leave the page as it was recorded; handles taken from the pool go back
+    if (to_mapped) for (auto h : hs) if (h) pool_.push_back(h);
+    set_want(p, mapped_[(size_t)p]);
+    return rc;
+  }
+  if (to_mapped) {
+    for (int s = 0; s < n_sub_; ++s) handles_[(size_t)p * n_sub_ + s] = hs[(size_t)s];
+  } else {
+    for (int s = 0; s < n_sub_; ++s) {
+      handles_[(size_t)p * n_sub_ + s] = 0;
+      if ((int64_t)pool_.size() < pool_cap_pages_ * n_sub_) {
+        pool_.push_back(hs[(size_t)s]);
+      } else {
+        auto t0 = std::chrono::steady_clock::now();
+        g_drv.MemRelease(hs[(size_t)s]);
+        t_us_[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        t_n_[1] += 1;
+        n_released_++;
+      }
+    }
+  }
+  set_phys(p, to_mapped);
   return 0;
 }
 
-// FTensor::unmap (ftensor.cpp:120-140): back to the zero page, handle to the pool.
-int VmmGroup::unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched) {
-  if (p < 0 || p >= n_pages_) { set_error("unmap: page %ld out of range [0, %ld)", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
-  if (!mapped_[(size_t)p]) return 0;
-  for (int s = 0; s < n_sub_; ++s) {
-    CUdeviceptr a = sub_addr(p, s);
-    CU_TIMED(2, g_drv.MemUnmap(a, unit_));
-    CU_TIMED(3, g_drv.MemMap(a, unit_, 0, zero_, 0));
-    put_handle(handles_[(size_t)p * n_sub_ + s]);
-    handles_[(size_t)p * n_sub_ + s] = 0;
-    touched.emplace_back(a, unit_);
+// One page transition, maps first.  A map that finds the pool empty while unmaps are pending lets one
+// unmap go first: it yields a handle without growing the footprint, and the work is due anyway.
+bool VmmGroup::process_next(Lock &lk) {
+  while (!qm_.empty()) {
+    int64_t p = qm_.front();
+    if (!(want_[(size_t)p] && !mapped_[(size_t)p])) { qm_.pop_front(); continue; }   // cancelled or done
+    if ((int64_t)pool_.size() < n_sub_ && need_unmap_ > 0) break;
+    qm_.pop_front();
+    transition(lk, p, true);
+    return true;
   }
-  mapped_[(size_t)p] = 0;
-  n_mapped_--;
+  while (!qu_.empty()) {
+    int64_t p = qu_.front();
+    qu_.pop_front();
+    if (!(!want_[(size_t)p] && mapped_[(size_t)p])) continue;
+    transition(lk, p, false);
+    return true;
+  }
+  return false;
+}
+
+void VmmGroup::worker_main() {
+  Lock lk(qmu_);
+  while (true) {
+    cv_work_.wait(lk, [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0; });
+    if (stop_ && need_map_ == 0 && need_unmap_ == 0) break;
+    bool did = process_next(lk);
+    cv_done_.notify_all();
+    if (!did) {
+      // counters say there is work but the queues are empty: cannot happen; avoid spinning if it does
+      if (stop_) break;
+      need_map_ = need_unmap_ = 0;
+      for (int64_t p = 0; p < n_pages_; ++p) {
+        bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
+        if (w && !ph) { need_map_++; qm_.push_back(p); }
+        if (!w && ph) { need_unmap_++; qu_.push_back(p); }
+      }
+    }
+  }
+  worker_running_ = false;
+  cv_done_.notify_all();
+}
+
+void VmmGroup::set_async(bool on) {
+  Lock lk(qmu_);
+  if (on == async_) return;
+  if (!on) {
+    lk.unlock();
+    stop_worker();
+    lk.lock();
+  }
+  async_ = on;
+}
+void VmmGroup::stop_worker() {
+  {
+    Lock lk(qmu_);
+    if (!worker_running_ && !worker_.joinable()) return;
+    stop_ = true;
+    cv_work_.notify_all();
+  }
+  if (worker_.joinable()) worker_.join();
+  Lock lk(qmu_);
+  stop_ = false;
+}
+
+// Inline reconciliation by the calling thread (synchronous mode, or nobody to wait for).
+int VmmGroup::drain(Lock &lk, bool maps_only) {
+  if (async_ && created_) {
+    if (!worker_running_) {
+      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
+      worker_running_ = true;
+      worker_ = std::thread([this] { worker_main(); });
+    }
+    cv_work_.notify_all();
+    // a page being unmapped right now that is wanted again does not show in need_map_ until the unmap is done
+    cv_done_.wait(lk, [&] {
+      if (werr_) return true;
+      if (need_map_ > 0) return false;
+      if (maps_only) return !(inflight_ >= 0 && !inflight_to_mapped_ && want_[(size_t)inflight_]);
+      return need_unmap_ == 0 && inflight_ < 0;
+    });
+  } else {
+    while (!werr_ && (need_map_ > 0 || (!maps_only && need_unmap_ > 0)))
+      if (!process_next(lk)) break;
+  }
+  if (werr_) {
+    int rc = werr_;
+    set_error("%s", werr_msg_.c_str());
+    werr_ = 0;
+    werr_msg_.clear();
+    return rc;
+  }
   return 0;
 }
 
-// cuMemSetAccess for every unit touched by a batch.  One call per unit: on this driver (580.x, B200) a
-// single call spanning several mappings is slower than the per-unit calls it replaces (8 units: 4.8 ms
-// against 8 x 0.19 ms, tools/probe_vmm.py), so adjacent units are deliberately NOT merged.
-int VmmGroup::set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &t) {
-  for (auto &u : t) CU_TIMED(4, g_drv.MemSetAccess(u.first, u.second, &access_, 1));
-  t.clear();
-  return 0;
+int VmmGroup::enqueue_events(const int64_t *ev, int64_t n) {
+  if (!created_) return 0;
+  if (n <= 0) return 1;
+  if (!driver()) return KVB_ERR_CUDA_;
+  Lock lk(qmu_);
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t p = ev[i] >> 1;
+    bool un = ev[i] & 1;
+    if (p < 0 || p >= n_pages_) { set_error("%s: page %ld out of range [0, %ld)", un ? "unmap" : "map", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
+    bool w = want_[(size_t)p];
+    if (w == !un) continue;   // "already mapped" / "not mapped" is tolerated (allocator.cpp:174-177, ftensor.cpp:104-107)
+    set_want(p, !un);
+    if (want_[(size_t)p] != (bool)mapped_[(size_t)p] || inflight_ == p) (un ? qu_ : qm_).push_back(p);
+    else n_elided_++;        // met its own pending opposite: nothing to do physically
+  }
+  n_map_calls_++;
+  if (async_ && (need_map_ > 0 || need_unmap_ > 0)) {
+    if (!worker_running_) {
+      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
+      worker_running_ = true;
+      worker_ = std::thread([this] { worker_main(); });
+    }
+    cv_work_.notify_all();
+  }
+  return 1;
+}
+
+int VmmGroup::wait_maps() {
+  if (!created_) return 0;
+  Lock lk(qmu_);
+  return drain(lk, true);
+}
+int VmmGroup::fence() {
+  if (!created_) return 0;
+  Lock lk(qmu_);
+  return drain(lk, false);
+}
+int64_t VmmGroup::pending_unmaps() {
+  Lock lk(qmu_);
+  return need_unmap_;
 }
 
 int VmmGroup::map_pages(const int64_t *ids, int64_t n) {
   if (!created_) return 0;
-  if (!driver()) return KVB_ERR_CUDA_;
-  ensure_device(dev_);
-  std::vector<std::pair<CUdeviceptr, size_t>> touched;
-  touched.reserve((size_t)n * n_sub_);
-  int rc = 0;
-  for (int64_t i = 0; i < n && !rc; ++i) rc = map_one(ids[i], touched);
-  int rc2 = set_access_merged(touched);
-  n_map_calls_++;
-  return rc ? rc : (rc2 ? rc2 : 1);
+  std::vector<int64_t> ev((size_t)std::max<int64_t>(n, 0));
+  for (int64_t i = 0; i < n; ++i) ev[(size_t)i] = ids[i] * 2;
+  int rc = enqueue_events(ev.data(), n);
+  if (rc < 0) return rc;
+  rc = fence();
+  return rc ? rc : 1;
 }
-
 int VmmGroup::unmap_pages(const int64_t *ids, int64_t n) {
   if (!created_) return 0;
-  if (!driver()) return KVB_ERR_CUDA_;
-  ensure_device(dev_);
-  std::vector<std::pair<CUdeviceptr, size_t>> touched;
-  touched.reserve((size_t)n * n_sub_);
-  int rc = 0;
-  for (int64_t i = 0; i < n && !rc; ++i) rc = unmap_one(ids[i], touched);
-  int rc2 = set_access_merged(touched);
+  std::vector<int64_t> ev((size_t)std::max<int64_t>(n, 0));
+  for (int64_t i = 0; i < n; ++i) ev[(size_t)i] = ids[i] * 2 + 1;
+  int rc = enqueue_events(ev.data(), n);
+  if (rc < 0) return rc;
   n_unmap_calls_++;
-  return rc ? rc : (rc2 ? rc2 : 1);
+  rc = fence();
+  return rc ? rc : 1;
 }
-
 int VmmGroup::apply_events(const int64_t *ev, int64_t n) {
   if (!created_) return 0;
-  if (n <= 0) return 1;
-  if (!driver()) return KVB_ERR_CUDA_;
-  ensure_device(dev_);
-  std::vector<std::pair<CUdeviceptr, size_t>> touched;
-  int rc = 0;
-  // Events are applied in order; SetAccess is flushed whenever a page is touched twice so that a
-  // later unmap never meets a mapping without access rights (harmless, but keeps the loop simple).
-  std::vector<int64_t> seen;
-  for (int64_t i = 0; i < n && !rc; ++i) {
-    int64_t p = ev[i] >> 1;
-    bool un = ev[i] & 1;
-    if (std::find(seen.begin(), seen.end(), p) != seen.end()) {
-      rc = set_access_merged(touched);
-      seen.clear();
-      if (rc) break;
-    }
-    seen.push_back(p);
-    rc = un ? unmap_one(p, touched) : map_one(p, touched);
-  }
-  int rc2 = set_access_merged(touched);
-  n_map_calls_++;
-  return rc ? rc : (rc2 ? rc2 : 1);
+  int rc = enqueue_events(ev, n);
+  if (rc < 0) return rc;
+  rc = fence();
+  return rc ? rc : 1;
 }
 
 void VmmGroup::pool_config(int64_t max_cached_pages) {
+  Lock lk(qmu_);
   pool_cap_pages_ = max_cached_pages;
   while ((int64_t)pool_.size() > pool_cap_pages_ * n_sub_ && g_drv.ok) {
     g_drv.MemRelease(pool_.back());
@@ -338,7 +483,10 @@ void VmmGroup::pool_config(int64_t max_cached_pages) {
 int VmmGroup::pool_prefill(int64_t n_pages) {
   if (!created_) { set_error("pool_prefill: tensors not created"); return KVB_ERR_STATE_; }
   if (!driver()) return KVB_ERR_CUDA_;
+  int rc = fence();
+  if (rc) return rc;
   cudaSetDevice(dev_);
+  Lock lk(qmu_);
   int64_t want = std::min<int64_t>(n_pages, pool_cap_pages_) * n_sub_;
   while ((int64_t)pool_.size() < want) {
     CUmemGenericAllocationHandle h;
@@ -348,8 +496,14 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
   }
   return 0;
 }
-int64_t VmmGroup::pooled_pages() { return n_sub_ ? (int64_t)pool_.size() / n_sub_ : 0; }
+// pages' worth of physical memory this group holds without a mapping that is wanted: pooled handles plus
+// pages whose unmap is still queued (their handles come back to the pool)
+int64_t VmmGroup::pooled_pages() {
+  Lock lk(qmu_);
+  return n_sub_ ? (int64_t)pool_.size() / n_sub_ + need_unmap_ : 0;
+}
 int64_t VmmGroup::pool_release(int64_t n_pages) {
+  Lock lk(qmu_);
   int64_t n = 0;
   while (n < n_pages * n_sub_ && !pool_.empty() && g_drv.ok) {
     g_drv.MemRelease(pool_.back());
@@ -361,10 +515,12 @@ int64_t VmmGroup::pool_release(int64_t n_pages) {
 }
 
 void VmmGroup::timing(double *out10) {
+  Lock lk(qmu_);
   for (int i = 0; i < 5; ++i) { out10[i] = t_us_[i]; out10[5 + i] = (double)t_n_[i]; }
 }
 
 void VmmGroup::stats(int64_t *s) {
+  Lock lk(qmu_);
   s[0] = n_mapped_;
   s[1] = (int64_t)pool_.size();
   s[2] = n_created_;
@@ -375,6 +531,8 @@ void VmmGroup::stats(int64_t *s) {
   s[7] = (int64_t)unit_ * n_sub_;
 }
 int64_t VmmGroup::mapped_pages(int64_t *out, int64_t cap) {
+  if (created_) fence();   // inspection sees the settled state
+  Lock lk(qmu_);
   int64_t n = 0;
   for (int64_t p = 0; p < n_pages_; ++p)
     if (mapped_[(size_t)p]) {
@@ -391,6 +549,7 @@ int VmmGroup::raw_control(int64_t n_pages, int64_t iters, double *map_us, double
   const Driver *d = driver();
   if (!d) return KVB_ERR_CUDA_;
   if (!created_) { set_error("raw_control: tensors not created"); return KVB_ERR_STATE_; }
+  fence();   // driver VMM calls of two threads do not overlap, they collide
   cudaSetDevice(dev_);
   size_t n_units = (size_t)n_pages * n_sub_;
   size_t bytes = n_units * unit_;

@@ -6,10 +6,13 @@
 
 #include <cuda.h>
 
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace kvb {
@@ -48,10 +51,26 @@ class VmmGroup {
   bool created() const { return created_; }
   const std::vector<VmmRange> &ranges() const { return ranges_; }
 
-  // page-id addressed batch ops (each runs the whole driver loop over all layers' ranges)
+  // page-id addressed batch ops (each runs the whole driver loop over all layers' ranges); synchronous:
+  // they return when the physical state equals the requested one
   int map_pages(const int64_t *ids, int64_t n);
   int unmap_pages(const int64_t *ids, int64_t n);
-  int apply_events(const int64_t *events, int64_t n);   // page*2 + is_unmap, in order
+  int apply_events(const int64_t *events, int64_t n);   // page*2 + is_unmap, in order; = enqueue + fence
+
+  // ---- asynchronous engine -----------------------------------------------------------------------
+  // Events only change the WANTED state of a page; one worker thread (driver VMM calls do not overlap
+  // across threads on this stack, tools/vmm_stall2.cu) reconciles physical with wanted state, maps
+  // before unmaps.  A map that meets its own page's pending unmap (or the reverse) cancels it: no driver
+  // call at all.  wait_maps() is what a scheduler step needs before its block ids are usable; unmaps
+  // drain in the background (the reference's prealloc thread hides map latency the same way,
+  // page_allocator.cpp:524-617, but changes the bookkeeping; this does not).
+  int enqueue_events(const int64_t *events, int64_t n);
+  int wait_maps();    // every wanted mapping is physically in place
+  int fence();        // physical state == wanted state
+  void set_async(bool on);
+  bool async() const { return async_; }
+  void set_sync_before_unmap(bool on) { sync_before_unmap_ = on; }
+  int64_t pending_unmaps();
   // reference byte offsets (page_allocator.cpp:619-631) -> page ids
   int64_t offset_to_page(int64_t off) const { return off / (int64_t)(contiguous_ ? unit_ : P_); }
 
@@ -68,15 +87,18 @@ class VmmGroup {
   int64_t num_kv() const { return nkv_; }
   int raw_control(int64_t n_pages, int64_t iters, double *map_us, double *unmap_us);
 
-  std::mutex mu;
+  std::mutex mu;   // serialises API callers (create, pool policy, inspection); the engine state has its own lock
 
  private:
-  int map_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched);
-  int unmap_one(int64_t p, std::vector<std::pair<CUdeviceptr, size_t>> &touched);
-  int set_access_merged(std::vector<std::pair<CUdeviceptr, size_t>> &touched);
+  using Lock = std::unique_lock<std::mutex>;
+  bool process_next(Lock &lk);              // one page transition; lock held on entry and exit, released around driver calls
+  int transition(Lock &lk, int64_t p, bool to_mapped);
+  void set_want(int64_t p, bool v);
+  void set_phys(int64_t p, bool v);
+  int drain(Lock &lk, bool maps_only);
+  void worker_main();
+  void stop_worker();
   CUdeviceptr sub_addr(int64_t p, int sub) const;
-  int get_handle(CUmemGenericAllocationHandle *h);
-  void put_handle(CUmemGenericAllocationHandle h);
 
   int dev_;
   size_t P_;
@@ -94,7 +116,18 @@ class VmmGroup {
   CUmemGenericAllocationHandle zero_ = 0;
   bool have_zero_ = false;
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
-  std::vector<uint8_t> mapped_;
+  std::vector<uint8_t> mapped_;   // physical state
+  std::vector<uint8_t> want_;     // state after every event received so far
+  std::deque<int64_t> qm_, qu_;   // pages whose wanted state may differ from the physical one (maps / unmaps)
+  int64_t need_map_ = 0, need_unmap_ = 0, inflight_ = -1;
+  bool inflight_to_mapped_ = false;
+  std::mutex qmu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::thread worker_;
+  bool worker_running_ = false, stop_ = false, async_ = false, sync_before_unmap_ = false;
+  int werr_ = 0;
+  std::string werr_msg_;
+  int64_t n_elided_ = 0;
   std::vector<CUmemGenericAllocationHandle> pool_;
   int64_t pool_cap_pages_ = -1;   // pages' worth of handles kept after unmap; -1 = default chosen in create()
   CUmemAllocationProp prop_{};

@@ -97,6 +97,23 @@ def mapped_pages(group_id: int = 0) -> List[int]:
     return buf[:n].tolist()
 
 
+def fence(group_id: int = 0) -> None:
+    """Wait until the group's VMM thread has applied every queued map AND unmap (kvb_vmm_fence)."""
+    _lib.check(_lib.load().kvb_vmm_fence(group_id), "vmm fence")
+
+
+def wait_maps(group_id: int = 0) -> None:
+    _lib.check(_lib.load().kvb_vmm_wait_maps(group_id), "vmm wait_maps")
+
+
+def set_async(on: bool, group_id: int = 0) -> None:
+    _lib.check(_lib.load().kvb_vmm_set_async(group_id, 1 if on else 0), "vmm set_async")
+
+
+def pending_unmaps(group_id: int = 0) -> int:
+    return int(_lib.check(_lib.load().kvb_vmm_pending_unmaps(group_id)))
+
+
 def vmm_stats(group_id: int = 0) -> Dict[str, int]:
     s = np.zeros(8, dtype=np.int64)
     _lib.check(_lib.load().kvb_vmm_stats(group_id, s.ctypes.data_as(_lib.p_i64)))

@@ -86,6 +86,50 @@ def test_map_unmap_by_offsets_is_idempotent(kvcached_fixture):
     assert st["pooled_handles"] == 2 and st["handles_created"] >= 3   # zero page + 2, parked in the pool
 
 
+@pytest.mark.parametrize("use_thread", [True, False])
+def test_async_engine_settles_to_the_wanted_state(kvcached_fixture, use_thread):
+    """Events only move the wanted state; the VMM thread (or the caller, KVB200_VMM_ASYNC=0) reconciles.
+    Opposite events on one page cancel; wait_maps() guarantees every wanted page is backed; fence() settles."""
+    import torch
+    f = kvcached_fixture
+    lib = _lib.load()
+    vmm_ops.set_async(use_thread)
+    L, bs, cell = f["L"], f["bs"], f["cell"]
+    kv = f["flat"].view(torch.int16).view(f["blocks"], L, 2, bs, cell // 2)
+    bpp = PAGE // (bs * cell)
+    rng = np.random.default_rng(5)
+    n_pages = 32
+    want = np.zeros(n_pages, dtype=bool)
+    created0 = vmm_ops.vmm_stats()["handles_created"]
+    for rnd in range(40):
+        k = int(rng.integers(1, 12))
+        pages = rng.integers(0, n_pages, size=k)
+        ev = []
+        for p in pages:                       # alternate per page, like the bookkeeping does
+            ev.append(int(p) * 2 + (1 if want[p] else 0))
+            want[p] = ~want[p]
+        a = np.asarray(ev, dtype=np.int64)
+        assert lib.kvb_vmm_enqueue_page_events(0, a.ctypes.data_as(_lib.p_i64), a.size) == 1, _lib.last_error()
+        vmm_ops.wait_maps()
+        for p in np.nonzero(want)[0][:4]:     # wanted pages are usable right after wait_maps()
+            kv[int(p) * bpp, 0, 0, 0, 0] = 1000 + int(p)
+        torch.cuda.synchronize()
+        for p in np.nonzero(want)[0][:4]:
+            assert int(kv[int(p) * bpp, 0, 0, 0, 0]) == 1000 + int(p)
+    vmm_ops.fence()
+    assert vmm_ops.pending_unmaps() == 0
+    assert vmm_ops.mapped_pages() == np.nonzero(want)[0].tolist()
+    for p in np.nonzero(~want)[0][:4]:        # settled unmapped pages read the zero page again
+        assert int(kv[int(p) * bpp, 0, 0, 0, 1]) == 0
+    # a page unmapped and mapped again before the thread got to it costs nothing
+    st = vmm_ops.vmm_stats()
+    assert st["handles_created"] - created0 <= n_pages
+    ids = np.arange(n_pages, dtype=np.int64)
+    assert lib.kvb_unmap_pages(0, ids.ctypes.data_as(_lib.p_i64), ids.size) == 1
+    assert vmm_ops.mapped_pages() == []
+    vmm_ops.set_async(True)
+
+
 @pytest.mark.parametrize("layout", ["vllm_contig", "sglang_contig", "per_layer", "mla"])
 @pytest.mark.parametrize("T_tokens", [1, 37, 4096])
 def test_kv_scatter_gather_bit_exact(layout, T_tokens):

@@ -26,10 +26,10 @@ if which in ("step", "both"):
 if which in ("kv", "both"):
     PAGE = 2 << 20
     vmm_ops.init_kvcached("cuda:0", PAGE, True)
-    L, bs, cell, blocks = 32, 16, 2048, 4096
+    L, bs, cell, blocks = 32, 16, 2048, max(4096, int(os.environ.get("NCU_T", "16384")) // 16 + 64)
     (rng_,) = vmm_ops.create_kv_tensors_raw(blocks * bs * cell * 2, L, 2)
     mg = KVCacheManager(blocks, bs, cell, L)
-    Tn = 16384
+    Tn = int(os.environ.get("NCU_T", "16384"))
     ids = np.asarray(mg.alloc(Tn // bs), dtype=np.int64)
     slots = torch.from_numpy(np.random.default_rng(0).permutation((ids[:, None] * bs + np.arange(bs)).reshape(-1))).cuda()
     k = torch.empty((L, Tn, cell // 2), dtype=torch.int16, device="cuda").random_()
