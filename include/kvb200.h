@@ -171,6 +171,8 @@ typedef struct kvb_mgr_config {
   int32_t device_index;        /* <0 = device of kvb_init, else cudaGetDevice                   */
   int32_t world_size;          /* >1: events are also exported for the TP broadcast             */
   double gpu_utilization;      /* <=0 = env KVCACHED_GPU_UTILIZATION or 0.95                    */
+  int64_t max_cached_blocks;   /* prefix-cache LRU cap: -1 unlimited, 0 evict on free, >0 cap (patches.py:247-257);
+                                  only the KVB_OP_PIN_* requests read it                                     */
 } kvb_mgr_config;
 
 /* one request of a batched step */
@@ -194,6 +196,16 @@ typedef struct kvb_op {
 #define KVB_OP_FREE_PAGES 11    /* PageAllocator.free_pages      page_allocator.cpp:264-310  */
 #define KVB_OP_PA_RESIZE 12     /* PageAllocator.resize          page_allocator.cpp:312-401  */
 #define KVB_OP_RESET_ORDER 13   /* PageAllocator.reset_free_page_order page_allocator.cpp:703-709 */
+/* prefix-cache pinning — ElasticBlockPool, kvcached/integration/vllm/patches.py:308-614.  Reference counts, the
+ * "has a cache key" flag and the insertion-ordered LRU of evictable blocks live on the device; the hash -> block
+ * dictionary stays with the caller (hashes are host data), which learns evicted ids from the result. */
+#define KVB_OP_PIN_NEW 14       /* get_new_blocks(n): evict the oldest evictable blocks if short, alloc n, ref=1   :483-517 */
+#define KVB_OP_PIN_TOUCH 15     /* touch(blocks): ref += 1, leave the evictable pool                                :519-533 */
+#define KVB_OP_PIN_MARK 16      /* cache_full_blocks: the listed blocks received a cache key                        :396-465 */
+#define KVB_OP_PIN_FREE 17      /* free_blocks(ordered): ref -= 1; at 0 keyed blocks join the LRU, others are freed;
+                                   then the LRU is cut back to max_cached_blocks                                    :535-568 */
+#define KVB_OP_PIN_EVICT 18     /* evict_blocks(ids): drop the keys; evictable ones are freed                       :570-588 */
+#define KVB_OP_PIN_RESET 19     /* reset_prefix_cache(): free every evictable block, drop every key                 :590-603 */
 
 /* a slice of an earlier request's result: ids = result(op)[lo:hi] (Python slice semantics, clipped) */
 typedef struct kvb_ref {
@@ -209,6 +221,8 @@ typedef struct kvb_res {
   int32_t n;       /* ids produced (ALLOC) / ids consumed (FREE)              */
   int64_t off;     /* offset of the first id in the id output buffer          */
   int64_t avail;   /* available_size() right after the request                */
+  int64_t aux;     /* PIN_NEW / PIN_FREE: number of evicted block ids; they sit in the id output buffer directly
+                      before `off` (PIN_NEW) or at `off` (PIN_FREE) so the caller can drop their cache keys     */
 } kvb_res;
 
 /* counters of the device state as of the last completed launch */
@@ -219,6 +233,7 @@ typedef struct kvb_mgr_stats {
   int64_t blocks_per_page, block_mem_size, page_size, mem_size;
   int64_t bad_frees, unknown_page_frees, launches, events;
   int64_t h2d_bytes, d2h_bytes;   /* bytes kvb_mgr_step copied host->device / device->host so far */
+  int64_t num_evictable_blocks;   /* len(_evictable_blocks) of the prefix-cache LRU (patches.py:605-606) */
 } kvb_mgr_stats;
 
 /* KVCacheManager.__init__ + _post_init — kv_cache_manager.py:60-243.  Returns NULL on error
@@ -269,7 +284,9 @@ int kvb_mgr_trace_reset_cursor(kvb_mgr *m);
 
 /* ---- state inspection (tests, debugging, the consistency audit) ---------------------------- */
 /* which: 0 free_page_list, 1 reserved_page_list, 2 reclaimed_page_list, 3 avail_pages (insertion
- * order), 4 full_pages (ascending), 5 reserved_blocks, 6 mapped pages per the bookkeeping (ascending) */
+ * order), 4 full_pages (ascending), 5 reserved_blocks, 6 mapped pages per the bookkeeping (ascending),
+ * 7 evictable blocks in LRU order (oldest first), 8 keyed blocks (ascending), 9 (block, ref_cnt) pairs of every
+ * block with ref_cnt != 0 (ascending, flattened) */
 int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_t cap);
 int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t page_id, int64_t *out, int64_t cap);
 /* drains the ordered page event log (page*2 + is_unmap) accumulated since the last drain */

@@ -21,7 +21,7 @@ class MgrConfig(C.Structure):          # kvb_mgr_config
                 ("min_reserved_pages", i64), ("max_reserved_pages", i64),
                 ("reserve_null_block", i32), ("async_sched", i32), ("contiguous_layout", i32),
                 ("attach_vmm", i32), ("device_index", i32), ("world_size", i32),
-                ("gpu_utilization", f64)]
+                ("gpu_utilization", f64), ("max_cached_blocks", i64)]
 
 
 class Op(C.Structure):                 # kvb_op
@@ -33,7 +33,7 @@ class Ref(C.Structure):                # kvb_ref
 
 
 class Res(C.Structure):                # kvb_res
-    _fields_ = [("status", i32), ("n", i32), ("off", i64), ("avail", i64)]
+    _fields_ = [("status", i32), ("n", i32), ("off", i64), ("avail", i64), ("aux", i64)]
 
 
 class MgrStats(C.Structure):           # kvb_mgr_stats
@@ -42,7 +42,8 @@ class MgrStats(C.Structure):           # kvb_mgr_stats
         "num_avail_blocks", "num_reserved_blocks", "in_shrink", "target_num_blocks",
         "num_avail_pages", "num_full_pages", "num_mapped_pages", "has_null_block",
         "blocks_per_page", "block_mem_size", "page_size", "mem_size",
-        "bad_frees", "unknown_page_frees", "launches", "events", "h2d_bytes", "d2h_bytes")]
+        "bad_frees", "unknown_page_frees", "launches", "events", "h2d_bytes", "d2h_bytes",
+        "num_evictable_blocks")]
 
 
 class KvLayout(C.Structure):           # kvb_kv_layout
@@ -53,6 +54,7 @@ class KvLayout(C.Structure):           # kvb_kv_layout
 
 OP_ALLOC, OP_FREE_IDS, OP_FREE_REF, OP_RESIZE, OP_TRIM, OP_TRY_RESERVE, OP_FREE_RESERVED, OP_AVAIL, OP_CLEAR, \
     OP_ALLOC_PAGE, OP_FREE_PAGES, OP_PA_RESIZE, OP_RESET_ORDER = range(1, 14)
+OP_PIN_NEW, OP_PIN_TOUCH, OP_PIN_MARK, OP_PIN_FREE, OP_PIN_EVICT, OP_PIN_RESET = range(14, 20)
 ST_OK, ST_FALSE, ST_NONE, ST_NO_PAGES, ST_ASSERT, ST_NULL_BLOCK, ST_CAPACITY = 1, 0, -1, -2, -3, -4, -5
 
 # name -> (restype, argtypes): every symbol include/kvb200.h declares

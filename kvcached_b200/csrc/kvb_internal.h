@@ -36,6 +36,9 @@ enum Sc : int {
   SC_UNKNOWN_FREES, // pages named by free() that are not in use (the reference logs and skips)
   SC_PHYS,          // physical page budget of the running launch
   SC_LAUNCHES,
+  SC_LRU_HEAD,      // evictable LRU: first ring index that may be live
+  SC_LRU_TAIL,      // one past the last entry
+  SC_LRU_COUNT,     // len(_evictable_blocks)
   SC_COUNT = 32
 };
 
@@ -68,6 +71,15 @@ struct DevState {
   int32_t *g_dist, *g_ord, *g_cnt, *g_next, *g_bkt, *g_ptf;  // large-call fallbacks of the smem tables
   int32_t g_bkt_cap;
   int64_t f_cap;                // capacity of fids / fpage
+  // prefix-cache pinning (ElasticBlockPool, integration/vllm/patches.py:308-614)
+  int32_t *pin_ref;             // [num_blocks] KVCacheBlock.ref_cnt
+  uint32_t *pin_keyed;          // bit per block: _block_id_to_key has the block
+  int32_t *lru;                 // _evictable_blocks in insertion order, -1 = tombstone
+  int32_t *lru_pos;             // [num_blocks] ring index or -1
+  int32_t *pin_last;            // [num_blocks] scratch: last list index naming the block (-1 idle)
+  int32_t *pin_in;              // [f_cap] scratch: the running PIN request's ids as int32 (-1 = not a block)
+  int32_t lru_cap;
+  int32_t max_cached;           // -1 unlimited, 0 evict on free, > 0 cap
   int64_t *ev;                  // page event log: page*2 + is_unmap
   const uint64_t *primes;       // libstdc++ __prime_list
 };

@@ -406,7 +406,7 @@ __device__ void alloc_walk(const DevState &c, Smem &s, const LaunchArgs &a, int 
       if (m.nseg >= SEG_CAP - 2) goto round_full;
       const kvb_op &o = s.ops[m.op - chunk_base];
       int64_t need = o.n;
-      kvb_res r;
+      kvb_res r{};
       if (avail_size(c, sc) < need || need < 0) {   // -> None, state unchanged
         r.status = to_reserved ? KVB_ST_FALSE : KVB_ST_NONE;
         r.n = 0;
@@ -526,7 +526,7 @@ __device__ void alloc_walk(const DevState &c, Smem &s, const LaunchArgs &a, int 
     }
     {
       // request finished (or failed)
-      kvb_res r;
+      kvb_res r{};
       r.status = m.failed ? KVB_ST_NO_PAGES : KVB_ST_OK;
       r.n = m.failed ? 0 : (int32_t)m.req_n;
       r.off = m.req_off;
@@ -690,7 +690,7 @@ __device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, i
   }
   // ---- per-request results ----
   if (tid < R) {
-    kvb_res r;
+    kvb_res r{};
     r.status = KVB_ST_OK;
     r.n = n_i;
     r.off = cursor + off_i;
@@ -1212,6 +1212,199 @@ __device__ void clear_all(const DevState &c, Smem &s, int order_only) {
   __syncthreads();
 }
 
+
+// ==================================================================================== prefix-cache pinning
+// ElasticBlockPool (kvcached/integration/vllm/patches.py:308-614) on the device: per-block ref_cnt, a bit per
+// block for "has a cache key" (_block_id_to_key), and _evictable_blocks — an insertion-ordered dict used as an
+// LRU — as an append-only ring with tombstones plus each block's ring position (the avail_pages idiom).
+
+// Compact the LRU ring (drop tombstones, keep order) when appending `room` more entries would overflow it.
+__device__ void lru_compact(const DevState &c, Smem &s, int room) {
+  int64_t *sc = s.sc;
+  const int head = (int)sc[SC_LRU_HEAD], tail = (int)sc[SC_LRU_TAIL];
+  if (tail + room <= c.lru_cap) return;   // uniform
+  int base = 0;
+  for (int i0 = head; i0 < tail; i0 += NT) {
+    int i = i0 + threadIdx.x;
+    int e = (i < tail) ? c.lru[i] : -1;
+    int tot;
+    int r = block_rank(e >= 0, s.wtot, &tot);
+    if (e >= 0) { c.lru[base + r] = e; c.lru_pos[e] = base + r; }   // lands at or below the chunk just read
+    base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { sc[SC_LRU_HEAD] = 0; sc[SC_LRU_TAIL] = base; }
+  __syncthreads();
+}
+
+// _evict_blocks_from_pool(k) (patches.py:467-481): pop the k oldest evictable blocks and drop their keys.
+// Their ids go to c.fids[0..k) — the argument of the ONE kv_cache_manager.free() that follows — and to
+// dst[0..k) for the caller.  Requires k <= SC_LRU_COUNT.
+__device__ void lru_pop_oldest(const DevState &c, Smem &s, int k, int64_t *dst) {
+  int64_t *sc = s.sc;
+  int head = (int)sc[SC_LRU_HEAD];
+  const int tail = (int)sc[SC_LRU_TAIL];
+  int got = 0;
+  while (got < k && head < tail) {   // uniform
+    const int i = head + threadIdx.x;
+    const int e = (i < tail) ? c.lru[i] : -1;
+    int tot;
+    const int r = block_rank(e >= 0, s.wtot, &tot);
+    if (e >= 0 && got + r < k) {
+      c.fids[got + r] = e;
+      if (dst) dst[got + r] = e;
+      c.lru[i] = -1;
+      c.lru_pos[e] = -1;
+      atomicAnd(&c.pin_keyed[e >> 5], ~(1u << (e & 31)));
+    }
+    if (got + tot <= k) {            // every live entry of the chunk was taken
+      head = head + NT < tail ? head + NT : tail;
+      got += tot;
+    } else {                         // the entry of rank k-got-1 is the last one taken
+      if (e >= 0 && got + r == k - 1) s.misc[MI_K] = i + 1;
+      __syncthreads();
+      head = s.misc[MI_K];
+      got = k;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    sc[SC_LRU_HEAD] = head;
+    sc[SC_LRU_COUNT] -= got;
+    if (sc[SC_LRU_COUNT] == 0) { sc[SC_LRU_HEAD] = 0; sc[SC_LRU_TAIL] = 0; }
+  }
+  __syncthreads();
+}
+
+// CTA-wide sum of a per-thread count (uniform result)
+__device__ __forceinline__ int block_sum(int v, int32_t *wtot) {
+  int tot;
+  block_exscan(v, wtot, &tot);
+  return tot;
+}
+
+// Stage the id list of a PIN request as int32 (-1 = not a block id) out of the caller's id pool.
+__device__ __forceinline__ void pin_stage(const DevState &c, const LaunchArgs &a, int64_t arg, int n, int32_t *dst) {
+  for (int j = threadIdx.x; j < n; j += NT) {
+    int64_t id = a.ids[arg + j];
+    dst[j] = (id >= 0 && id < c.num_blocks) ? (int32_t)id : -1;
+  }
+}
+
+// touch(blocks) (patches.py:519-533): ref_cnt += 1 per occurrence; the block leaves the evictable pool.
+__device__ void pin_touch(const DevState &c, Smem &s, const LaunchArgs &a, int64_t arg, int n) {
+  int removed = 0;
+  for (int j = threadIdx.x; j < n; j += NT) {
+    int64_t id = a.ids[arg + j];
+    if (id < 0 || id >= c.num_blocks) continue;
+    atomicAdd(&c.pin_ref[id], 1);
+    int pos = atomicExch(&c.lru_pos[id], -1);
+    if (pos >= 0) { c.lru[pos] = -1; removed++; }
+  }
+  int tot = block_sum(removed, s.wtot);
+  if (threadIdx.x == 0) {
+    s.sc[SC_LRU_COUNT] -= tot;
+    if (s.sc[SC_LRU_COUNT] == 0) { s.sc[SC_LRU_HEAD] = 0; s.sc[SC_LRU_TAIL] = 0; }
+  }
+  __syncthreads();
+}
+
+// free_blocks(ordered_blocks) with caching on (patches.py:546-568).  Sequential semantics: ref_cnt -= 1 per
+// occurrence; the occurrence that reaches 0 (= the LAST occurrence of that block in the list) either appends
+// the block to the LRU (keyed) or to the list handed to kv_cache_manager.free (not keyed), both in list order;
+// then the LRU is cut back to max_cached_blocks (oldest first, a second free call).
+// Returns the number of blocks evicted by the cap; their ids are written to dst.
+__device__ int pin_free(const DevState &c, Smem &s, const LaunchArgs &a, int64_t arg, int n, int64_t *dst) {
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+  lru_compact(c, s, n);
+  pin_stage(c, a, arg, n, c.pin_in);
+  __syncthreads();
+  for (int j = tid; j < n; j += NT) {
+    int id = c.pin_in[j];
+    if (id >= 0) { atomicMax(&c.pin_last[id], j); atomicSub(&c.pin_ref[id], 1); }
+  }
+  __syncthreads();
+  const int tail = (int)sc[SC_LRU_TAIL];
+  int nk = 0, nu = 0;
+  for (int j0 = 0; j0 < n; j0 += NT) {
+    int j = j0 + tid;
+    int id = (j < n) ? c.pin_in[j] : -1;
+    bool last = id >= 0 && c.pin_last[id] == j;
+    bool zero = last && c.pin_ref[id] == 0;
+    bool keyed = zero && ((c.pin_keyed[id >> 5] >> (id & 31)) & 1u);
+    int tk, tu;
+    int rk = block_rank(zero && keyed, s.wtot, &tk);
+    int ru = block_rank(zero && !keyed, s.wtot2, &tu);
+    if (zero && keyed) { c.lru[tail + nk + rk] = id; c.lru_pos[id] = tail + nk + rk; }
+    if (zero && !keyed) c.fids[nu + ru] = id;
+    if (last) c.pin_last[id] = -1;
+    nk += tk;
+    nu += tu;
+  }
+  if (tid == 0) { sc[SC_LRU_TAIL] = tail + nk; sc[SC_LRU_COUNT] += nk; }
+  __syncthreads();
+  if (nu > 0) free_core(c, s, a, nu, 0);
+  int k = 0;
+  if (c.max_cached >= 0 && sc[SC_LRU_COUNT] > c.max_cached) {
+    k = (int)(sc[SC_LRU_COUNT] - c.max_cached);
+    __syncthreads();
+    lru_pop_oldest(c, s, k, dst);
+    free_core(c, s, a, k, 0);
+  }
+  return k;
+}
+
+// evict_blocks(block_ids) (patches.py:570-588), ids in the caller's set-iteration order: keys are dropped;
+// blocks sitting in the LRU are removed from it and freed (one free call, list order).
+__device__ void pin_evict(const DevState &c, Smem &s, const LaunchArgs &a, int64_t arg, int n) {
+  const int tid = threadIdx.x;
+  pin_stage(c, a, arg, n, c.pin_in);
+  __syncthreads();
+  int nf = 0;
+  for (int j0 = 0; j0 < n; j0 += NT) {
+    int j = j0 + tid;
+    int id = (j < n) ? c.pin_in[j] : -1;
+    bool inl = false;
+    if (id >= 0) {
+      atomicAnd(&c.pin_keyed[id >> 5], ~(1u << (id & 31)));
+      int pos = c.lru_pos[id];
+      if (pos >= 0) { c.lru[pos] = -1; c.lru_pos[id] = -1; inl = true; }
+    }
+    int tot;
+    int r = block_rank(inl, s.wtot, &tot);
+    if (inl) c.fids[nf + r] = id;
+    nf += tot;
+  }
+  if (tid == 0) {
+    s.sc[SC_LRU_COUNT] -= nf;
+    if (s.sc[SC_LRU_COUNT] == 0) { s.sc[SC_LRU_HEAD] = 0; s.sc[SC_LRU_TAIL] = 0; }
+  }
+  __syncthreads();
+  if (nf > 0) free_core(c, s, a, nf, 0);
+}
+
+// reset_prefix_cache() (patches.py:590-603): every evictable block is freed (LRU order, one call), every key dropped.
+__device__ void pin_reset(const DevState &c, Smem &s, const LaunchArgs &a) {
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+  const int head = (int)sc[SC_LRU_HEAD], tail = (int)sc[SC_LRU_TAIL];
+  int nf = 0;
+  for (int i0 = head; i0 < tail; i0 += NT) {
+    int i = i0 + tid;
+    int e = (i < tail) ? c.lru[i] : -1;
+    int tot;
+    int r = block_rank(e >= 0, s.wtot, &tot);
+    if (e >= 0) { c.fids[nf + r] = e; c.lru_pos[e] = -1; }
+    nf += tot;
+  }
+  const int64_t nwords = (c.num_blocks + 31) / 32;
+  for (int64_t i = tid; i < nwords; i += NT) c.pin_keyed[i] = 0;
+  if (tid == 0) { sc[SC_LRU_HEAD] = 0; sc[SC_LRU_TAIL] = 0; sc[SC_LRU_COUNT] = 0; }
+  __syncthreads();
+  if (nf > 0) free_core(c, s, a, nf, 0);
+}
+
 }  // namespace
 
 // ==================================================================================== the step kernel
@@ -1252,7 +1445,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         for (int j = tid; j < o.n; j += NT) c.fids[j] = a.ids[o.arg + j];
         __syncthreads();
         free_core(c, s, a, o.n, 1);
-        if (tid == 0) { kvb_res r; r.status = KVB_ST_OK; r.n = s.misc[MI_D]; r.off = 0; r.avail = 0; a.res[op] = r; }
+        if (tid == 0) { kvb_res r{}; r.status = KVB_ST_OK; r.n = s.misc[MI_D]; r.off = 0; r.avail = 0; a.res[op] = r; }
         op++;
         continue;
       }
@@ -1297,7 +1490,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           if (!too_many) free_core(c, s, a, n, 0);
           if (tid == 0) {
             if (o.kind == KVB_OP_FREE_RESERVED) { sc[SC_NRB] = 0; sc[SC_RB_HEAD] = 0; }
-            kvb_res r; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           __syncthreads();
@@ -1306,7 +1499,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         }
         case KVB_OP_RESIZE: {   // KVCacheManager.resize, kv_cache_manager.py:381-401
           if (tid == 0) {
-            kvb_res r; r.n = 0; r.off = 0;
+            kvb_res r{}; r.n = 0; r.off = 0;
             int cap_err = 0;
             if (pa_resize(c, sc, o.arg, &cap_err)) {
               if (sc[SC_INSHRINK]) { sc[SC_INSHRINK] = 0; sc[SC_TARGET] = -1; }
@@ -1329,7 +1522,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         }
         case KVB_OP_PA_RESIZE: {
           if (tid == 0) {
-            kvb_res r; r.n = 0; r.off = 0;
+            kvb_res r{}; r.n = 0; r.off = 0;
             int cap_err = 0;
             r.status = pa_resize(c, sc, o.arg, &cap_err) ? KVB_ST_OK : (cap_err ? KVB_ST_CAPACITY : KVB_ST_FALSE);
             r.avail = avail_size(c, sc);
@@ -1342,7 +1535,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         case KVB_OP_TRIM: {
           if (tid == 0) {
             pa_trim(c, sc);
-            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           __syncthreads();
@@ -1351,7 +1544,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         }
         case KVB_OP_AVAIL: {
           if (tid == 0) {
-            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           op++;
@@ -1361,7 +1554,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           // free_reserved(); free_pages(all); trim(); reset_free_page_order(); counters = 0
           clear_all(c, s, 0);
           if (tid == 0) {
-            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           __syncthreads();
@@ -1371,7 +1564,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         case KVB_OP_RESET_ORDER: {
           clear_all(c, s, 1);
           if (tid == 0) {
-            kvb_res r; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           __syncthreads();
@@ -1380,7 +1573,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         }
         case KVB_OP_ALLOC_PAGE: {   // PageAllocator::alloc_page, page_allocator.cpp:161-237
           if (tid == 0) {
-            kvb_res r; r.n = 0; r.off = -1;
+            kvb_res r{}; r.n = 0; r.off = -1;
             if (sc[SC_RL_SIZE] > 0) {
               r.off = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
               sc[SC_NFREE] -= 1;
@@ -1426,7 +1619,75 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
               }
               done++;
             }
-            kvb_res r; r.status = KVB_ST_OK; r.n = done; r.off = 0; r.avail = avail_size(c, sc);
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = done; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_PIN_NEW: {   // get_new_blocks(n), patches.py:483-517
+          const int n = o.n;
+          int64_t evicted = 0;
+          int st = KVB_ST_NONE;
+          if (n >= 0 && (int64_t)n <= avail_size(c, sc) + sc[SC_LRU_COUNT]) {
+            for (int it = 0; it < 2; ++it) {
+              const int64_t A = avail_size(c, sc);
+              if (A < n && sc[SC_LRU_COUNT] > 0) {
+                const int k = (int)((n - A) < sc[SC_LRU_COUNT] ? (n - A) : sc[SC_LRU_COUNT]);
+                __syncthreads();
+                lru_pop_oldest(c, s, k, a.out_ids + sc[SC_OUT_CURSOR]);
+                if (tid == 0) sc[SC_OUT_CURSOR] += k;
+                __syncthreads();
+                free_core(c, s, a, k, 0);
+                evicted += k;
+              }
+              if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
+              __syncthreads();
+              st = a.res[op].status;
+              if (st != KVB_ST_NONE) break;   // ids, or RuntimeError("No free pages left") which the pool does not catch
+            }
+            if (st == KVB_ST_OK) {
+              const int64_t off = a.res[op].off;
+              for (int t = tid; t < n; t += NT) c.pin_ref[a.out_ids[off + t]] = 1;
+            }
+          } else if (tid == 0) {   // "Cannot get n free blocks from the pool": ValueError, nothing changed
+            kvb_res r{}; r.status = KVB_ST_NONE; r.n = 0; r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); r.aux = 0;
+            a.res[op] = r;
+          }
+          __syncthreads();
+          if (tid == 0) a.res[op].aux = evicted;
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_PIN_TOUCH:
+        case KVB_OP_PIN_MARK:
+        case KVB_OP_PIN_FREE:
+        case KVB_OP_PIN_EVICT:
+        case KVB_OP_PIN_RESET: {
+          int64_t aux = 0;
+          const int64_t off0 = sc[SC_OUT_CURSOR];
+          const bool too_many = o.n > c.f_cap;
+          if (too_many) {
+          } else if (o.kind == KVB_OP_PIN_TOUCH) {
+            pin_touch(c, s, a, o.arg, o.n);
+          } else if (o.kind == KVB_OP_PIN_MARK) {   // cache_full_blocks: _block_id_to_key[block_id] = key (patches.py:463-465)
+            for (int j = tid; j < o.n; j += NT) {
+              int64_t id = a.ids[o.arg + j];
+              if (id >= 0 && id < c.num_blocks) atomicOr(&c.pin_keyed[id >> 5], 1u << (id & 31));
+            }
+          } else if (o.kind == KVB_OP_PIN_FREE) {
+            aux = pin_free(c, s, a, o.arg, o.n, a.out_ids + off0);
+          } else if (o.kind == KVB_OP_PIN_EVICT) {
+            pin_evict(c, s, a, o.arg, o.n);
+          } else {
+            pin_reset(c, s, a);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            sc[SC_OUT_CURSOR] = off0 + aux;
+            kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = o.n; r.off = off0; r.avail = avail_size(c, sc); r.aux = aux;
             a.res[op] = r;
           }
           __syncthreads();
@@ -1434,7 +1695,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           break;
         }
         default: {
-          if (tid == 0) { kvb_res r; r.status = KVB_ERR_INVALID; r.n = 0; r.off = 0; r.avail = 0; a.res[op] = r; }
+          if (tid == 0) { kvb_res r{}; r.status = KVB_ERR_INVALID; r.n = 0; r.off = 0; r.avail = 0; a.res[op] = r; }
           op++;
           break;
         }
@@ -1492,7 +1753,8 @@ __global__ void kvb_init_state_kernel(DevState c, int64_t num_total_pages) {
     if (p < num_total_pages) c.fl[p] = (int32_t)p;
   }
   const int64_t nwords = (c.num_blocks + 31) / 32;
-  for (int64_t wd = i; wd < nwords + 4; wd += stride) c.bitmap[wd] = 0;
+  for (int64_t wd = i; wd < nwords + 4; wd += stride) { c.bitmap[wd] = 0; c.pin_keyed[wd] = 0; }
+  for (int64_t b = i; b < c.num_blocks; b += stride) { c.pin_ref[b] = 0; c.lru_pos[b] = -1; c.pin_last[b] = -1; }
   if (i < SC_COUNT) {
     int64_t v = 0;
     if (i == SC_NFREE || i == SC_NTOTAL || i == SC_FL_SIZE) v = num_total_pages;

@@ -312,6 +312,11 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   size_t o_g[5];
   for (auto &o : o_g) o = carve(cap_pages * 4);
   size_t o_bkt = carve((size_t)bkt_cap * 4);
+  s.lru_cap = (int32_t)(2 * c.num_blocks + 2048);
+  s.max_cached = (int32_t)std::max<int64_t>(-1, std::min<int64_t>(c.max_cached_blocks, INT32_MAX));
+  size_t o_pref = carve((size_t)c.num_blocks * 4), o_pkey = carve((size_t)(nwords + 8) * 4);
+  size_t o_lru = carve((size_t)s.lru_cap * 4), o_lpos = carve((size_t)c.num_blocks * 4);
+  size_t o_plast = carve((size_t)c.num_blocks * 4), o_pin = carve((size_t)m->f_cap * 4);
   size_t o_ev = carve((size_t)s.ev_cap * 8);
   size_t o_pr = carve((size_t)kNumPrimes * 8);
   m->d_block_bytes = off;
@@ -340,6 +345,12 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   s.g_next = (int32_t *)(b + o_g[3]);
   s.g_ptf = (int32_t *)(b + o_g[4]);
   s.g_bkt = (int32_t *)(b + o_bkt);
+  s.pin_ref = (int32_t *)(b + o_pref);
+  s.pin_keyed = (uint32_t *)(b + o_pkey);
+  s.lru = (int32_t *)(b + o_lru);
+  s.lru_pos = (int32_t *)(b + o_lpos);
+  s.pin_last = (int32_t *)(b + o_plast);
+  s.pin_in = (int32_t *)(b + o_pin);
   s.ev = (int64_t *)(b + o_ev);
   s.primes = (const uint64_t *)(b + o_pr);
   static_assert(sizeof(unsigned long) == sizeof(uint64_t), "LP64 expected");
@@ -409,7 +420,11 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
   int64_t need_out = 0;
   for (int64_t i = 0; i < n_ops; ++i) {
     if (ops[i].kind == KVB_OP_ALLOC && ops[i].n > 0) need_out += ops[i].n;
-    if (ops[i].kind == KVB_OP_FREE_IDS || ops[i].kind == KVB_OP_FREE_PAGES) {
+    if (ops[i].kind == KVB_OP_PIN_NEW && ops[i].n > 0) need_out += 2 * (int64_t)ops[i].n;   // evicted ids + new ids
+    if (ops[i].kind == KVB_OP_PIN_FREE && ops[i].n > 0) need_out += ops[i].n;               // ids evicted by the cap
+    const bool pin_list = ops[i].kind == KVB_OP_PIN_TOUCH || ops[i].kind == KVB_OP_PIN_MARK ||
+                          ops[i].kind == KVB_OP_PIN_FREE || ops[i].kind == KVB_OP_PIN_EVICT;
+    if (ops[i].kind == KVB_OP_FREE_IDS || ops[i].kind == KVB_OP_FREE_PAGES || pin_list) {
       if (ops[i].n < 0 || ops[i].arg < 0 || ops[i].arg + ops[i].n > n_ids) { set_error("free request %ld indexes outside the id pool", (long)i); return KVB_ERR_INVALID; }
       if (ops[i].n > m->f_cap) { set_error("free of %d ids exceeds the pool's block count", ops[i].n); return KVB_ERR_INVALID; }
     }
@@ -424,7 +439,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
   for (int64_t i = 0; i < n_ops; ++i)
     settle |= ops[i].kind == KVB_OP_TRIM || ops[i].kind == KVB_OP_CLEAR || ops[i].kind == KVB_OP_RESIZE ||
               ops[i].kind == KVB_OP_PA_RESIZE;
-  if (need_out > out_cap) { set_error("out_ids capacity %ld < %ld ids requested", (long)out_cap, (long)need_out); return KVB_ERR_OVERFLOW; }
+  if (need_out > out_cap) { set_error("out_ids capacity %ld < %ld ids requested (alloc n, get_new_blocks 2n, free_blocks n)", (long)out_cap, (long)need_out); return KVB_ERR_OVERFLOW; }
   size_t b_ops = (size_t)n_ops * sizeof(kvb_op), b_ids = (size_t)n_ids * 8, b_refs = align_up((size_t)n_refs * sizeof(kvb_ref), 8);
   size_t in_bytes = b_ops + b_ids + b_refs;
   size_t b_res = (size_t)n_ops * sizeof(kvb_res);
@@ -619,6 +634,7 @@ extern "C" int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *o) {
   o->events = m->total_events;
   o->h2d_bytes = m->h2d_bytes;
   o->d2h_bytes = m->d2h_bytes;
+  o->num_evictable_blocks = sc[SC_LRU_COUNT];
   return 0;
 }
 
@@ -764,6 +780,20 @@ extern "C" int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_
     for (int64_t i = 0; i < size; ++i)
       CUDA_TRY(cudaMemcpy(&h[(size_t)i], m->st.rb + ((head + i) & m->st.rb_mask), 8, cudaMemcpyDeviceToHost));
     v = h;
+  } else if (which == 7) {   // _evictable_blocks in LRU order
+    int64_t head = sc[SC_LRU_HEAD], tail = sc[SC_LRU_TAIL];
+    std::vector<int32_t> h((size_t)std::max<int64_t>(tail - head, 0));
+    if (!h.empty()) CUDA_TRY(cudaMemcpy(h.data(), m->st.lru + head, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int32_t e : h) if (e >= 0) v.push_back(e);
+  } else if (which == 8) {   // blocks that hold a cache key
+    int64_t nwords = (m->cfg.num_blocks + 31) / 32;
+    std::vector<uint32_t> h((size_t)nwords);
+    CUDA_TRY(cudaMemcpy(h.data(), m->st.pin_keyed, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < m->cfg.num_blocks; ++b) if ((h[(size_t)(b >> 5)] >> (b & 31)) & 1u) v.push_back(b);
+  } else if (which == 9) {   // (block, ref_cnt) of every referenced block
+    std::vector<int32_t> h((size_t)m->cfg.num_blocks);
+    CUDA_TRY(cudaMemcpy(h.data(), m->st.pin_ref, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < m->cfg.num_blocks; ++b) if (h[(size_t)b]) { v.push_back(b); v.push_back(h[(size_t)b]); }
   } else {
     set_error("dump_list: unknown list %d", which);
     return KVB_ERR_INVALID;

@@ -31,7 +31,7 @@ from ._lib import (OP_ALLOC, OP_AVAIL, OP_CLEAR, OP_FREE_IDS, OP_FREE_REF, OP_FR
 
 OP_DTYPE = np.dtype([("kind", "<i4"), ("n", "<i4"), ("arg", "<i8")])
 REF_DTYPE = np.dtype([("op", "<i4"), ("lo", "<i4"), ("hi", "<i4")])
-RES_DTYPE = np.dtype([("status", "<i4"), ("n", "<i4"), ("off", "<i8"), ("avail", "<i8")])
+RES_DTYPE = np.dtype([("status", "<i4"), ("n", "<i4"), ("off", "<i8"), ("avail", "<i8"), ("aux", "<i8")])
 
 KV_TENSOR_WAIT_TIMEOUT = float(os.environ.get("KVCACHED_KV_TENSOR_WAIT_TIMEOUT", "10"))  # kv_cache_manager.py:41
 SANITY_CHECK = os.environ.get("KVCACHED_SANITY_CHECK", "false").lower() in ("1", "true")
@@ -94,7 +94,7 @@ class KVCacheManager:
                  pp_rank: int = 0, async_sched: bool = False, reserve_null_block: bool = False,
                  num_kv_buffers: int = 2, group_id: int = 0, *, page_size: Optional[int] = None,
                  attach_vmm: Optional[bool] = None, device_index: int = -1,
-                 min_reserved_pages: int = -1, max_reserved_pages: int = -1):
+                 min_reserved_pages: int = -1, max_reserved_pages: int = -1, max_cached_blocks: int = -1):
         lib = _lib.load()
         self._lib = lib
         self.num_blocks = num_blocks
@@ -123,7 +123,7 @@ class KVCacheManager:
         self.attach_vmm = attach_vmm
         self._cfg = MgrConfig(num_blocks, block_size, cell_size, num_layers, num_kv_buffers, page_size, group_id,
                               min_reserved_pages, max_reserved_pages, int(reserve_null_block), int(async_sched),
-                              -1, int(attach_vmm), device_index, world_size, 0.0)
+                              -1, int(attach_vmm), device_index, world_size, 0.0, max_cached_blocks)
         self._h = None
         self.null_block: Optional[List[int]] = None
         self.page_allocator = _PageAllocatorView(self)
@@ -330,7 +330,7 @@ class KVCacheManager:
 
     def _dump(self, which: int) -> List[int]:
         self._wait_post_init()
-        cap = max(self.num_blocks + 64, 4096)
+        cap = max((2 if which == 9 else 1) * self.num_blocks + 64, 4096)
         buf = np.empty(cap, dtype=np.int64)
         n = self._lib.kvb_mgr_dump_list(self._h, which, _p64(buf), cap)
         if n < 0:

@@ -9,7 +9,8 @@ FIELDS = ["r", "avail", "pages", "nab", "ap", "fp", "rb", "shrink", "mapped"]
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
+    names = sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
+    return [n for n in names if not n.startswith("pool_")]   # pool_*: prefix-cache fixtures (test_pool_*.py)
 
 
 def load_golden(name):
