@@ -173,6 +173,11 @@ typedef struct kvb_mgr_config {
   double gpu_utilization;      /* <=0 = env KVCACHED_GPU_UTILIZATION or 0.95                    */
   int64_t max_cached_blocks;   /* prefix-cache LRU cap: -1 unlimited, 0 evict on free, >0 cap (patches.py:247-257);
                                   only the KVB_OP_PIN_* requests read it                                     */
+  int32_t publish_shm;         /* usage segment for kvctl / kvtop (mem_info_tracker.hpp): 1 on, 0 off,
+                                  <0 = env KVB200_SHM, else on iff attach_vmm                               */
+  int32_t pad_;
+  char ipc_name[64];           /* "" = KVCACHED_IPC_NAME or kvcached_engine_<pgid>, "_g<group>" appended for
+                                  group != 0 (mem_info_tracker.hpp:150-166, :235-247)                       */
 } kvb_mgr_config;
 
 /* one request of a batched step */
@@ -297,6 +302,16 @@ int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap);
 int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms);
 /* device pointer + word count of the used-block bitmap (tests, external sweeps) */
 int kvb_mgr_bitmap(kvb_mgr *m, uint64_t *dev_ptr, int64_t *n_words32);
+
+/* ---- usage segment: /dev/shm/<ipc_name>, int64 {total_size, used_size, prealloc_size}, flock-protected —
+ * the reference's wire format (csrc/inc/mem_info_tracker.hpp:25-36, kvcached/cli/utils.py:29-153), so kvctl and
+ * kvtop work unchanged.  The manager publishes used = in-use pages * L * P * nKV and prealloc = reserved pages *
+ * L * P * nKV once per step (page_allocator.cpp:688-701) and applies a changed total_size (kvctl limit) as
+ * KVCacheManager.resize(total / L / nKV) before its next alloc (kv_cache_manager.py:258-260). */
+int kvb_mgr_shm_name(kvb_mgr *m, char *out, int cap);          /* length, 0 = publishing is off            */
+int64_t kvb_mgr_shm_publishes(kvb_mgr *m);                     /* segment writes so far                    */
+int kvb_shm_read(const char *ipc_name, int64_t *out3);         /* get_kv_cache_limit, cli/utils.py:104-113 */
+int kvb_shm_set_limit(const char *ipc_name, int64_t total_bytes, int create);   /* update_kv_cache_limit :116-141 */
 
 /* ---- tensor parallel: rank-consistent page mapping ----------------------------------------
  * After a step, rank 0's page events sit in a fixed device buffer

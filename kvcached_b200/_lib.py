@@ -21,7 +21,8 @@ class MgrConfig(C.Structure):          # kvb_mgr_config
                 ("min_reserved_pages", i64), ("max_reserved_pages", i64),
                 ("reserve_null_block", i32), ("async_sched", i32), ("contiguous_layout", i32),
                 ("attach_vmm", i32), ("device_index", i32), ("world_size", i32),
-                ("gpu_utilization", f64), ("max_cached_blocks", i64)]
+                ("gpu_utilization", f64), ("max_cached_blocks", i64),
+                ("publish_shm", i32), ("pad_", i32), ("ipc_name", C.c_char * 64)]
 
 
 class Op(C.Structure):                 # kvb_op
@@ -74,6 +75,10 @@ SIGNATURES = {
     "kvb_map_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_unmap_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_apply_page_events": (C.c_int, [i64, p_i64, i64]),
+    "kvb_mgr_shm_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "kvb_mgr_shm_publishes": (i64, [C.c_void_p]),
+    "kvb_shm_read": (C.c_int, [C.c_char_p, p_i64]),
+    "kvb_shm_set_limit": (C.c_int, [C.c_char_p, i64, C.c_int]),
     "kvb_vmm_enqueue_page_events": (C.c_int, [i64, p_i64, i64]),
     "kvb_vmm_wait_maps": (C.c_int, [i64]),
     "kvb_vmm_fence": (C.c_int, [i64]),

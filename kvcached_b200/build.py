@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkvb200.so")
-SOURCES = ["kvb_kernels.cu", "kvb_manager.cpp", "kvb_vmm.cpp", "kvb_capi.cpp"]
-HEADERS = ["kvb_internal.h", "kvb_vmm.h", os.path.join("..", "..", "include", "kvb200.h")]
+SOURCES = ["kvb_kernels.cu", "kvb_manager.cpp", "kvb_vmm.cpp", "kvb_capi.cpp", "kvb_shm.cpp"]
+HEADERS = ["kvb_internal.h", "kvb_vmm.h", "kvb_shm.h", os.path.join("..", "..", "include", "kvb200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
          "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=default,-Wall,-Wno-unused-function",

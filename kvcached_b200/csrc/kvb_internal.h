@@ -111,6 +111,7 @@ struct LaunchArgs {
                           // 2: cursor continues, event log restarts (relaunch of a partially done step)
   int32_t group_only;     // 1: requests are FREE_IDS probes for kvb_group_indices_by_page (state untouched)
   int64_t *grp_pages, *grp_counts, *grp_ids;   // outputs of group_only
+  int64_t resize_target;  // per-layer size the shm limit asks for (-1: none), page_allocator.cpp:764-782
   kvb_res *host_res;      // zero-copy step: pinned host mirrors the kernel fills itself (else null)
   int64_t *host_out;
 };

@@ -198,6 +198,20 @@ __device__ int pa_resize(const DevState &c, int64_t *sc, int64_t new_mem_size, i
   return 1;
 }
 
+// KVCacheManager.resize, kv_cache_manager.py:381-401 (thread 0): returns the request status
+__device__ int mgr_resize(const DevState &c, int64_t *sc, int64_t new_mem_size) {
+  int cap_err = 0;
+  if (pa_resize(c, sc, new_mem_size, &cap_err)) {
+    if (sc[SC_INSHRINK]) { sc[SC_INSHRINK] = 0; sc[SC_TARGET] = -1; }
+    return KVB_ST_OK;
+  }
+  if (cap_err) return KVB_ST_CAPACITY;
+  if (sc[SC_NRB] > 0) return KVB_ST_ASSERT;
+  sc[SC_INSHRINK] = 1;
+  sc[SC_TARGET] = new_mem_size / c.B;
+  return KVB_ST_FALSE;
+}
+
 // PageAllocator::trim, csrc/page_allocator.cpp:403-427 (thread 0)
 __device__ void pa_trim(const DevState &c, int64_t *sc) {
   while (sc[SC_RL_SIZE] > 0) {
@@ -1449,6 +1463,13 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         op++;
         continue;
       }
+      if (a.resize_target > 0 && (o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_TRY_RESERVE || o.kind == KVB_OP_PIN_NEW)) {
+        // _alloc() first applies a limit change published through the shm segment (kv_cache_manager.py:258-260,
+        // page_allocator.cpp:764-782); the result is ignored there too.  Repeating it for the later requests of
+        // a run changes nothing, so once per alloc-type request (= once per run) is exact.
+        if (tid == 0) mgr_resize(c, sc, a.resize_target);
+        __syncthreads();
+      }
       switch (o.kind) {
         case KVB_OP_ALLOC: {
           // end of the run of consecutive ALLOC requests inside the staged chunk
@@ -1500,19 +1521,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         case KVB_OP_RESIZE: {   // KVCacheManager.resize, kv_cache_manager.py:381-401
           if (tid == 0) {
             kvb_res r{}; r.n = 0; r.off = 0;
-            int cap_err = 0;
-            if (pa_resize(c, sc, o.arg, &cap_err)) {
-              if (sc[SC_INSHRINK]) { sc[SC_INSHRINK] = 0; sc[SC_TARGET] = -1; }
-              r.status = KVB_ST_OK;
-            } else if (cap_err) {
-              r.status = KVB_ST_CAPACITY;
-            } else if (sc[SC_NRB] > 0) {
-              r.status = KVB_ST_ASSERT;
-            } else {
-              sc[SC_INSHRINK] = 1;
-              sc[SC_TARGET] = o.arg / c.B;
-              r.status = KVB_ST_FALSE;
-            }
+            r.status = mgr_resize(c, sc, o.arg);
             r.avail = avail_size(c, sc);
             a.res[op] = r;
           }

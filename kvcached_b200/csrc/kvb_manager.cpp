@@ -10,11 +10,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 
 #include "kvb_internal.h"
+#include "kvb_shm.h"
 #include "kvb_vmm.h"
 
 using namespace kvb;
@@ -102,6 +104,8 @@ struct kvb_mgr {
   Summary *t_sum = nullptr;   // device
   std::vector<int64_t> t_steps;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::unique_ptr<ShmUsage> shm;   // usage publishing + limit (mem_info_tracker.hpp); null = off
+  int64_t shm_publishes = 0;
 };
 
 namespace {
@@ -211,6 +215,7 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
   a.grp_ids = grp_ids;
   a.host_res = host_res;
   a.host_out = host_out;
+  a.resize_target = (m->shm && !group_only) ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
   int rc = launch_step(m->st, a, m->stream);
   if (rc != 0) {
     set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -366,6 +371,17 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   m->last.sc[SC_NFREE] = m->last.sc[SC_NTOTAL] = m->last.sc[SC_FL_SIZE] = m->max_pages;
   m->last.sc[SC_TARGET] = -1;
 
+  // usage publishing (PageAllocator ctor, page_allocator.cpp:126-130): on for managers that drive real tensors,
+  // or when asked for; total = mem_size * num_layers * num_kv_buffers (:120)
+  {
+    int want = c.publish_shm;
+    if (want < 0) { const char *e = getenv("KVB200_SHM"); want = e && *e ? atoi(e) : (c.attach_vmm ? 1 : 0); }
+    if (want) {
+      m->shm.reset(new ShmUsage(m->mem_size * c.num_layers * c.num_kv_buffers, c.group_id, c.ipc_name[0] ? c.ipc_name : nullptr));
+      if (!m->shm->ok()) m->shm.reset();   // like the reference: logged, not fatal (mem_info_tracker.hpp:218-222)
+    }
+  }
+
   // _post_init: reserve the null block (kv_cache_manager.py:233-243)
   if (c.reserve_null_block) {
     int64_t id = -1;
@@ -512,6 +528,11 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     if (hs->ops_done <= 0) { set_error("step kernel made no progress at request %ld", (long)done); return KVB_ERR_STATE; }
     done += hs->ops_done;
     first = false;
+  }
+  if (m->shm) {   // PageAllocator::update_memory_usage (page_allocator.cpp:688-701), once per step
+    const int64_t per_page = m->cfg.num_layers * m->P * m->cfg.num_kv_buffers;
+    const int64_t *sc = m->last.sc;
+    m->shm_publishes += m->shm->publish((sc[SC_NTOTAL] - sc[SC_NFREE]) * per_page, sc[SC_RL_SIZE] * per_page);
   }
   if (settle && m->cfg.attach_vmm) {   // also when this step produced no events of its own: earlier frees may be queued
     VmmGroup *g = vmm_group(m->cfg.group_id, false);
@@ -924,6 +945,24 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   int rc = g->enqueue_events(ev.data(), hdr[1]);
   if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
   return rc < 0 ? rc : 0;
+}
+
+// ---- shm usage segment (kvctl / kvtop wire format) ---------------------------------------------------------
+extern "C" int kvb_mgr_shm_name(kvb_mgr *m, char *out, int cap) {
+  if (!m || !out || cap <= 0) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (!m->shm) { out[0] = 0; return 0; }
+  snprintf(out, (size_t)cap, "%s", m->shm->name().c_str());
+  return (int)m->shm->name().size();
+}
+extern "C" int64_t kvb_mgr_shm_publishes(kvb_mgr *m) { return m ? m->shm_publishes : KVB_ERR_INVALID; }
+extern "C" int kvb_shm_read(const char *ipc_name, int64_t *out3) {
+  if (!ipc_name || !out3) return KVB_ERR_INVALID;
+  return shm_read(ipc_name, out3) == 0 ? 0 : KVB_ERR_STATE;
+}
+extern "C" int kvb_shm_set_limit(const char *ipc_name, int64_t total_bytes, int create) {
+  if (!ipc_name || total_bytes < 0) return KVB_ERR_INVALID;
+  return shm_set_limit(ipc_name, total_bytes, create != 0) == 0 ? 0 : KVB_ERR_STATE;
 }
 
 // kernels launched by this library since load (bookkeeping steps, audits, KV scatter/gather)

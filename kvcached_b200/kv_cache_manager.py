@@ -37,6 +37,18 @@ KV_TENSOR_WAIT_TIMEOUT = float(os.environ.get("KVCACHED_KV_TENSOR_WAIT_TIMEOUT",
 SANITY_CHECK = os.environ.get("KVCACHED_SANITY_CHECK", "false").lower() in ("1", "true")
 
 
+def shm_read(ipc_name: str):
+    """get_kv_cache_limit (kvcached/cli/utils.py:104-113): (total_size, used_size, prealloc_size) or None."""
+    out = np.zeros(3, dtype=np.int64)
+    rc = _lib.load().kvb_shm_read(ipc_name.encode(), out.ctypes.data_as(_lib.p_i64))
+    return None if rc != 0 else tuple(int(x) for x in out)
+
+
+def shm_set_limit(ipc_name: str, total_bytes: int, create: bool = False) -> bool:
+    """update_kv_cache_limit (kvcached/cli/utils.py:116-141): what `kvctl limit` writes."""
+    return _lib.load().kvb_shm_set_limit(ipc_name.encode(), int(total_bytes), 1 if create else 0) == 0
+
+
 class KVCachedConfigError(ValueError):
     """Block larger than a page (kv_cache_manager.py:104-116)."""
 
@@ -72,7 +84,19 @@ class _PageAllocatorView:
         return block_id * block_mem_size // self._m.page_size
 
     def get_resize_target(self) -> int:
-        return -1
+        """page_allocator.cpp:780-782: the per-layer size the shm limit asks for, -1 if it equals the current one."""
+        return self.check_and_get_resize_target(self._m.mem_size)
+
+    def check_and_get_resize_target(self, cur_mem_size: int) -> int:
+        """mem_info_tracker.hpp:187-200"""
+        name = self._m.shm_name()
+        if not name:
+            return -1
+        info = shm_read(name)
+        if info is None:
+            return -1
+        per_layer = info[0] // self._m.num_layers // self._m.num_kv_buffers
+        return per_layer if per_layer != cur_mem_size else -1
 
     def trim(self) -> None:
         self._m.trim()
@@ -94,7 +118,8 @@ class KVCacheManager:
                  pp_rank: int = 0, async_sched: bool = False, reserve_null_block: bool = False,
                  num_kv_buffers: int = 2, group_id: int = 0, *, page_size: Optional[int] = None,
                  attach_vmm: Optional[bool] = None, device_index: int = -1,
-                 min_reserved_pages: int = -1, max_reserved_pages: int = -1, max_cached_blocks: int = -1):
+                 min_reserved_pages: int = -1, max_reserved_pages: int = -1, max_cached_blocks: int = -1,
+                 publish_shm: Optional[bool] = None, ipc_name: str = ""):
         lib = _lib.load()
         self._lib = lib
         self.num_blocks = num_blocks
@@ -123,7 +148,8 @@ class KVCacheManager:
         self.attach_vmm = attach_vmm
         self._cfg = MgrConfig(num_blocks, block_size, cell_size, num_layers, num_kv_buffers, page_size, group_id,
                               min_reserved_pages, max_reserved_pages, int(reserve_null_block), int(async_sched),
-                              -1, int(attach_vmm), device_index, world_size, 0.0, max_cached_blocks)
+                              -1, int(attach_vmm), device_index, world_size, 0.0, max_cached_blocks,
+                              -1 if publish_shm is None else int(bool(publish_shm)), 0, ipc_name.encode()[:63])
         self._h = None
         self.null_block: Optional[List[int]] = None
         self.page_allocator = _PageAllocatorView(self)
@@ -320,6 +346,13 @@ class KVCacheManager:
             else:
                 ret.append(None)
         return ret
+
+    def shm_name(self) -> str:
+        """Name of the usage segment under /dev/shm ('' = publishing is off)."""
+        self._wait_post_init()
+        buf = C.create_string_buffer(128)
+        n = self._lib.kvb_mgr_shm_name(self._h, buf, 128)
+        return buf.value.decode() if n > 0 else ""
 
     # ------------------------------------------------------------------ inspection
     def stats(self) -> MgrStats:

@@ -212,7 +212,7 @@ class PageAllocator:
         attach = bool(lib.kvb_is_initialized())   # tensors may not exist yet: the manager waits for them (post-init)
         self._m = KVCacheManager(mem_size_per_layer // page_size, 1, page_size, num_layers, world_size, pp_rank,
                                  async_sched, False, num_kv_buffers, group_id, page_size=page_size,
-                                 attach_vmm=attach)
+                                 attach_vmm=attach, ipc_name=ipc_name)
         self._attach = attach
 
     # -- requests ------------------------------------------------------------------------------
@@ -284,10 +284,10 @@ class PageAllocator:
         return self._m.page_allocator.get_avail_physical_pages()
 
     def check_and_get_resize_target(self, cur_mem_size: int) -> int:
-        return -1
+        return self._m.page_allocator.check_and_get_resize_target(cur_mem_size)
 
     def get_resize_target(self) -> int:
-        return -1
+        return self._m.page_allocator.get_resize_target()
 
     def get_page_id(self, block_id: int, block_mem_size: int) -> int:
         return int(_lib.load().kvb_page_id_of_block(block_id, block_mem_size, self.page_size))
