@@ -331,8 +331,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                   "map_plus_unmap_vs_raw": (pctl(mm, 0.5) + pctl(uu, 0.5)) /
                                                            (pctl(a.tolist(), 0.5) + pctl(b.tolist(), 0.5))}
         map_unmap["page_bytes"] = vst["page_bytes"]
-        map_unmap["note"] = ("one compound page = all 32 layers' K and V pages (128 MiB); raw = the same "
-                             "cuMemUnmap+cuMemMap+cuMemSetAccess calls on pre-created handles, same process")
+        map_unmap["note"] = (f"one compound page = all {cfg['num_layers']} layers' K and V pages "
+                             f"({vst['page_bytes'] >> 20} MiB); raw = the same cuMemUnmap+cuMemMap+cuMemSetAccess calls on "
+                             "pre-created handles, same process")
         lib.kvb_vmm_pool_config(0, 16)
     barrier()
     if tp is not None:
