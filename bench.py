@@ -395,6 +395,44 @@ def ours_main(args, rank: int, world: int, local_rank: int):
         mgr.free(ids)
     if tp is not None:
         tp.sync()
+    del k, v
+    torch.cuda.empty_cache()
+
+    # ================= bitmap sweep on a stress size (2^30 blocks = 128 MiB bitmap streams HBM) ===
+    sweep = None
+    micro = None
+    if rank == 0:
+        o4 = np.zeros(4)
+        o5 = np.zeros(4)
+        rc = lib.kvb_audit_stress(local_rank, 1 << 30, 64, 20, o4.ctypes.data_as(_lib.p_f64))
+        rc2 = lib.kvb_audit_stress(local_rank, 1 << 31, 64, 20, o5.ctypes.data_as(_lib.p_f64))
+        if rc == 0:
+            sweep = {"kernel": "kvb_audit_kernel (uint4 bitmap sweep + popc, 2^30 blocks, 64 blocks/page)",
+                     "ms": float(o4[0]), "algorithmic_bytes_per_launch": int(o4[1]),
+                     "gbs": float(o4[1]) / float(o4[0]) / 1e6, "used_blocks_counted": int(o4[2]),
+                     "note": "the pool's own bitmap is 11 KB (L2-resident, launch-bound): audit of the live pool "
+                             f"takes {mgr.audit()[4] * 1e3:.1f} us"}
+            if rc2 == 0:
+                sweep["at_2^31_blocks"] = {"ms": float(o5[0]), "algorithmic_bytes_per_launch": int(o5[1]),
+                                           "gbs": float(o5[1]) / float(o5[0]) / 1e6}
+            sweep["frac_of_hbm_peak"] = sweep["gbs"] / float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)) \
+                if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else sweep["gbs"] / 6650.0
+        else:
+            sweep = {"error": _lib.last_error()}
+        # T-micro (benchmarks/bench_alloc/bench_alloc.py:57-62): alloc(k); free(h) pairs through the single-request API
+        micro = {}
+        mm = R.manager_from_config(cfg, attach_vmm=False, device_index=local_rank)
+        mm.set_phys_free_pages(1 << 40)
+        pinned = mm.alloc(1)                                   # no-churn variant: one pinned block keeps the page
+        for kk, iters in ((1, 2000), (16, 2000), (256, 1000)):
+            for _ in range(50):
+                mm.free(mm.alloc_np(kk))
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                mm.free(mm.alloc_np(kk))
+            micro[f"k{kk}_pair_us"] = (time.perf_counter() - t0) / iters * 1e6
+        mm.free(pinned)
+        mm.close()
     clk = clocks.stop()
 
     peaks = {}
@@ -428,7 +466,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
                                "timed region"},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "map_unmap": map_unmap, "kv_scatter": kv,
+                "map_unmap": map_unmap, "kv_scatter": kv, "bitmap_sweep": sweep, "micro_alloc_free": micro,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)

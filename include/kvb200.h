@@ -211,6 +211,11 @@ typedef struct kvb_op {
                                    then the LRU is cut back to max_cached_blocks                                    :535-568 */
 #define KVB_OP_PIN_EVICT 18     /* evict_blocks(ids): drop the keys; evictable ones are freed                       :570-588 */
 #define KVB_OP_PIN_RESET 19     /* reset_prefix_cache(): free every evictable block, drop every key                 :590-603 */
+/* SGLang paged allocator (kvcached/integration/sglang/patches.py:188-297), issued by kvb_mgr_alloc_extend /
+ * kvb_mgr_alloc_decode / kvb_mgr_free_slots: sequence lengths and slot indices are DEVICE arrays */
+#define KVB_OP_ALLOC_EXTEND 20
+#define KVB_OP_ALLOC_DECODE 21
+#define KVB_OP_FREE_SLOTS 22
 
 /* a slice of an earlier request's result: ids = result(op)[lo:hi] (Python slice semantics, clipped) */
 typedef struct kvb_ref {
@@ -273,6 +278,28 @@ int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *out);
 /* parity/test hooks: override the physical-page budget (<0 = live cudaMemGetInfo) */
 int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n);
 
+/* ---- SGLang paged allocator: allocate + expand to token slot indices on the device ---------------------------
+ * ElasticPagedTokenToKVPoolAllocator.alloc_extend / alloc_decode / free
+ * (kvcached/integration/sglang/patches.py:188-297).  The reference counts the new pages on the host
+ * (get_num_new_pages on CPU copies of the lengths), calls kv_cache_manager.alloc, ships the ids back with
+ * torch.tensor(list) and expands them with SGLang's Triton kernels alloc_extend_kernel / alloc_decode_kernel
+ * (sglang/srt/mem_cache/allocator.py; SGLang is a dependency of the reference, not part of it).  Here ONE launch
+ * counts the new pages from the device arrays, runs the block allocation and writes the slot indices:
+ *   part 1  the rest of the sequence's last partial page:   last_loc + 1 + t
+ *   part 2  whole new pages:                                 block * page_size + t % page_size
+ *   part 3  the new partial tail page:                       last new block * page_size + t
+ * (decode: one token per sequence: last_loc + 1, or new block * page_size when seq_len % page_size == 1).
+ * All array arguments are DEVICE pointers to int64; `stream` is the stream that produced them (NULL = legacy
+ * default).  Returns 1, or KVB_ST_NONE when available_size() < new pages (the reference returns None; nothing
+ * is written), or <0.  *num_new_pages receives the page count.  page_size = tokens per block. */
+int kvb_mgr_alloc_extend(kvb_mgr *m, int64_t bs, uint64_t prefix_lens, uint64_t seq_lens, uint64_t last_loc,
+                         int64_t extend_num_tokens, uint64_t out_indices, void *stream, int64_t *num_new_pages);
+int kvb_mgr_alloc_decode(kvb_mgr *m, int64_t bs, uint64_t seq_lens, uint64_t last_loc, uint64_t out_indices,
+                         void *stream, int64_t *num_new_pages);
+/* free(free_index): kv_cache_manager.free(torch.unique(free_index // page_size)) — the unique sorted block list is
+ * built on the device (bitmap of touched blocks + ordered popc compaction).  Returns the number of blocks freed. */
+int64_t kvb_mgr_free_slots(kvb_mgr *m, uint64_t free_index, int64_t n, void *stream);
+
 /* ---- resident traces: requests and results stay in HBM ------------------------------------
  * Upload a whole trace once; then run ranges of it.  FREE_REF refs name absolute request indices.
  * kvb_mgr_trace_run launches one kernel per step range [step_begin, step_end) given by
@@ -300,6 +327,9 @@ int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap);
  * bitmap and checks them against the per-page counters.  out4 = {used blocks, in-use pages,
  * fully-free in-use pages, mismatching pages}.  device_ms (optional) = kernel time. */
 int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms);
+/* the same sweep over a synthetic bitmap big enough to stream from HBM (the pool's own is L2-resident):
+ * out4 = {avg kernel ms, algorithmic bytes per launch = bitmap + 8 B per page, used blocks counted, expected} */
+int kvb_audit_stress(int device_index, int64_t num_blocks, int32_t blocks_per_page, int32_t iters, double *out4);
 /* device pointer + word count of the used-block bitmap (tests, external sweeps) */
 int kvb_mgr_bitmap(kvb_mgr *m, uint64_t *dev_ptr, int64_t *n_words32);
 

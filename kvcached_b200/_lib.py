@@ -75,6 +75,10 @@ SIGNATURES = {
     "kvb_map_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_unmap_pages": (C.c_int, [i64, p_i64, i64]),
     "kvb_apply_page_events": (C.c_int, [i64, p_i64, i64]),
+    "kvb_mgr_alloc_extend": (C.c_int, [C.c_void_p, i64, u64, u64, u64, i64, u64, C.c_void_p, p_i64]),
+    "kvb_mgr_alloc_decode": (C.c_int, [C.c_void_p, i64, u64, u64, u64, C.c_void_p, p_i64]),
+    "kvb_mgr_free_slots": (i64, [C.c_void_p, u64, i64, C.c_void_p]),
+    "kvb_audit_stress": (C.c_int, [C.c_int, i64, i32, i32, p_f64]),
     "kvb_mgr_shm_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kvb_mgr_shm_publishes": (i64, [C.c_void_p]),
     "kvb_shm_read": (C.c_int, [C.c_char_p, p_i64]),

@@ -77,6 +77,7 @@ struct DevState {
   int32_t *lru;                 // _evictable_blocks in insertion order, -1 = tombstone
   int32_t *lru_pos;             // [num_blocks] ring index or -1
   int32_t *pin_last;            // [num_blocks] scratch: last list index naming the block (-1 idle)
+  uint32_t *tmp_bits;           // bit per block, all zero between requests (FREE_SLOTS: blocks named by the slots)
   int32_t *pin_in;              // [f_cap] scratch: the running PIN request's ids as int32 (-1 = not a block)
   int32_t lru_cap;
   int32_t max_cached;           // -1 unlimited, 0 evict on free, > 0 cap
@@ -111,6 +112,11 @@ struct LaunchArgs {
                           // 2: cursor continues, event log restarts (relaunch of a partially done step)
   int32_t group_only;     // 1: requests are FREE_IDS probes for kvb_group_indices_by_page (state untouched)
   int64_t *grp_pages, *grp_counts, *grp_ids;   // outputs of group_only
+  // SGLang paged allocator requests (KVB_OP_ALLOC_EXTEND / ALLOC_DECODE / FREE_SLOTS): device arrays
+  const int64_t *slot_pre, *slot_seq, *slot_last;   // [slot_bs]; FREE_SLOTS: slot_pre = free_index[n]
+  int64_t *slot_out;                                // token slot indices
+  int64_t slot_tokens;                              // capacity of slot_out
+  int32_t slot_bs, slot_ps;
   int64_t resize_target;  // per-layer size the shm limit asks for (-1: none), page_allocator.cpp:764-782
   kvb_res *host_res;      // zero-copy step: pinned host mirrors the kernel fills itself (else null)
   int64_t *host_out;
@@ -122,7 +128,7 @@ size_t step_kernel_smem_bytes();
 // launches (host side, defined in kvb_kernels.cu)
 int launch_step(const DevState &st, const LaunchArgs &a, void *stream);
 int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream);
-int launch_audit(const DevState &st, int64_t *d_out4, void *stream);
+int launch_audit(const DevState &st, int64_t *d_out4, void *stream, bool zero_counters = true);
 int launch_dump_avail(const DevState &st, int64_t *d_out, int64_t *d_n, void *stream);
 int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, void *k, void *v, int32_t l0,
                    int32_t l1, int gather, void *stream);

@@ -1419,6 +1419,95 @@ __device__ void pin_reset(const DevState &c, Smem &s, const LaunchArgs &a) {
   if (nf > 0) free_core(c, s, a, nf, 0);
 }
 
+
+// ==================================================================================== SGLang slot expansion
+// get_num_new_pages + the index arithmetic of SGLang's alloc_extend_kernel / alloc_decode_kernel
+// (kvcached/integration/sglang/patches.py:188-279 calls them; SGLang, sglang/srt/mem_cache/allocator.py).
+// Pass 1: per sequence new pages = ceil(seq/ps) - ceil(pre/ps) and extend length seq - pre, exclusive-scanned
+// over the batch (first page / first output position of every sequence).  Returns {pages, tokens} (uniform).
+__device__ void slots_scan(const DevState &c, Smem &s, const LaunchArgs &a, int decode, int64_t *n_pages, int64_t *n_tok) {
+  const int bs = a.slot_bs, ps = a.slot_ps;
+  int64_t carry_p = 0, carry_t = 0;
+  for (int i0 = 0; i0 < bs; i0 += NT) {
+    const int i = i0 + threadIdx.x;
+    int np = 0, el = 0;
+    if (i < bs) {
+      const int64_t seq = a.slot_seq[i];
+      const int64_t pre = decode ? seq - 1 : a.slot_pre[i];
+      np = (int)((seq + ps - 1) / ps - (pre + ps - 1) / ps);
+      el = (int)(seq - pre);
+      if (np < 0) np = 0;
+      if (el < 0) el = 0;
+    }
+    int tp, tt;
+    const int ep = block_exscan(np, s.wtot, &tp);
+    const int et = block_exscan(el, s.wtot2, &tt);
+    if (i < bs) { c.fpage[i] = (int32_t)(carry_p + ep); c.fids[i] = carry_t + et; }
+    carry_p += tp;
+    carry_t += tt;
+  }
+  *n_pages = carry_p;
+  *n_tok = carry_t;
+}
+
+// Pass 2: one warp per sequence writes its slot indices; `ids` = the block ids just allocated.
+__device__ void slots_expand(const DevState &c, const LaunchArgs &a, int decode, const int64_t *ids) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t ps = a.slot_ps;
+  for (int i = w; i < a.slot_bs; i += NW) {
+    const int64_t seq = a.slot_seq[i];
+    const int64_t pre = decode ? seq - 1 : a.slot_pre[i];
+    const int64_t last = a.slot_last[i];
+    const int64_t pages_before = (pre + ps - 1) / ps, pages_after = (seq + ps - 1) / ps;
+    const int64_t *pg = ids + c.fpage[i];
+    if (decode) {
+      if (lane == 0) a.slot_out[i] = (pages_after == pages_before) ? last + 1 : pg[0] * ps;
+      continue;
+    }
+    int64_t *out = a.slot_out + c.fids[i];
+    const int64_t full_before = pages_before * ps;
+    const int64_t part1 = (seq < full_before ? seq : full_before) - pre;          // rest of the old partial page
+    for (int64_t t = lane; t < part1; t += 32) out[t] = last + 1 + t;
+    if (pre + part1 == seq) continue;
+    const int64_t part2 = seq / ps * ps - full_before;                            // whole new pages
+    for (int64_t t = lane; t < part2; t += 32) out[part1 + t] = pg[t / ps] * ps + t % ps;
+    if (pre + part1 + part2 == seq) continue;
+    const int64_t part3 = seq - seq / ps * ps;                                    // new partial tail page
+    const int64_t tailpg = pg[pages_after - pages_before - 1];
+    for (int64_t t = lane; t < part3; t += 32) out[part1 + part2 + t] = tailpg * ps + t;
+  }
+}
+
+// free(free_index): blocks = sorted unique(free_index // page_size) -> c.fids; returns their count (uniform).
+__device__ int slots_unique_blocks(const DevState &c, Smem &s, const LaunchArgs &a, int64_t n) {
+  const int tid = threadIdx.x;
+  const int64_t ps = a.slot_ps;
+  for (int64_t j = tid; j < n; j += NT) {
+    int64_t slot = a.slot_pre[j];
+    if (slot < 0) continue;
+    int64_t b = slot / ps;
+    if (b < c.num_blocks) atomicOr(&c.tmp_bits[b >> 5], 1u << (b & 31));
+  }
+  __syncthreads();
+  const int64_t nwords = (c.num_blocks + 31) / 32;
+  int base = 0;
+  for (int64_t w0 = 0; w0 < nwords; w0 += NT) {
+    const int64_t wi = w0 + tid;
+    unsigned wd = (wi < nwords) ? c.tmp_bits[wi] : 0u;
+    int tot;
+    int pos = base + block_exscan(__popc(wd), s.wtot, &tot);
+    if (wd) c.tmp_bits[wi] = 0;   // scratch goes back to all-zero
+    while (wd) {
+      int b = __ffs(wd) - 1;
+      wd &= wd - 1;
+      c.fids[pos++] = (wi << 5) + b;
+    }
+    base += tot;
+  }
+  __syncthreads();
+  return base;
+}
+
 }  // namespace
 
 // ==================================================================================== the step kernel
@@ -1703,6 +1792,50 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           op++;
           break;
         }
+        case KVB_OP_ALLOC_EXTEND:
+        case KVB_OP_ALLOC_DECODE: {
+          const int decode = o.kind == KVB_OP_ALLOC_DECODE;
+          int64_t npg, ntok;
+          slots_scan(c, s, a, decode, &npg, &ntok);
+          int st = KVB_ST_OK;
+          if ((decode ? (int64_t)a.slot_bs : ntok) > a.slot_tokens || npg > INT_MAX) {
+            st = KVB_ERR_OVERFLOW;                 // caller's index buffer is too small
+          } else if (npg > 0) {                    // the reference skips alloc() when no page is needed (:217, :258)
+            if (tid == 0) {
+              s.ops[op - chunk_base].n = (int32_t)npg;
+              if (a.resize_target > 0) mgr_resize(c, sc, a.resize_target);   // alloc()'s limit check, kv_cache_manager.py:258-260
+            }
+            __syncthreads();
+            if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
+            __syncthreads();
+            st = a.res[op].status;
+          }
+          if (st == KVB_ST_OK) slots_expand(c, a, decode, a.out_ids + (npg > 0 ? a.res[op].off : 0));
+          __syncthreads();
+          if (tid == 0) {
+            kvb_res r{};
+            if (npg > 0 && st != KVB_ERR_OVERFLOW) r = a.res[op];
+            else { r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); }
+            r.status = st;
+            r.n = st == KVB_ST_OK ? (int32_t)npg : 0;
+            r.aux = decode ? a.slot_bs : ntok;    // slot indices written
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_FREE_SLOTS: {
+          const int nb = slots_unique_blocks(c, s, a, o.arg);
+          if (nb > 0) free_core(c, s, a, nb, 0);
+          if (tid == 0) {
+            kvb_res r{}; r.status = KVB_ST_OK; r.n = nb; r.off = 0; r.avail = avail_size(c, sc);
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
         default: {
           if (tid == 0) { kvb_res r{}; r.status = KVB_ERR_INVALID; r.n = 0; r.off = 0; r.avail = 0; a.res[op] = r; }
           op++;
@@ -1762,7 +1895,7 @@ __global__ void kvb_init_state_kernel(DevState c, int64_t num_total_pages) {
     if (p < num_total_pages) c.fl[p] = (int32_t)p;
   }
   const int64_t nwords = (c.num_blocks + 31) / 32;
-  for (int64_t wd = i; wd < nwords + 4; wd += stride) { c.bitmap[wd] = 0; c.pin_keyed[wd] = 0; }
+  for (int64_t wd = i; wd < nwords + 4; wd += stride) { c.bitmap[wd] = 0; c.pin_keyed[wd] = 0; c.tmp_bits[wd] = 0; }
   for (int64_t b = i; b < c.num_blocks; b += stride) { c.pin_ref[b] = 0; c.lru_pos[b] = -1; c.pin_last[b] = -1; }
   if (i < SC_COUNT) {
     int64_t v = 0;
@@ -1770,6 +1903,20 @@ __global__ void kvb_init_state_kernel(DevState c, int64_t num_total_pages) {
     if (i == SC_TARGET) v = -1;
     c.sc[i] = v;
   }
+}
+
+// streaming 128-bit accesses (no L1 allocation): shared by the audit sweep and the KV scatter / gather
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
 }
 
 // ==================================================================================== audit sweep
@@ -1793,47 +1940,118 @@ __device__ __forceinline__ void audit_page(const DevState &c, int64_t p, unsigne
   }
 }
 
+// Streaming path of the audit (bpp in {32, 64, 128}: a uint4 of bitmap = PPV whole pages): UNR independent 128-bit
+// bitmap loads plus the matching state / count vectors are issued before anything is consumed.  HBM-bound at
+// scale: 16 B of bitmap + 8 B of counters per page.
+template <int PPV>
+__device__ __forceinline__ void audit_stream(const DevState &c, int64_t gtid, int64_t gthreads, unsigned long long &used,
+                                             unsigned long long &inuse, unsigned long long &empties,
+                                             unsigned long long &bad) {
+  const int64_t nvec = ((int64_t)c.max_pages + PPV - 1) / PPV;
+  const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
+  constexpr int UNR = 4;
+  for (int64_t q0 = gtid; q0 < nvec; q0 += gthreads * UNR) {
+    uint4 v[UNR];
+    int st[UNR][PPV], cn[UNR][PPV];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int64_t q = q0 + (int64_t)k * gthreads;
+      v[k] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int x = 0; x < PPV; ++x) { st[k][x] = PG_NONE; cn[k][x] = 0; }
+      if (q < nvec) {
+        v[k] = ld_stream(b4 + q);
+        const int64_t p = q * PPV;
+        if (PPV == 4 && p + 4 <= c.max_pages) {
+          int4 a = *reinterpret_cast<const int4 *>(c.pg_state + p), b = *reinterpret_cast<const int4 *>(c.pg_cnt + p);
+          st[k][0] = a.x; st[k][1 % PPV] = a.y; st[k][2 % PPV] = a.z; st[k][3 % PPV] = a.w;
+          cn[k][0] = b.x; cn[k][1 % PPV] = b.y; cn[k][2 % PPV] = b.z; cn[k][3 % PPV] = b.w;
+        } else if (PPV == 2 && p + 2 <= c.max_pages) {
+          int2 a = *reinterpret_cast<const int2 *>(c.pg_state + p), b = *reinterpret_cast<const int2 *>(c.pg_cnt + p);
+          st[k][0] = a.x; st[k][1 % PPV] = a.y;
+          cn[k][0] = b.x; cn[k][1 % PPV] = b.y;
+        } else {
+#pragma unroll
+          for (int x = 0; x < PPV; ++x)
+            if (p + x < c.max_pages) { st[k][x] = c.pg_state[p + x]; cn[k][x] = c.pg_cnt[p + x]; }
+        }
+      }
+    }
+    unsigned u32 = 0, in32 = 0, em32 = 0, bad32 = 0;
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int64_t q = q0 + (int64_t)k * gthreads;
+      if (q >= nvec) continue;
+      unsigned up[PPV];
+      if (PPV == 4) { up[0] = __popc(v[k].x); up[1 % PPV] = __popc(v[k].y); up[2 % PPV] = __popc(v[k].z); up[3 % PPV] = __popc(v[k].w); }
+      else if (PPV == 2) { up[0] = __popc(v[k].x) + __popc(v[k].y); up[1 % PPV] = __popc(v[k].z) + __popc(v[k].w); }
+      else { up[0] = __popc(v[k].x) + __popc(v[k].y) + __popc(v[k].z) + __popc(v[k].w); }
+#pragma unroll
+      for (int x = 0; x < PPV; ++x) {
+        if (q * PPV + x < c.max_pages) {
+          u32 += up[x];
+          if (st[k][x] != PG_NONE) {
+            in32++;
+            em32 += (up[x] == 0);
+            bad32 += ((int)up[x] != c.bpp - cn[k][x]);
+          } else {
+            bad32 += (up[x] != 0);
+          }
+        }
+      }
+    }
+    used += u32; inuse += in32; empties += em32; bad += bad32;
+  }
+}
+
 __global__ void __launch_bounds__(256) kvb_audit_kernel(DevState c, int64_t *out4, int mode) {
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
   unsigned long long used = 0, inuse = 0, empties = 0, bad = 0;
   if (mode == 0) {
-    const int ppv = 128 / c.bpp;          // pages per uint4: 4, 2 or 1
-    const int wpp = c.bpp / 32;           // words per page: 1, 2 or 4
-    const int64_t nvec = ((int64_t)c.max_pages + ppv - 1) / ppv;
-    const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
-    for (int64_t q = gtid; q < nvec; q += gthreads) {
-      uint4 v = b4[q];
-      unsigned wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < ppv) {
-          int64_t p = q * ppv + k;
-          if (p < c.max_pages) {
-            unsigned u = 0;
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-              if (x < wpp) u += __popc(wd[k * wpp + x]);
-            audit_page(c, p, u, used, inuse, empties, bad);
-          }
-        }
-      }
-    }
+    if (c.bpp == 32) audit_stream<4>(c, gtid, gthreads, used, inuse, empties, bad);
+    else if (c.bpp == 64) audit_stream<2>(c, gtid, gthreads, used, inuse, empties, bad);
+    else audit_stream<1>(c, gtid, gthreads, used, inuse, empties, bad);
   } else if (mode == 1) {
+    // bpp = 128 * g: g adjacent lanes hold one page; UNR independent loads in flight, shuffle-reduce each
     const int g = c.bpp / 128;
     const int64_t nvec = (int64_t)c.max_pages * g;
     const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
-    const int64_t span = (nvec + gthreads - 1) / gthreads;
+    constexpr int UNR = 4;
+    const int64_t span = (nvec + gthreads * UNR - 1) / (gthreads * UNR);
     for (int64_t it = 0; it < span; ++it) {   // uniform trip count: shuffles need the whole warp
-      int64_t q = it * gthreads + gtid;
-      unsigned u = 0;
-      if (q < nvec) {
-        uint4 v = b4[q];
-        u = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+      unsigned u[UNR];
+      int64_t q[UNR];
+      int st[UNR], cn[UNR];
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {          // every load of the trip is issued before anything is consumed
+        q[k] = (it * UNR + k) * gthreads + gtid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        st[k] = PG_NONE;
+        cn[k] = 0;
+        if (q[k] < nvec) {
+          v = ld_stream(b4 + q[k]);
+          if ((q[k] % g) == 0) { st[k] = c.pg_state[q[k] / g]; cn[k] = c.pg_cnt[q[k] / g]; }
+        }
+        u[k] = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
       }
-      for (int d = 1; d < g; d <<= 1) u += __shfl_xor_sync(0xffffffffu, u, d);
-      if (q < nvec && (q % g) == 0) audit_page(c, q / g, u, used, inuse, empties, bad);
+      unsigned u32 = 0, in32 = 0, em32 = 0, bad32 = 0;
+#pragma unroll
+      for (int k = 0; k < UNR; ++k) {
+        for (int d = 1; d < g; d <<= 1) u[k] += __shfl_xor_sync(0xffffffffu, u[k], d);
+        if (q[k] < nvec && (q[k] % g) == 0) {
+          u32 += u[k];
+          if (st[k] != PG_NONE) {
+            in32++;
+            em32 += (u[k] == 0);
+            bad32 += ((int)u[k] != c.bpp - cn[k]);
+          } else {
+            bad32 += (u[k] != 0);
+          }
+        }
+      }
+      used += u32; inuse += in32; empties += em32; bad += bad32;
     }
   } else {
     const int64_t warp = gtid >> 5, nwarps = gthreads >> 5;
@@ -1891,19 +2109,6 @@ __global__ void kvb_dump_avail_kernel(DevState c, int64_t *out, int64_t *n_out) 
 // L1 (streaming, no reuse) and stores are full 128-byte lines.  Grid = persistent CTAs, a multiple
 // of the SM count; work items are (token, layer, kv) cells, token-fastest inside a layer so that a
 // CTA's concurrent source reads are contiguous.
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) {
-  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
-}
-
 // `g` lanes (a power of two, chosen by the launcher so that a lane moves ~4 vectors) serve one cell;
 // a warp serves 32/g cells at once, so small cells (TP shards, 256 B) keep every lane busy.
 template <int GATHER>
@@ -1976,9 +2181,11 @@ int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream)
   return (int)cudaGetLastError();
 }
 
-int launch_audit(const DevState &st, int64_t *d_out4, void *stream) {
-  cudaError_t e = cudaMemsetAsync(d_out4, 0, 4 * sizeof(int64_t), (cudaStream_t)stream);
-  if (e != cudaSuccess) return (int)e;
+int launch_audit(const DevState &st, int64_t *d_out4, void *stream, bool zero_counters) {
+  if (zero_counters) {
+    cudaError_t e = cudaMemsetAsync(d_out4, 0, 4 * sizeof(int64_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   int mode = 2;
   if (st.exact && (st.bpp == 32 || st.bpp == 64 || st.bpp == 128)) mode = 0;
   else if (st.exact && st.bpp % 128 == 0 && st.bpp / 128 <= 32 && ((st.bpp / 128) & (st.bpp / 128 - 1)) == 0) mode = 1;

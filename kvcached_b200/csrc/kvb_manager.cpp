@@ -195,8 +195,12 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n, bool settle = false) 
 int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int64_t *d_ids, const kvb_ref *d_refs,
            kvb_res *d_res, int64_t *d_outids, int64_t out_cap, Summary *d_sum, int arena_mode, int group_only,
            int64_t *grp_pages = nullptr, int64_t *grp_counts = nullptr, int64_t *grp_ids = nullptr,
-           kvb_res *host_res = nullptr, int64_t *host_out = nullptr) {
+           kvb_res *host_res = nullptr, int64_t *host_out = nullptr, const LaunchArgs *slots = nullptr) {
   LaunchArgs a{};
+  if (slots) {
+    a.slot_pre = slots->slot_pre; a.slot_seq = slots->slot_seq; a.slot_last = slots->slot_last;
+    a.slot_out = slots->slot_out; a.slot_tokens = slots->slot_tokens; a.slot_bs = slots->slot_bs; a.slot_ps = slots->slot_ps;
+  }
   a.ops = d_ops;
   a.op_begin = op_begin;
   a.op_end = op_end;
@@ -322,6 +326,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   size_t o_pref = carve((size_t)c.num_blocks * 4), o_pkey = carve((size_t)(nwords + 8) * 4);
   size_t o_lru = carve((size_t)s.lru_cap * 4), o_lpos = carve((size_t)c.num_blocks * 4);
   size_t o_plast = carve((size_t)c.num_blocks * 4), o_pin = carve((size_t)m->f_cap * 4);
+  size_t o_tbits = carve((size_t)(nwords + 8) * 4);
   size_t o_ev = carve((size_t)s.ev_cap * 8);
   size_t o_pr = carve((size_t)kNumPrimes * 8);
   m->d_block_bytes = off;
@@ -356,6 +361,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   s.lru_pos = (int32_t *)(b + o_lpos);
   s.pin_last = (int32_t *)(b + o_plast);
   s.pin_in = (int32_t *)(b + o_pin);
+  s.tmp_bits = (uint32_t *)(b + o_tbits);
   s.ev = (int64_t *)(b + o_ev);
   s.primes = (const uint64_t *)(b + o_pr);
   static_assert(sizeof(unsigned long) == sizeof(uint64_t), "LP64 expected");
@@ -666,6 +672,95 @@ extern "C" int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n) {
   return 0;
 }
 
+// ============================================================================================ SGLang slot requests
+// One request whose inputs / outputs are the caller's DEVICE arrays; the host only learns status and counts.
+static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg, int64_t arena_cap, void *stream, kvb_res *res) {
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  size_t o_res = align_up(sizeof(Summary), 16), o_ids = o_res + 64;
+  int rc = ensure_io(m, sizeof(kvb_op), o_ids + (size_t)arena_cap * 8);
+  if (rc) return rc;
+  kvb_op op{kind, 0, arg};
+  memcpy(m->h_in, &op, sizeof(op));
+  // order our launch after whatever produced the arrays on the caller's stream
+  CUDA_TRY(cudaEventRecord(m->ev0, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev0, 0));
+  volatile int64_t *vseq = &((Summary *)m->h_out)->seq;
+  *vseq = 0;
+  m->h2d_bytes += (int64_t)sizeof(kvb_op);
+  rc = launch(m, (const kvb_op *)m->h_in, 0, 1, nullptr, nullptr, (kvb_res *)(m->d_out + o_res), (int64_t *)(m->d_out + o_ids),
+              arena_cap, (Summary *)m->h_out, 0, 0, nullptr, nullptr, nullptr, (kvb_res *)(m->h_out + o_res),
+              (int64_t *)(m->h_out + o_ids), &sl);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(m->stream));   // the index array is complete when the call returns (host-ordered for the caller)
+  if (*vseq != m->seq) { set_error("slot request: kernel finished without publishing its summary"); return KVB_ERR_STATE; }
+  const Summary *hs = (const Summary *)m->h_out;
+  m->last = *hs;
+  m->d2h_bytes += (int64_t)(40 * 8 + hs->ev_inline_n * 8 + sizeof(kvb_res) + hs->out_used * 8);
+  if (hs->n_events > 0) {
+    if (hs->n_events <= hs->ev_inline_n) {
+      rc = apply_events(m, hs->ev_inline, hs->n_events);
+    } else {
+      std::vector<int64_t> ev((size_t)hs->n_events);
+      CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev + hs->ev_begin, (size_t)hs->n_events * 8, cudaMemcpyDeviceToHost));
+      rc = apply_events(m, ev.data(), hs->n_events);
+    }
+    if (rc) return rc;
+  }
+  if (m->shm) {
+    const int64_t per_page = m->cfg.num_layers * m->P * m->cfg.num_kv_buffers;
+    const int64_t *sc = m->last.sc;
+    m->shm_publishes += m->shm->publish((sc[SC_NTOTAL] - sc[SC_NFREE]) * per_page, sc[SC_RL_SIZE] * per_page);
+  }
+  memcpy(res, m->h_out + o_res, sizeof(kvb_res));
+  return 0;
+}
+
+static int alloc_slots(kvb_mgr *m, int kind, int64_t bs, uint64_t pre, uint64_t seq, uint64_t last, int64_t tokens,
+                       uint64_t out, void *stream, int64_t *num_new_pages) {
+  if (!m || bs <= 0 || bs > m->f_cap || !seq || !last || !out || (kind == KVB_OP_ALLOC_EXTEND && (!pre || tokens < 0))) {
+    set_error("alloc_extend / alloc_decode: bad argument");
+    return KVB_ERR_INVALID;
+  }
+  LaunchArgs sl{};
+  sl.slot_pre = (const int64_t *)(uintptr_t)pre;
+  sl.slot_seq = (const int64_t *)(uintptr_t)seq;
+  sl.slot_last = (const int64_t *)(uintptr_t)last;
+  sl.slot_out = (int64_t *)(uintptr_t)out;
+  sl.slot_tokens = kind == KVB_OP_ALLOC_DECODE ? bs : tokens;
+  sl.slot_bs = (int32_t)bs;
+  sl.slot_ps = (int32_t)m->cfg.block_size;
+  // new pages <= extend tokens / page_size + one partial page per sequence
+  int64_t arena = (kind == KVB_OP_ALLOC_DECODE ? 0 : tokens / m->cfg.block_size) + bs + 8;
+  kvb_res r{};
+  std::lock_guard<std::mutex> lk(m->mu);
+  int rc = slots_locked(m, kind, sl, 0, arena, stream, &r);
+  if (rc) return rc;
+  if (num_new_pages) *num_new_pages = r.n;
+  if (r.status == KVB_ST_OK) return 1;
+  if (r.status == KVB_ERR_OVERFLOW) { set_error("alloc_extend: the sequences need %ld slot indices, the buffer holds %ld", (long)r.aux, (long)sl.slot_tokens); return KVB_ERR_OVERFLOW; }
+  return r.status;
+}
+extern "C" int kvb_mgr_alloc_extend(kvb_mgr *m, int64_t bs, uint64_t prefix_lens, uint64_t seq_lens, uint64_t last_loc,
+                                    int64_t extend_num_tokens, uint64_t out_indices, void *stream, int64_t *num_new_pages) {
+  return alloc_slots(m, KVB_OP_ALLOC_EXTEND, bs, prefix_lens, seq_lens, last_loc, extend_num_tokens, out_indices, stream, num_new_pages);
+}
+extern "C" int kvb_mgr_alloc_decode(kvb_mgr *m, int64_t bs, uint64_t seq_lens, uint64_t last_loc, uint64_t out_indices,
+                                    void *stream, int64_t *num_new_pages) {
+  return alloc_slots(m, KVB_OP_ALLOC_DECODE, bs, 0, seq_lens, last_loc, bs, out_indices, stream, num_new_pages);
+}
+extern "C" int64_t kvb_mgr_free_slots(kvb_mgr *m, uint64_t free_index, int64_t n, void *stream) {
+  if (!m || n < 0 || (n > 0 && !free_index)) { set_error("free_slots: bad argument"); return KVB_ERR_INVALID; }
+  if (n == 0) return 0;   // patches.py:283-284
+  LaunchArgs sl{};
+  sl.slot_pre = (const int64_t *)(uintptr_t)free_index;
+  sl.slot_ps = (int32_t)m->cfg.block_size;
+  kvb_res r{};
+  std::lock_guard<std::mutex> lk(m->mu);
+  int rc = slots_locked(m, KVB_OP_FREE_SLOTS, sl, n, 8, stream, &r);
+  if (rc) return rc;
+  return r.n;
+}
+
 // ============================================================================================ resident traces
 extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t *ids, int64_t n_ids,
                                     const kvb_ref *refs, int64_t n_refs, const int64_t *step_offsets, int64_t n_steps,
@@ -863,6 +958,93 @@ extern "C" int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms) {
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   if (device_ms) CUDA_TRY(cudaEventElapsedTime(device_ms, m->ev0, m->ev1));
   CUDA_TRY(cudaMemcpy(out4, m->d_scratch + 8, 32, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// The audit sweep on a bitmap large enough to stream from HBM (the pool's own bitmap is 11 KB and L2-resident):
+// num_blocks bits + per-page state/count words, pattern = every third page fully used, every seventh half used.
+// out = {avg kernel ms, algorithmic bytes per launch (bitmap + 8 B per page), used blocks counted, used blocks expected}
+extern "C" int kvb_audit_stress(int device_index, int64_t num_blocks, int32_t blocks_per_page, int32_t iters, double *out4) {
+  if (num_blocks <= 0 || blocks_per_page <= 0 || blocks_per_page % 32 || num_blocks % blocks_per_page || iters <= 0 || !out4) {
+    set_error("audit_stress: num_blocks must be a positive multiple of blocks_per_page, itself a multiple of 32");
+    return KVB_ERR_INVALID;
+  }
+  if (ensure_device(device_index < 0 ? 0 : device_index)) { set_error("cudaSetDevice failed"); return KVB_ERR_CUDA; }
+  const int64_t pages = num_blocks / blocks_per_page, nwords = num_blocks / 32, wpp = blocks_per_page / 32;
+  if (pages > INT32_MAX) { set_error("audit_stress: too many pages"); return KVB_ERR_INVALID; }
+  DevState st{};
+  st.P = 2 << 20;
+  st.B = st.P / blocks_per_page;
+  st.bpp = blocks_per_page;
+  st.exact = 1;
+  st.num_blocks = num_blocks;
+  st.max_pages = (int32_t)pages;
+  int64_t *d_out = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&] {
+    if (st.bitmap) cudaFree(st.bitmap);
+    if (st.pg_state) cudaFree(st.pg_state);
+    if (st.pg_cnt) cudaFree(st.pg_cnt);
+    if (d_out) cudaFree(d_out);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define ST_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e_)); cleanup(); return KVB_ERR_CUDA; } } while (0)
+  ST_TRY(cudaMalloc((void **)&st.bitmap, (size_t)(nwords + 8) * 4));
+  ST_TRY(cudaMalloc((void **)&st.pg_state, (size_t)pages * 4));
+  ST_TRY(cudaMalloc((void **)&st.pg_cnt, (size_t)pages * 4));
+  ST_TRY(cudaMalloc((void **)&d_out, 64));
+  ST_TRY(cudaEventCreate(&e0));
+  ST_TRY(cudaEventCreate(&e1));
+  {
+    // host-built pattern, uploaded in slabs
+    const int64_t slab_pages = 1 << 16;
+    std::vector<uint32_t> bm((size_t)(slab_pages * wpp));
+    std::vector<int32_t> ps((size_t)slab_pages), pc((size_t)slab_pages);
+    for (int64_t p0 = 0; p0 < pages; p0 += slab_pages) {
+      int64_t n = std::min(slab_pages, pages - p0);
+      for (int64_t i = 0; i < n; ++i) {
+        int64_t p = p0 + i;
+        int used = (p % 3 == 0) ? blocks_per_page : (p % 7 == 0 ? blocks_per_page / 2 : 0);
+        for (int64_t w = 0; w < wpp; ++w) {
+          int64_t left = used - w * 32;
+          bm[(size_t)(i * wpp + w)] = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+        }
+        ps[(size_t)i] = used == blocks_per_page ? PG_FULL : (used ? PG_AVAIL : PG_NONE);
+        pc[(size_t)i] = used ? blocks_per_page - used : 0;
+      }
+      ST_TRY(cudaMemcpy(st.bitmap + p0 * wpp, bm.data(), (size_t)(n * wpp) * 4, cudaMemcpyHostToDevice));
+      ST_TRY(cudaMemcpy(st.pg_state + p0, ps.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+      ST_TRY(cudaMemcpy(st.pg_cnt + p0, pc.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  int64_t expect = 0;
+  for (int64_t p = 0; p < pages; ++p) expect += (p % 3 == 0) ? blocks_per_page : (p % 7 == 0 ? blocks_per_page / 2 : 0);
+  for (int w = 0; w < 3; ++w)
+    if (launch_audit(st, d_out, nullptr) != 0) { set_error("audit launch failed"); cleanup(); return KVB_ERR_CUDA; }
+  ST_TRY(cudaDeviceSynchronize());
+  float total_ms = 0;
+  for (int it = 0; it < iters; ++it) {   // the kernel alone: its counter memset sits outside the event pair
+    ST_TRY(cudaMemsetAsync(d_out, 0, 32, nullptr));
+    ST_TRY(cudaEventRecord(e0, nullptr));
+    if (launch_audit(st, d_out, nullptr, false) != 0) { set_error("audit launch failed"); cleanup(); return KVB_ERR_CUDA; }
+    ST_TRY(cudaEventRecord(e1, nullptr));
+    ST_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    ST_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    total_ms += ms;
+    g_total_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  int64_t h[4] = {0, 0, 0, 0};
+  ST_TRY(cudaMemcpy(h, d_out, 32, cudaMemcpyDeviceToHost));
+#undef ST_TRY
+  out4[0] = total_ms / iters;
+  out4[1] = (double)(nwords * 4 + pages * 8);
+  out4[2] = (double)h[0];
+  out4[3] = (double)expect;
+  int bad = (h[0] != expect || h[3] != 0) ? 1 : 0;
+  cleanup();
+  if (bad) { set_error("audit_stress: counted %ld used blocks (expected %ld), %ld mismatching pages", (long)h[0], (long)expect, (long)h[3]); return KVB_ERR_STATE; }
   return 0;
 }
 
