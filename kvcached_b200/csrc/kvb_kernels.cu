@@ -2016,6 +2016,7 @@ __global__ void __launch_bounds__(256) kvb_audit_kernel(DevState c, int64_t *out
   } else if (mode == 1) {
     // bpp = 128 * g: g adjacent lanes hold one page; UNR independent loads in flight, shuffle-reduce each
     const int g = c.bpp / 128;
+    const int gsh = __ffs(g) - 1;             // g is a power of two: no 64-bit divisions in the loop
     const int64_t nvec = (int64_t)c.max_pages * g;
     const uint4 *b4 = reinterpret_cast<const uint4 *>(c.bitmap);
     constexpr int UNR = 4;
@@ -2032,7 +2033,7 @@ __global__ void __launch_bounds__(256) kvb_audit_kernel(DevState c, int64_t *out
         cn[k] = 0;
         if (q[k] < nvec) {
           v = ld_stream(b4 + q[k]);
-          if ((q[k] % g) == 0) { st[k] = c.pg_state[q[k] / g]; cn[k] = c.pg_cnt[q[k] / g]; }
+          if ((q[k] & (g - 1)) == 0) { st[k] = c.pg_state[q[k] >> gsh]; cn[k] = c.pg_cnt[q[k] >> gsh]; }
         }
         u[k] = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
       }
@@ -2040,7 +2041,7 @@ __global__ void __launch_bounds__(256) kvb_audit_kernel(DevState c, int64_t *out
 #pragma unroll
       for (int k = 0; k < UNR; ++k) {
         for (int d = 1; d < g; d <<= 1) u[k] += __shfl_xor_sync(0xffffffffu, u[k], d);
-        if (q[k] < nvec && (q[k] % g) == 0) {
+        if (q[k] < nvec && (q[k] & (g - 1)) == 0) {
           u32 += u[k];
           if (st[k] != PG_NONE) {
             in32++;
