@@ -330,6 +330,9 @@ int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms);
 /* the same sweep over a synthetic bitmap big enough to stream from HBM (the pool's own is L2-resident):
  * out4 = {avg kernel ms, algorithmic bytes per launch = bitmap + 8 B per page, used blocks counted, expected} */
 int kvb_audit_stress(int device_index, int64_t num_blocks, int32_t blocks_per_page, int32_t iters, double *out4);
+/* tuning aid: cycles per phase [0..15] and mark counts [16..31] of the step kernel in a -DKVB_PROFILE build
+ * (all zero in the product build) */
+int kvb_mgr_profile(kvb_mgr *m, int64_t *out32, int reset);
 /* device pointer + word count of the used-block bitmap (tests, external sweeps) */
 int kvb_mgr_bitmap(kvb_mgr *m, uint64_t *dev_ptr, int64_t *n_words32);
 

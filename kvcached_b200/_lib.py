@@ -78,6 +78,7 @@ SIGNATURES = {
     "kvb_mgr_alloc_extend": (C.c_int, [C.c_void_p, i64, u64, u64, u64, i64, u64, C.c_void_p, p_i64]),
     "kvb_mgr_alloc_decode": (C.c_int, [C.c_void_p, i64, u64, u64, u64, C.c_void_p, p_i64]),
     "kvb_mgr_free_slots": (i64, [C.c_void_p, u64, i64, C.c_void_p]),
+    "kvb_mgr_profile": (C.c_int, [C.c_void_p, p_i64, C.c_int]),
     "kvb_audit_stress": (C.c_int, [C.c_int, i64, i32, i32, p_f64]),
     "kvb_mgr_shm_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "kvb_mgr_shm_publishes": (i64, [C.c_void_p]),
@@ -144,7 +145,7 @@ def load() -> C.CDLL:
     if not os.path.isfile(LIB_PATH) or os.environ.get("KVB200_REBUILD") == "1":
         from . import build as _build
         _build.build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(os.environ.get("KVB200_LIB", LIB_PATH))   # KVB200_LIB: an alternative build (tuning experiments)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = the library does not match the header
         fn.restype = res

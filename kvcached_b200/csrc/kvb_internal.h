@@ -83,6 +83,7 @@ struct DevState {
   int32_t max_cached;           // -1 unlimited, 0 evict on free, > 0 cap
   int64_t *ev;                  // page event log: page*2 + is_unmap
   const uint64_t *primes;       // libstdc++ __prime_list
+  long long *prof;              // -DKVB_PROFILE builds: [0..15] cycles per phase, [16..31] marks (else null)
 };
 
 // What one launch publishes for the host (written last; pinned host or device memory).
@@ -122,7 +123,10 @@ struct LaunchArgs {
   int64_t *host_out;
 };
 
-constexpr int kStepThreads = 512;
+#ifndef KVB_STEP_THREADS
+#define KVB_STEP_THREADS 512
+#endif
+constexpr int kStepThreads = KVB_STEP_THREADS;   // 256, 384 or 512 (>= OPS_CHUNK, multiple of 32)
 
 size_t step_kernel_smem_bytes();
 // launches (host side, defined in kvb_kernels.cu)

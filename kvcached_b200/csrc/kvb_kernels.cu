@@ -38,6 +38,22 @@ namespace kvb {
 
 namespace {
 
+// Phase timing of the step kernel (tuning aid): build with -DKVB_PROFILE, read with kvb_mgr_profile().
+// Thread 0 charges the cycles since the previous mark to `slot`.  Compiled out of the product build.
+#ifdef KVB_PROFILE
+#define KVB_PROF(slot)                                                                 \
+  do {                                                                                 \
+    if (threadIdx.x == 0) {                                                            \
+      long long t_ = clock64();                                                        \
+      c.prof[slot] += t_ - s.prof_t;                                                   \
+      c.prof[16 + (slot)] += 1;                                                        \
+      s.prof_t = t_;                                                                   \
+    }                                                                                  \
+  } while (0)
+#else
+#define KVB_PROF(slot) do { } while (0)
+#endif
+
 constexpr int NT = kStepThreads;
 constexpr int NW = NT / 32;
 constexpr int OPS_CHUNK = 256;   // requests staged in shared memory at a time
@@ -98,6 +114,7 @@ struct Smem {
   int32_t misc[16];
   int64_t tmp64[NT];
   AllocSim sim;
+  long long prof_t;
 };
 
 enum : int { MI_D = 0, MI_NB0, MI_E, MI_USE_G, MI_STOP, MI_BASE_A, MI_BASE_B, MI_N, MI_BAD, MI_UNK, MI_K };
@@ -391,6 +408,95 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
     nb = next_bkt(c, primes32, want);
   }
   if (lane < D) ord[lane] = cur_slot;
+}
+
+// The same rule for 32 < D <= 32 * HT_WK keys, still one warp: lane l holds positions l, 32 + l, 64 + l, ... of S
+// in registers; per phase the bucket of every key gets its first position (atomicMin into a shared table), each
+// key the number of later keys of its bucket (chunks walked from the back: __match_any_sync inside a chunk plus
+// the bucket's running count), run leaders a suffix sum of run sizes, and S is permuted through shared memory.
+// A request that decoded for a few hundred tokens names 40-130 pages: the sequential replay costs ~500 cycles a
+// key there, this ~40.  tab_first / tab_cnt hold >= the final bucket count entries; perm >= 2 * 32 * HT_WK words.
+constexpr int HT_WK = 8;
+__device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uint32_t *primes32, const int32_t *keys,
+                                                    int D, int nb, int32_t *ord, int32_t *tab_first, int32_t *tab_cnt,
+                                                    int64_t *perm) {
+  const int lane = threadIdx.x & 31;
+  const unsigned gt = ~((2u << lane) - 1u);   // lanes above mine
+  int32_t *suf_at = reinterpret_cast<int32_t *>(perm + 32 * HT_WK);
+  int slot[HT_WK];
+  unsigned key[HT_WK];
+#pragma unroll
+  for (int k = 0; k < HT_WK; ++k) {
+    const int p = 32 * k + lane;
+    slot[k] = p;
+    key[k] = p < D ? (unsigned)keys[p] : 0u;
+  }
+  while (true) {
+    const int upto = D < nb ? D : nb;        // keys in the container when this bucket count ends
+    int b[HT_WK], later[HT_WK];
+#pragma unroll
+    for (int k = 0; k < HT_WK; ++k) {
+      const int p = 32 * k + lane;
+      b[k] = p < upto ? (int)(key[k] % (unsigned)nb) : -1;
+      if (b[k] >= 0) { tab_first[b[k]] = INT_MAX; tab_cnt[b[k]] = 0; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < HT_WK; ++k)
+      if (b[k] >= 0) atomicMin(&tab_first[b[k]], 32 * k + lane);
+    __syncwarp();
+    // keys of my bucket at later positions: chunks from the back
+#pragma unroll
+    for (int k = HT_WK - 1; k >= 0; --k) {
+      later[k] = 0;
+      if (32 * k >= upto) continue;          // uniform
+      const int bb = b[k] >= 0 ? b[k] : -1 - lane;
+      const unsigned m = __match_any_sync(0xffffffffu, bb);
+      if (b[k] >= 0) later[k] = tab_cnt[b[k]] + __popc(m & gt);
+      __syncwarp();
+      if (b[k] >= 0 && (m & gt) == 0) tab_cnt[b[k]] += __popc(m);   // the group's highest lane
+      __syncwarp();
+    }
+    // inclusive suffix sum, over positions, of the run sizes held by run leaders (first key of a bucket)
+    int carry = 0;
+#pragma unroll
+    for (int k = HT_WK - 1; k >= 0; --k) {
+      if (32 * k >= upto) continue;          // uniform
+      const int p = 32 * k + lane;
+      int v = (b[k] >= 0 && tab_first[b[k]] == p) ? tab_cnt[b[k]] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_down_sync(0xffffffffu, v, d);
+        if (lane + d < 32) v += y;
+      }
+      if (b[k] >= 0) suf_at[p] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 0);
+    }
+    __syncwarp();
+    // new position = keys of buckets that first appear after mine + later keys of my bucket
+#pragma unroll
+    for (int k = 0; k < HT_WK; ++k)
+      if (b[k] >= 0) {
+        const int newpos = suf_at[tab_first[b[k]]] - tab_cnt[b[k]] + later[k];
+        perm[newpos] = ((int64_t)slot[k] << 32) | key[k];
+      }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < HT_WK; ++k)
+      if (b[k] >= 0) {
+        const int64_t e = perm[32 * k + lane];
+        slot[k] = (int)(e >> 32);
+        key[k] = (unsigned)e;
+      }
+    __syncwarp();
+    if (upto >= D) break;
+    int64_t want = (int64_t)upto + 2;         // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb))
+    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+    nb = next_bkt(c, primes32, want);
+  }
+#pragma unroll
+  for (int k = 0; k < HT_WK; ++k)
+    if (32 * k + lane < D) ord[32 * k + lane] = slot[k];
 }
 
 // bucket count the table ends with (decides shared vs global tables before the replay)
@@ -907,6 +1013,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
   }
   if (bad) atomicAdd(&s.misc[MI_BAD], bad);
   __syncthreads();
+  KVB_PROF(4);
 
   // ---- F1: first index naming each page (only run heads can be first) ---------------------------
   for (int j = tid; j < n; j += NT) {
@@ -947,17 +1054,22 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     D += tot;
   }
   __syncthreads();
+  KVB_PROF(5);
 
   // ---- F3: dict order (one lane) || per-page FIFO ranks (one warp) --------------------------------
   // groups.reserve(n / bpp + 1): csrc/page_allocator.cpp:477
   int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
-  const bool use_g = (D > HT_D_CAP) || (D > 32 && ht_final_buckets(c, s.primes32, D, nb0) > HT_NB_CAP);
+  const int nb_final = D > 32 ? ht_final_buckets(c, s.primes32, D, nb0) : nb0;
+  const bool use_g = (D > HT_D_CAP) || (D > 32 && nb_final > HT_NB_CAP);
+  const bool multi = D > 32 && D <= 32 * HT_WK && nb_final <= HT_D_CAP;   // tab_cnt = ht_next holds HT_D_CAP entries
   int32_t *keys = use_g ? c.g_dist : s.ht_key;
   int32_t *ord = use_g ? c.g_ord : s.ht_ord;
   int32_t *cnt = use_g ? c.g_cnt : s.ht_cnt;
   if (w == 0) {
     if (D <= 32) {
       ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);   // registers + warp votes
+    } else if (multi) {
+      ht_order_warp_multi(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
     } else if (!use_g) {
       for (int b = lane; b < nb0; b += 32) s.ht_bkt[b] = -1;
       __syncwarp();
@@ -967,6 +1079,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
       __syncwarp();
       if (lane == 0) ht_order_seq(c, s.primes32, c.g_dist, D, nb0, c.g_next, c.g_bkt, c.g_ord);
     }
+    KVB_PROF(11);
   } else if (w == 1) {
     for (int j0 = 0; j0 < n; j0 += 32) {
       int j = j0 + lane;
@@ -995,6 +1108,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     }
   }
   __syncthreads();
+  KVB_PROF(6);
 
   if (group_only) {
     // pages in dict order, their id counts, ids regrouped by page
@@ -1077,6 +1191,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     E += totE;
   }
   __syncthreads();
+  KVB_PROF(7);
 
   // ---- F5: PageAllocator::free_pages(pages_to_free) (page_allocator.cpp:264-310) --------------------
   int rl_size = (int)sc[SC_RL_SIZE], fl_size = (int)sc[SC_FL_SIZE];
@@ -1116,6 +1231,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     }
   }
   __syncthreads();
+  KVB_PROF(8);
 }
 
 // Gather the ids of a FREE_REF request into c.fids: concat of result(op)[lo:hi] of earlier requests.
@@ -1530,6 +1646,9 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   __syncthreads();
   const int64_t ev_begin = sc[SC_NEV];
   const int64_t out_begin = sc[SC_OUT_CURSOR];
+#ifdef KVB_PROFILE
+  if (tid == 0) s.prof_t = clock64();
+#endif
 
   int op = a.op_begin;
   while (op < a.op_end && !s.misc[MI_STOP]) {
@@ -1569,11 +1688,14 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           __syncthreads();
           int e = s.misc[MI_K];
           if (e - op > NT) e = op + NT;
+          KVB_PROF(0);
           if (alloc_run_fast(c, s, a, chunk_base, op, e)) {
             op = e;
+            KVB_PROF(1);
           } else {
             alloc_run(c, s, a, chunk_base, op, e, 0);
             op = s.sim.op;   // == e unless the output buffer ran out
+            KVB_PROF(2);
           }
           break;
         }
@@ -1596,6 +1718,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
             for (int j = tid; j < n; j += NT) c.fids[j] = c.rb[(int)((sc[SC_RB_HEAD] + j) & c.rb_mask)];
           }
           __syncthreads();
+          KVB_PROF(3);
           const bool too_many = n > c.f_cap;   // more ids than blocks exist: cannot be a valid call
           if (!too_many) free_core(c, s, a, n, 0);
           if (tid == 0) {
@@ -1849,6 +1972,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
 
   // publish
   __syncthreads();
+  KVB_PROF(9);
   if (tid < SC_COUNT) c.sc[tid] = sc[tid];
   Summary *sm = a.summary;
   if (sm) {
@@ -1877,6 +2001,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
       sm->seq = a.seq;   // written last: the host may poll it
     }
   }
+  KVB_PROF(10);
 }
 
 // ==================================================================================== init

@@ -368,6 +368,10 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   if (cudaMemcpy((void *)s.primes, std::__detail::__prime_list, kNumPrimes * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     return fail("cudaMemcpy(primes)");
   if (cudaMalloc((void **)&m->d_scratch, 64 * 8) != cudaSuccess) return fail("cudaMalloc(scratch)");
+  if (cudaMemset(m->d_scratch, 0, 64 * 8) != cudaSuccess) return fail("cudaMemset(scratch)");
+#ifdef KVB_PROFILE
+  s.prof = (long long *)(m->d_scratch + 32);   // upper half of the scratch block
+#endif
   if (cudaMalloc((void **)&m->t_sum, sizeof(Summary)) != cudaSuccess) return fail("cudaMalloc(summary)");
 
   int rc = launch_init_state(s, m->max_pages, m->stream);
@@ -1145,6 +1149,17 @@ extern "C" int kvb_shm_read(const char *ipc_name, int64_t *out3) {
 extern "C" int kvb_shm_set_limit(const char *ipc_name, int64_t total_bytes, int create) {
   if (!ipc_name || total_bytes < 0) return KVB_ERR_INVALID;
   return shm_set_limit(ipc_name, total_bytes, create != 0) == 0 ? 0 : KVB_ERR_STATE;
+}
+
+// -DKVB_PROFILE builds: cycles per phase [0..15] and mark counts [16..31] of the step kernel; zeroes otherwise
+extern "C" int kvb_mgr_profile(kvb_mgr *m, int64_t *out32, int reset) {
+  if (!m || !out32) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (ensure_device(m->dev)) return KVB_ERR_CUDA;
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  CUDA_TRY(cudaMemcpy(out32, m->d_scratch + 32, 32 * 8, cudaMemcpyDeviceToHost));
+  if (reset) CUDA_TRY(cudaMemset(m->d_scratch + 32, 0, 32 * 8));
+  return 0;
 }
 
 // kernels launched by this library since load (bookkeeping steps, audits, KV scatter/gather)

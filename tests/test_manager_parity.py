@@ -147,6 +147,26 @@ def test_group_indices_by_page_device_vs_libstdcxx():
     for ids in cases:
         assert m.group_indices_by_page(ids) == oracle.group_indices_by_page(ids, 32768), f"n={len(ids)}"
     m.close()
+    # 33..256 distinct pages (the multi-key warp replay of the hash order), few and many ids per page, small and
+    # large reserve() hints, every rehash count
+    m = _mgr(cfg)
+    for D in (33, 34, 47, 48, 64, 97, 98, 128, 199, 200, 255, 256, 257, 300):
+        for per_page in (1, 2, 7):
+            pages = rng.choice(1024, size=D, replace=False)
+            ids = (pages[:, None] * 64 + rng.integers(0, 64, size=(D, 1)) + np.arange(per_page)[None, :] * 0).reshape(-1)
+            if per_page > 1:
+                ids = np.concatenate([pages * 64 + j for j in range(per_page)])
+                rng.shuffle(ids)
+            ids = ids.tolist()
+            assert m.group_indices_by_page(ids) == oracle.group_indices_by_page(ids, 32768), f"D={D} per_page={per_page}"
+    # clustered keys (many collisions per bucket) and a request-like id list: one long run + scattered singles
+    for D in (40, 100, 250):
+        ids = [int(p) * 64 * 23 % 65536 for p in range(D)]
+        ids = list(dict.fromkeys(ids))
+        assert m.group_indices_by_page(ids) == oracle.group_indices_by_page(ids, 32768), f"clustered D={D}"
+        ids = list(range(5000, 5000 + 41)) + [int(x) * 64 + 3 for x in rng.choice(900, size=D, replace=False)]
+        assert m.group_indices_by_page(ids) == oracle.group_indices_by_page(ids, 32768), f"request-like D={D}"
+    m.close()
     # MLA geometry: blocks straddle page edges, 1820 per page
     cfg = T.make_config("mla_p1", 60000)
     m = _mgr(cfg)
