@@ -243,6 +243,13 @@ class ElasticBlockPool:
         return []
 
     # ------------------------------------------------------------------ inspection (tests)
+    @property
+    def _evictable_blocks(self):
+        """Read-only view with the reference attribute's shape (OrderedDict block_id -> block, oldest first),
+        rebuilt from the device LRU on every access — for tests and debugging, not for the serving path."""
+        from collections import OrderedDict
+        return OrderedDict((b, self.kv_block_pool[b]) for b in self.evictable_ids())
+
     def evictable_ids(self) -> List[int]:
         return self.kv_cache_manager._dump(7)
 

@@ -368,8 +368,13 @@ __device__ __forceinline__ void ht_order_seq(const DevState &c, const uint32_t *
 // first — i.e. S sorted by (first position of my bucket in S, my position in S), both descending.  A rehash
 // re-places the current list front to back under the new nb, which is the same rule applied to S = current
 // order; keys inserted afterwards simply extend S.  Lane l holds the key at position l of S.
+#ifdef KVB_PROFILE
+#define KVB_PROF_W(slot) do { if (threadIdx.x == 0) { long long t_ = clock64(); c.prof[slot] += t_ - *pt; c.prof[16 + (slot)] += 1; *pt = t_; } } while (0)
+#else
+#define KVB_PROF_W(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t *primes32, const int32_t *keys,
-                                              int D, int nb, int32_t *ord, int32_t *scratch64) {
+                                              int D, int nb, int32_t *ord, int32_t *scratch64, long long *pt = nullptr) {
   const int lane = threadIdx.x & 31;
   const unsigned gt = ~((2u << lane) - 1u);   // lanes above mine
   // cur_slot / cur_key = slot index and key of the element at S position `lane` (valid for lane < placed)
@@ -383,7 +388,9 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
     if (lane >= placed && lane < upto) { cur_slot = lane; cur_key = (unsigned)keys[lane]; }
     const bool in = lane < upto;
     const unsigned b = in ? cur_key % (unsigned)nb : 0xffffffffu - lane;
+    KVB_PROF_W(12);
     const unsigned grp = __match_any_sync(0xffffffffu, b);
+    KVB_PROF_W(13);
     const int gfirst = __ffs(grp) - 1;                  // first position of my bucket in S
     const int later_in_grp = __popc(grp & gt);
     // keys whose bucket first appears after mine come before me: suffix sum of run sizes over run leaders
@@ -396,12 +403,14 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
     int before = __shfl_sync(0xffffffffu, suf, (gfirst + 1) & 31);
     if (gfirst == 31) before = 0;
     const int newpos = before + later_in_grp;
+    KVB_PROF_W(14);
     // permute through shared memory: position p takes the element whose newpos == p
     if (in) { scratch64[newpos] = cur_slot; scratch64[32 + newpos] = (int)cur_key; }
     __syncwarp();
     if (in) { cur_slot = scratch64[lane]; cur_key = (unsigned)scratch64[32 + lane]; }
     __syncwarp();
     placed = upto;
+    KVB_PROF_W(15);
     if (placed >= D) break;
     int64_t want = (int64_t)placed + 2;                 // _M_need_rehash -> _M_next_bkt(max(n+1+1, 2*nb))
     if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
@@ -1067,7 +1076,11 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
   int32_t *cnt = use_g ? c.g_cnt : s.ht_cnt;
   if (w == 0) {
     if (D <= 32) {
+#ifdef KVB_PROFILE
+      ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next, &s.prof_t);
+#else
       ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);   // registers + warp votes
+#endif
     } else if (multi) {
       ht_order_warp_multi(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
     } else if (!use_g) {

@@ -19,7 +19,7 @@ prof = np.zeros(32, dtype=np.int64)
 lib.kvb_mgr_profile(m._h, prof.ctypes.data_as(_lib.p_i64), 0)
 if prof.any():
     names = ["pre-alloc/idle", "alloc fast", "alloc general", "free: stage ids", "F0 classify", "F1+F2 distinct pages", "F3 dict order + ranks",
-             "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work"]
+             "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work", "w32: phase head (next_bkt, mod)", "w32: match_any", "w32: suffix scan", "w32: permute"]
     tot = prof[:16].sum()
     for i, n in enumerate(names):
         if prof[16 + i]:
