@@ -2303,6 +2303,21 @@ static int sm_count() {
   return g_sm_count;
 }
 
+// Persistent grid = SMs x CTAs of this kernel that are resident at once (registers decide: 3 for the audit, 6 / 8
+// for scatter / gather): every CTA runs the same number of grid-stride trips, no partial last wave.
+template <typename K>
+static int resident_grid(K kernel, int threads, int *cache) {
+  if (!*cache) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm <= 0) {
+      cudaGetLastError();
+      per_sm = 4;
+    }
+    *cache = per_sm * sm_count();
+  }
+  return *cache;
+}
+
 int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -2328,7 +2343,8 @@ int launch_audit(const DevState &st, int64_t *d_out4, void *stream, bool zero_co
   int mode = 2;
   if (st.exact && (st.bpp == 32 || st.bpp == 64 || st.bpp == 128)) mode = 0;
   else if (st.exact && st.bpp % 128 == 0 && st.bpp / 128 <= 32 && ((st.bpp / 128) & (st.bpp / 128 - 1)) == 0) mode = 1;
-  kvb_audit_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(st, d_out4, mode);
+  static int grid_audit = 0;
+  kvb_audit_kernel<<<resident_grid(kvb_audit_kernel, 256, &grid_audit), 256, 0, (cudaStream_t)stream>>>(st, d_out4, mode);
   return (int)cudaGetLastError();
 }
 
@@ -2345,7 +2361,8 @@ int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, vo
   int g = 32;                        // lanes per cell: largest power of two with >= 4 vectors per lane
   while (g > 1 && g * 4 > vec) g >>= 1;
   int64_t want = (cells * g + 255) / 256;
-  int64_t grid = (int64_t)sm_count() * 8;   // persistent: 8 resident CTAs of 256 threads per SM
+  static int grid_sc = 0, grid_ga = 0;
+  int64_t grid = gather ? resident_grid(kvb_kv_copy_kernel<1>, 256, &grid_ga) : resident_grid(kvb_kv_copy_kernel<0>, 256, &grid_sc);
   if (want < grid) grid = want;
   if (gather)
     kvb_kv_copy_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,
