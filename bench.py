@@ -292,6 +292,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     h2d = (s1.h2d_bytes - bytes0[0]) / K
     d2h = (s1.d2h_bytes - bytes0[1]) / K
     vst = vmm_ops.vmm_stats()
+    est = vmm_ops.engine_stats()
     mapped_now = vmm_ops.mapped_pages()
     if rank == 0:
         assert sorted(mapped_now) == mgr.mapped_pages(), "VMM mapping must equal the bookkeeping's mapped set"
@@ -461,7 +462,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "dtype": "int64", "data": "synthetic", "config": workload_config(world), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_total / K, "scheduler_steps": len(plan.steps),
-                        "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"]},
+                        "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"],
+                                "map_ahead_depth": est["depth"], "map_ahead_hits": est["prefetch_hits"],
+                                "events_elided": est["elided"]},
                         "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
                                "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
                                "timed region"},

@@ -109,6 +109,15 @@ int kvb_vmm_wait_maps(int64_t group_id);
 int kvb_vmm_fence(int64_t group_id);
 int kvb_vmm_set_async(int64_t group_id, int on);
 int64_t kvb_vmm_pending_unmaps(int64_t group_id);
+/* Map-ahead: the step kernel publishes the next pages its free list will hand out; the VMM thread maps up to `depth`
+ * of them in its idle time (wanted maps > hinted maps > unmaps), so the map event that follows costs nothing on
+ * the scheduler's path.  Physical state only: the bookkeeping (mapped set, counters, page order) is unchanged —
+ * unlike the reference's prealloc thread (page_allocator.cpp:524-617), whose reserved list alters results with
+ * timing.  depth 0 = off; default KVB200_VMM_PREFETCH or 5 (the reference's KVCACHED_MIN_RESERVED_PAGES). */
+int kvb_vmm_prefetch_config(int64_t group_id, int depth);
+int64_t kvb_vmm_prefetched_pages(int64_t group_id, int64_t *out, int64_t cap);   /* hinted + mapped, not yet wanted */
+/* out8 = {events elided, map-ahead hits, pages mapped ahead now, need_map, need_unmap, need_hinted, hints, depth} */
+int kvb_vmm_engine_stats(int64_t group_id, int64_t *out8);
 
 /* physical-handle pool (no cuMemCreate / cuMemRelease on the hot path; page.cpp:10-25 creates and
  * releases one handle per map).  `max_cached` handles are kept after unmap, the rest released;

@@ -89,6 +89,9 @@ SIGNATURES = {
     "kvb_vmm_fence": (C.c_int, [i64]),
     "kvb_vmm_set_async": (C.c_int, [i64, C.c_int]),
     "kvb_vmm_pending_unmaps": (i64, [i64]),
+    "kvb_vmm_prefetch_config": (C.c_int, [i64, C.c_int]),
+    "kvb_vmm_prefetched_pages": (i64, [i64, p_i64, i64]),
+    "kvb_vmm_engine_stats": (C.c_int, [i64, p_i64]),
     "kvb_vmm_pool_config": (C.c_int, [i64, i64]),
     "kvb_vmm_pool_prefill": (C.c_int, [i64, i64]),
     "kvb_vmm_stats": (C.c_int, [i64, p_i64]),

@@ -118,6 +118,25 @@ int64_t kvb_vmm_pending_unmaps(int64_t group_id) {
   if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
   return g->pending_unmaps();
 }
+int kvb_vmm_prefetch_config(int64_t group_id, int depth) {
+  VmmGroup *g = vmm_group(group_id, true);
+  if (!g) return KVB_ERR_STATE;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_prefetch_depth(depth);
+  if (depth <= 0) g->set_prefetch_hints(nullptr, 0);
+  return 0;
+}
+int64_t kvb_vmm_prefetched_pages(int64_t group_id, int64_t *out, int64_t cap) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  return g->prefetched_pages(out, cap);
+}
+int kvb_vmm_engine_stats(int64_t group_id, int64_t *out8) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  g->engine_stats(out8);
+  return 0;
+}
 int kvb_vmm_pool_config(int64_t group_id, int64_t max_cached) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;

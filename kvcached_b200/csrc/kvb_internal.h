@@ -96,6 +96,8 @@ struct Summary {
   int64_t sc[SC_COUNT];
   int64_t ev_inline_n;
   int64_t ev_inline[256];
+  int64_t next_free_n;    // how many entries of next_free are valid
+  int64_t next_free[16];  // the pages alloc_page() will MAP next: the front of free_page_list (map-ahead hints)
 };
 
 struct LaunchArgs {

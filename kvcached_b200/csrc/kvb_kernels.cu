@@ -1993,6 +1993,11 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
     int64_t nin = nev < EV_INLINE ? nev : EV_INLINE;
     for (int i = tid; i < nin; i += NT) sm->ev_inline[i] = c.ev[ev_begin + i];
     if (tid < SC_COUNT) sm->sc[tid] = sc[tid];
+    if (tid < 16) {   // map-ahead hints: reserved pages are mapped already, so the next mappings are the free list's front
+      const int64_t fls = sc[SC_FL_SIZE];
+      sm->next_free[tid] = tid < fls ? c.fl[(int)((sc[SC_FL_HEAD] + tid) & c.q_mask)] : -1;
+      if (tid == 0) sm->next_free_n = fls < 16 ? fls : 16;
+    }
     if (a.host_res) {
       // zero-copy step: results go straight to the caller's pinned host buffers over PCIe; the
       // summary's sequence number (written last, after a system-scope fence) is what the host polls.

@@ -544,12 +544,18 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     const int64_t *sc = m->last.sc;
     m->shm_publishes += m->shm->publish((sc[SC_NTOTAL] - sc[SC_NFREE]) * per_page, sc[SC_RL_SIZE] * per_page);
   }
-  if (settle && m->cfg.attach_vmm) {   // also when this step produced no events of its own: earlier frees may be queued
+  if (m->cfg.attach_vmm) {
     VmmGroup *g = vmm_group(m->cfg.group_id, false);
     if (g && g->created()) {
       std::lock_guard<std::mutex> lk(g->mu);
-      rc = g->fence();
-      if (rc) return rc;
+      const Summary *hs2 = (const Summary *)m->h_out;
+      if (settle) {   // memory goes back on purpose: nothing stays mapped ahead, and earlier queued unmaps settle too
+        g->set_prefetch_hints(nullptr, 0);
+        rc = g->fence();
+        if (rc) return rc;
+      } else {        // map-ahead hints: the pages the free list will hand out next
+        g->set_prefetch_hints(hs2->next_free, hs2->next_free_n);
+      }
     }
   }
   memcpy(res, m->h_out + o_res, b_res);
@@ -714,6 +720,13 @@ static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg,
     const int64_t per_page = m->cfg.num_layers * m->P * m->cfg.num_kv_buffers;
     const int64_t *sc = m->last.sc;
     m->shm_publishes += m->shm->publish((sc[SC_NTOTAL] - sc[SC_NFREE]) * per_page, sc[SC_RL_SIZE] * per_page);
+  }
+  if (m->cfg.attach_vmm) {
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g && g->created()) {
+      std::lock_guard<std::mutex> lk(g->mu);
+      g->set_prefetch_hints(hs->next_free, hs->next_free_n);
+    }
   }
   memcpy(res, m->h_out + o_res, sizeof(kvb_res));
   return 0;
@@ -1100,14 +1113,17 @@ extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   int64_t n = (int64_t)m->pending_events.size();
-  if (n > kTpWords - 2) { set_error("tp_export: %ld page events exceed the broadcast buffer (%ld)", (long)n, (long)(kTpWords - 2)); return KVB_ERR_OVERFLOW; }
-  size_t bytes = (size_t)(2 + n) * 8;
+  int64_t nh = std::max<int64_t>(0, std::min<int64_t>(m->last.next_free_n, 16));
+  if (n + nh + 3 > kTpWords) { set_error("tp_export: %ld page events exceed the broadcast buffer (%ld)", (long)n, (long)(kTpWords - 3 - nh)); return KVB_ERR_OVERFLOW; }
+  size_t bytes = (size_t)(3 + n + nh) * 8;
   int rc = ensure_io(m, bytes, 0);
   if (rc) return rc;
   int64_t *h = (int64_t *)m->h_in;
   h[0] = m->seq;
   h[1] = n;
   if (n) memcpy(h + 2, m->pending_events.data(), (size_t)n * 8);
+  h[2 + n] = nh;                       // map-ahead hints ride along: followers pre-map the same pages
+  for (int64_t i = 0; i < nh; ++i) h[3 + n + i] = m->last.next_free[i];
   m->pending_events.clear();
   CUDA_TRY(cudaMemcpyAsync((void *)(uintptr_t)dst, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1123,13 +1139,18 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   if (seq_out) *seq_out = hdr[0];
   if (n_out) *n_out = hdr[1];
-  if (hdr[1] < 0 || hdr[1] > kTpWords - 2) { set_error("tp_apply: corrupt header n=%ld", (long)hdr[1]); return KVB_ERR_INVALID; }
-  if (hdr[1] == 0) return 0;
-  std::vector<int64_t> ev((size_t)hdr[1]);
-  CUDA_TRY(cudaMemcpy(ev.data(), (const void *)(uintptr_t)(src + 16), (size_t)hdr[1] * 8, cudaMemcpyDeviceToHost));
+  if (hdr[1] < 0 || hdr[1] > kTpWords - 3) { set_error("tp_apply: corrupt header n=%ld", (long)hdr[1]); return KVB_ERR_INVALID; }
+  // events, then [nh, hints...]; one copy of the tail that can hold both
+  std::vector<int64_t> ev((size_t)hdr[1] + 17);
+  CUDA_TRY(cudaMemcpy(ev.data(), (const void *)(uintptr_t)(src + 16), ev.size() * 8 <= (size_t)(kTpWords - 2) * 8 ? ev.size() * 8 : (size_t)(kTpWords - 2) * 8, cudaMemcpyDeviceToHost));
   std::lock_guard<std::mutex> lk(g->mu);
-  int rc = g->enqueue_events(ev.data(), hdr[1]);
-  if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
+  int rc = 0;
+  if (hdr[1] > 0) {
+    rc = g->enqueue_events(ev.data(), hdr[1]);
+    if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
+  }
+  int64_t nh = ev[(size_t)hdr[1]];
+  if (nh >= 0 && nh <= 16 && hdr[1] + 1 + nh <= kTpWords - 2) g->set_prefetch_hints(ev.data() + hdr[1] + 1, nh);
   return rc < 0 ? rc : 0;
 }
 

@@ -176,6 +176,13 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   handles_.assign((size_t)n_pages_ * n_sub_, 0);
   mapped_.assign((size_t)n_pages_, 0);
   want_.assign((size_t)n_pages_, 0);
+  spec_.assign((size_t)n_pages_, 0);
+  {
+    // pages mapped ahead of demand; the reference keeps KVCACHED_MIN_RESERVED_PAGES (5) pre-mapped by default
+    const char *e = getenv("KVB200_VMM_PREFETCH");
+    int d = e && *e ? atoi(e) : 5;
+    prefetch_depth_ = d < 0 ? 0 : (d > 16 ? 16 : d);
+  }
   {
     // KVB200_VMM_ASYNC=0: the calling thread runs the driver loop itself and every call returns settled
     const char *e = getenv("KVB200_VMM_ASYNC");
@@ -221,24 +228,25 @@ CUdeviceptr VmmGroup::sub_addr(int64_t p, int sub) const {
     }                                                                        \
   }
 
-void VmmGroup::set_want(int64_t p, bool v) {
-  bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
-  if (w == v) return;
+// One place where a page's (wanted, hinted, physical) state changes, so that the work counters stay exact:
+//   need_map   wanted and not mapped          need_unmap  mapped, neither wanted nor hinted
+//   need_spec  hinted, not wanted, not mapped  n_spec_mapped  hinted pages mapped ahead of their event
+void VmmGroup::update(int64_t p, int want, int spec, int phys) {
+  bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p];
   need_map_ -= (w && !ph);
-  need_unmap_ -= (!w && ph);
-  want_[(size_t)p] = v;
-  need_map_ += (v && !ph);
-  need_unmap_ += (!v && ph);
-}
-void VmmGroup::set_phys(int64_t p, bool v) {
-  bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
-  if (ph == v) return;
-  need_map_ -= (w && !ph);
-  need_unmap_ -= (!w && ph);
-  mapped_[(size_t)p] = v;
-  n_mapped_ += v ? 1 : -1;
-  need_map_ += (w && !v);
-  need_unmap_ += (!w && v);
+  need_unmap_ -= (ph && !w && !sp);
+  need_spec_ -= (sp && !w && !ph);
+  n_spec_mapped_ -= (sp && !w && ph);
+  if (want >= 0) w = want != 0;
+  if (spec >= 0) sp = spec != 0;
+  if (phys >= 0 && ph != (phys != 0)) { ph = phys != 0; n_mapped_ += ph ? 1 : -1; }
+  want_[(size_t)p] = w;
+  spec_[(size_t)p] = sp;
+  mapped_[(size_t)p] = ph;
+  need_map_ += (w && !ph);
+  need_unmap_ += (ph && !w && !sp);
+  need_spec_ += (sp && !w && !ph);
+  n_spec_mapped_ += (sp && !w && ph);
 }
 
 int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
@@ -284,7 +292,7 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
     if (!werr_) { werr_ = rc; werr_msg_ = emsg; }
     // leave the page as it was recorded; handles taken from the pool go back
     if (to_mapped) for (auto h : hs) if (h) pool_.push_back(h);
-    set_want(p, mapped_[(size_t)p]);
+    update(p, mapped_[(size_t)p], 0, -1);
     return rc;
   }
   if (to_mapped) {
@@ -318,10 +326,18 @@ bool VmmGroup::process_next(Lock &lk) {
     transition(lk, p, true);
     return true;
   }
+  while (need_map_ == 0 && !qs_.empty()) {   // hinted maps: only when no wanted map is waiting
+    int64_t p = qs_.front();
+    if (!(spec_[(size_t)p] && !want_[(size_t)p] && !mapped_[(size_t)p])) { qs_.pop_front(); continue; }
+    if ((int64_t)pool_.size() < n_sub_ && need_unmap_ > 0) break;   // an unmap yields the handle
+    qs_.pop_front();
+    transition(lk, p, true);
+    return true;
+  }
   while (!qu_.empty()) {
     int64_t p = qu_.front();
     qu_.pop_front();
-    if (!(!want_[(size_t)p] && mapped_[(size_t)p])) continue;
+    if (!(!want_[(size_t)p] && !spec_[(size_t)p] && mapped_[(size_t)p])) continue;
     transition(lk, p, false);
     return true;
   }
@@ -331,18 +347,19 @@ bool VmmGroup::process_next(Lock &lk) {
 void VmmGroup::worker_main() {
   Lock lk(qmu_);
   while (true) {
-    cv_work_.wait(lk, [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0; });
+    cv_work_.wait(lk, [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0 || need_spec_ > 0; });
     if (stop_ && need_map_ == 0 && need_unmap_ == 0) break;
     bool did = process_next(lk);
     cv_done_.notify_all();
     if (!did) {
       // counters say there is work but the queues are empty: cannot happen; avoid spinning if it does
       if (stop_) break;
-      need_map_ = need_unmap_ = 0;
+      need_map_ = need_unmap_ = need_spec_ = 0;
       for (int64_t p = 0; p < n_pages_; ++p) {
-        bool w = want_[(size_t)p], ph = mapped_[(size_t)p];
+        bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p];
         if (w && !ph) { need_map_++; qm_.push_back(p); }
-        if (!w && ph) { need_unmap_++; qu_.push_back(p); }
+        if (!w && !sp && ph) { need_unmap_++; qu_.push_back(p); }
+        if (sp && !w && !ph) { need_spec_++; qs_.push_back(p); }
       }
     }
   }
@@ -386,7 +403,8 @@ int VmmGroup::drain(Lock &lk, bool maps_only) {
       if (werr_) return true;
       if (need_map_ > 0) return false;
       if (maps_only) return !(inflight_ >= 0 && !inflight_to_mapped_ && want_[(size_t)inflight_]);
-      return need_unmap_ == 0 && inflight_ < 0;
+      // a hinted (unwanted) map in flight is nobody's business
+      return need_unmap_ == 0 && (inflight_ < 0 || (inflight_to_mapped_ && !want_[(size_t)inflight_]));
     });
   } else {
     while (!werr_ && (need_map_ > 0 || (!maps_only && need_unmap_ > 0)))
@@ -413,9 +431,11 @@ int VmmGroup::enqueue_events(const int64_t *ev, int64_t n) {
     if (p < 0 || p >= n_pages_) { set_error("%s: page %ld out of range [0, %ld)", un ? "unmap" : "map", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
     bool w = want_[(size_t)p];
     if (w == !un) continue;   // "already mapped" / "not mapped" is tolerated (allocator.cpp:174-177, ftensor.cpp:104-107)
+    if (!un && spec_[(size_t)p] && mapped_[(size_t)p] && inflight_ != p) n_prefetch_hits_++;   // mapped ahead: no wait
     set_want(p, !un);
-    if (want_[(size_t)p] != (bool)mapped_[(size_t)p] || inflight_ == p) (un ? qu_ : qm_).push_back(p);
-    else n_elided_++;        // met its own pending opposite: nothing to do physically
+    const bool settled = un ? (!mapped_[(size_t)p] || spec_[(size_t)p]) : (bool)mapped_[(size_t)p];
+    if (!settled || inflight_ == p) (un ? qu_ : qm_).push_back(p);
+    else n_elided_++;        // met its own pending opposite / was mapped ahead: nothing to do physically
   }
   n_map_calls_++;
   if (async_ && (need_map_ > 0 || need_unmap_ > 0)) {
@@ -439,6 +459,53 @@ int VmmGroup::fence() {
   Lock lk(qmu_);
   return drain(lk, false);
 }
+void VmmGroup::set_prefetch_depth(int depth) {
+  Lock lk(qmu_);
+  prefetch_depth_ = depth < 0 ? 0 : (depth > 16 ? 16 : depth);
+}
+
+// New hint window: pages that left it without being wanted go back to the zero page, new ones are queued for
+// the VMM thread's idle time.  No waiting here.
+void VmmGroup::set_prefetch_hints(const int64_t *pages, int64_t n) {
+  if (!created_) return;
+  Lock lk(qmu_);
+  if (!async_ || prefetch_depth_ <= 0) n = 0;
+  if (n > prefetch_depth_) n = prefetch_depth_;
+  bool same = (int64_t)hints_.size() == n;
+  for (int64_t i = 0; same && i < n; ++i) same = hints_[(size_t)i] == pages[i];
+  if (same) return;
+  std::vector<int64_t> old;
+  old.swap(hints_);
+  for (int64_t i = 0; i < n; ++i)
+    if (pages[i] >= 0 && pages[i] < n_pages_) hints_.push_back(pages[i]);
+  for (int64_t p : old) update(p, -1, 0, -1);
+  for (int64_t p : hints_) {
+    update(p, -1, 1, -1);
+    if (!want_[(size_t)p] && !mapped_[(size_t)p]) qs_.push_back(p);
+  }
+  for (int64_t p : old)
+    if (!spec_[(size_t)p] && !want_[(size_t)p] && (mapped_[(size_t)p] || inflight_ == p)) qu_.push_back(p);
+  if (need_spec_ > 0 || need_unmap_ > 0) {
+    if (!worker_running_) {
+      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
+      worker_running_ = true;
+      worker_ = std::thread([this] { worker_main(); });
+    }
+    cv_work_.notify_all();
+  }
+}
+
+int64_t VmmGroup::prefetched_pages(int64_t *out, int64_t cap) {
+  Lock lk(qmu_);
+  int64_t n = 0;
+  for (int64_t p : hints_)
+    if (spec_[(size_t)p] && !want_[(size_t)p] && mapped_[(size_t)p]) {
+      if (n >= cap) return -5;
+      out[n++] = p;
+    }
+  return n;
+}
+
 int64_t VmmGroup::pending_unmaps() {
   Lock lk(qmu_);
   return need_unmap_;
@@ -500,7 +567,7 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
 // pages whose unmap is still queued (their handles come back to the pool)
 int64_t VmmGroup::pooled_pages() {
   Lock lk(qmu_);
-  return n_sub_ ? (int64_t)pool_.size() / n_sub_ + need_unmap_ : 0;
+  return n_sub_ ? (int64_t)pool_.size() / n_sub_ + need_unmap_ + n_spec_mapped_ : 0;
 }
 int64_t VmmGroup::pool_release(int64_t n_pages) {
   Lock lk(qmu_);
@@ -512,6 +579,18 @@ int64_t VmmGroup::pool_release(int64_t n_pages) {
     n++;
   }
   return n_sub_ ? n / n_sub_ : 0;
+}
+
+void VmmGroup::engine_stats(int64_t *s) {
+  Lock lk(qmu_);
+  s[0] = n_elided_;
+  s[1] = n_prefetch_hits_;
+  s[2] = n_spec_mapped_;
+  s[3] = need_map_;
+  s[4] = need_unmap_;
+  s[5] = need_spec_;
+  s[6] = (int64_t)hints_.size();
+  s[7] = prefetch_depth_;
 }
 
 void VmmGroup::timing(double *out10) {
@@ -531,11 +610,11 @@ void VmmGroup::stats(int64_t *s) {
   s[7] = (int64_t)unit_ * n_sub_;
 }
 int64_t VmmGroup::mapped_pages(int64_t *out, int64_t cap) {
-  if (created_) fence();   // inspection sees the settled state
+  if (created_) fence();   // inspection sees the settled state; pages mapped ahead of their event are not "mapped"
   Lock lk(qmu_);
   int64_t n = 0;
   for (int64_t p = 0; p < n_pages_; ++p)
-    if (mapped_[(size_t)p]) {
+    if (mapped_[(size_t)p] && want_[(size_t)p]) {
       if (n >= cap) return -5;
       out[n++] = p;
     }

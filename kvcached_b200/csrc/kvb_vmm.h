@@ -66,7 +66,17 @@ class VmmGroup {
   // page_allocator.cpp:524-617, but changes the bookkeeping; this does not).
   int enqueue_events(const int64_t *events, int64_t n);
   int wait_maps();    // every wanted mapping is physically in place
-  int fence();        // physical state == wanted state
+  int fence();        // every wanted mapping in place, every unwanted (and not hinted) page back on the zero page
+  // Map-ahead: the pages the bookkeeping will hand out next (the front of its free page list, published by the
+  // step kernel) are mapped by the VMM thread while it has nothing else to do, so the map event that follows
+  // finds them in place.  Physical state only — the bookkeeping's mapped set, counters and page order do not
+  // change (the reference's prealloc thread, page_allocator.cpp:524-617, moves pages to its reserved list and so
+  // changes results with timing).  Priority: wanted maps > hinted maps > unmaps.  A hinted page that falls out of
+  // the hint window without being wanted is unmapped again.  Off in synchronous mode and when depth is 0.
+  void set_prefetch_hints(const int64_t *pages, int64_t n);
+  void set_prefetch_depth(int depth);
+  int prefetch_depth() const { return prefetch_depth_; }
+  int64_t prefetched_pages(int64_t *out, int64_t cap);   // hinted, physically mapped, not (yet) wanted
   void set_async(bool on);
   bool async() const { return async_; }
   void set_sync_before_unmap(bool on) { sync_before_unmap_ = on; }
@@ -77,6 +87,7 @@ class VmmGroup {
   void pool_config(int64_t max_cached);
   int pool_prefill(int64_t n_pages);
   void stats(int64_t *s8);
+  void engine_stats(int64_t *s8);   // {events elided, map-ahead hits, pages mapped ahead now, need_map, need_unmap, need_spec, hints, depth}
   void timing(double *out10);   // us spent in / calls of {create, release, unmap, map, setaccess}
   int64_t mapped_pages(int64_t *out, int64_t cap);
   int64_t pooled_pages();
@@ -93,8 +104,9 @@ class VmmGroup {
   using Lock = std::unique_lock<std::mutex>;
   bool process_next(Lock &lk);              // one page transition; lock held on entry and exit, released around driver calls
   int transition(Lock &lk, int64_t p, bool to_mapped);
-  void set_want(int64_t p, bool v);
-  void set_phys(int64_t p, bool v);
+  void update(int64_t p, int want, int spec, int phys);   // -1 = keep; maintains the need_* counters
+  void set_want(int64_t p, bool v) { update(p, v, -1, -1); }
+  void set_phys(int64_t p, bool v) { update(p, -1, -1, v); }
   int drain(Lock &lk, bool maps_only);
   void worker_main();
   void stop_worker();
@@ -118,8 +130,11 @@ class VmmGroup {
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
   std::vector<uint8_t> mapped_;   // physical state
   std::vector<uint8_t> want_;     // state after every event received so far
-  std::deque<int64_t> qm_, qu_;   // pages whose wanted state may differ from the physical one (maps / unmaps)
-  int64_t need_map_ = 0, need_unmap_ = 0, inflight_ = -1;
+  std::vector<uint8_t> spec_;     // hinted: map ahead of the event
+  std::deque<int64_t> qm_, qu_, qs_;   // pages whose wanted state may differ from the physical one (maps / unmaps / hinted maps)
+  std::vector<int64_t> hints_;
+  int prefetch_depth_ = 0;
+  int64_t need_map_ = 0, need_unmap_ = 0, need_spec_ = 0, n_spec_mapped_ = 0, n_prefetch_hits_ = 0, inflight_ = -1;
   bool inflight_to_mapped_ = false;
   std::mutex qmu_;
   std::condition_variable cv_work_, cv_done_;

@@ -114,6 +114,24 @@ def pending_unmaps(group_id: int = 0) -> int:
     return int(_lib.check(_lib.load().kvb_vmm_pending_unmaps(group_id)))
 
 
+def set_prefetch(depth: int, group_id: int = 0) -> None:
+    """Pages the VMM thread maps ahead of the bookkeeping's next allocations (0 = off)."""
+    _lib.check(_lib.load().kvb_vmm_prefetch_config(group_id, int(depth)), "vmm prefetch_config")
+
+
+def prefetched_pages(group_id: int = 0) -> List[int]:
+    buf = np.empty(64, dtype=np.int64)
+    n = _lib.check(_lib.load().kvb_vmm_prefetched_pages(group_id, buf.ctypes.data_as(_lib.p_i64), buf.size))
+    return buf[:n].tolist()
+
+
+def engine_stats(group_id: int = 0) -> Dict[str, int]:
+    s = np.zeros(8, dtype=np.int64)
+    _lib.check(_lib.load().kvb_vmm_engine_stats(group_id, s.ctypes.data_as(_lib.p_i64)))
+    keys = ["elided", "prefetch_hits", "mapped_ahead", "need_map", "need_unmap", "need_hinted", "hints", "depth"]
+    return dict(zip(keys, s.tolist()))
+
+
 def vmm_stats(group_id: int = 0) -> Dict[str, int]:
     s = np.zeros(8, dtype=np.int64)
     _lib.check(_lib.load().kvb_vmm_stats(group_id, s.ctypes.data_as(_lib.p_i64)))

@@ -26,6 +26,7 @@ def kvcached_fixture():
     cell = H * D * 2
     per_layer = blocks * bs * cell * 2           # K and V
     (flat,) = vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", L)
+    vmm_ops.set_prefetch(0)                      # zero-page expectations below need pages to be mapped on demand only
     mgr = KVCacheManager(blocks, bs, cell, L)
     yield dict(mgr=mgr, flat=flat, L=L, blocks=blocks, bs=bs, cell=cell, H=H, D=D)
     mgr.close()
@@ -84,6 +85,52 @@ def test_map_unmap_by_offsets_is_idempotent(kvcached_fixture):
     assert vmm_ops.mapped_pages() == []
     st = vmm_ops.vmm_stats()
     assert st["pooled_handles"] == 2 and st["handles_created"] >= 3   # zero page + 2, parked in the pool
+
+
+def test_map_ahead_follows_the_free_list(kvcached_fixture):
+    """The VMM thread maps the next pages of the bookkeeping's free list in its idle time: the map event that
+    follows is a no-op on the scheduler's path, the bookkeeping's mapped set never shows the extra pages, and
+    trim() hands everything back."""
+    import time
+    import torch
+    f = kvcached_fixture
+    m, L, bs, cell = f["mgr"], f["L"], f["bs"], f["cell"]
+    kv = f["flat"].view(torch.int16).view(f["blocks"], L, 2, bs, cell // 2)
+    bpp = PAGE // (bs * cell)
+    vmm_ops.set_prefetch(4)
+
+    def settle():
+        vmm_ops.fence()
+        t0 = time.time()
+        while vmm_ops.engine_stats()["need_hinted"] and time.time() - t0 < 5:
+            time.sleep(0.001)
+
+    try:
+        a = m.alloc(2 * bpp)                              # pages 0, 1
+        settle()
+        assert m.free_page_list()[:4] == [2, 3, 4, 5] == vmm_ops.prefetched_pages()
+        assert vmm_ops.mapped_pages() == [0, 1] == m.mapped_pages()
+        assert vmm_ops.vmm_stats()["mapped_pages"] == 6   # physically: 2 wanted + 4 ahead
+        e0, t0 = vmm_ops.engine_stats(), vmm_ops.vmm_timing()
+        b = m.alloc(2 * bpp)                              # pages 2, 3: already in place
+        e1, t1 = vmm_ops.engine_stats(), vmm_ops.vmm_timing()
+        assert e1["prefetch_hits"] == e0["prefetch_hits"] + 2
+        assert b == list(range(2 * bpp, 4 * bpp))
+        kv[2 * bpp, :, :, 0, 0] = 321
+        kv[3 * bpp, :, :, 0, 0] = 654
+        torch.cuda.synchronize()
+        settle()
+        assert vmm_ops.prefetched_pages() == [4, 5, 6, 7]  # the window moved with the free list
+        assert int(kv[2 * bpp, 0, 0, 0, 0]) == 321 and int(kv[3 * bpp, L - 1, 1, 0, 0]) == 654
+        assert vmm_ops.mapped_pages() == [0, 1, 2, 3]
+        m.free(a + b)
+        m.trim()                                          # settle point: hints dropped, everything unmapped
+        assert vmm_ops.prefetched_pages() == [] and vmm_ops.mapped_pages() == []
+        assert vmm_ops.vmm_stats()["mapped_pages"] == 0
+        torch.cuda.synchronize()
+        assert int(kv[2 * bpp, 0, 0, 0, 0]) == 0          # back on the zero page
+    finally:
+        vmm_ops.set_prefetch(0)
 
 
 @pytest.mark.parametrize("use_thread", [True, False])
