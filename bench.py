@@ -266,10 +266,12 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     if world > 1:
         from kvcached_b200 import tp as TP
         tp = TP.TpPageSync(mgr if rank == 0 else None, group_id=0, rank=rank, world=world, device=dev)
+    vt0 = None
     for it in range(W + K):
         if it == W:
             s0 = mgr.stats()
             bytes0 = (s0.h2d_bytes, s0.d2h_bytes)
+            vt0 = vmm_ops.vmm_timing()
         flush_buf.fill_(it & 0xff)
         barrier()
         t0 = time.perf_counter()
@@ -293,6 +295,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     d2h = (s1.d2h_bytes - bytes0[1]) / K
     vst = vmm_ops.vmm_stats()
     est = vmm_ops.engine_stats()
+    vt1 = vmm_ops.vmm_timing()
+    drv_ms = sum(vt1[k] - vt0[k] for k in ("unmap_ms", "map_ms", "setaccess_ms", "create_ms", "release_ms")) / K
+    transitions = (vt1["unmap_calls"] - vt0["unmap_calls"]) / K
     mapped_now = vmm_ops.mapped_pages()
     if rank == 0:
         assert sorted(mapped_now) == mgr.mapped_pages(), "VMM mapping must equal the bookkeeping's mapped set"
@@ -463,8 +468,13 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_total / K, "scheduler_steps": len(plan.steps),
                         "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"],
-                                "map_ahead_depth": est["depth"], "map_ahead_hits": est["prefetch_hits"],
-                                "events_elided": est["elided"]},
+                                "page_transitions_per_replay": transitions, "driver_ms_per_replay": drv_ms,
+                                "page_events_per_replay": 1744 if world == 1 else None,
+                                "map_ahead_hits": est["prefetch_hits"], "retention_hits": est["retention_hits"],
+                                "pages_retained_at_end": est["retained"],
+                                "policy": "async VMM thread; map-ahead 5 pages; unmapped pages keep their handle until the "
+                                          "allocator is quiet for 2 s, at most while 20% of the device stays free "
+                                          "(KVB200_VMM_PREFETCH / KVB200_VMM_RETAIN_MS / KVB200_RETAIN_FREE_FRACTION)"},
                         "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
                                "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
                                "timed region"},

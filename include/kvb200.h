@@ -108,6 +108,20 @@ int kvb_vmm_enqueue_page_events(int64_t group_id, const int64_t *events, int64_t
 int kvb_vmm_wait_maps(int64_t group_id);
 int kvb_vmm_fence(int64_t group_id);
 int kvb_vmm_set_async(int64_t group_id, int on);
+/* Retention: a page the bookkeeping unmapped keeps its physical handle mapped until the allocator has been quiet (no
+ * map event) for `ms` milliseconds (default KVB200_VMM_RETAIN_MS or 2000; 0 = unmap at once).  Mapped again before
+ * that it costs nothing.  It goes back to the
+ * zero page and its memory to the device earlier when a map needs a handle that can neither come from the pool nor
+ * be created within the KVCACHED_GPU_UTILIZATION headroom (the page retained last goes first: the free page list is
+ * a FIFO), when the pool cap is exceeded, under memory pressure and at settle points (trim / clear / resize /
+ * kvctl limit, kvb_vmm_settle).  Idle pooled handles above KVB200_POOL_FLOOR (16) are released after the same
+ * time.  The reference's hysteresis is count-based: max_reserved_pages stay mapped (page_allocator.cpp:264-310). */
+int kvb_vmm_set_retention_ms(int64_t group_id, double ms);
+/* Retained pages are kept only while at least this fraction of the device stays free for everybody else (default
+ * KVB200_RETAIN_FREE_FRACTION or 0.20): a co-located model always sees that much memory, and as it takes it the VMM
+ * thread hands retained pages back (newest first) until the reserve is whole again. */
+int kvb_vmm_set_retain_free_fraction(int64_t group_id, double fraction);
+int kvb_vmm_settle(int64_t group_id);
 int64_t kvb_vmm_pending_unmaps(int64_t group_id);
 /* Map-ahead: the step kernel publishes the next pages its free list will hand out; the VMM thread maps up to `depth`
  * of them in its idle time (wanted maps > hinted maps > unmaps), so the map event that follows costs nothing on
@@ -116,7 +130,8 @@ int64_t kvb_vmm_pending_unmaps(int64_t group_id);
  * timing.  depth 0 = off; default KVB200_VMM_PREFETCH or 5 (the reference's KVCACHED_MIN_RESERVED_PAGES). */
 int kvb_vmm_prefetch_config(int64_t group_id, int depth);
 int64_t kvb_vmm_prefetched_pages(int64_t group_id, int64_t *out, int64_t cap);   /* hinted + mapped, not yet wanted */
-/* out8 = {events elided, map-ahead hits, pages mapped ahead now, need_map, need_unmap, need_hinted, hints, depth} */
+/* out8 = {events elided, map-ahead hits, pages mapped ahead now, need_map, forced unmaps pending, need_hinted,
+ *         pages retained now, retention hits} */
 int kvb_vmm_engine_stats(int64_t group_id, int64_t *out8);
 
 /* physical-handle pool (no cuMemCreate / cuMemRelease on the hot path; page.cpp:10-25 creates and

@@ -106,6 +106,26 @@ int kvb_vmm_fence(int64_t group_id) {
   std::lock_guard<std::mutex> lk(g->mu);
   return g->fence();
 }
+int kvb_vmm_settle(int64_t group_id) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  return g->settle();
+}
+int kvb_vmm_set_retention_ms(int64_t group_id, double ms) {
+  VmmGroup *g = vmm_group(group_id, true);
+  if (!g) return KVB_ERR_STATE;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_retention_ms(ms);
+  return 0;
+}
+int kvb_vmm_set_retain_free_fraction(int64_t group_id, double f) {
+  VmmGroup *g = vmm_group(group_id, true);
+  if (!g) return KVB_ERR_STATE;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_retain_free_fraction(f);
+  return 0;
+}
 int kvb_vmm_set_async(int64_t group_id, int on) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;

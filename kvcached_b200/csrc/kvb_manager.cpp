@@ -141,9 +141,13 @@ int64_t phys_free_pages(kvb_mgr *m) {
   if (m->phys_cached >= 0 && now - m->phys_time_us < m->phys_refresh_us) return m->phys_cached;
   m->phys_time_us = now;
   size_t fr = 0, tot = 0;
-  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
+  // with live tensors the VMM thread samples device memory; the scheduler thread stays out of the driver
+  VmmGroup *gq = m->cfg.attach_vmm ? vmm_group(m->cfg.group_id, false) : nullptr;
+  if (!(gq && gq->cached_meminfo(&fr, &tot))) {
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
   }
   double headroom = (double)tot * (1.0 - m->gpu_util);
   double avail = (double)fr - headroom;
@@ -186,7 +190,7 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n, bool settle = false) 
   std::lock_guard<std::mutex> lk(g->mu);
   g->set_sync_before_unmap(m->cfg.async_sched != 0);
   int rc = g->enqueue_events(ev, n);
-  if (rc >= 0) rc = (g->async() && !settle) ? g->wait_maps() : g->fence();
+  if (rc >= 0) rc = (g->async() && !settle) ? g->wait_maps() : (settle ? g->settle() : g->fence());
   m->phys_cached = -1;   // physical memory just changed hands
   return rc < 0 ? rc : 0;
 }
@@ -551,7 +555,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
       const Summary *hs2 = (const Summary *)m->h_out;
       if (settle) {   // memory goes back on purpose: nothing stays mapped ahead, and earlier queued unmaps settle too
         g->set_prefetch_hints(nullptr, 0);
-        rc = g->fence();
+        rc = g->settle();
         if (rc) return rc;
       } else {        // map-ahead hints: the pages the free list will hand out next
         g->set_prefetch_hints(hs2->next_free, hs2->next_free_n);

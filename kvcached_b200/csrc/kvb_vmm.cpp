@@ -96,7 +96,7 @@ VmmGroup::~VmmGroup() {
   }
   for (auto h : handles_)
     if (h) d->MemRelease(h);
-  for (auto h : pool_) d->MemRelease(h);
+  for (auto &e : pool_) d->MemRelease(e.h);
   if (have_zero_) d->MemRelease(zero_);
 }
 
@@ -177,6 +177,20 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   mapped_.assign((size_t)n_pages_, 0);
   want_.assign((size_t)n_pages_, 0);
   spec_.assign((size_t)n_pages_, 0);
+  force_.assign((size_t)n_pages_, 0);
+  ret_seq_.assign((size_t)n_pages_, 0);
+  {
+    // how long an unmapped page keeps its physical handle / an idle handle stays pooled (0 = not at all)
+    const char *e = getenv("KVB200_VMM_RETAIN_MS");
+    retention_ms_ = e && *e ? atof(e) : 2000.0;
+    if (retention_ms_ < 0) retention_ms_ = 0;
+    const char *u = getenv("KVCACHED_GPU_UTILIZATION");
+    gpu_util_ = u && *u ? atof(u) : 0.95;
+    const char *rf = getenv("KVB200_RETAIN_FREE_FRACTION");
+    retain_free_frac_ = rf && *rf ? atof(rf) : 0.20;
+    const char *fl = getenv("KVB200_POOL_FLOOR");
+    pool_floor_ = fl && *fl ? atoll(fl) : 16;
+  }
   {
     // pages mapped ahead of demand; the reference keeps KVCACHED_MIN_RESERVED_PAGES (5) pre-mapped by default
     const char *e = getenv("KVB200_VMM_PREFETCH");
@@ -228,25 +242,128 @@ CUdeviceptr VmmGroup::sub_addr(int64_t p, int sub) const {
     }                                                                        \
   }
 
-// One place where a page's (wanted, hinted, physical) state changes, so that the work counters stay exact:
-//   need_map   wanted and not mapped          need_unmap  mapped, neither wanted nor hinted
-//   need_spec  hinted, not wanted, not mapped  n_spec_mapped  hinted pages mapped ahead of their event
-void VmmGroup::update(int64_t p, int want, int spec, int phys) {
-  bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p];
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// One place where a page's (wanted, hinted, physical, forced) state changes, so that the counters stay exact:
+//   need_map    wanted, not mapped                  need_spec      hinted, not wanted, not mapped
+//   need_unmap  mapped, unwanted, unhinted, FORCED  n_retained     mapped, unwanted, unhinted, not forced
+//   n_spec_mapped  hinted pages mapped ahead of their event
+void VmmGroup::update(int64_t p, int want, int spec, int phys, int force) {
+  bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p], f = force_[(size_t)p];
   need_map_ -= (w && !ph);
-  need_unmap_ -= (ph && !w && !sp);
+  need_unmap_ -= (ph && !w && !sp && f);
+  n_retained_ -= (ph && !w && !sp && !f);
   need_spec_ -= (sp && !w && !ph);
   n_spec_mapped_ -= (sp && !w && ph);
   if (want >= 0) w = want != 0;
   if (spec >= 0) sp = spec != 0;
   if (phys >= 0 && ph != (phys != 0)) { ph = phys != 0; n_mapped_ += ph ? 1 : -1; }
+  if (force >= 0) f = force != 0;
+  if (w || sp || !ph) f = false;
   want_[(size_t)p] = w;
   spec_[(size_t)p] = sp;
   mapped_[(size_t)p] = ph;
+  force_[(size_t)p] = f;
   need_map_ += (w && !ph);
-  need_unmap_ += (ph && !w && !sp);
+  need_unmap_ += (ph && !w && !sp && f);
+  n_retained_ += (ph && !w && !sp && !f);
   need_spec_ += (sp && !w && !ph);
   n_spec_mapped_ += (sp && !w && ph);
+}
+
+// A mapped page that is neither wanted nor hinted any more.
+void VmmGroup::make_unwanted(int64_t p) {
+  if (!mapped_[(size_t)p] || want_[(size_t)p] || spec_[(size_t)p]) return;
+  if (async_ && retention_ms_ > 0 && !force_[(size_t)p]) {
+    retained_.push_back(Retained{p, ++ret_seq_[(size_t)p], now_ms()});
+    // the pool cap bounds idle handles, retained ones included
+    while ((int64_t)pool_.size() / n_sub_ + n_retained_ > pool_cap_pages_ && force_one_retained(false)) {}
+  } else {
+    update(p, -1, -1, -1, 1);
+    qu_.push_back(p);
+  }
+}
+
+bool VmmGroup::force_one_retained(bool newest) {
+  while (!retained_.empty()) {
+    Retained r = newest ? retained_.back() : retained_.front();
+    if (newest) retained_.pop_back(); else retained_.pop_front();
+    const size_t p = (size_t)r.p;
+    if (ret_seq_[p] != r.seq || !mapped_[p] || want_[p] || spec_[p] || force_[p]) continue;   // stale entry
+    update(r.p, -1, -1, -1, 1);
+    qu_.push_back(r.p);
+    return true;
+  }
+  return false;
+}
+
+void VmmGroup::expire(double now) {
+  if (retention_ms_ <= 0) return;
+  while (!retained_.empty()) {
+    const Retained &r = retained_.front();
+    const size_t p = (size_t)r.p;
+    const bool live = ret_seq_[p] == r.seq && mapped_[p] && !want_[p] && !spec_[p] && !force_[p];
+    // the clock runs while the allocator is quiet: as long as pages keep being mapped, the FIFO free list will
+    // come back to this one, and memory others need is handed over by the reserve rule below, not by age
+    if (live && now - std::max(r.t_ms, last_map_ms_) < retention_ms_) break;
+    if (live) {
+      update(r.p, -1, -1, -1, 1);
+      qu_.push_back(r.p);
+      release_debt_ += n_sub_;          // its handle goes back to the device, not to the pool
+    }
+    retained_.pop_front();
+  }
+  // somebody else took memory: retained pages go back until the reserve is whole again (newest first, like a steal)
+  if (mem_total_ > 0 && n_retained_ > 0) {
+    const double reserve = std::max(retain_free_frac_, 1.0 - gpu_util_) * mem_total_;
+    double short_by = reserve - mem_free_ - (double)(need_unmap_ + release_debt_ / n_sub_) * (double)unit_ * n_sub_;
+    while (short_by > 0 && force_one_retained(true)) {
+      release_debt_ += n_sub_;
+      short_by -= (double)unit_ * n_sub_;
+    }
+  }
+  // idle pooled handles above the floor go back to the device too (oldest first, a few per wake-up)
+  for (int k = 0; k < 8 && (int64_t)pool_.size() > pool_floor_ * n_sub_ &&
+                  now - std::max(pool_.front().t_ms, last_map_ms_) >= retention_ms_; ++k) {
+    g_drv.MemRelease(pool_.front().h);
+    pool_.pop_front();
+    n_released_++; mem_free_ += (double)unit_;
+  }
+}
+
+// Device memory is sampled on the VMM thread only (cudaMemGetInfo is a driver round trip like the VMM calls and
+// stalls like them); between samples our own creates and releases are accounted.
+void VmmGroup::poll_meminfo(Lock &lk) {
+  lk.unlock();
+  ensure_device(dev_);
+  size_t fr = 0, tot = 0;
+  bool ok = cudaMemGetInfo(&fr, &tot) == cudaSuccess;
+  if (!ok) cudaGetLastError();
+  lk.lock();
+  if (ok) { mem_free_ = (double)fr; mem_total_ = (double)tot; mem_t_ms_ = now_ms(); }
+}
+
+bool VmmGroup::cached_meminfo(size_t *free_bytes, size_t *total_bytes) {
+  Lock lk(qmu_);
+  if (!worker_running_ || now_ms() - mem_t_ms_ > 250.0 || mem_total_ <= 0) return false;
+  *free_bytes = (size_t)(mem_free_ > 0 ? mem_free_ : 0);
+  *total_bytes = (size_t)mem_total_;
+  return true;
+}
+
+// Headroom for one more page under KVCACHED_GPU_UTILIZATION, like the bookkeeping's own available-memory
+// arithmetic (page_allocator.cpp:442-455), from the VMM thread's last sample.
+bool VmmGroup::can_create(bool soft) {
+  if (mem_total_ <= 0) return true;   // never sampled (synchronous mode): let the driver decide
+  const double reserve = soft ? std::max(retain_free_frac_, 1.0 - gpu_util_) : (1.0 - gpu_util_);
+  return mem_free_ - (double)unit_ * n_sub_ >= mem_total_ * reserve;
+}
+
+void VmmGroup::set_retain_free_fraction(double f) {
+  Lock lk(qmu_);
+  retain_free_frac_ = f < 0 ? 0 : (f > 1 ? 1 : f);
 }
 
 int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
@@ -255,7 +372,7 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   int need_create = 0;
   if (to_mapped) {
     for (int s = 0; s < n_sub_; ++s) {
-      if (!pool_.empty()) { hs[(size_t)s] = pool_.back(); pool_.pop_back(); } else need_create++;
+      if (!pool_.empty()) { hs[(size_t)s] = pool_.back().h; pool_.pop_back(); } else need_create++;
     }
   } else {
     for (int s = 0; s < n_sub_; ++s) hs[(size_t)s] = handles_[(size_t)p * n_sub_ + s];
@@ -288,11 +405,12 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   inflight_ = -1;
   for (int i = 0; i < 5; ++i) { t_us_[i] += tt[i]; t_n_[i] += tn[i]; }
   n_created_ += created;
+  mem_free_ -= (double)created * (double)unit_;
   if (rc) {
     if (!werr_) { werr_ = rc; werr_msg_ = emsg; }
     // leave the page as it was recorded; handles taken from the pool go back
-    if (to_mapped) for (auto h : hs) if (h) pool_.push_back(h);
-    update(p, mapped_[(size_t)p], 0, -1);
+    if (to_mapped) for (auto h : hs) if (h) pool_.push_back(PoolEnt{h, now_ms()});
+    update(p, mapped_[(size_t)p], 0, -1, 0);
     return rc;
   }
   if (to_mapped) {
@@ -300,18 +418,20 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   } else {
     for (int s = 0; s < n_sub_; ++s) {
       handles_[(size_t)p * n_sub_ + s] = 0;
-      if ((int64_t)pool_.size() < pool_cap_pages_ * n_sub_) {
-        pool_.push_back(hs[(size_t)s]);
+      if (release_debt_ <= 0 && (int64_t)pool_.size() < pool_cap_pages_ * n_sub_) {
+        pool_.push_back(PoolEnt{hs[(size_t)s], now_ms()});
       } else {
+        if (release_debt_ > 0) release_debt_--;
         auto t0 = std::chrono::steady_clock::now();
         g_drv.MemRelease(hs[(size_t)s]);
         t_us_[1] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         t_n_[1] += 1;
-        n_released_++;
+        n_released_++; mem_free_ += (double)unit_;
       }
     }
   }
   set_phys(p, to_mapped);
+  if (to_mapped) make_unwanted(p);   // wanted no more while it was being mapped: retain or unmap
   return 0;
 }
 
@@ -321,7 +441,12 @@ bool VmmGroup::process_next(Lock &lk) {
   while (!qm_.empty()) {
     int64_t p = qm_.front();
     if (!(want_[(size_t)p] && !mapped_[(size_t)p])) { qm_.pop_front(); continue; }   // cancelled or done
-    if ((int64_t)pool_.size() < n_sub_ && need_unmap_ > 0) break;
+    if ((int64_t)pool_.size() < n_sub_) {
+      // no idle handle: a pending unmap yields one; else create within the headroom; else take the page
+      // retained last (the FIFO free list needs it last) — only then create regardless and let the driver say no
+      if (need_unmap_ > 0) break;
+      if (!can_create(true) && force_one_retained(true)) break;   // (with nothing retained: create down to the headroom,
+    }                                                             //  and past it only to let the driver say no)
     qm_.pop_front();
     transition(lk, p, true);
     return true;
@@ -329,7 +454,13 @@ bool VmmGroup::process_next(Lock &lk) {
   while (need_map_ == 0 && !qs_.empty()) {   // hinted maps: only when no wanted map is waiting
     int64_t p = qs_.front();
     if (!(spec_[(size_t)p] && !want_[(size_t)p] && !mapped_[(size_t)p])) { qs_.pop_front(); continue; }
-    if ((int64_t)pool_.size() < n_sub_ && need_unmap_ > 0) break;   // an unmap yields the handle
+    if ((int64_t)pool_.size() < n_sub_) {
+      if (need_unmap_ > 0) break;                      // an unmap yields the handle
+      if (!can_create(true)) {                         // map-ahead never eats into the reserve
+        if (!force_one_retained(true)) { qs_.pop_front(); continue; }
+        break;
+      }
+    }
     qs_.pop_front();
     transition(lk, p, true);
     return true;
@@ -337,7 +468,7 @@ bool VmmGroup::process_next(Lock &lk) {
   while (!qu_.empty()) {
     int64_t p = qu_.front();
     qu_.pop_front();
-    if (!(!want_[(size_t)p] && !spec_[(size_t)p] && mapped_[(size_t)p])) continue;
+    if (!(!want_[(size_t)p] && !spec_[(size_t)p] && mapped_[(size_t)p] && force_[(size_t)p])) continue;
     transition(lk, p, false);
     return true;
   }
@@ -347,8 +478,12 @@ bool VmmGroup::process_next(Lock &lk) {
 void VmmGroup::worker_main() {
   Lock lk(qmu_);
   while (true) {
-    cv_work_.wait(lk, [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0 || need_spec_ > 0; });
+    cv_work_.wait_for(lk, std::chrono::milliseconds(50),
+                      [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0 || need_spec_ > 0; });
     if (stop_ && need_map_ == 0 && need_unmap_ == 0) break;
+    if (now_ms() - mem_t_ms_ > 5.0) poll_meminfo(lk);
+    expire(now_ms());
+    if (need_map_ == 0 && need_unmap_ == 0 && need_spec_ == 0) continue;   // timer wake-up, nothing due
     bool did = process_next(lk);
     cv_done_.notify_all();
     if (!did) {
@@ -356,9 +491,9 @@ void VmmGroup::worker_main() {
       if (stop_) break;
       need_map_ = need_unmap_ = need_spec_ = 0;
       for (int64_t p = 0; p < n_pages_; ++p) {
-        bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p];
+        bool w = want_[(size_t)p], sp = spec_[(size_t)p], ph = mapped_[(size_t)p], f = force_[(size_t)p];
         if (w && !ph) { need_map_++; qm_.push_back(p); }
-        if (!w && !sp && ph) { need_unmap_++; qu_.push_back(p); }
+        if (!w && !sp && ph && f) { need_unmap_++; qu_.push_back(p); }
         if (sp && !w && !ph) { need_spec_++; qs_.push_back(p); }
       }
     }
@@ -390,14 +525,18 @@ void VmmGroup::stop_worker() {
 }
 
 // Inline reconciliation by the calling thread (synchronous mode, or nobody to wait for).
+void VmmGroup::ensure_worker(Lock &lk) {
+  if (!worker_running_) {
+    if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
+    worker_running_ = true;
+    worker_ = std::thread([this] { worker_main(); });
+  }
+  cv_work_.notify_all();
+}
+
 int VmmGroup::drain(Lock &lk, bool maps_only) {
   if (async_ && created_) {
-    if (!worker_running_) {
-      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
-      worker_running_ = true;
-      worker_ = std::thread([this] { worker_main(); });
-    }
-    cv_work_.notify_all();
+    ensure_worker(lk);
     // a page being unmapped right now that is wanted again does not show in need_map_ until the unmap is done
     cv_done_.wait(lk, [&] {
       if (werr_) return true;
@@ -431,21 +570,22 @@ int VmmGroup::enqueue_events(const int64_t *ev, int64_t n) {
     if (p < 0 || p >= n_pages_) { set_error("%s: page %ld out of range [0, %ld)", un ? "unmap" : "map", (long)p, (long)n_pages_); return KVB_ERR_INVALID_; }
     bool w = want_[(size_t)p];
     if (w == !un) continue;   // "already mapped" / "not mapped" is tolerated (allocator.cpp:174-177, ftensor.cpp:104-107)
-    if (!un && spec_[(size_t)p] && mapped_[(size_t)p] && inflight_ != p) n_prefetch_hits_++;   // mapped ahead: no wait
+    if (!un && mapped_[(size_t)p] && inflight_ != p) {
+      if (spec_[(size_t)p]) n_prefetch_hits_++;          // mapped ahead: no wait
+      else n_retention_hits_++;                          // still holds the handle it had: nothing to do
+    }
     set_want(p, !un);
-    const bool settled = un ? (!mapped_[(size_t)p] || spec_[(size_t)p]) : (bool)mapped_[(size_t)p];
-    if (!settled || inflight_ == p) (un ? qu_ : qm_).push_back(p);
-    else n_elided_++;        // met its own pending opposite / was mapped ahead: nothing to do physically
+    if (!un) last_map_ms_ = now_ms();
+    if (un) {
+      if (mapped_[(size_t)p]) make_unwanted(p);          // retained, or its unmap is queued (hinted pages stay)
+      else if (inflight_ != p) n_elided_++;              // met its own pending map: nothing to do physically
+    } else {
+      if (!mapped_[(size_t)p] || inflight_ == p) qm_.push_back(p);
+      else n_elided_++;
+    }
   }
   n_map_calls_++;
-  if (async_ && (need_map_ > 0 || need_unmap_ > 0)) {
-    if (!worker_running_) {
-      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
-      worker_running_ = true;
-      worker_ = std::thread([this] { worker_main(); });
-    }
-    cv_work_.notify_all();
-  }
+  if (async_ && (need_map_ > 0 || need_unmap_ > 0 || n_retained_ > 0)) ensure_worker(lk);
   return 1;
 }
 
@@ -459,6 +599,20 @@ int VmmGroup::fence() {
   Lock lk(qmu_);
   return drain(lk, false);
 }
+int VmmGroup::settle() {
+  if (!created_) return 0;
+  Lock lk(qmu_);
+  while (force_one_retained(false)) {}
+  return drain(lk, false);
+}
+
+void VmmGroup::set_retention_ms(double ms) {
+  Lock lk(qmu_);
+  retention_ms_ = ms < 0 ? 0 : ms;
+  if (retention_ms_ == 0) while (force_one_retained(false)) {}
+  if (async_ && need_unmap_ > 0) ensure_worker(lk);
+}
+
 void VmmGroup::set_prefetch_depth(int depth) {
   Lock lk(qmu_);
   prefetch_depth_ = depth < 0 ? 0 : (depth > 16 ? 16 : depth);
@@ -484,15 +638,8 @@ void VmmGroup::set_prefetch_hints(const int64_t *pages, int64_t n) {
     if (!want_[(size_t)p] && !mapped_[(size_t)p]) qs_.push_back(p);
   }
   for (int64_t p : old)
-    if (!spec_[(size_t)p] && !want_[(size_t)p] && (mapped_[(size_t)p] || inflight_ == p)) qu_.push_back(p);
-  if (need_spec_ > 0 || need_unmap_ > 0) {
-    if (!worker_running_) {
-      if (worker_.joinable()) { lk.unlock(); worker_.join(); lk.lock(); }
-      worker_running_ = true;
-      worker_ = std::thread([this] { worker_main(); });
-    }
-    cv_work_.notify_all();
-  }
+    if (!spec_[(size_t)p]) make_unwanted(p);   // mapped ahead in vain: retained or unmapped (in flight: transition() does it)
+  if (need_spec_ > 0 || need_unmap_ > 0) ensure_worker(lk);
 }
 
 int64_t VmmGroup::prefetched_pages(int64_t *out, int64_t cap) {
@@ -527,6 +674,17 @@ int VmmGroup::unmap_pages(const int64_t *ids, int64_t n) {
   int rc = enqueue_events(ev.data(), n);
   if (rc < 0) return rc;
   n_unmap_calls_++;
+  {
+    // the direct API keeps the reference's meaning: these pages are on the zero page when the call returns
+    Lock lk(qmu_);
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t p = ids[i];
+      if (p >= 0 && p < n_pages_ && mapped_[(size_t)p] && !want_[(size_t)p] && !spec_[(size_t)p] && !force_[(size_t)p]) {
+        update(p, -1, -1, -1, 1);
+        qu_.push_back(p);
+      }
+    }
+  }
   rc = fence();
   return rc ? rc : 1;
 }
@@ -541,11 +699,13 @@ int VmmGroup::apply_events(const int64_t *ev, int64_t n) {
 void VmmGroup::pool_config(int64_t max_cached_pages) {
   Lock lk(qmu_);
   pool_cap_pages_ = max_cached_pages;
+  while ((int64_t)pool_.size() / n_sub_ + n_retained_ > pool_cap_pages_ && force_one_retained(false)) {}
   while ((int64_t)pool_.size() > pool_cap_pages_ * n_sub_ && g_drv.ok) {
-    g_drv.MemRelease(pool_.back());
-    pool_.pop_back();
-    n_released_++;
+    g_drv.MemRelease(pool_.front().h);
+    pool_.pop_front();
+    n_released_++; mem_free_ += (double)unit_;
   }
+  if (async_ && need_unmap_ > 0) ensure_worker(lk);
 }
 int VmmGroup::pool_prefill(int64_t n_pages) {
   if (!created_) { set_error("pool_prefill: tensors not created"); return KVB_ERR_STATE_; }
@@ -559,7 +719,7 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
     CUmemGenericAllocationHandle h;
     CU_TRY(g_drv.MemCreate(&h, unit_, &prop_, 0));
     n_created_++;
-    pool_.push_back(h);
+    pool_.push_back(PoolEnt{h, now_ms()});
   }
   return 0;
 }
@@ -567,18 +727,22 @@ int VmmGroup::pool_prefill(int64_t n_pages) {
 // pages whose unmap is still queued (their handles come back to the pool)
 int64_t VmmGroup::pooled_pages() {
   Lock lk(qmu_);
-  return n_sub_ ? (int64_t)pool_.size() / n_sub_ + need_unmap_ + n_spec_mapped_ : 0;
+  return n_sub_ ? (int64_t)pool_.size() / n_sub_ + need_unmap_ + n_retained_ + n_spec_mapped_ : 0;
 }
 int64_t VmmGroup::pool_release(int64_t n_pages) {
   Lock lk(qmu_);
   int64_t n = 0;
   while (n < n_pages * n_sub_ && !pool_.empty() && g_drv.ok) {
-    g_drv.MemRelease(pool_.back());
-    pool_.pop_back();
-    n_released_++;
+    g_drv.MemRelease(pool_.front().h);
+    pool_.pop_front();
+    n_released_++; mem_free_ += (double)unit_;
     n++;
   }
-  return n_sub_ ? n / n_sub_ : 0;
+  // still short: retained pages give their memory back too (the VMM thread unmaps them, their handles are released)
+  int64_t got = n_sub_ ? n / n_sub_ : 0;
+  for (int64_t k = got; k < n_pages && force_one_retained(false); ++k) { release_debt_ += n_sub_; got++; }
+  if (async_ && need_unmap_ > 0) ensure_worker(lk);
+  return got;
 }
 
 void VmmGroup::engine_stats(int64_t *s) {
@@ -589,8 +753,8 @@ void VmmGroup::engine_stats(int64_t *s) {
   s[3] = need_map_;
   s[4] = need_unmap_;
   s[5] = need_spec_;
-  s[6] = (int64_t)hints_.size();
-  s[7] = prefetch_depth_;
+  s[6] = n_retained_;
+  s[7] = n_retention_hits_;
 }
 
 void VmmGroup::timing(double *out10) {

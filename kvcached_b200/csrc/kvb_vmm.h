@@ -73,6 +73,20 @@ class VmmGroup {
   // change (the reference's prealloc thread, page_allocator.cpp:524-617, moves pages to its reserved list and so
   // changes results with timing).  Priority: wanted maps > hinted maps > unmaps.  A hinted page that falls out of
   // the hint window without being wanted is unmapped again.  Off in synchronous mode and when depth is 0.
+  // Retention: a page the bookkeeping unmapped keeps its physical handle mapped (its data is stale, nobody else's)
+  // until the allocator has been quiet (no map event) for `ms` milliseconds; if the bookkeeping maps it again
+  // before that, nothing happens at all.  It is put
+  // back on the zero page and its handle released earlier when a map needs a handle that can neither come from the
+  // pool nor be created within the memory headroom (the most recently retained page goes first: the free page list
+  // is a FIFO, so that page is the one needed last), when the pool cap is exceeded, at settle points and under
+  // memory pressure.  Idle pooled handles are released after the same time.  0 = unmap at once (and in
+  // synchronous mode).  Count-based hysteresis is what the reference has (max_reserved_pages, page_allocator.cpp:264-310).
+  void set_retention_ms(double ms);
+  // Retained pages are a cache in memory nobody asked for yet: they are kept only while at least this fraction of
+  // the device stays free for everybody else (a co-located model always sees that much, and as it takes it the VMM
+  // thread hands retained pages back to restore it).  Default KVB200_RETAIN_FREE_FRACTION or 0.20.
+  void set_retain_free_fraction(double f);
+  int settle();       // fence + every retained page back on the zero page (trim / clear / resize / kvctl limit)
   void set_prefetch_hints(const int64_t *pages, int64_t n);
   void set_prefetch_depth(int depth);
   int prefetch_depth() const { return prefetch_depth_; }
@@ -81,6 +95,10 @@ class VmmGroup {
   bool async() const { return async_; }
   void set_sync_before_unmap(bool on) { sync_before_unmap_ = on; }
   int64_t pending_unmaps();
+  // Free / total device memory as last seen by the VMM thread (it polls every few milliseconds while it works and
+  // at every idle wake-up, and accounts for its own cuMemCreate / cuMemRelease in between), so that the scheduler
+  // thread never enters the driver for available_size().  False if there is no recent sample.
+  bool cached_meminfo(size_t *free_bytes, size_t *total_bytes);
   // reference byte offsets (page_allocator.cpp:619-631) -> page ids
   int64_t offset_to_page(int64_t off) const { return off / (int64_t)(contiguous_ ? unit_ : P_); }
 
@@ -104,9 +122,15 @@ class VmmGroup {
   using Lock = std::unique_lock<std::mutex>;
   bool process_next(Lock &lk);              // one page transition; lock held on entry and exit, released around driver calls
   int transition(Lock &lk, int64_t p, bool to_mapped);
-  void update(int64_t p, int want, int spec, int phys);   // -1 = keep; maintains the need_* counters
-  void set_want(int64_t p, bool v) { update(p, v, -1, -1); }
-  void set_phys(int64_t p, bool v) { update(p, -1, -1, v); }
+  void update(int64_t p, int want, int spec, int phys, int force = -1);   // -1 = keep; maintains the counters
+  void set_want(int64_t p, bool v) { update(p, v, -1, -1, v ? 0 : -1); }
+  void set_phys(int64_t p, bool v) { update(p, -1, -1, v, v ? -1 : 0); }
+  void make_unwanted(int64_t p);            // a mapped page nobody wants or hints: retain it, or queue its unmap
+  bool force_one_retained(bool newest);     // pick a retained page and queue its unmap
+  void expire(double now_ms);               // retention / idle-pool time-outs (VMM thread)
+  bool can_create(bool soft);               // room for one more page above the retention reserve (soft) / the utilisation headroom
+  void poll_meminfo(Lock &lk);              // cudaMemGetInfo on the VMM thread (lock released around the call)
+  void ensure_worker(Lock &lk);
   int drain(Lock &lk, bool maps_only);
   void worker_main();
   void stop_worker();
@@ -131,6 +155,15 @@ class VmmGroup {
   std::vector<uint8_t> mapped_;   // physical state
   std::vector<uint8_t> want_;     // state after every event received so far
   std::vector<uint8_t> spec_;     // hinted: map ahead of the event
+  std::vector<uint8_t> force_;    // unwanted + mapped + must go back to the zero page now (else: retained)
+  std::vector<uint32_t> ret_seq_; // validates entries of retained_
+  struct Retained { int64_t p; uint32_t seq; double t_ms; };
+  std::deque<Retained> retained_; // oldest first
+  struct PoolEnt { CUmemGenericAllocationHandle h; double t_ms; };
+  double retention_ms_ = 0;
+  int64_t n_retained_ = 0, n_retention_hits_ = 0, release_debt_ = 0, pool_floor_ = 16;
+  double mem_t_ms_ = -1e18, gpu_util_ = 0.95, retain_free_frac_ = 0.20, last_map_ms_ = -1e18;
+  double mem_free_ = 0, mem_total_ = 0;     // bytes, as of mem_t_ms_ (adjusted by our own creates / releases)
   std::deque<int64_t> qm_, qu_, qs_;   // pages whose wanted state may differ from the physical one (maps / unmaps / hinted maps)
   std::vector<int64_t> hints_;
   int prefetch_depth_ = 0;
@@ -143,7 +176,7 @@ class VmmGroup {
   int werr_ = 0;
   std::string werr_msg_;
   int64_t n_elided_ = 0;
-  std::vector<CUmemGenericAllocationHandle> pool_;
+  std::deque<PoolEnt> pool_;      // idle physical handles, most recently returned last
   int64_t pool_cap_pages_ = -1;   // pages' worth of handles kept after unmap; -1 = default chosen in create()
   CUmemAllocationProp prop_{};
   CUmemAccessDesc access_{};

@@ -102,6 +102,21 @@ def fence(group_id: int = 0) -> None:
     _lib.check(_lib.load().kvb_vmm_fence(group_id), "vmm fence")
 
 
+def settle(group_id: int = 0) -> None:
+    """fence() + every retained page back on the zero page (what trim / clear / resize do)."""
+    _lib.check(_lib.load().kvb_vmm_settle(group_id), "vmm settle")
+
+
+def set_retention(ms: float, group_id: int = 0) -> None:
+    """How long an unmapped page keeps its physical handle mapped (0 = unmap at once)."""
+    _lib.check(_lib.load().kvb_vmm_set_retention_ms(group_id, float(ms)), "vmm set_retention_ms")
+
+
+def set_retain_free_fraction(fraction: float, group_id: int = 0) -> None:
+    """Retained pages are kept only while this fraction of the device stays free for everybody else."""
+    _lib.check(_lib.load().kvb_vmm_set_retain_free_fraction(group_id, float(fraction)), "vmm set_retain_free_fraction")
+
+
 def wait_maps(group_id: int = 0) -> None:
     _lib.check(_lib.load().kvb_vmm_wait_maps(group_id), "vmm wait_maps")
 
@@ -128,7 +143,7 @@ def prefetched_pages(group_id: int = 0) -> List[int]:
 def engine_stats(group_id: int = 0) -> Dict[str, int]:
     s = np.zeros(8, dtype=np.int64)
     _lib.check(_lib.load().kvb_vmm_engine_stats(group_id, s.ctypes.data_as(_lib.p_i64)))
-    keys = ["elided", "prefetch_hits", "mapped_ahead", "need_map", "need_unmap", "need_hinted", "hints", "depth"]
+    keys = ["elided", "prefetch_hits", "mapped_ahead", "need_map", "need_unmap", "need_hinted", "retained", "retention_hits"]
     return dict(zip(keys, s.tolist()))
 
 

@@ -133,6 +133,67 @@ def test_map_ahead_follows_the_free_list(kvcached_fixture):
         vmm_ops.set_prefetch(0)
 
 
+def test_retention_keeps_the_handle_until_it_is_needed_or_times_out(kvcached_fixture):
+    """A page the bookkeeping unmapped stays on its own physical handle: mapped again soon it costs no driver call;
+    after the retention time, or at a settle point, it is back on the zero page and the memory back on the device."""
+    import time
+    import torch
+    f = kvcached_fixture
+    m, L, bs, cell = f["mgr"], f["L"], f["bs"], f["cell"]
+    kv = f["flat"].view(torch.int16).view(f["blocks"], L, 2, bs, cell // 2)
+    bpp = PAGE // (bs * cell)
+    lib = _lib.load()
+    try:
+        vmm_ops.set_retention(60_000)
+        ids = np.arange(12, 16, dtype=np.int64)               # pages 12..15 through the event interface
+        ev_map, ev_unmap = ids * 2, ids * 2 + 1
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
+        vmm_ops.wait_maps()
+        kv[12 * bpp, 0, 0, 0, 0] = 77
+        torch.cuda.synchronize()
+        t0 = vmm_ops.vmm_timing()
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
+        vmm_ops.fence()
+        e = vmm_ops.engine_stats()
+        assert e["retained"] == 4 and vmm_ops.mapped_pages() == [] and vmm_ops.vmm_stats()["mapped_pages"] == 4
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
+        vmm_ops.wait_maps()
+        t1 = vmm_ops.vmm_timing()
+        assert t1["unmap_calls"] == t0["unmap_calls"] and t1["setaccess_calls"] == t0["setaccess_calls"]   # no driver call at all
+        assert vmm_ops.engine_stats()["retention_hits"] == e["retention_hits"] + 4
+        assert int(kv[12 * bpp, 0, 0, 0, 0]) == 77           # the same physical page (a fresh one would be equally valid)
+        # time-out: the VMM thread hands the memory back on its own
+        vmm_ops.set_retention(150)
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
+        released0 = vmm_ops.vmm_stats()["handles_released"]
+        t_end = time.time() + 10
+        while time.time() < t_end and (vmm_ops.engine_stats()["retained"] or vmm_ops.pending_unmaps()):
+            time.sleep(0.02)
+        assert vmm_ops.engine_stats()["retained"] == 0 and vmm_ops.vmm_stats()["mapped_pages"] == 0
+        assert vmm_ops.vmm_stats()["handles_released"] >= released0 + 4
+        torch.cuda.synchronize()
+        assert int(kv[12 * bpp, 0, 0, 0, 0]) == 0            # zero page again
+        # the reserve: retained pages are handed back while less than the given fraction of the device is free
+        vmm_ops.set_retention(60_000)
+        vmm_ops.set_retain_free_fraction(0.9999)
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
+        t_end = time.time() + 10
+        while time.time() < t_end and (vmm_ops.engine_stats()["retained"] or vmm_ops.pending_unmaps()):
+            time.sleep(0.02)
+        assert vmm_ops.engine_stats()["retained"] == 0 and vmm_ops.vmm_stats()["mapped_pages"] == 0
+        vmm_ops.set_retain_free_fraction(0.20)
+        # retention off: every unmap is applied at once
+        vmm_ops.set_retention(0)
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
+        assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
+        vmm_ops.fence()
+        assert vmm_ops.vmm_stats()["mapped_pages"] == 0 and vmm_ops.engine_stats()["retained"] == 0
+    finally:
+        vmm_ops.set_retention(2000)
+        vmm_ops.set_retain_free_fraction(0.20)
+
+
 @pytest.mark.parametrize("use_thread", [True, False])
 def test_async_engine_settles_to_the_wanted_state(kvcached_fixture, use_thread):
     """Events only move the wanted state; the VMM thread (or the caller, KVB200_VMM_ASYNC=0) reconciles.
@@ -164,8 +225,10 @@ def test_async_engine_settles_to_the_wanted_state(kvcached_fixture, use_thread):
         for p in np.nonzero(want)[0][:4]:
             assert int(kv[int(p) * bpp, 0, 0, 0, 0]) == 1000 + int(p)
     vmm_ops.fence()
-    assert vmm_ops.pending_unmaps() == 0
     assert vmm_ops.mapped_pages() == np.nonzero(want)[0].tolist()
+    vmm_ops.settle()                          # retained pages give their handles back
+    assert vmm_ops.pending_unmaps() == 0 and vmm_ops.engine_stats()["retained"] == 0
+    assert vmm_ops.vmm_stats()["mapped_pages"] == int(want.sum())
     for p in np.nonzero(~want)[0][:4]:        # settled unmapped pages read the zero page again
         assert int(kv[int(p) * bpp, 0, 0, 0, 1]) == 0
     # a page unmapped and mapped again before the thread got to it costs nothing

@@ -14,11 +14,12 @@ plan = R.HostStepPlan(ct)
 vmm_ops.init_kvcached("cuda:0", PAGE, True)
 vmm_ops.create_kv_tensors_raw(cfg["num_blocks"] * 16 * 2048 * 2, 32, 2)
 m = R.manager_from_config(cfg)
-depths = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0,5").split(",")]
+depths = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "0,5").split(",")]   # negative: retention off, depth = -x-1
 res = {d: [] for d in depths}
 for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 5):
     for d in depths:
-        vmm_ops.set_prefetch(d)
+        vmm_ops.set_prefetch(d if d >= 0 else -d - 1)
+        vmm_ops.set_retention(2000 if d >= 0 else 0)
         a = vmm_ops.vmm_timing(); e0 = vmm_ops.engine_stats()
         t0 = time.perf_counter()
         R.replay_host_steps(m, plan, keep_results=False)
@@ -30,7 +31,8 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 5):
         calls = b["unmap_calls"] - a["unmap_calls"]
         res[d].append(t2 - t0)
         print(f"it {it} depth {d}: replay {t1-t0:.3f} s + fence {t2-t1:.3f} s = {t2-t0:.3f} s; driver {drv/1e3:.3f} s in {calls} transitions "
-              f"({drv/max(calls,1)*1e3:.0f} us each); hits {e1['prefetch_hits']-e0['prefetch_hits']}", flush=True)
+              f"({drv/max(calls,1)*1e3:.0f} us each); ahead hits {e1['prefetch_hits']-e0['prefetch_hits']} retention hits {e1['retention_hits']-e0['retention_hits']} "
+              f"retained {e1['retained']} free GiB {torch.cuda.mem_get_info()[0]/2**30:.1f}", flush=True)
 for d in depths:
     print(f"depth {d}: median {np.median(res[d]):.3f} s  min {min(res[d]):.3f} s  -> {ct.n_calls/np.median(res[d]):.0f} ops/s (best {ct.n_calls/min(res[d]):.0f})")
 m.close(); vmm_ops.shutdown_kvcached()
