@@ -107,7 +107,8 @@ SIGNATURES = {
     "kvb_vmm_probe2": (C.c_int, [C.c_int, i64, i64, C.c_int, i64, p_f64]),
     "kvb_mgr_create": (C.c_void_p, [C.POINTER(MgrConfig)]),
     "kvb_mgr_destroy": (C.c_int, [C.c_void_p]),
-    "kvb_mgr_step": (i64, [C.c_void_p, C.POINTER(Op), i64, p_i64, i64, C.POINTER(Ref), i64, C.POINTER(Res), p_i64, i64]),
+    # pointer arguments as plain addresses: the per-step call passes ndarray.ctypes.data (no POINTER objects built per call)
+    "kvb_mgr_step": (i64, [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
     "kvb_mgr_alloc": (i64, [C.c_void_p, i64, p_i64, i64]),
     "kvb_mgr_free": (C.c_int, [C.c_void_p, p_i64, i64]),
     "kvb_mgr_resize": (C.c_int, [C.c_void_p, i64]),

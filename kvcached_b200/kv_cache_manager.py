@@ -310,10 +310,10 @@ class KVCacheManager:
         n_ids = 0 if ids is None else int(ids.size)
         n_refs = 0 if refs is None else int(refs.shape[0])
         rc = self._lib.kvb_mgr_step(
-            self._h, ops.ctypes.data_as(C.POINTER(_lib.Op)), n,
-            _p64(ids) if n_ids else None, n_ids,
-            refs.ctypes.data_as(C.POINTER(_lib.Ref)) if n_refs else None, n_refs,
-            res.ctypes.data_as(C.POINTER(_lib.Res)), _p64(out), out.size)
+            self._h, ops.ctypes.data, n,
+            ids.ctypes.data if n_ids else None, n_ids,
+            refs.ctypes.data if n_refs else None, n_refs,
+            res.ctypes.data, out.ctypes.data, out.size)
         if rc < 0:
             raise KvbError(f"kvb_mgr_step failed ({rc}): {_lib.last_error()}")
         return res, out[:rc]
