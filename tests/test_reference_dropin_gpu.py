@@ -94,3 +94,73 @@ def test_unmodified_reference_manager_runs_on_our_extension(reference_manager_mo
         assert int(kv[ids[0], 1, 1, 0, 0]) == 11 and int(kv[ids[-1], 2, 0, 0, 0]) == 22
     finally:
         our_vmm_ops.shutdown_kvcached()
+
+
+@pytest.mark.parametrize("engine", ["vllm", "sglang"])
+def test_unmodified_reference_integration_interfaces_on_our_stack(reference_manager_module, engine, monkeypatch):
+    """The reference's own integration entry points — init_kvcached / alloc_kv_cache / get_kv_cache_manager of
+    kvcached/integration/{vllm,sglang}/interfaces.py, unmodified — on our extension AND our KVCacheManager (the
+    one-line patch of INTEGRATION.md section 2): tokens written by our fused scatter kernel are read back through the
+    per-layer views the reference builds (vllm/interfaces.py:291-298, sglang/interfaces.py:168-173), and the SGLang
+    slot allocator expands block ids to exactly the slots those views address."""
+    import numpy as np
+    import torch
+    import kvcached_b200
+    from kvcached_b200 import kv_ops
+    torch.cuda.init()
+    itf = importlib.import_module(f"kvcached.integration.{engine}.interfaces")
+    monkeypatch.setattr(itf, "KVCacheManager", kvcached_b200.KVCacheManager)       # <- section 2 of INTEGRATION.md
+    L, bs, H, D = 32, 16, 8, 128
+    cell = H * D * 2
+    itf.init_kvcached(device="cuda:0")
+    try:
+        if engine == "vllm":
+            views = itf.alloc_kv_cache((2, 4096, bs, H, D), bs, torch.float16, "cuda:0", L)
+            assert len(views) == L and tuple(views[0].shape[:1]) == (2,) and tuple(views[0].shape[2:]) == (bs, H, D)
+            mgr = itf.get_kv_cache_manager(4096, bs, cell, L)
+            lay = kv_ops.layout_vllm_contiguous(views[0].data_ptr(), L, bs, cell, 2)
+        else:
+            k_views, v_views = itf.alloc_kv_cache((4096 * bs, H, D), torch.float16, "cuda:0", L, page_size=bs)
+            assert len(k_views) == L == len(v_views) and tuple(k_views[0].shape[1:]) == (H, D)
+            mgr = itf.get_kv_cache_manager(4096, bs, cell, L)                       # reserves the null block, like SGLang
+            assert mgr.null_block == [0]
+            lay = kv_ops.layout_sglang_contiguous(k_views[0].data_ptr(), L, cell, 2, block_size=bs)
+        assert isinstance(mgr, kvcached_b200.KVCacheManager) and mgr._post_init_done.wait(timeout=30.0)
+        ids = np.asarray(mgr.alloc(40), dtype=np.int64)
+        T_tok = 300
+        slots_np = np.random.default_rng(1).permutation((ids[:, None] * bs + np.arange(bs)).reshape(-1))[:T_tok]
+        slots = torch.from_numpy(slots_np).cuda()
+        k = torch.empty((L, T_tok, cell // 2), dtype=torch.int16, device="cuda").random_()
+        v = torch.empty_like(k).random_()
+        kv_ops.kv_scatter(lay, slots, k, v)
+        torch.cuda.synchronize()
+        blk, tok = slots // bs, slots % bs
+        for layer in (0, 1, L // 2, L - 1):
+            if engine == "vllm":
+                got_k = views[layer][0][blk, tok]          # (T, H, D) through the reference's permuted view
+                got_v = views[layer][1][blk, tok]
+            else:
+                got_k, got_v = k_views[layer][slots], v_views[layer][slots]
+            assert torch.equal(got_k.contiguous().view(torch.int16).view(T_tok, -1), k[layer])
+            assert torch.equal(got_v.contiguous().view(torch.int16).view(T_tok, -1), v[layer])
+        if engine == "sglang":
+            from kvcached_b200.sglang_alloc import ElasticPagedTokenToKVPoolAllocator
+
+            class _Pool:                                    # what SGLang's memory pool exposes to its allocator
+                kvcached_allocator = mgr
+            al = ElasticPagedTokenToKVPoolAllocator(4096 * bs, bs, torch.float16, "cuda:0", _Pool())
+            pre = torch.tensor([0, 0], dtype=torch.int64, device="cuda")
+            seq = torch.tensor([40, 17], dtype=torch.int64, device="cuda")
+            last = torch.tensor([-1, -1], dtype=torch.int64, device="cuda")
+            out = al.alloc_extend(pre, pre.cpu(), seq, seq.cpu(), last, 57)
+            assert out is not None and out.numel() == 57
+            o = out.cpu().numpy()
+            assert np.array_equal(o[:40] % bs, np.arange(40) % bs) and np.array_equal(o[40:] % bs, np.arange(17) % bs)
+            k_views[3][out] = 7.0                           # writable through the reference's view = pages are mapped
+            torch.cuda.synchronize()
+            assert float(k_views[3][out[5]].flatten()[0]) == 7.0
+            al.free(out)
+        mgr.free(ids.tolist())
+        mgr.close()
+    finally:
+        itf.shutdown_kvcached()
