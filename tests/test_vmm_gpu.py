@@ -102,7 +102,7 @@ def test_map_ahead_follows_the_free_list(kvcached_fixture):
     def settle():
         vmm_ops.fence()
         t0 = time.time()
-        while vmm_ops.engine_stats()["need_hinted"] and time.time() - t0 < 5:
+        while vmm_ops.engine_stats()["need_hinted"] and time.time() - t0 < 60:
             time.sleep(0.001)
 
     try:
@@ -166,7 +166,7 @@ def test_retention_keeps_the_handle_until_it_is_needed_or_times_out(kvcached_fix
         vmm_ops.set_retention(150)
         assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
         released0 = vmm_ops.vmm_stats()["handles_released"]
-        t_end = time.time() + 10
+        t_end = time.time() + 60
         while time.time() < t_end and (vmm_ops.engine_stats()["retained"] or vmm_ops.pending_unmaps()):
             time.sleep(0.02)
         assert vmm_ops.engine_stats()["retained"] == 0 and vmm_ops.vmm_stats()["mapped_pages"] == 0
@@ -178,7 +178,7 @@ def test_retention_keeps_the_handle_until_it_is_needed_or_times_out(kvcached_fix
         vmm_ops.set_retain_free_fraction(0.9999)
         assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
         assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
-        t_end = time.time() + 10
+        t_end = time.time() + 60
         while time.time() < t_end and (vmm_ops.engine_stats()["retained"] or vmm_ops.pending_unmaps()):
             time.sleep(0.02)
         assert vmm_ops.engine_stats()["retained"] == 0 and vmm_ops.vmm_stats()["mapped_pages"] == 0
