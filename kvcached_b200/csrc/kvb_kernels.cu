@@ -1180,6 +1180,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
     int totS, totE;
     int rs = block_rank(live && !empty, s.wtot, &totS);
     int re = block_rank(live && empty, s.wtot2, &totE);
+    int d_nab = 0, d_av = 0, d_fu = 0;
     if (live) {
       if (st == PG_AVAIL) c.ap[c.pg_pos[p]] = -1;   // avail_pages.pop(page_id)
       long long dnab = add;
@@ -1194,11 +1195,20 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
         c.pg_state[p] = PG_AVAIL;
         c.pg_cnt[p] = newc;
       }
-      atomicAdd((unsigned long long *)&s.acc[0], (unsigned long long)dnab);
-      int dav = (empty ? 0 : 1) - (st == PG_AVAIL ? 1 : 0);
-      int dfu = -(st == PG_FULL ? 1 : 0);
-      if (dav) atomicAdd((unsigned long long *)&s.acc[1], (unsigned long long)(long long)dav);
-      if (dfu) atomicAdd((unsigned long long *)&s.acc[2], (unsigned long long)(long long)dfu);
+      d_nab = (int)dnab;
+      d_av = (empty ? 0 : 1) - (st == PG_AVAIL ? 1 : 0);
+      d_fu = -(st == PG_FULL ? 1 : 0);
+    }
+    // counter deltas: one warp reduction + one shared atomic per warp instead of three contended atomics per page
+    {
+      const int s_nab = __reduce_add_sync(0xffffffffu, d_nab);
+      const int s_av = __reduce_add_sync(0xffffffffu, d_av);
+      const int s_fu = __reduce_add_sync(0xffffffffu, d_fu);
+      if (lane == 0) {
+        if (s_nab) atomicAdd((unsigned long long *)&s.acc[0], (unsigned long long)(long long)s_nab);
+        if (s_av) atomicAdd((unsigned long long *)&s.acc[1], (unsigned long long)(long long)s_av);
+        if (s_fu) atomicAdd((unsigned long long *)&s.acc[2], (unsigned long long)(long long)s_fu);
+      }
     }
     tail += totS;
     E += totE;
