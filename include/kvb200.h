@@ -129,6 +129,16 @@ int64_t kvb_vmm_pending_unmaps(int64_t group_id);
  * unlike the reference's prealloc thread (page_allocator.cpp:524-617), whose reserved list alters results with
  * timing.  depth 0 = off; default KVB200_VMM_PREFETCH or 5 (the reference's KVCACHED_MIN_RESERVED_PAGES). */
 int kvb_vmm_prefetch_config(int64_t group_id, int depth);
+int kvb_vmm_set_prefetch_hints(int64_t group_id, const int64_t *pages, int64_t n);   /* what kvb_mgr_step does with the kernel's list */
+/* Host-logic test aid: replaces the CUDA VMM driver calls with legality-checking stand-ins (map only onto
+ * unmapped reserved space, unmap / set-access only whole mappings, release only unmapped handles) that count calls
+ * and model a device of `total_bytes`, so the engine's decisions are testable without a GPU.  Must be called before
+ * the first VMM call of the process.  out10 = {creates, releases, maps, unmaps, set-access, violations, live
+ * handles, live mappings, (unused), handle bytes}. */
+int kvb_vmm_mock_driver(int64_t total_bytes, int latency_us);
+int kvb_vmm_mock_set_other_bytes(int64_t bytes);   /* memory taken by "somebody else" */
+int kvb_vmm_mock_stats(int64_t *out10);
+const char *kvb_vmm_mock_last_violation(void);
 int64_t kvb_vmm_prefetched_pages(int64_t group_id, int64_t *out, int64_t cap);   /* hinted + mapped, not yet wanted */
 /* out8 = {events elided, map-ahead hits, pages mapped ahead now, need_map, forced unmaps pending, need_hinted,
  *         pages retained now, retention hits} */

@@ -93,6 +93,11 @@ SIGNATURES = {
     "kvb_vmm_set_retain_free_fraction": (C.c_int, [i64, f64]),
     "kvb_vmm_pending_unmaps": (i64, [i64]),
     "kvb_vmm_prefetch_config": (C.c_int, [i64, C.c_int]),
+    "kvb_vmm_set_prefetch_hints": (C.c_int, [i64, p_i64, i64]),
+    "kvb_vmm_mock_driver": (C.c_int, [i64, C.c_int]),
+    "kvb_vmm_mock_set_other_bytes": (C.c_int, [i64]),
+    "kvb_vmm_mock_stats": (C.c_int, [p_i64]),
+    "kvb_vmm_mock_last_violation": (C.c_char_p, []),
     "kvb_vmm_prefetched_pages": (i64, [i64, p_i64, i64]),
     "kvb_vmm_engine_stats": (C.c_int, [i64, p_i64]),
     "kvb_vmm_pool_config": (C.c_int, [i64, i64]),

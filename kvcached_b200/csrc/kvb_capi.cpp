@@ -138,6 +138,17 @@ int64_t kvb_vmm_pending_unmaps(int64_t group_id) {
   if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
   return g->pending_unmaps();
 }
+int kvb_vmm_set_prefetch_hints(int64_t group_id, const int64_t *pages, int64_t n) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_prefetch_hints(pages, n);
+  return 0;
+}
+int kvb_vmm_mock_driver(int64_t total_bytes, int latency_us) { return vmm_mock_driver(total_bytes, latency_us); }
+int kvb_vmm_mock_set_other_bytes(int64_t bytes) { vmm_mock_set_other_bytes(bytes); return 0; }
+int kvb_vmm_mock_stats(int64_t *out10) { if (!out10) return KVB_ERR_INVALID; vmm_mock_stats(out10); return 0; }
+const char *kvb_vmm_mock_last_violation(void) { return vmm_mock_last_violation(); }
 int kvb_vmm_prefetch_config(int64_t group_id, int depth) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <thread>
 
 namespace kvb {
 
@@ -62,6 +63,153 @@ const Driver *driver() {
   return &g_drv;
 }
 
+
+// ------------------------------------------------------------------------------------------ mock driver
+// A stand-in for the seven VMM driver calls that checks their legality (map only onto unmapped reserved space,
+// unmap / set-access only whole mappings, release only unmapped handles, no leaks) and counts them, so that the
+// engine's host logic — the part that decides WHICH calls are made — is testable without a GPU
+// (tests/test_vmm_engine_cpu.py).  Test infrastructure inside the library: installed only by kvb_vmm_mock_driver().
+namespace mock {
+struct Map { size_t size; CUmemGenericAllocationHandle h; bool access; };
+static std::mutex mu;
+static std::map<CUdeviceptr, size_t> reservations;
+static std::map<CUdeviceptr, Map> mappings;
+static std::map<CUmemGenericAllocationHandle, int> handles;   // handle -> live mappings
+static CUmemGenericAllocationHandle next_handle = 0x1000;
+static CUdeviceptr next_va = 0x7000000000ull;
+static int64_t n_create, n_release, n_map, n_unmap, n_access, n_violations;
+static double total_bytes = 64.0 * (1 << 30), other_bytes = 0, handle_bytes = 0;
+static int latency_us = 0;
+static char last_violation[256] = "";
+static bool installed = false;
+
+static void violate(const char *what) { n_violations++; snprintf(last_violation, sizeof(last_violation), "%s", what); }
+static void nap() { if (latency_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(latency_us)); }
+
+static CUresult AddressReserve(CUdeviceptr *p, size_t size, size_t, CUdeviceptr, unsigned long long) {
+  std::lock_guard<std::mutex> lk(mu);
+  *p = next_va;
+  next_va += (size + (1ull << 30)) & ~((1ull << 21) - 1);
+  reservations[*p] = size;
+  return CUDA_SUCCESS;
+}
+static CUresult AddressFree(CUdeviceptr p, size_t size) {
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = reservations.find(p);
+  if (it == reservations.end() || it->second != size) { violate("cuMemAddressFree of an unknown range"); return CUDA_ERROR_INVALID_VALUE; }
+  for (auto &m : mappings) if (m.first >= p && m.first < p + size) { violate("cuMemAddressFree with live mappings"); break; }
+  reservations.erase(it);
+  return CUDA_SUCCESS;
+}
+static CUresult Create(CUmemGenericAllocationHandle *h, size_t size, const CUmemAllocationProp *, unsigned long long) {
+  nap();
+  std::lock_guard<std::mutex> lk(mu);
+  if (handle_bytes + other_bytes + (double)size > total_bytes) return CUDA_ERROR_OUT_OF_MEMORY;
+  *h = next_handle++;
+  handles[*h] = 0;
+  handle_bytes += (double)size;
+  n_create++;
+  (void)size;
+  return CUDA_SUCCESS;
+}
+static std::map<CUmemGenericAllocationHandle, size_t> handle_size;
+static CUresult Release(CUmemGenericAllocationHandle h) {
+  nap();
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = handles.find(h);
+  if (it == handles.end()) { violate("cuMemRelease of an unknown handle"); return CUDA_ERROR_INVALID_VALUE; }
+  if (it->second != 0) violate("cuMemRelease of a handle that is still mapped");
+  handle_bytes -= (double)handle_size[h];
+  handles.erase(it);
+  n_release++;
+  return CUDA_SUCCESS;
+}
+static CUresult MapFn(CUdeviceptr p, size_t size, size_t, CUmemGenericAllocationHandle h, unsigned long long) {
+  std::lock_guard<std::mutex> lk(mu);
+  n_map++;
+  if (!handles.count(h)) { violate("cuMemMap of an unknown handle"); return CUDA_ERROR_INVALID_VALUE; }
+  bool inside = false;
+  for (auto &r : reservations) if (p >= r.first && p + size <= r.first + r.second) inside = true;
+  if (!inside) { violate("cuMemMap outside any reservation"); return CUDA_ERROR_INVALID_VALUE; }
+  auto nx = mappings.lower_bound(p);
+  if (nx != mappings.end() && nx->first < p + size) { violate("cuMemMap over an existing mapping"); return CUDA_ERROR_INVALID_VALUE; }
+  if (nx != mappings.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second.size > p) { violate("cuMemMap over an existing mapping"); return CUDA_ERROR_INVALID_VALUE; } }
+  mappings[p] = Map{size, h, false};
+  handles[h]++;
+  return CUDA_SUCCESS;
+}
+static CUresult Unmap(CUdeviceptr p, size_t size) {
+  nap();
+  std::lock_guard<std::mutex> lk(mu);
+  n_unmap++;
+  // whole mappings inside [p, p+size) go; a partial overlap is an error
+  bool any = false;
+  for (auto it = mappings.lower_bound(p); it != mappings.end() && it->first < p + size;) {
+    if (it->first + it->second.size > p + size) { violate("cuMemUnmap splits a mapping"); return CUDA_ERROR_INVALID_VALUE; }
+    handles[it->second.h]--;
+    it = mappings.erase(it);
+    any = true;
+  }
+  if (!any && size < (1ull << 33)) { violate("cuMemUnmap of an unmapped range"); return CUDA_ERROR_INVALID_VALUE; }
+  return CUDA_SUCCESS;
+}
+static CUresult SetAccess(CUdeviceptr p, size_t size, const CUmemAccessDesc *, size_t) {
+  nap();
+  std::lock_guard<std::mutex> lk(mu);
+  n_access++;
+  size_t covered = 0;
+  for (auto it = mappings.lower_bound(p); it != mappings.end() && it->first < p + size; ++it) { it->second.access = true; covered += it->second.size; }
+  if (covered != size) { violate("cuMemSetAccess over a range that is not fully mapped"); return CUDA_ERROR_INVALID_VALUE; }
+  return CUDA_SUCCESS;
+}
+static CUresult Granularity(size_t *g, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) { *g = 2u << 20; return CUDA_SUCCESS; }
+static CUresult ErrorString(CUresult r, const char **s) { *s = r == CUDA_ERROR_OUT_OF_MEMORY ? "out of memory (mock)" : "invalid value (mock)"; return CUDA_SUCCESS; }
+}  // namespace mock
+
+int vmm_mock_driver(int64_t total_bytes, int latency_us) {
+  std::call_once(g_drv_once, [] {});   // the real resolution must not overwrite the mock later
+  {
+    std::lock_guard<std::mutex> lk(mock::mu);
+    mock::total_bytes = (double)total_bytes;
+    mock::latency_us = latency_us;
+    mock::other_bytes = 0;
+    mock::installed = true;
+  }
+  g_drv.MemAddressReserve = mock::AddressReserve;
+  g_drv.MemAddressFree = mock::AddressFree;
+  g_drv.MemCreate = [](CUmemGenericAllocationHandle *h, size_t size, const CUmemAllocationProp *p, unsigned long long f) {
+    CUresult r = mock::Create(h, size, p, f);
+    if (r == CUDA_SUCCESS) { std::lock_guard<std::mutex> lk(mock::mu); mock::handle_size[*h] = size; }
+    return r;
+  };
+  g_drv.MemRelease = mock::Release;
+  g_drv.MemMap = mock::MapFn;
+  g_drv.MemUnmap = mock::Unmap;
+  g_drv.MemSetAccess = mock::SetAccess;
+  g_drv.MemGetAllocationGranularity = mock::Granularity;
+  g_drv.GetErrorString = mock::ErrorString;
+  g_drv.ok = true;
+  return 0;
+}
+bool vmm_mock_installed() { return mock::installed; }
+void vmm_mock_set_other_bytes(int64_t bytes) { std::lock_guard<std::mutex> lk(mock::mu); mock::other_bytes = (double)bytes; }
+void vmm_mock_stats(int64_t *o) {
+  std::lock_guard<std::mutex> lk(mock::mu);
+  o[0] = mock::n_create; o[1] = mock::n_release; o[2] = mock::n_map; o[3] = mock::n_unmap; o[4] = mock::n_access;
+  o[5] = mock::n_violations; o[6] = (int64_t)mock::handles.size(); o[7] = (int64_t)mock::mappings.size();
+  int64_t leaked = 0;
+  for (auto &h : mock::handles) if (h.second < 0) leaked++;
+  o[8] = leaked; o[9] = (int64_t)mock::handle_bytes;
+}
+const char *vmm_mock_last_violation() { return mock::last_violation; }
+static bool mock_meminfo(size_t *fr, size_t *tot) {
+  std::lock_guard<std::mutex> lk(mock::mu);
+  double f = mock::total_bytes - mock::other_bytes - mock::handle_bytes;
+  *fr = (size_t)(f > 0 ? f : 0);
+  *tot = (size_t)mock::total_bytes;
+  return true;
+}
+
 static const char *cu_str(CUresult r) {
   const char *s = nullptr;
   if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
@@ -89,7 +237,7 @@ VmmGroup::~VmmGroup() {
   stop_worker();   // drains what is queued, then exits
   const Driver *d = g_drv.ok ? &g_drv : nullptr;
   if (!d) return;
-  cudaSetDevice(dev_);
+  if (!mock::installed) cudaSetDevice(dev_);
   if (va_base_) {
     d->MemUnmap(va_base_, va_bytes_);      // tolerate stale mappings at teardown (ftensor.cpp:78-98)
     d->MemAddressFree(va_base_, va_bytes_);
@@ -108,7 +256,7 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     return (int)ranges_.size();
   }
   if (size_per_layer <= 0 || num_layers <= 0 || num_kv <= 0) { set_error("create_kv_tensors: bad sizes"); return KVB_ERR_INVALID_; }
-  if (cudaSetDevice(dev_) != cudaSuccess || cudaFree(0) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", dev_); return KVB_ERR_CUDA_; }
+  if (!mock::installed && (cudaSetDevice(dev_) != cudaSuccess || cudaFree(0) != cudaSuccess)) { set_error("cudaSetDevice(%d) failed", dev_); return KVB_ERR_CUDA_; }
   // allocator.cpp:130-136: round the per-layer size up to the page size
   size_t aligned = ((size_t)size_per_layer + P_ - 1) / P_ * P_;
   L_ = num_layers;
@@ -169,7 +317,7 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     }
   }
   // the zero page must read as zeros
-  if (cudaMemset((void *)ranges_[0].base, 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+  if (!mock::installed && (cudaMemset((void *)ranges_[0].base, 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
     set_error("zero page memset failed: %s", cudaGetErrorString(cudaGetLastError()));
     return KVB_ERR_CUDA_;
   }
@@ -337,10 +485,15 @@ void VmmGroup::expire(double now) {
 // stalls like them); between samples our own creates and releases are accounted.
 void VmmGroup::poll_meminfo(Lock &lk) {
   lk.unlock();
-  ensure_device(dev_);
   size_t fr = 0, tot = 0;
-  bool ok = cudaMemGetInfo(&fr, &tot) == cudaSuccess;
-  if (!ok) cudaGetLastError();
+  bool ok;
+  if (mock::installed) {
+    ok = mock_meminfo(&fr, &tot);
+  } else {
+    ensure_device(dev_);
+    ok = cudaMemGetInfo(&fr, &tot) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+  }
   lk.lock();
   if (ok) { mem_free_ = (double)fr; mem_total_ = (double)tot; mem_t_ms_ = now_ms(); }
 }
@@ -389,9 +542,9 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   int64_t tn[5] = {0, 0, 0, 0, 0};
   char emsg[384] = "";
   int rc = 0, created = 0;
-  ensure_device(dev_);
+  if (!mock::installed) ensure_device(dev_);
   // the engine may still have kernels in flight on pages about to be unmapped (page_allocator.cpp:671-673)
-  if (sync_first) cudaDeviceSynchronize();
+  if (sync_first && !mock::installed) cudaDeviceSynchronize();
   if (to_mapped) {
     for (int s = 0; s < n_sub_ && !rc; ++s)
       if (!hs[(size_t)s]) {

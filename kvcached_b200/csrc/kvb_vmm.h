@@ -196,6 +196,12 @@ VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
 // cudaSetDevice only when the calling thread is on another device (cudaSetDevice itself costs tens of
 // microseconds on this stack; cudaGetDevice does not)
 int ensure_device(int dev);
+// mock driver (host-logic tests without a GPU): legality-checking stand-ins for the VMM driver calls
+int vmm_mock_driver(int64_t total_bytes, int latency_us);
+bool vmm_mock_installed();
+void vmm_mock_set_other_bytes(int64_t bytes);
+void vmm_mock_stats(int64_t *out10);
+const char *vmm_mock_last_violation();
 int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out8);
 int vmm_probe3(int dev, size_t unit, int64_t M, int64_t iters, double *out7);
 int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out3);
