@@ -448,7 +448,6 @@ bool VmmGroup::force_one_retained(bool newest) {
 }
 
 void VmmGroup::expire(double now) {
-  if (retention_ms_ <= 0) return;
   while (!retained_.empty()) {
     const Retained &r = retained_.front();
     const size_t p = (size_t)r.p;
@@ -552,11 +551,22 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
         if (!rc) created++; else hs[(size_t)s] = 0;
       }
   }
+  int done = 0;
   for (int s = 0; s < n_sub_ && !rc; ++s) {
     CUdeviceptr a = sub_addr(p, s);
     CU_TIMED_L(2, g_drv.MemUnmap(a, unit_));
     CU_TIMED_L(3, g_drv.MemMap(a, unit_, 0, to_mapped ? hs[(size_t)s] : zero_, 0));
     CU_TIMED_L(4, g_drv.MemSetAccess(a, unit_, &access_, 1));
+    if (!rc) done++;
+  }
+  if (rc && to_mapped) {
+    // a map that failed half way (per-layer layout): the units already switched go back to the zero page, so that
+    // the page is recorded as it really is and its handles can return to the pool unmapped
+    for (int s = 0; s <= done && s < n_sub_; ++s) {
+      CUdeviceptr a = sub_addr(p, s);
+      g_drv.MemUnmap(a, unit_);
+      if (g_drv.MemMap(a, unit_, 0, zero_, 0) == CUDA_SUCCESS) g_drv.MemSetAccess(a, unit_, &access_, 1);
+    }
   }
   lk.lock();
   inflight_ = -1;

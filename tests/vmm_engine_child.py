@@ -231,6 +231,30 @@ def case_random_per_layer():
     assert end["handles"] == 0 and end["mappings"] == 0
 
 
+def case_oom():
+    """A device too small for what is wanted, nothing retained to take: the driver's refusal surfaces as an error of the
+    call that waited for the map, the page is recorded as not mapped, nothing leaks."""
+    layers = 4
+    unit = PAGE * layers * 2
+    setup(total_gib=5 * unit / (1 << 30), n_pages=64, layers=layers)     # zero page + 4 units
+    vmm_ops.set_prefetch(0)
+    events(range(10), False)
+    rc = lib.kvb_vmm_wait_maps(0)
+    assert rc < 0 and "out of memory" in _lib.last_error(), (rc, _lib.last_error())
+    lib.kvb_vmm_fence(0)
+    got = vmm_ops.mapped_pages()
+    assert len(got) == 4 and set(got) <= set(range(10))
+    st = no_violations()
+    assert st["creates"] == 5
+    events(got, True)
+    events([20], False)                                  # a retained handle makes room
+    vmm_ops.wait_maps()
+    assert vmm_ops.mapped_pages() == [20]
+    vmm_ops.shutdown_kvcached()
+    end = no_violations()
+    assert end["handles"] == 0 and end["mappings"] == 0
+
+
 if __name__ == "__main__":
     globals()["case_" + sys.argv[1]]()
     print("OK", sys.argv[1])
