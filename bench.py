@@ -344,6 +344,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     barrier()
     if tp is not None:
         tp.sync()          # rank 0's trim reaches the other ranks
+    vmm_ops.settle()       # every rank hands its retained pages back before the KV buffers are allocated
 
     # ================= fused KV scatter / gather through the mapped range ======================================
     L, bs, cell = cfg["num_layers"], cfg["block_size"], cfg["cell_size"]
