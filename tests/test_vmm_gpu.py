@@ -335,3 +335,41 @@ def test_raw_control_and_pool(kvcached_fixture):
     rc = lib.kvb_vmm_raw_control(0, n, iters, 1, a.ctypes.data_as(_lib.p_f64), b.ctypes.data_as(_lib.p_f64))
     assert rc == 0, _lib.last_error()
     assert (a > 0).all() and (b > 0).all()
+
+
+@pytest.mark.parametrize("unified", [False, True])
+def test_per_layer_and_unified_pool_mapping(unified):
+    """Non-contiguous layouts (allocator.cpp:178-207): one flat tensor per layer; an offset maps, in every layer, the K
+    page at `off` and the V page at `off + size / 2` (per-layer), or the single page at `off` (unified pool, K and V
+    interleaved inside it).  Everything else keeps reading the zero page."""
+    import torch
+    torch.cuda.init()
+    L, pages = 3, 8
+    vmm_ops.init_kvcached("cuda:0", PAGE, False)
+    try:
+        vmm_ops.set_prefetch(0)
+        per_layer = pages * PAGE * 2
+        tens = vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", L, 2, 0, unified)
+        assert len(tens) == L and all(t.numel() * 2 == per_layer for t in tens)
+        half = per_layer // 2 // 2                       # int16 elements to the V half
+        epp = PAGE // 2                                  # int16 elements per page
+        assert vmm_ops.map_to_kv_tensors([2 * PAGE, 5 * PAGE])
+        assert vmm_ops.mapped_pages() == [2, 5]
+        for l, t in enumerate(tens):
+            t[2 * epp + 7] = 100 + l                     # K page 2 (per-layer) / page 2 (unified)
+            t[5 * epp] = 200 + l
+            if not unified:
+                t[half + 2 * epp + 9] = 300 + l          # V page 2
+        torch.cuda.synchronize()
+        for l, t in enumerate(tens):
+            assert int(t[2 * epp + 7]) == 100 + l and int(t[5 * epp]) == 200 + l
+            assert int(t[3 * epp + 7]) == 0 and int(t[0]) == 0          # unmapped pages: zero page
+            if not unified:
+                assert int(t[half + 2 * epp + 9]) == 300 + l
+        st = vmm_ops.vmm_stats()
+        assert st["bytes_mapped"] == 2 * PAGE * (L if unified else 2 * L)
+        assert vmm_ops.unmap_from_kv_tensors([2 * PAGE, 5 * PAGE])
+        torch.cuda.synchronize()
+        assert vmm_ops.mapped_pages() == [] and int(tens[0][2 * epp + 7]) == 0
+    finally:
+        vmm_ops.shutdown_kvcached()

@@ -231,6 +231,35 @@ def case_random_per_layer():
     assert end["handles"] == 0 and end["mappings"] == 0
 
 
+def case_layouts():
+    """Handles per page id by layout (allocator.cpp:161-209): contiguous = 1 compound page of L * nKV * P bytes, per-layer =
+    2 * L pages (K at off, V at off + size / 2), unified pool = L pages (K and V interleaved inside the page)."""
+    L = 5
+    for contiguous, unified, per_page, unit in ((True, False, 1, PAGE * L * 2), (False, False, 2 * L, PAGE), (False, True, L, PAGE)):
+        assert lib.kvb_vmm_mock_driver(64 << 30, 0) == 0
+        vmm_ops.init_kvcached("cuda:0", PAGE, contiguous)
+        rngs = vmm_ops.create_kv_tensors_raw(16 * PAGE * 2, L, 2, 0, unified)
+        assert len(rngs) == (1 if contiguous else L)
+        n_pages = 16 if not unified else 32               # unified: the whole per-layer range is one pool of pages
+        vmm_ops.set_async(False)
+        vmm_ops.set_prefetch(0)
+        a = no_violations()
+        events([2, 7], False)
+        vmm_ops.fence()
+        b = no_violations()
+        assert b["creates"] - a["creates"] == 2 * per_page and b["unmaps"] - a["unmaps"] == 2 * per_page
+        assert b["handle_bytes"] - a["handle_bytes"] == 2 * per_page * unit
+        assert vmm_ops.mapped_pages() == [2, 7]
+        bad = np.asarray([n_pages * 2], dtype=np.int64)   # a page beyond the range is refused, nothing touched
+        assert lib.kvb_vmm_enqueue_page_events(0, bad.ctypes.data_as(_lib.p_i64), 1) < 0
+        events([2, 7], True)
+        vmm_ops.fence()
+        assert vmm_ops.mapped_pages() == [] and vmm_ops.vmm_stats()["pooled_handles"] == 2 * per_page
+        vmm_ops.shutdown_kvcached()
+        end = no_violations()
+        assert end["handles"] == 0 and end["mappings"] == 0
+
+
 def case_oom():
     """A device too small for what is wanted, nothing retained to take: the driver's refusal surfaces as an error of the
     call that waited for the map, the page is recorded as not mapped, nothing leaks."""
