@@ -311,10 +311,13 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     map_unmap = {}
     if rank == 0:
         mgr.trim()
-        lib.kvb_vmm_pool_config(0, 128)
+        n_list = (1, 8, 64, 512) if world == 1 else (1, 8, 64)      # SURVEY 8(d); 512 compound pages = 64 GiB at TP1
+        lib.kvb_vmm_pool_config(0, 640)
         lib.kvb_vmm_pool_prefill(0, 72)
-        for n in (1, 8, 64):
-            iters = 30 if n < 64 else 8
+        for n in n_list:
+            iters = 30 if n < 64 else (8 if n < 512 else 3)
+            if n == 512:
+                lib.kvb_vmm_pool_prefill(0, 512)
             ids = np.arange(100, 100 + n, dtype=np.int64)
             p = ids.ctypes.data_as(_lib.p_i64)
             mm, uu = [], []
