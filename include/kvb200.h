@@ -117,10 +117,13 @@ int kvb_vmm_set_async(int64_t group_id, int on);
  * kvctl limit, kvb_vmm_settle).  Idle pooled handles above KVB200_POOL_FLOOR (16) are released after the same
  * time.  The reference's hysteresis is count-based: max_reserved_pages stay mapped (page_allocator.cpp:264-310). */
 int kvb_vmm_set_retention_ms(int64_t group_id, double ms);
-/* Retained pages are kept only while at least this fraction of the device stays free for everybody else (default
- * KVB200_RETAIN_FREE_FRACTION or 0.20): a co-located model always sees that much memory, and as it takes it the VMM
- * thread hands retained pages back (newest first) until the reserve is whole again. */
-int kvb_vmm_set_retain_free_fraction(int64_t group_id, double fraction);
+/* The reserve retained pages must leave free.  While somebody else's footprint on the device is growing (another
+ * process, or this process's own allocations) and for 10 s after it last grew: `fraction` of the device (default
+ * KVB200_RETAIN_FREE_FRACTION or 0.20) — the VMM thread hands retained pages back (newest first) until it is whole.
+ * While nobody else moves: the KVCACHED_GPU_UTILIZATION headroom plus `quiet_margin` (default
+ * KVB200_RETAIN_QUIET_MARGIN or 0.02 of the device; < 0 = keep), which a co-located model that wakes up sees as
+ * available at once; taking any of it switches the larger reserve on within one poll (5-50 ms). */
+int kvb_vmm_set_retain_free_fraction(int64_t group_id, double fraction, double quiet_margin);
 int kvb_vmm_settle(int64_t group_id);
 int64_t kvb_vmm_pending_unmaps(int64_t group_id);
 /* Map-ahead: the step kernel publishes the next pages its free list will hand out; the VMM thread maps up to `depth`

@@ -119,11 +119,11 @@ int kvb_vmm_set_retention_ms(int64_t group_id, double ms) {
   g->set_retention_ms(ms);
   return 0;
 }
-int kvb_vmm_set_retain_free_fraction(int64_t group_id, double f) {
+int kvb_vmm_set_retain_free_fraction(int64_t group_id, double f, double quiet_margin) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;
   std::lock_guard<std::mutex> lk(g->mu);
-  g->set_retain_free_fraction(f);
+  g->set_retain_free_fraction(f, quiet_margin);
   return 0;
 }
 int kvb_vmm_set_async(int64_t group_id, int on) {

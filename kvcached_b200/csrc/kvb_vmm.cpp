@@ -336,6 +336,8 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     gpu_util_ = u && *u ? atof(u) : 0.95;
     const char *rf = getenv("KVB200_RETAIN_FREE_FRACTION");
     retain_free_frac_ = rf && *rf ? atof(rf) : 0.20;
+    const char *qm = getenv("KVB200_RETAIN_QUIET_MARGIN");
+    quiet_margin_ = qm && *qm ? atof(qm) : 0.02;
     const char *fl = getenv("KVB200_POOL_FLOOR");
     pool_floor_ = fl && *fl ? atoll(fl) : 16;
   }
@@ -464,7 +466,7 @@ void VmmGroup::expire(double now) {
   }
   // somebody else took memory: retained pages go back until the reserve is whole again (newest first, like a steal)
   if (mem_total_ > 0 && n_retained_ > 0) {
-    const double reserve = std::max(retain_free_frac_, 1.0 - gpu_util_) * mem_total_;
+    const double reserve = reserve_fraction(now) * mem_total_;
     double short_by = reserve - mem_free_ - (double)(need_unmap_ + release_debt_ / n_sub_) * (double)unit_ * n_sub_;
     while (short_by > 0 && force_one_retained(true)) {
       release_debt_ += n_sub_;
@@ -494,7 +496,26 @@ void VmmGroup::poll_meminfo(Lock &lk) {
     if (!ok) cudaGetLastError();
   }
   lk.lock();
-  if (ok) { mem_free_ = (double)fr; mem_total_ = (double)tot; mem_t_ms_ = now_ms(); }
+  if (ok) {
+    mem_free_ = (double)fr;
+    mem_total_ = (double)tot;
+    mem_t_ms_ = now_ms();
+    // everybody else's footprint = used memory that is not our handles; a rise of one page over the lowest level
+    // seen since the last rise means somebody is taking memory: the larger reserve applies for the next 10 s
+    const double ours = (double)(n_created_ - n_released_) * (double)unit_;
+    const double others = mem_total_ - mem_free_ - ours;
+    if (others_base_ < 0 || others < others_base_) others_base_ = others;
+    if (others > others_base_ + (double)unit_ * n_sub_) {
+      contended_until_ms_ = mem_t_ms_ + 10000.0;
+      others_base_ = others;
+    }
+  }
+}
+
+double VmmGroup::reserve_fraction(double now) const {
+  const double headroom = 1.0 - gpu_util_;
+  if (now < contended_until_ms_) return std::max(retain_free_frac_, headroom);
+  return std::min(std::max(retain_free_frac_, headroom), headroom + quiet_margin_);
 }
 
 bool VmmGroup::cached_meminfo(size_t *free_bytes, size_t *total_bytes) {
@@ -509,13 +530,14 @@ bool VmmGroup::cached_meminfo(size_t *free_bytes, size_t *total_bytes) {
 // arithmetic (page_allocator.cpp:442-455), from the VMM thread's last sample.
 bool VmmGroup::can_create(bool soft) {
   if (mem_total_ <= 0) return true;   // never sampled (synchronous mode): let the driver decide
-  const double reserve = soft ? std::max(retain_free_frac_, 1.0 - gpu_util_) : (1.0 - gpu_util_);
+  const double reserve = soft ? reserve_fraction(now_ms()) : (1.0 - gpu_util_);
   return mem_free_ - (double)unit_ * n_sub_ >= mem_total_ * reserve;
 }
 
-void VmmGroup::set_retain_free_fraction(double f) {
+void VmmGroup::set_retain_free_fraction(double f, double quiet_margin) {
   Lock lk(qmu_);
   retain_free_frac_ = f < 0 ? 0 : (f > 1 ? 1 : f);
+  if (quiet_margin >= 0) quiet_margin_ = quiet_margin > 1 ? 1 : quiet_margin;
 }
 
 int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {

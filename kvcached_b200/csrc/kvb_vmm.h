@@ -82,10 +82,13 @@ class VmmGroup {
   // memory pressure.  Idle pooled handles are released after the same time.  0 = unmap at once (and in
   // synchronous mode).  Count-based hysteresis is what the reference has (max_reserved_pages, page_allocator.cpp:264-310).
   void set_retention_ms(double ms);
-  // Retained pages are a cache in memory nobody asked for yet: they are kept only while at least this fraction of
-  // the device stays free for everybody else (a co-located model always sees that much, and as it takes it the VMM
-  // thread hands retained pages back to restore it).  Default KVB200_RETAIN_FREE_FRACTION or 0.20.
-  void set_retain_free_fraction(double f);
+  // Retained pages are a cache in memory nobody asked for yet.  While somebody else's footprint on the device is
+  // growing (another process, or this process's own torch allocations) — and for 10 s after it last grew — they are
+  // kept only as long as this fraction of the device stays free (default KVB200_RETAIN_FREE_FRACTION or 0.20): the
+  // VMM thread hands retained pages back until the reserve is whole again.  While nobody else moves, the reserve is
+  // the utilisation headroom plus KVB200_RETAIN_QUIET_MARGIN (0.02 of the device): a co-located model that wakes up
+  // always sees that margin as available, and taking any of it switches the larger reserve on within one poll.
+  void set_retain_free_fraction(double f, double quiet_margin = -1);
   int settle();       // fence + every retained page back on the zero page (trim / clear / resize / kvctl limit)
   void set_prefetch_hints(const int64_t *pages, int64_t n);
   void set_prefetch_depth(int depth);
@@ -164,6 +167,8 @@ class VmmGroup {
   int64_t n_retained_ = 0, n_retention_hits_ = 0, release_debt_ = 0, pool_floor_ = 16;
   double mem_t_ms_ = -1e18, gpu_util_ = 0.95, retain_free_frac_ = 0.20, last_map_ms_ = -1e18;
   double mem_free_ = 0, mem_total_ = 0;     // bytes, as of mem_t_ms_ (adjusted by our own creates / releases)
+  double quiet_margin_ = 0.02, others_base_ = -1, contended_until_ms_ = -1e18;
+  double reserve_fraction(double now) const;
   std::deque<int64_t> qm_, qu_, qs_;   // pages whose wanted state may differ from the physical one (maps / unmaps / hinted maps)
   std::vector<int64_t> hints_;
   int prefetch_depth_ = 0;

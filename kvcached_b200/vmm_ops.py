@@ -112,9 +112,11 @@ def set_retention(ms: float, group_id: int = 0) -> None:
     _lib.check(_lib.load().kvb_vmm_set_retention_ms(group_id, float(ms)), "vmm set_retention_ms")
 
 
-def set_retain_free_fraction(fraction: float, group_id: int = 0) -> None:
-    """Retained pages are kept only while this fraction of the device stays free for everybody else."""
-    _lib.check(_lib.load().kvb_vmm_set_retain_free_fraction(group_id, float(fraction)), "vmm set_retain_free_fraction")
+def set_retain_free_fraction(fraction: float, quiet_margin: float = -1.0, group_id: int = 0) -> None:
+    """The free-memory reserve of retained pages: `fraction` of the device while somebody else's footprint grows,
+    headroom + `quiet_margin` while nobody else moves (quiet_margin < 0 keeps the current one)."""
+    _lib.check(_lib.load().kvb_vmm_set_retain_free_fraction(group_id, float(fraction), float(quiet_margin)),
+               "vmm set_retain_free_fraction")
 
 
 def wait_maps(group_id: int = 0) -> None:

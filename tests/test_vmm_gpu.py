@@ -175,14 +175,14 @@ def test_retention_keeps_the_handle_until_it_is_needed_or_times_out(kvcached_fix
         assert int(kv[12 * bpp, 0, 0, 0, 0]) == 0            # zero page again
         # the reserve: retained pages are handed back while less than the given fraction of the device is free
         vmm_ops.set_retention(60_000)
-        vmm_ops.set_retain_free_fraction(0.9999)
+        vmm_ops.set_retain_free_fraction(0.9999, 0.9999)
         assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
         assert lib.kvb_vmm_enqueue_page_events(0, ev_unmap.ctypes.data_as(_lib.p_i64), 4) == 1
         t_end = time.time() + 60
         while time.time() < t_end and (vmm_ops.engine_stats()["retained"] or vmm_ops.pending_unmaps()):
             time.sleep(0.02)
         assert vmm_ops.engine_stats()["retained"] == 0 and vmm_ops.vmm_stats()["mapped_pages"] == 0
-        vmm_ops.set_retain_free_fraction(0.20)
+        vmm_ops.set_retain_free_fraction(0.20, 0.02)
         # retention off: every unmap is applied at once
         vmm_ops.set_retention(0)
         assert lib.kvb_vmm_enqueue_page_events(0, ev_map.ctypes.data_as(_lib.p_i64), 4) == 1
@@ -191,7 +191,7 @@ def test_retention_keeps_the_handle_until_it_is_needed_or_times_out(kvcached_fix
         assert vmm_ops.vmm_stats()["mapped_pages"] == 0 and vmm_ops.engine_stats()["retained"] == 0
     finally:
         vmm_ops.set_retention(2000)
-        vmm_ops.set_retain_free_fraction(0.20)
+        vmm_ops.set_retain_free_fraction(0.20, 0.02)
 
 
 @pytest.mark.parametrize("use_thread", [True, False])

@@ -139,7 +139,8 @@ def case_steal_and_reserve():
     setup(total_gib=41 * unit / (1 << 30), n_pages=200, layers=layers)
     vmm_ops.set_prefetch(0)
     vmm_ops.set_retention(600_000)
-    vmm_ops.set_retain_free_fraction(0.20)                 # 8.2 of 41 units stay free: a create is allowed while free - 1 >= 8.2,
+    vmm_ops.set_retain_free_fraction(0.20, 0.15)           # reserve 0.20 both while quiet (headroom 0.05 + 0.15) and contended:
+                                                           # 8.2 of 41 units stay free, a create is allowed while free - 1 >= 8.2,
                                                            # i.e. up to 32 handles including the zero page
     events(range(20), False)
     vmm_ops.wait_maps()
@@ -167,6 +168,35 @@ def case_steal_and_reserve():
     vmm_ops.shutdown_kvcached()
     e = no_violations()
     assert e["handles"] == 0 and e["mappings"] == 0
+
+
+def case_quiet_and_contended_reserve():
+    """While nobody else moves, retained pages may fill the device up to headroom + quiet margin; when somebody else's
+    footprint grows, the larger reserve applies and the VMM thread hands retained pages back until it is whole."""
+    layers = 4
+    unit = PAGE * layers * 2
+    setup(total_gib=41 * unit / (1 << 30), n_pages=200, layers=layers)
+    vmm_ops.set_prefetch(0)
+    vmm_ops.set_retention(600_000)
+    vmm_ops.set_retain_free_fraction(0.50, 0.0)            # contended: half the device free; quiet: the 5 % headroom
+    events(range(30), False)
+    vmm_ops.wait_maps()
+    events(range(30), True)
+    vmm_ops.fence()
+    time.sleep(0.3)                                         # several polls: nobody else moves, nothing is handed back
+    a = no_violations()
+    assert vmm_ops.engine_stats()["retained"] == 30 and a["releases"] == 0
+    lib.kvb_vmm_mock_set_other_bytes(int(3 * unit))         # somebody takes three pages' worth
+    assert wait_quiet(lambda: mock_stats()["handle_bytes"] <= (41 - 3 - 20.5) * unit)
+    b = no_violations()
+    assert b["releases"] >= 13 and vmm_ops.engine_stats()["retained"] <= 17
+    # the pages retained FIRST survive (the FIFO free list needs them first)
+    events(range(0, 8), False)
+    vmm_ops.wait_maps()
+    assert vmm_ops.engine_stats()["retention_hits"] == 8
+    vmm_ops.shutdown_kvcached()
+    end = no_violations()
+    assert end["handles"] == 0 and end["mappings"] == 0
 
 
 def case_map_ahead():
