@@ -477,8 +477,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                 "map_ahead_hits": est["prefetch_hits"], "retention_hits": est["retention_hits"],
                                 "pages_retained_at_end": est["retained"],
                                 "policy": "async VMM thread; map-ahead 5 pages; unmapped pages keep their handle until the "
-                                          "allocator is quiet for 2 s, at most while 20% of the device stays free "
-                                          "(KVB200_VMM_PREFETCH / KVB200_VMM_RETAIN_MS / KVB200_RETAIN_FREE_FRACTION)"},
+                                          "allocator is quiet for 2 s, leaving free the utilisation headroom + 2% of the "
+                                          "device, or 20% while anybody else's footprint grows (KVB200_VMM_PREFETCH / "
+                                          "KVB200_VMM_RETAIN_MS / KVB200_RETAIN_FREE_FRACTION / KVB200_RETAIN_QUIET_MARGIN)"},
                         "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
                                "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
                                "timed region"},
