@@ -1138,23 +1138,30 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   if (!src) return KVB_ERR_INVALID;
   VmmGroup *g = vmm_group(group_id, false);
   if (!g || !g->created()) { set_error("tp_apply: KV tensors of group %ld are not created", (long)group_id); return KVB_ERR_STATE; }
-  int64_t hdr[2] = {0, 0};
-  CUDA_TRY(cudaMemcpyAsync(hdr, (const void *)(uintptr_t)src, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  // ONE device->host copy of the whole (8 KB) buffer into pinned memory and one stream synchronisation per step
+  static thread_local int64_t *pinned = nullptr;
+  if (!pinned && cudaHostAlloc((void **)&pinned, (size_t)kTpWords * 8, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    pinned = nullptr;
+  }
+  std::vector<int64_t> pageable;
+  int64_t *buf = pinned;
+  if (!buf) { pageable.resize((size_t)kTpWords); buf = pageable.data(); }
+  CUDA_TRY(cudaMemcpyAsync(buf, (const void *)(uintptr_t)src, (size_t)kTpWords * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  const int64_t hdr[2] = {buf[0], buf[1]};
   if (seq_out) *seq_out = hdr[0];
   if (n_out) *n_out = hdr[1];
   if (hdr[1] < 0 || hdr[1] > kTpWords - 3) { set_error("tp_apply: corrupt header n=%ld", (long)hdr[1]); return KVB_ERR_INVALID; }
-  // events, then [nh, hints...]; one copy of the tail that can hold both
-  std::vector<int64_t> ev((size_t)hdr[1] + 17);
-  CUDA_TRY(cudaMemcpy(ev.data(), (const void *)(uintptr_t)(src + 16), ev.size() * 8 <= (size_t)(kTpWords - 2) * 8 ? ev.size() * 8 : (size_t)(kTpWords - 2) * 8, cudaMemcpyDeviceToHost));
+  const int64_t *ev = buf + 2;
   std::lock_guard<std::mutex> lk(g->mu);
   int rc = 0;
   if (hdr[1] > 0) {
-    rc = g->enqueue_events(ev.data(), hdr[1]);
+    rc = g->enqueue_events(ev, hdr[1]);
     if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
   }
   int64_t nh = ev[(size_t)hdr[1]];
-  if (nh >= 0 && nh <= 16 && hdr[1] + 1 + nh <= kTpWords - 2) g->set_prefetch_hints(ev.data() + hdr[1] + 1, nh);
+  if (nh >= 0 && nh <= 16 && hdr[1] + 1 + nh <= kTpWords - 2) g->set_prefetch_hints(ev + hdr[1] + 1, nh);
   return rc < 0 ? rc : 0;
 }
 
