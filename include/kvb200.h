@@ -253,6 +253,8 @@ typedef struct kvb_op {
 #define KVB_OP_ALLOC_EXTEND 20
 #define KVB_OP_ALLOC_DECODE 21
 #define KVB_OP_FREE_SLOTS 22
+#define KVB_OP_ALLOC_DEV 23     /* alloc(n) with the ids written to a DEVICE array (SGLang token allocator, patches.py:101-103) */
+#define KVB_OP_FREE_DEV 24      /* free(ids) with the ids read, in order, from a DEVICE array            (patches.py:105-113) */
 
 /* a slice of an earlier request's result: ids = result(op)[lo:hi] (Python slice semantics, clipped) */
 typedef struct kvb_ref {
@@ -336,6 +338,13 @@ int kvb_mgr_alloc_decode(kvb_mgr *m, int64_t bs, uint64_t seq_lens, uint64_t las
 /* free(free_index): kv_cache_manager.free(torch.unique(free_index // page_size)) — the unique sorted block list is
  * built on the device (bitmap of touched blocks + ordered popc compaction).  Returns the number of blocks freed. */
 int64_t kvb_mgr_free_slots(kvb_mgr *m, uint64_t free_index, int64_t n, void *stream);
+
+/* ElasticTokenToKVPoolAllocator (page_size 1, kvcached/integration/sglang/patches.py:60-118): alloc(need_size) returns a
+ * device tensor of ids, free(free_index) takes one — both without the list / torch.tensor(list) round trip of the
+ * reference.  kvb_mgr_alloc_device returns n, KVB_ST_NONE or <0; kvb_mgr_free_device frees the ids in array order (the
+ * order decides the per-page FIFO, so it is kept). */
+int64_t kvb_mgr_alloc_device(kvb_mgr *m, int64_t n, uint64_t out_ids_dev, void *stream);
+int kvb_mgr_free_device(kvb_mgr *m, uint64_t ids_dev, int64_t n, void *stream);
 
 /* ---- resident traces: requests and results stay in HBM ------------------------------------
  * Upload a whole trace once; then run ranges of it.  FREE_REF refs name absolute request indices.

@@ -78,6 +78,8 @@ SIGNATURES = {
     "kvb_mgr_alloc_extend": (C.c_int, [C.c_void_p, i64, u64, u64, u64, i64, u64, C.c_void_p, p_i64]),
     "kvb_mgr_alloc_decode": (C.c_int, [C.c_void_p, i64, u64, u64, u64, C.c_void_p, p_i64]),
     "kvb_mgr_free_slots": (i64, [C.c_void_p, u64, i64, C.c_void_p]),
+    "kvb_mgr_alloc_device": (i64, [C.c_void_p, i64, u64, C.c_void_p]),
+    "kvb_mgr_free_device": (C.c_int, [C.c_void_p, u64, i64, C.c_void_p]),
     "kvb_mgr_profile": (C.c_int, [C.c_void_p, p_i64, C.c_int]),
     "kvb_audit_stress": (C.c_int, [C.c_int, i64, i32, i32, p_f64]),
     "kvb_mgr_shm_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

@@ -1695,7 +1695,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         op++;
         continue;
       }
-      if (a.resize_target > 0 && (o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_TRY_RESERVE || o.kind == KVB_OP_PIN_NEW)) {
+      if (a.resize_target > 0 && (o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_TRY_RESERVE || o.kind == KVB_OP_PIN_NEW || o.kind == KVB_OP_ALLOC_DEV)) {
         // _alloc() first applies a limit change published through the shm segment (kv_cache_manager.py:258-260,
         // page_allocator.cpp:764-782); the result is ignored there too.  Repeating it for the later requests of
         // a run changes nothing, so once per alloc-type request (= once per run) is exact.
@@ -1966,6 +1966,33 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
             r.status = st;
             r.n = st == KVB_ST_OK ? (int32_t)npg : 0;
             r.aux = decode ? a.slot_bs : ntok;    // slot indices written
+            a.res[op] = r;
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_ALLOC_DEV: {   // alloc(n); ids also land in the caller's device array
+          if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
+          __syncthreads();
+          if (a.res[op].status == KVB_ST_OK) {
+            const int64_t off = a.res[op].off;
+            for (int t = tid; t < o.n; t += NT) a.slot_out[t] = a.out_ids[off + t];
+          }
+          __syncthreads();
+          op++;
+          break;
+        }
+        case KVB_OP_FREE_DEV: {    // free(ids), ids taken in order from the caller's device array
+          const int n = (int)o.arg;
+          const bool too_many = n > c.f_cap;
+          if (!too_many) {
+            for (int j = tid; j < n; j += NT) c.fids[j] = a.slot_pre[j];
+            __syncthreads();
+            free_core(c, s, a, n, 0);
+          }
+          if (tid == 0) {
+            kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
           __syncthreads();

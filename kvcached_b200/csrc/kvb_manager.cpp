@@ -688,12 +688,13 @@ extern "C" int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n) {
 
 // ============================================================================================ SGLang slot requests
 // One request whose inputs / outputs are the caller's DEVICE arrays; the host only learns status and counts.
-static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg, int64_t arena_cap, void *stream, kvb_res *res) {
+static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg, int64_t arena_cap, void *stream, kvb_res *res,
+                        int32_t op_n = 0) {
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   size_t o_res = align_up(sizeof(Summary), 16), o_ids = o_res + 64;
   int rc = ensure_io(m, sizeof(kvb_op), o_ids + (size_t)arena_cap * 8);
   if (rc) return rc;
-  kvb_op op{kind, 0, arg};
+  kvb_op op{kind, op_n, arg};
   memcpy(m->h_in, &op, sizeof(op));
   // order our launch after whatever produced the arrays on the caller's stream
   CUDA_TRY(cudaEventRecord(m->ev0, (cudaStream_t)stream));
@@ -780,6 +781,31 @@ extern "C" int64_t kvb_mgr_free_slots(kvb_mgr *m, uint64_t free_index, int64_t n
   int rc = slots_locked(m, KVB_OP_FREE_SLOTS, sl, n, 8, stream, &r);
   if (rc) return rc;
   return r.n;
+}
+
+extern "C" int64_t kvb_mgr_alloc_device(kvb_mgr *m, int64_t n, uint64_t out_ids_dev, void *stream) {
+  if (!m || n < 0 || n > INT32_MAX || (n > 0 && !out_ids_dev)) { set_error("alloc_device: bad argument"); return KVB_ERR_INVALID - 100; }
+  LaunchArgs sl{};
+  sl.slot_out = (int64_t *)(uintptr_t)out_ids_dev;
+  sl.slot_tokens = n;
+  sl.slot_ps = (int32_t)m->cfg.block_size;
+  kvb_res r{};
+  std::lock_guard<std::mutex> lk(m->mu);
+  int rc = slots_locked(m, KVB_OP_ALLOC_DEV, sl, 0, n + 8, stream, &r, (int32_t)n);
+  if (rc) return rc - 100;
+  return r.status == KVB_ST_OK ? r.n : r.status;
+}
+extern "C" int kvb_mgr_free_device(kvb_mgr *m, uint64_t ids_dev, int64_t n, void *stream) {
+  if (!m || n < 0 || (n > 0 && !ids_dev)) { set_error("free_device: bad argument"); return KVB_ERR_INVALID; }
+  if (n == 0) return 0;
+  LaunchArgs sl{};
+  sl.slot_pre = (const int64_t *)(uintptr_t)ids_dev;
+  sl.slot_ps = (int32_t)m->cfg.block_size;
+  kvb_res r{};
+  std::lock_guard<std::mutex> lk(m->mu);
+  int rc = slots_locked(m, KVB_OP_FREE_DEV, sl, n, 8, stream, &r);
+  if (rc) return rc;
+  return r.status == KVB_ST_OK ? 0 : r.status;
 }
 
 // ============================================================================================ resident traces

@@ -18,6 +18,78 @@ from ._lib import ST_NO_PAGES, ST_NONE, KvbError
 from .kv_cache_manager import KVCacheManager
 
 
+class ElasticTokenToKVPoolAllocator:
+    """SGLang's token-level allocator (page_size 1) — the class `inject_elastic_allocator` builds
+    (kvcached/integration/sglang/patches.py:60-118): alloc(need_size) -> int64 device tensor of slot ids (or None),
+    free(free_index), available_size(), clear(), free-group batching.  Ids go kernel -> device tensor and back without
+    ever becoming a Python list."""
+
+    def __init__(self, size: int, dtype, device: str, kvcache, *args, **kwargs) -> None:
+        import torch
+        self._torch = torch
+        mgr = getattr(kvcache, "kvcached_allocator", kvcache)
+        if not isinstance(mgr, KVCacheManager):
+            raise ValueError("ElasticTokenToKVPoolAllocator requires an elastic KV pool")
+        self.size = size
+        self.page_size = 1
+        self.dtype = dtype
+        self.device = device
+        self.kvcached_allocator = mgr
+        self.is_not_in_free_group = True
+        self.free_group: List = []
+        self._lib = _lib.load()
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream().cuda_stream)
+
+    def available_size(self) -> int:
+        return min(self.kvcached_allocator.available_size(), self.size)      # patches.py:92-99
+
+    def alloc(self, need_size: int):
+        torch = self._torch
+        out = torch.empty((need_size,), dtype=torch.int64, device=self.device)
+        if need_size == 0:
+            return out
+        m = self.kvcached_allocator
+        m._wait_post_init()
+        rc = self._lib.kvb_mgr_alloc_device(m._h, need_size, out.data_ptr(), self._stream())
+        if rc == need_size:
+            return out
+        if rc == ST_NONE:
+            return None
+        if rc == ST_NO_PAGES:
+            raise RuntimeError("No free pages left")
+        raise KvbError(f"alloc_device failed ({rc}): {_lib.last_error()}")
+
+    def free(self, free_index) -> None:
+        if free_index.numel() == 0:
+            return
+        if not self.is_not_in_free_group:
+            self.free_group.append(free_index)
+            return
+        idx = free_index if free_index.dtype == self._torch.int64 and free_index.is_contiguous() else \
+            free_index.to(self._torch.int64).contiguous()
+        m = self.kvcached_allocator
+        m._wait_post_init()
+        rc = self._lib.kvb_mgr_free_device(m._h, idx.data_ptr(), idx.numel(), self._stream())
+        if rc < 0:
+            raise KvbError(f"free_device failed ({rc}): {_lib.last_error()}")
+
+    def free_group_begin(self) -> None:
+        self.is_not_in_free_group = False
+        self.free_group = []
+
+    def free_group_end(self) -> None:
+        self.is_not_in_free_group = True
+        if self.free_group:
+            self.free(self._torch.cat(self.free_group))
+
+    def clear(self) -> None:
+        self.kvcached_allocator.clear()
+        self.is_not_in_free_group = True
+        self.free_group = []
+
+
 class ElasticPagedTokenToKVPoolAllocator:
     def __init__(self, size: int, page_size: int, dtype, device: str, kvcache, *args, **kwargs) -> None:
         import torch

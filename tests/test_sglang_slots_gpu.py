@@ -122,3 +122,49 @@ def test_extend_decode_free_match_oracle(page, cell, blocks, seed):
         assert m.audit()[3] == 0
     finally:
         m.close()
+
+
+def test_token_level_allocator_keeps_ids_on_the_device():
+    """ElasticTokenToKVPoolAllocator (page_size 1): alloc -> device tensor, free(device tensor) in the tensor's order —
+    ids, free-list order and every later allocation equal the oracle fed with the same lists."""
+    import torch
+    from kvcached_b200.sglang_alloc import ElasticTokenToKVPoolAllocator
+    blocks, cell, L = 30000, 1152, 4                       # MLA token slots: 1820 per page, straddling page edges
+    m = KVCacheManager(blocks, 1, cell, L, num_kv_buffers=1, page_size=P, attach_vmm=False)
+    m.set_phys_free_pages(1 << 40)
+    o = oracle.manager_from_config(dict(num_blocks=blocks, block_size=1, cell_size=cell, num_layers=L, num_kv_buffers=1,
+                                        page_size=P, reserve_null_block=False))
+    o.set_phys_free_pages(1 << 40)
+    al = ElasticTokenToKVPoolAllocator(blocks, torch.bfloat16, "cuda:0", m)
+    rng = np.random.default_rng(9)
+    held = []
+    try:
+        for rnd in range(40):
+            if held and rng.random() < 0.45:
+                i = int(rng.integers(0, len(held)))
+                t = held.pop(i)
+                perm = torch.from_numpy(rng.permutation(t.numel())).cuda()
+                t = t[perm]                                 # SGLang frees in whatever order its request pool hands back
+                o.free(t.cpu().tolist())
+                al.free(t)
+            else:
+                n = int(rng.integers(1, 4000))
+                want = o.alloc(n)
+                got = al.alloc(n)
+                if want is None:
+                    assert got is None
+                else:
+                    assert got.device.type == "cuda" and got.cpu().tolist() == want
+                    held.append(got)
+            _snap_equal(m, o)
+        al.free_group_begin()
+        for t in held[:2]:
+            al.free(t)
+        assert m.available_size() == o.available_size()     # nothing freed yet
+        al.free_group_end()
+        if held[:2]:
+            o.free(torch.cat(held[:2]).cpu().tolist())
+        _snap_equal(m, o)
+        assert m.audit()[3] == 0
+    finally:
+        m.close()
