@@ -164,3 +164,48 @@ def test_unmodified_reference_integration_interfaces_on_our_stack(reference_mana
         mgr.close()
     finally:
         itf.shutdown_kvcached()
+
+
+def test_unmodified_reference_sglang_mla_interface(reference_manager_module, monkeypatch):
+    """BASELINE configs[3] (DeepSeek-V3 MLA latent KV, SGLang): the reference's `alloc_kv_cache(..., attention_type="MLA")`
+    (sglang/interfaces.py:139-143: one buffer per layer, views of [tokens, L, 1, 576]) over our extension, tokens written by
+    the fused kernel with one KV buffer per layer, slots from the device-side paged allocator."""
+    import numpy as np
+    import torch
+    import kvcached_b200
+    from kvcached_b200 import kv_ops
+    from kvcached_b200.sglang_alloc import ElasticPagedTokenToKVPoolAllocator
+    torch.cuda.init()
+    itf = importlib.import_module("kvcached.integration.sglang.interfaces")
+    monkeypatch.setattr(itf, "KVCacheManager", kvcached_b200.KVCacheManager)
+    L, ps, dim = 61, 64, 576
+    cell = dim * 2
+    itf.init_kvcached(device="cuda:0")
+    try:
+        bufs = itf.alloc_kv_cache((1400 * ps, 1, dim), torch.bfloat16, "cuda:0", L, page_size=ps, attention_type="MLA")
+        assert len(bufs) == L and tuple(bufs[0].shape[1:]) == (1, dim)
+        mgr = itf.get_kv_cache_manager(1400, ps, cell, L, reserve_null_block=True, num_kv_buffers=1)
+        assert mgr._post_init_done.wait(timeout=30.0) and mgr.null_block == [0]
+        assert mgr.stats().blocks_per_page == (2 << 20) // (ps * cell) == 28        # blocks straddle page edges
+        al = ElasticPagedTokenToKVPoolAllocator(1400 * ps, ps, torch.bfloat16, "cuda:0", mgr)
+        pre = torch.zeros(3, dtype=torch.int64, device="cuda")
+        seq = torch.tensor([300, 64, 1000], dtype=torch.int64, device="cuda")
+        last = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+        slots = al.alloc_extend(pre, None, seq, None, last, 1364)
+        assert slots is not None and slots.numel() == 1364 and len(set(slots.cpu().tolist())) == 1364
+        lay = kv_ops.layout_sglang_contiguous(bufs[0].data_ptr(), L, cell, 1, block_size=ps)
+        k = torch.empty((L, 1364, cell // 2), dtype=torch.int16, device="cuda").random_()
+        kv_ops.kv_scatter(lay, slots, k)
+        torch.cuda.synchronize()
+        for layer in (0, 7, L - 1):
+            got = bufs[layer][slots].contiguous().view(torch.int16).view(1364, -1)
+            assert torch.equal(got, k[layer])
+        back = torch.zeros_like(k)
+        kv_ops.kv_gather(lay, slots, back)
+        torch.cuda.synchronize()
+        assert torch.equal(back, k)
+        al.free(slots)
+        assert mgr.available_size() > 0
+        mgr.close()
+    finally:
+        itf.shutdown_kvcached()
