@@ -408,6 +408,51 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     del k, v
     torch.cuda.empty_cache()
 
+    # ================= the per-rank scatter at the TP shard shapes, on this GPU (ranks do not interact) ==========
+    # Llama-3.3-70B: 80 layers, 8 KV heads sharded over TP ranks -> cell 2048 / 1024 / 512 / 256 B (BASELINE configs[4])
+    shard = None
+    if rank == 0 and world == 1:
+        shard = {}
+        mgr.close()
+        vmm_ops.shutdown_kvcached()
+        for tpn, cell_s in ((1, 2048), (2, 1024), (4, 512), (8, 256)):
+            Ls, Ts = 80, 65536
+            blocks_s = Ts // bs + 64
+            vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
+            per_layer_s = -(-blocks_s * bs * cell_s * 2 // (2 * PAGE)) * 2 * PAGE
+            (rng_s,) = vmm_ops.create_kv_tensors_raw(per_layer_s, Ls, 2)
+            ms_ = KVCacheManager(blocks_s, bs, cell_s, Ls)
+            ids_s = ms_.alloc_np(Ts // bs)
+            slots_s = torch.from_numpy(np.random.default_rng(tpn).permutation(
+                (ids_s[:, None] * bs + np.arange(bs)[None, :]).reshape(-1))).to(dev)
+            ks = torch.empty((Ls, Ts, cell_s // 2), dtype=torch.int16, device=dev).random_()
+            vs = torch.empty_like(ks).random_()
+            lay_s = kv_ops.layout_vllm_contiguous(rng_s[0], Ls, bs, cell_s, 2)
+            alg_s = Ts * Ls * 4 * cell_s + 8 * Ts
+            row = {}
+            for name, fn in (("scatter", kv_ops.kv_scatter), ("gather", kv_ops.kv_gather)):
+                for _ in range(3):
+                    fn(lay_s, slots_s, ks, vs)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    fn(lay_s, slots_s, ks, vs)
+                e1.record()
+                torch.cuda.synchronize()
+                row[name + "_gbs_per_gpu"] = alg_s / (e0.elapsed_time(e1) / 10) / 1e6
+            row["cell_bytes"] = cell_s
+            row["frac_of_hbm_peak_scatter"] = None
+            shard[f"tp{tpn}"] = row
+            del ks, vs
+            ms_.close()
+            vmm_ops.shutdown_kvcached()
+            torch.cuda.empty_cache()
+        # the rest of the bench needs the original group again
+        vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
+        vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
+        mgr = R.manager_from_config(cfg, device_index=local_rank)
+
     # ================= bitmap sweep on a stress size (2^30 blocks = 128 MiB bitmap streams HBM) ===
     sweep = None
     micro = None
@@ -453,6 +498,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    if shard:
+        for row in shard.values():
+            row["frac_of_hbm_peak_scatter"] = row["scatter_gbs_per_gpu"] / peak
     roofline = {"kernel": "kvb_kv_copy_kernel<scatter> (fused 32-layer paged KV scatter, T=65536 tokens)",
                 "bound": "hbm", "achieved": kv["scatter"]["gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                 "frac": kv["scatter"]["gbs_per_gpu"] / peak,
@@ -484,7 +532,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
                                "timed region"},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "map_unmap": map_unmap, "kv_scatter": kv, "bitmap_sweep": sweep, "micro_alloc_free": micro,
+                "map_unmap": map_unmap, "kv_scatter": kv, "kv_scatter_tp_shards_on_one_gpu": shard,
+                "bitmap_sweep": sweep, "micro_alloc_free": micro,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)
