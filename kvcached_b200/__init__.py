@@ -2,6 +2,8 @@
 
   vmm_ops            the reference's `kvcached.vmm_ops` surface (virtual KV tensors, map/unmap, PageAllocator)
   KVCacheManager     alloc / free / available_size / resize / trim / reserve on device-resident state
+  block_pool         ElasticBlockPool: prefix-cache pinning (vLLM), ref counts / LRU on the device
+  sglang_alloc       SGLang token-level and paged allocators: ids and slot indices stay on the device
   kv_ops             fused paged KV scatter / gather
   tp                 rank-consistent page mapping: one NCCL broadcast of the kernel's page list
   trace / replay     synthetic traces and the three replay modes
@@ -12,3 +14,4 @@ manager without the library raises.
 __version__ = "0.1.0"
 
 from .kv_cache_manager import KVCachedConfigError, KVCacheManager  # noqa: E402,F401
+from .block_pool import ElasticBlockPool  # noqa: E402,F401
