@@ -646,7 +646,11 @@ bool VmmGroup::process_next(Lock &lk) {
     if ((int64_t)pool_.size() < n_sub_) {
       if (need_unmap_ > 0) break;                      // an unmap yields the handle
       if (!can_create(true)) {                         // map-ahead never eats into the reserve
-        if (!force_one_retained(true)) { qs_.pop_front(); continue; }
+        if (!force_one_retained(true)) {               // no memory for it: the hint is dropped, not parked
+          qs_.pop_front();
+          update(p, -1, 0, -1);
+          continue;
+        }
         break;
       }
     }

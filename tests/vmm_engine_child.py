@@ -290,6 +290,30 @@ def case_layouts():
         assert end["handles"] == 0 and end["mappings"] == 0
 
 
+def case_hints_without_memory():
+    """Map-ahead hints when there is no memory for them and nothing retained to take: the hints are dropped (the VMM
+    thread goes back to sleep instead of retrying forever) and wanted maps still surface the driver's refusal."""
+    layers = 4
+    unit = PAGE * layers * 2
+    setup(total_gib=4 * unit / (1 << 30), n_pages=64, layers=layers)     # zero page + 3 units
+    vmm_ops.set_prefetch(4)
+    vmm_ops.set_retention(0)
+    events([0, 1, 2], False)
+    vmm_ops.wait_maps()
+    hints([10, 11, 12, 13])
+    assert wait_quiet(lambda: vmm_ops.engine_stats()["need_hinted"] == 0)
+    import resource
+    c0 = resource.getrusage(resource.RUSAGE_SELF)
+    time.sleep(0.5)
+    c1 = resource.getrusage(resource.RUSAGE_SELF)
+    assert (c1.ru_utime + c1.ru_stime) - (c0.ru_utime + c0.ru_stime) < 0.2, "the VMM thread must not spin"
+    assert vmm_ops.prefetched_pages() == [] and vmm_ops.mapped_pages() == [0, 1, 2]
+    no_violations()
+    vmm_ops.shutdown_kvcached()
+    end = no_violations()
+    assert end["handles"] == 0 and end["mappings"] == 0
+
+
 def case_oom():
     """A device too small for what is wanted, nothing retained to take: the driver's refusal surfaces as an error of the
     call that waited for the map, the page is recorded as not mapped, nothing leaks."""
