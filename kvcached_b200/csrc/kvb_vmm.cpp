@@ -353,11 +353,9 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     async_ = !(e && e[0] == '0');
   }
   if (pool_cap_pages_ < 0) {
-    // Physical handles are recycled, not released: on this driver every cuMemCreate / cuMemRelease cycle
-    // makes later cuMemUnmap / cuMemSetAccess calls slower (tools/probe_e2e.py: 0.6 ms -> 8 ms per unmap
-    // after three replays of churn).  Default: keep every handle; the manager hands memory back as soon as
-    // the device's free memory drops under the utilisation headroom (pool_release, driven by the same
-    // cudaMemGetInfo poll available_size() needs) and on kvb_vmm_pool_config(group, n).
+    // Physical handles are recycled rather than released per unmap (page.cpp:10-25 creates and releases one per map):
+    // the pool cap bounds idle + retained handles; idle ones go back to the device after the retention time
+    // (expire()), all of them when the device runs short (phys_free_pages -> pool_release) or on pool_config.
     const char *e = getenv("KVB200_HANDLE_POOL_PAGES");
     int64_t pages = e ? atoll(e) : -1;
     if (pages < 0) pages = n_pages_;   // recycle everything; memory goes back on pressure (pool_release) or trim
