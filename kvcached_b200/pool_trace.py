@@ -79,8 +79,99 @@ def make_scenario(seed: int, n_requests: int = 64, n_prefixes: int = 20, zipf_a:
             "str_hash": p_str_hash > 0}
 
 
+def drive_pool_groups(pool, scenario: dict, snap: Callable[[object], dict]) -> List[dict]:
+    """The same flow for a model with several KV-cache groups (hybrid attention: full + sliding window): every request
+    holds one block list per group, a prefix hit needs ALL groups (get_cached_block(hash, [g0, g1]) is all-or-nothing,
+    patches.py:379-394), touch() gets the tuple-of-lists form (:523-529), keys carry the group id (:260-274)."""
+    groups = scenario["groups"]
+    bs = scenario["block_size"]
+    reqs = scenario["requests"]
+    blocks: Dict[int, list] = {}
+    n_hashed: Dict[int, int] = {}
+    robj: Dict[int, Request] = {}
+    records = []
+    for ev in scenario["events"]:
+        kind, res = ev[0], None
+        if kind == "arrive":
+            r = ev[1]
+            q = reqs[r]
+            hashes = [bytes.fromhex(h) for h in q["hashes"]]
+            req = Request(r, hashes + [bytes.fromhex(h) for h in q["decode_hashes"]])
+            hits = [[] for _ in groups]
+            for h in hashes:
+                b = pool.get_cached_block(h, groups)
+                if b is None:
+                    break
+                for g in range(len(groups)):
+                    hits[g].append(b[g])
+            n_hit = len(hits[0])
+            n_prompt = len(hashes) + (1 if q["partial"] else 0)
+            pool.touch(tuple(hits))
+            per_group, ok = [], True
+            for g in range(len(groups)):
+                try:
+                    per_group.append(hits[g] + pool.get_new_blocks(n_prompt - n_hit))
+                except ValueError:
+                    ok = False
+                    break
+            if not ok:
+                for g, bl in enumerate(per_group):
+                    pool.free_blocks(list(reversed(bl)))
+                for g in range(len(per_group), len(groups)):
+                    pool.free_blocks(list(reversed(hits[g])))
+                res = "ERR:ValueError"
+                blocks[r] = None
+            else:
+                for g, gid in enumerate(groups):
+                    pool.cache_full_blocks(req, per_group[g], n_hit, len(hashes), bs, gid)
+                blocks[r], n_hashed[r], robj[r] = per_group, len(hashes), req
+                res = {"hit": n_hit, "ids": [[b.block_id for b in bl] for bl in per_group]}
+        elif kind == "decode":
+            r = ev[1]
+            if blocks.get(r) is None:
+                res = "skipped"
+            else:
+                try:
+                    new_ids = []
+                    for g, gid in enumerate(groups):
+                        nb = pool.get_new_blocks(1)
+                        blocks[r][g].extend(nb)
+                        new_ids.append(nb[0].block_id)
+                    full = min(len(blocks[r][0]) - 1, len(robj[r].block_hashes))
+                    if full > n_hashed[r]:
+                        for g, gid in enumerate(groups):
+                            pool.cache_full_blocks(robj[r], blocks[r][g], n_hashed[r], full, bs, gid)
+                        n_hashed[r] = full
+                    res = {"ids": new_ids}
+                except ValueError:
+                    res = "ERR:ValueError"
+        elif kind == "finish":
+            r = ev[1]
+            if blocks.get(r) is None:
+                res = "skipped"
+            else:
+                for bl in blocks[r]:
+                    pool.free_blocks(list(reversed(bl)))
+                res = {"freed": sum(len(bl) for bl in blocks[r])}
+                blocks[r] = None
+        elif kind == "evict":
+            r, k = ev[1], ev[2]
+            bl = blocks.get(r)
+            ids = [b.block_id for b in bl[0][:k]] if bl else list(range(1, 1 + k))
+            pool.evict_blocks(set(ids))
+            res = {"ids": ids}
+        elif kind == "reset":
+            res = bool(pool.reset_prefix_cache())
+        else:
+            raise ValueError(f"unknown event {ev}")
+        records.append({"ev": ev, "r": res, **snap(pool)})
+    return records
+
+
 def drive_pool(pool, scenario: dict, snap: Callable[[object], dict], null_ok: bool = True) -> List[dict]:
     """Runs the scenario; returns one record per event: {"ev": [...], "r": result, **snap(pool)}."""
+    if scenario.get("groups"):
+        return drive_pool_groups(pool, scenario, snap)
     gid = scenario["group_id"]
     bs = scenario["block_size"]
     reqs = scenario["requests"]

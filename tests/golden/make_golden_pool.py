@@ -39,6 +39,8 @@ CASES = {
     "pool_mla1_tokens": (dict(MLA1, num_blocks=20000, max_cached_blocks=1000),            # SGLang page_size 1 geometry
                          dict(seed=7, n_requests=40, prefix_blocks=(16, 200), suffix_blocks=(0, 64), decode_blocks=(0, 40),
                               block_size=1)),
+    "pool_two_groups": (dict(LLAMA, num_blocks=1536, max_cached_blocks=120),            # hybrid attention: two KV-cache groups
+                        dict(seed=10, n_requests=48, concurrency=6, groups=[0, 1])),
     "pool_nocache": (dict(LLAMA, num_blocks=1024, max_cached_blocks=1000, enable_caching=False), dict(seed=8, n_requests=32)),
 }
 
@@ -48,7 +50,11 @@ def main():
     env = build_ref.ref_env(cpu_only=not os.path.exists("/dev/nvidiactl"))
     env["KVCACHED_LOG_LEVEL"] = "ERROR"
     for name, (cfg, kw) in CASES.items():
+        kw = dict(kw)
+        groups = kw.pop("groups", None)
         fix = {"name": name, "config": cfg, "scenario": PT.make_scenario(**kw)}
+        if groups:
+            fix["scenario"]["groups"] = groups
         with tempfile.TemporaryDirectory() as d:
             with open(os.path.join(d, "s.json"), "w") as f:
                 json.dump(fix, f)
