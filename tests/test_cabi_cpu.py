@@ -103,3 +103,26 @@ def test_decode_trace_is_balanced_in_the_oracle():
     for op in tr["ops"]:
         res.append(oracle.apply_op(m, op, res))
     assert m.available_size() == a0 and m.scalars()["inuse_pages"] == 0
+
+
+def test_request_kinds_and_status_codes_match_the_header():
+    """Every KVB_OP_* / KVB_ST_* value of include/kvb200.h has the same value in the ctypes binding."""
+    import re
+    from kvcached_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "kvb200.h")).read()
+    ops = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define KVB_OP_(\w+) (\d+)", hdr)}
+    assert len(ops) >= 24
+    py = {"ALLOC": _lib.OP_ALLOC, "FREE_IDS": _lib.OP_FREE_IDS, "FREE_REF": _lib.OP_FREE_REF, "RESIZE": _lib.OP_RESIZE,
+          "TRIM": _lib.OP_TRIM, "TRY_RESERVE": _lib.OP_TRY_RESERVE, "FREE_RESERVED": _lib.OP_FREE_RESERVED,
+          "AVAIL": _lib.OP_AVAIL, "CLEAR": _lib.OP_CLEAR, "ALLOC_PAGE": _lib.OP_ALLOC_PAGE, "FREE_PAGES": _lib.OP_FREE_PAGES,
+          "PA_RESIZE": _lib.OP_PA_RESIZE, "RESET_ORDER": _lib.OP_RESET_ORDER, "PIN_NEW": _lib.OP_PIN_NEW,
+          "PIN_TOUCH": _lib.OP_PIN_TOUCH, "PIN_MARK": _lib.OP_PIN_MARK, "PIN_FREE": _lib.OP_PIN_FREE,
+          "PIN_EVICT": _lib.OP_PIN_EVICT, "PIN_RESET": _lib.OP_PIN_RESET}
+    for k, v in py.items():
+        assert ops[k] == v, k
+    assert sorted(ops.values()) == list(range(1, len(ops) + 1)), "request kinds are dense"
+    st = {m.group(1): int(m.group(2).strip("()")) for m in re.finditer(r"#define KVB_ST_(\w+) (\(?-?\d+\)?)", hdr)}
+    assert (st["OK"], st["FALSE"], st["NONE"], st["NO_PAGES"], st["ASSERT"]) == \
+           (_lib.ST_OK, _lib.ST_FALSE, _lib.ST_NONE, _lib.ST_NO_PAGES, _lib.ST_ASSERT)
+    import ctypes as C
+    assert C.sizeof(_lib.Res) == 32 and C.sizeof(_lib.Op) == 16 and C.sizeof(_lib.Ref) == 12
