@@ -133,15 +133,6 @@ int64_t kvb_vmm_pending_unmaps(int64_t group_id);
  * timing.  depth 0 = off; default KVB200_VMM_PREFETCH or 5 (the reference's KVCACHED_MIN_RESERVED_PAGES). */
 int kvb_vmm_prefetch_config(int64_t group_id, int depth);
 int kvb_vmm_set_prefetch_hints(int64_t group_id, const int64_t *pages, int64_t n);   /* what kvb_mgr_step does with the kernel's list */
-/* Host-logic test aid: replaces the CUDA VMM driver calls with legality-checking stand-ins (map only onto
- * unmapped reserved space, unmap / set-access only whole mappings, release only unmapped handles) that count calls
- * and model a device of `total_bytes`, so the engine's decisions are testable without a GPU.  Must be called before
- * the first VMM call of the process.  out10 = {creates, releases, maps, unmaps, set-access, violations, live
- * handles, live mappings, (unused), handle bytes}. */
-int kvb_vmm_mock_driver(int64_t total_bytes, int latency_us);
-int kvb_vmm_mock_set_other_bytes(int64_t bytes);   /* memory taken by "somebody else" */
-int kvb_vmm_mock_stats(int64_t *out10);
-const char *kvb_vmm_mock_last_violation(void);
 int64_t kvb_vmm_prefetched_pages(int64_t group_id, int64_t *out, int64_t cap);   /* hinted + mapped, not yet wanted */
 /* out8 = {events elided, map-ahead hits, pages mapped ahead now, need_map, forced unmaps pending, need_hinted,
  *         pages retained now, retention hits} */
@@ -170,18 +161,6 @@ int64_t kvb_vmm_avail_physical_pages(int64_t group_id, int64_t num_layers, int64
  * per-iteration microseconds.  compound=1 uses the group's compound page size, else page_size. */
 int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int compound,
                         double *map_us, double *unmap_us);
-
-/* per-call driver costs in microseconds (measurement aid, cf. benchmarks/bench_vmm/bench_vmm.cpp):
- * out8 = {cuMemCreate, cuMemMap, cuMemSetAccess per unit, cuMemSetAccess whole range (one call),
- *         cuMemUnmap per unit, cuMemUnmap whole range (one call), cuMemRelease, unmap+map+setaccess per unit} */
-int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t iters, double *out8);
-/* map/unmap cycle cost against M live zero-page mappings: mode bit0 = one cuMemSetAccess over the whole range
- * at init instead of one per unit, bit1 = cycle units of a separate small reservation.
- * out3 = {us per map cycle, us per unmap cycle, init ms} */
-/* cycle cost against M live physical mappings: inside the same reservation / in a separate one / in one placed
- * directly behind it.  out7 = {same_map, same_unmap, separate_map, separate_unmap, adjacent_map, adjacent_unmap, adjacent?} */
-int kvb_vmm_probe3(int device_index, int64_t unit_bytes, int64_t m_units, int64_t iters, double *out7);
-int kvb_vmm_probe2(int device_index, int64_t unit_bytes, int64_t m_units, int mode, int64_t iters, double *out3);
 
 /* ------------------------------------------------------------------------------------------
  * 2. Device-resident block manager
@@ -393,13 +372,46 @@ int kvb_shm_read(const char *ipc_name, int64_t *out3);         /* get_kv_cache_l
 int kvb_shm_set_limit(const char *ipc_name, int64_t total_bytes, int create);   /* update_kv_cache_limit :116-141 */
 
 /* ---- tensor parallel: rank-consistent page mapping ----------------------------------------
- * After a step, rank 0's page events sit in a fixed device buffer
- * [seq, n, e0 .. e(n-1), 0 ...] of kvb_tp_buffer_words() int64 words.  The host side broadcasts
- * that buffer with ONE NCCL broadcast (torch.distributed) and every other rank calls
- * kvb_tp_apply on its copy.  Replaces kvcached/tp_ipc_util.py:96-267. */
+ * Replaces kvcached/tp_ipc_util.py:96-267 (one AF_UNIX connection + pickle round trip per rank per map/unmap call).
+ *
+ * (1) The mailbox — no per-step collective.  kvb_tp_init(name, rank, world, group, mgr, flags):
+ *       rank 0 (mgr = its block manager) creates the POSIX shared-memory ring /dev/shm/<name>[_g<group>], registers
+ *         it with CUDA as mapped pinned host memory and waits for the other ranks; from then on the step KERNEL
+ *         writes each step's page list (and the map-ahead hints) straight into the next ring slot — plain stores
+ *         over PCIe, a system-scope fence, then the slot's sequence word.  Steps without page events publish nothing.
+ *       ranks > 0 (mgr = NULL) open the ring and start one thread that polls the sequence word, feeds the list to the
+ *         rank's own VMM engine (same wait-for-maps rule as kvb_mgr_step) and acknowledges in the ring.
+ *     kvb_mgr_step on rank 0 returns when a step's MAPS are in place on EVERY rank (the reference waits for every
+ *     worker's reply, tp_ipc_util.py:160-170); unmaps drain behind it on every rank.  Lists longer than one slot
+ *     (256 events: clear / trim / resize of a big pool) and boxes where CUDA cannot register the segment
+ *     (flags bit 0, or KVB200_TP_DEVICE_DIRECT=0) are relayed into the same ring by rank 0's host thread, in chunks.
+ *     All ranks of a TP group live on one node (that is what the reference's AF_UNIX sockets assume too).
+ *     flags bit 1 on rank 0 with mgr = NULL: external producer — the ring is fed through kvb_tp_publish only.
+ *     kvb_tp_fence: rank 0 — every rank applied everything published; others — this rank did.
+ *     kvb_tp_publish: the producer side for hosts that obtain page lists elsewhere (events[i] = page*2 + is_unmap).
+ *     kvb_tp_stats out8 = {records published, records applied (rank 0: slowest rank), events applied by this rank,
+ *       device-direct (1/0), records written by the kernel, records relayed by the host, acknowledgement waits,
+ *       microseconds spent in those waits}. */
+int kvb_tp_init(const char *name, int rank, int world_size, int64_t group_id, kvb_mgr *mgr, int flags);
+int kvb_tp_fence(int64_t group_id);
+int kvb_tp_publish(int64_t group_id, int64_t seq, const int64_t *events, int64_t n, const int64_t *hints,
+                   int64_t n_hints, int flags);
+int kvb_tp_stats(int64_t group_id, int64_t *out8);
+int kvb_tp_shutdown(int64_t group_id);
+int kvb_mgr_tp_detach(kvb_mgr *m);
+/* (2) The collective path — the checker of (1), and the transport for groups that span nodes.  After a step, rank 0's
+ * pending page events are packed as [seq, n, e0 .. e(n-1), n_hints, hints ..., more] into a buffer of
+ * kvb_tp_buffer_words() int64 words (`more`, the last word, = 1 when the list continues in another buffer: lists of
+ * any length travel in chunks); the host side broadcasts each buffer with ONE NCCL broadcast (torch.distributed) and
+ * every other rank applies it.  kvb_mgr_tp_export / kvb_tp_pack return 1 while more chunks remain, 0 after the last;
+ * kvb_tp_apply / kvb_tp_apply_host return the buffer's `more` (maps are waited for when the list is complete). */
 int64_t kvb_tp_buffer_words(void);
 int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst_device_ptr, void *stream);
+int kvb_mgr_tp_export_host(kvb_mgr *m, int64_t *dst);
+int kvb_tp_pack(int64_t seq, const int64_t *events, int64_t n, int64_t *cursor, const int64_t *hints, int64_t n_hints,
+                int64_t *buf);
 int kvb_tp_apply(int64_t group_id, uint64_t src_device_ptr, void *stream, int64_t *seq_out, int64_t *n_out);
+int kvb_tp_apply_host(int64_t group_id, const int64_t *buf, int64_t *seq_out, int64_t *n_out);
 
 /* ------------------------------------------------------------------------------------------
  * 3. Page arithmetic helpers — InternalPage statics, csrc/page_allocator.cpp:87-100, :457-498
@@ -432,9 +444,11 @@ typedef struct kvb_kv_layout {
   int32_t pad_;
 } kvb_kv_layout;
 
-/* src layout: [num_kv][num_layers][T][cell_bytes] contiguous (k_src = kv 0, v_src = kv 1; v may be 0
- * when num_kv == 1).  slots[T] are token slots (block = slot / block_size).  layer_begin/layer_end
- * select the layers one launch covers (0, num_layers = fused all-layer launch).
+/* src layout: [layer_end - layer_begin][T][cell_bytes] contiguous per buffer (k_src = K, v_src = V; v may be 0
+ * when num_kv == 1): the dense buffers hold exactly the layers of THIS launch, first launched layer first — the
+ * fused all-layer call (0, num_layers) passes [num_layers][T][cell], a per-layer call (l, l+1) passes the engine's
+ * own [T, H, D] tensor of that layer.  slots[T] are token slots (block = slot / block_size); a negative slot is
+ * padding and moves nothing (its dense row is left untouched by the gather).
  * Pointers are DEVICE addresses; `stream` is a cudaStream_t (NULL = legacy default stream). */
 int kvb_kv_scatter(const kvb_kv_layout *lay, uint64_t slots_dev, int64_t T, uint64_t k_src, uint64_t v_src,
                    int32_t layer_begin, int32_t layer_end, void *stream);

@@ -96,10 +96,6 @@ SIGNATURES = {
     "kvb_vmm_pending_unmaps": (i64, [i64]),
     "kvb_vmm_prefetch_config": (C.c_int, [i64, C.c_int]),
     "kvb_vmm_set_prefetch_hints": (C.c_int, [i64, p_i64, i64]),
-    "kvb_vmm_mock_driver": (C.c_int, [i64, C.c_int]),
-    "kvb_vmm_mock_set_other_bytes": (C.c_int, [i64]),
-    "kvb_vmm_mock_stats": (C.c_int, [p_i64]),
-    "kvb_vmm_mock_last_violation": (C.c_char_p, []),
     "kvb_vmm_prefetched_pages": (i64, [i64, p_i64, i64]),
     "kvb_vmm_engine_stats": (C.c_int, [i64, p_i64]),
     "kvb_vmm_pool_config": (C.c_int, [i64, i64]),
@@ -109,15 +105,12 @@ SIGNATURES = {
     "kvb_vmm_mapped_pages": (i64, [i64, p_i64, i64]),
     "kvb_vmm_avail_physical_pages": (i64, [i64, i64, i64, f64]),
     "kvb_vmm_raw_control": (C.c_int, [i64, i64, i64, C.c_int, p_f64, p_f64]),
-    "kvb_vmm_probe": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
-    "kvb_vmm_probe3": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
-    "kvb_vmm_probe2": (C.c_int, [C.c_int, i64, i64, C.c_int, i64, p_f64]),
     "kvb_mgr_create": (C.c_void_p, [C.POINTER(MgrConfig)]),
     "kvb_mgr_destroy": (C.c_int, [C.c_void_p]),
     # pointer arguments as plain addresses: the per-step call passes ndarray.ctypes.data (no POINTER objects built per call)
     "kvb_mgr_step": (i64, [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
-    "kvb_mgr_alloc": (i64, [C.c_void_p, i64, p_i64, i64]),
-    "kvb_mgr_free": (C.c_int, [C.c_void_p, p_i64, i64]),
+    "kvb_mgr_alloc": (i64, [C.c_void_p, i64, C.c_void_p, i64]),
+    "kvb_mgr_free": (C.c_int, [C.c_void_p, C.c_void_p, i64]),
     "kvb_mgr_resize": (C.c_int, [C.c_void_p, i64]),
     "kvb_mgr_trim": (C.c_int, [C.c_void_p]),
     "kvb_mgr_try_to_reserve": (C.c_int, [C.c_void_p, i64]),
@@ -138,6 +131,15 @@ SIGNATURES = {
     "kvb_tp_buffer_words": (i64, []),
     "kvb_mgr_tp_export": (C.c_int, [C.c_void_p, u64, C.c_void_p]),
     "kvb_tp_apply": (C.c_int, [i64, u64, C.c_void_p, p_i64, p_i64]),
+    "kvb_mgr_tp_export_host": (C.c_int, [C.c_void_p, p_i64]),
+    "kvb_tp_pack": (C.c_int, [i64, p_i64, i64, p_i64, p_i64, i64, p_i64]),
+    "kvb_tp_apply_host": (C.c_int, [i64, p_i64, p_i64, p_i64]),
+    "kvb_tp_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, i64, C.c_void_p, C.c_int]),
+    "kvb_tp_fence": (C.c_int, [i64]),
+    "kvb_tp_publish": (C.c_int, [i64, i64, p_i64, i64, p_i64, i64, C.c_int]),
+    "kvb_tp_stats": (C.c_int, [i64, p_i64]),
+    "kvb_tp_shutdown": (C.c_int, [i64]),
+    "kvb_mgr_tp_detach": (C.c_int, [C.c_void_p]),
     "kvb_page_block_range": (None, [i64, i64, i64, p_i64, p_i64]),
     "kvb_page_num_blocks": (i64, [i64, i64]),
     "kvb_page_id_of_block": (i64, [i64, i64, i64]),
@@ -147,6 +149,18 @@ SIGNATURES = {
     "kvb_kv_scatter_host": (C.c_int, [C.POINTER(KvLayout), p_i64, i64, C.c_void_p, C.c_void_p]),
     "kvb_kv_gather_host": (C.c_int, [C.POINTER(KvLayout), p_i64, i64, C.c_void_p, C.c_void_p]),
 }
+
+# include/kvb200_test.h: exported by libkvb200_test.so only (mock VMM driver, driver-cost probes)
+TEST_SIGNATURES = {
+    "kvb_vmm_mock_driver": (C.c_int, [i64, C.c_int]),
+    "kvb_vmm_mock_set_other_bytes": (C.c_int, [i64]),
+    "kvb_vmm_mock_stats": (C.c_int, [p_i64]),
+    "kvb_vmm_mock_last_violation": (C.c_char_p, []),
+    "kvb_vmm_probe": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
+    "kvb_vmm_probe2": (C.c_int, [C.c_int, i64, i64, C.c_int, i64, p_f64]),
+    "kvb_vmm_probe3": (C.c_int, [C.c_int, i64, i64, i64, p_f64]),
+}
+TEST_LIB_PATH = os.path.join(HERE, "libkvb200_test.so")
 
 _lib = None
 
@@ -159,11 +173,20 @@ def load() -> C.CDLL:
     if not os.path.isfile(LIB_PATH) or os.environ.get("KVB200_REBUILD") == "1":
         from . import build as _build
         _build.build()
-    lib = C.CDLL(os.environ.get("KVB200_LIB", LIB_PATH))   # KVB200_LIB: an alternative build (tuning experiments)
+    # KVB200_LIB: an alternative build (tuning experiments) or "test" = libkvb200_test.so (tests/, tools/ only)
+    path = os.environ.get("KVB200_LIB", LIB_PATH)
+    if path == "test":
+        path = TEST_LIB_PATH
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = the library does not match the header
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in TEST_SIGNATURES.items():   # present in the test library only
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     _lib = lib
     return lib
 

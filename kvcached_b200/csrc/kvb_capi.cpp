@@ -11,6 +11,9 @@
 
 #include "kvb_internal.h"
 #include "kvb_vmm.h"
+#ifdef KVB_TEST_HOOKS
+#include "../../include/kvb200_test.h"
+#endif
 
 using namespace kvb;
 namespace kvb { extern std::atomic<int64_t> g_total_launches; }
@@ -145,10 +148,12 @@ int kvb_vmm_set_prefetch_hints(int64_t group_id, const int64_t *pages, int64_t n
   g->set_prefetch_hints(pages, n);
   return 0;
 }
+#ifdef KVB_TEST_HOOKS   /* include/kvb200_test.h — libkvb200_test.so only */
 int kvb_vmm_mock_driver(int64_t total_bytes, int latency_us) { return vmm_mock_driver(total_bytes, latency_us); }
 int kvb_vmm_mock_set_other_bytes(int64_t bytes) { vmm_mock_set_other_bytes(bytes); return 0; }
 int kvb_vmm_mock_stats(int64_t *out10) { if (!out10) return KVB_ERR_INVALID; vmm_mock_stats(out10); return 0; }
 const char *kvb_vmm_mock_last_violation(void) { return vmm_mock_last_violation(); }
+#endif
 int kvb_vmm_prefetch_config(int64_t group_id, int depth) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;
@@ -227,6 +232,7 @@ int kvb_vmm_raw_control(int64_t group_id, int64_t n_pages, int64_t iters, int co
   return g->raw_control(n_pages, iters, map_us, unmap_us);
 }
 
+#ifdef KVB_TEST_HOOKS   /* include/kvb200_test.h — libkvb200_test.so only */
 int kvb_vmm_probe(int device_index, int64_t unit_bytes, int64_t n_units, int64_t iters, double *out8) {
   if (unit_bytes <= 0 || unit_bytes % (2 << 20) || n_units <= 0 || iters <= 0 || !out8) { set_error("vmm_probe: bad argument"); return KVB_ERR_INVALID; }
   return vmm_probe(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, n_units, iters, out8);
@@ -241,6 +247,7 @@ int kvb_vmm_probe3(int device_index, int64_t unit_bytes, int64_t m_units, int64_
   if (unit_bytes <= 0 || unit_bytes % (2 << 20) || m_units < 0 || iters <= 0 || !out7) { set_error("vmm_probe3: bad argument"); return KVB_ERR_INVALID; }
   return vmm_probe3(device_index < 0 ? 0 : device_index, (size_t)unit_bytes, m_units, iters, out7);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------ page helpers
 // InternalPage::get_block_range / get_num_blocks / PageAllocator::get_page_id (page_allocator.cpp:87-100, :457-460)

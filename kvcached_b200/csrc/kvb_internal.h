@@ -98,6 +98,7 @@ struct Summary {
   int64_t ev_inline[256];
   int64_t next_free_n;    // how many entries of next_free are valid
   int64_t next_free[16];  // the pages alloc_page() will MAP next: the front of free_page_list (map-ahead hints)
+  int64_t tp_published;   // 1 = this launch wrote its page list into the TP mailbox itself (kvb_tp.h)
 };
 
 struct LaunchArgs {
@@ -123,6 +124,11 @@ struct LaunchArgs {
   int64_t resize_target;  // per-layer size the shm limit asks for (-1: none), page_allocator.cpp:764-782
   kvb_res *host_res;      // zero-copy step: pinned host mirrors the kernel fills itself (else null)
   int64_t *host_out;
+  // tensor-parallel mailbox (kvb_tp.h): device view of the shared ring, null = nothing to push
+  int64_t *tp_ring;       // slot r % slots at tp_ring + (r & tp_mask) * tp_slot_words
+  int64_t *tp_published;  // header word: records published so far
+  int64_t tp_pub;         // record number this launch may write
+  int32_t tp_mask, tp_slot_words, tp_flags, tp_pad;
 };
 
 #ifndef KVB_STEP_THREADS

@@ -2036,6 +2036,19 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
       sm->next_free[tid] = tid < fls ? c.fl[(int)((sc[SC_FL_HEAD] + tid) & c.q_mask)] : -1;
       if (tid == 0) sm->next_free_n = fls < 16 ? fls : 16;
     }
+    // Tensor parallel: this launch's page list goes straight into the mailbox every rank of the node polls (kvb_tp.h)
+    // — plain stores into mapped host memory, a system-scope fence, then the slot's sequence word.  Lists longer
+    // than a slot are left to the host relay (clear / trim of a big pool); steps without events publish nothing.
+    const bool tp_push = a.tp_ring && nev > 0 && nev <= EV_INLINE;
+    if (tp_push) {
+      int64_t *slot = a.tp_ring + (size_t)(a.tp_pub & a.tp_mask) * a.tp_slot_words;
+      for (int i = tid; i < (int)nev; i += NT) slot[8 + 16 + i] = c.ev[ev_begin + i];
+      if (tid < 16) {
+        const int64_t fls = sc[SC_FL_SIZE];
+        slot[8 + tid] = tid < fls ? c.fl[(int)((sc[SC_FL_HEAD] + tid) & c.q_mask)] : -1;
+      }
+      __threadfence_system();
+    }
     if (a.host_res) {
       // zero-copy step: results go straight to the caller's pinned host buffers over PCIe; the
       // summary's sequence number (written last, after a system-scope fence) is what the host polls.
@@ -2048,6 +2061,19 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
     }
     __syncthreads();
     if (tid == 0) {
+      if (tp_push) {
+        int64_t *slot = a.tp_ring + (size_t)(a.tp_pub & a.tp_mask) * a.tp_slot_words;
+        const int64_t fls = sc[SC_FL_SIZE];
+        slot[1] = a.seq;
+        slot[2] = nev;
+        slot[3] = 0;                                   // no continuation
+        slot[4] = (a.tp_flags & 1) ? 0 : (fls < 16 ? fls : 16);
+        slot[5] = a.tp_flags;
+        __threadfence_system();
+        *reinterpret_cast<volatile int64_t *>(slot) = a.tp_pub + 1;   // followers poll this word
+        *reinterpret_cast<volatile int64_t *>(a.tp_published) = a.tp_pub + 1;
+      }
+      sm->tp_published = tp_push ? 1 : 0;
       sm->ops_done = op - a.op_begin;
       sm->out_used = sc[SC_OUT_CURSOR] - out_begin;
       sm->n_events = nev;
@@ -2312,6 +2338,7 @@ __global__ void __launch_bounds__(256) kvb_kv_copy_kernel(kvb_kv_layout lay, con
     int layer = (int)(rest % nl);
     int kv = (int)(rest / nl);
     int64_t slot = slots[tok];
+    if (slot < 0) continue;                   // padding entries (engines pad slot mappings with -1) move nothing
     int64_t blk = slot / lay.block_size;
     int inb = (int)(slot - blk * lay.block_size);
     unsigned char *paged = reinterpret_cast<unsigned char *>(lay.base) + blk * lay.stride_block +
@@ -2340,21 +2367,30 @@ __global__ void __launch_bounds__(256) kvb_kv_copy_kernel(kvb_kv_layout lay, con
 // ==================================================================================== host launchers
 size_t step_kernel_smem_bytes() { return sizeof(Smem); }
 
-static int g_sm_count = 0;
+// Everything cached here is per DEVICE (managers may live on several GPUs of one process): SM count, resident
+// grid sizes, and the step kernel's dynamic shared-memory attribute, which belongs to the device's context.
+constexpr int kMaxDev = 64;
+static int cur_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return (dev >= 0 && dev < kMaxDev) ? dev : 0;
+}
+static int g_sm_count[kMaxDev];
 static int sm_count() {
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  int dev = cur_dev();
+  if (!g_sm_count[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count[dev] = n > 0 ? n : 148;
   }
-  return g_sm_count;
+  return g_sm_count[dev];
 }
 
 // Persistent grid = SMs x CTAs of this kernel that are resident at once (registers decide: 3 for the audit, 6 / 8
 // for scatter / gather): every CTA runs the same number of grid-stride trips, no partial last wave.
 template <typename K>
-static int resident_grid(K kernel, int threads, int *cache) {
+static int resident_grid(K kernel, int threads, int *cache_by_dev) {
+  int *cache = cache_by_dev + cur_dev();
   if (!*cache) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm <= 0) {
@@ -2367,12 +2403,13 @@ static int resident_grid(K kernel, int threads, int *cache) {
 }
 
 int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDev];
+  const int dev = cur_dev();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kvb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kvb_step_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
   return (int)cudaGetLastError();
@@ -2391,8 +2428,8 @@ int launch_audit(const DevState &st, int64_t *d_out4, void *stream, bool zero_co
   int mode = 2;
   if (st.exact && (st.bpp == 32 || st.bpp == 64 || st.bpp == 128)) mode = 0;
   else if (st.exact && st.bpp % 128 == 0 && st.bpp / 128 <= 32 && ((st.bpp / 128) & (st.bpp / 128 - 1)) == 0) mode = 1;
-  static int grid_audit = 0;
-  kvb_audit_kernel<<<resident_grid(kvb_audit_kernel, 256, &grid_audit), 256, 0, (cudaStream_t)stream>>>(st, d_out4, mode);
+  static int grid_audit[kMaxDev];
+  kvb_audit_kernel<<<resident_grid(kvb_audit_kernel, 256, grid_audit), 256, 0, (cudaStream_t)stream>>>(st, d_out4, mode);
   return (int)cudaGetLastError();
 }
 
@@ -2416,8 +2453,8 @@ int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, vo
   while (g > 1 && g * 4 > vec) g >>= 1;
   while (g < min_lanes && g * 4 <= vec) g <<= 1;   // doubling keeps >= 2 vectors per lane
   int64_t want = (cells * g + 255) / 256;
-  static int grid_sc = 0, grid_ga = 0;
-  int64_t grid = gather ? resident_grid(kvb_kv_copy_kernel<1>, 256, &grid_ga) : resident_grid(kvb_kv_copy_kernel<0>, 256, &grid_sc);
+  static int grid_sc[kMaxDev], grid_ga[kMaxDev];
+  int64_t grid = gather ? resident_grid(kvb_kv_copy_kernel<1>, 256, grid_ga) : resident_grid(kvb_kv_copy_kernel<0>, 256, grid_sc);
   if (want < grid) grid = want;
   if (gather)
     kvb_kv_copy_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,

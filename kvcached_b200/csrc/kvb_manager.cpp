@@ -17,6 +17,7 @@
 
 #include "kvb_internal.h"
 #include "kvb_shm.h"
+#include "kvb_tp.h"
 #include "kvb_vmm.h"
 
 using namespace kvb;
@@ -106,6 +107,9 @@ struct kvb_mgr {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::unique_ptr<ShmUsage> shm;   // usage publishing + limit (mem_info_tracker.hpp); null = off
   int64_t shm_publishes = 0;
+  bool tp_on = false;              // kvb_tp_init attached this manager (rank 0) to the group's TP mailbox
+  int tp_flags_next = 0;           // flags of the record the next launch may push (kTpFlagSettle)
+  double tp_timeout_ms = 60000.0;
 };
 
 namespace {
@@ -195,6 +199,37 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n, bool settle = false) 
   return rc < 0 ? rc : 0;
 }
 
+// The page map / unmap list of one launch: to the other TP ranks first (so that they work while this rank does),
+// then to this rank's own VMM engine; when the list contains a map, wait until every rank has it in place — the ids
+// the step hands out must be backed everywhere before they are used (the reference waits for every worker's reply,
+// tp_ipc_util.py:160-170).
+int deliver_events(kvb_mgr *m, const Summary *hs, bool settle) {
+  const int64_t n = hs->n_events;
+  if (n <= 0) return 0;
+  std::vector<int64_t> big;
+  const int64_t *ev = hs->ev_inline;
+  if (n > hs->ev_inline_n) {
+    big.resize((size_t)n);
+    CUDA_TRY(cudaMemcpy(big.data(), m->st.ev + hs->ev_begin, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    ev = big.data();
+  }
+  TpMailbox *tp = m->tp_on ? tp_mailbox(m->cfg.group_id) : nullptr;
+  bool has_map = false;
+  if (tp) {
+    for (int64_t i = 0; i < n && !has_map; ++i) has_map = !(ev[i] & 1);
+    if (hs->tp_published) {
+      tp->note_device_record();
+    } else {
+      int rc = tp->publish(hs->seq, ev, n, hs->next_free, settle ? 0 : hs->next_free_n, settle ? kTpFlagSettle : 0);
+      if (rc) return rc;
+    }
+  }
+  int rc = apply_events(m, ev, n, settle);
+  if (rc) return rc;
+  if (tp && (has_map || settle)) rc = tp->wait_applied(m->tp_timeout_ms);
+  return rc;
+}
+
 // One launch over requests [op_begin, op_end) of a device-resident request array.
 int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int64_t *d_ids, const kvb_ref *d_refs,
            kvb_res *d_res, int64_t *d_outids, int64_t out_cap, Summary *d_sum, int arena_mode, int group_only,
@@ -224,6 +259,21 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
   a.host_res = host_res;
   a.host_out = host_out;
   a.resize_target = (m->shm && !group_only) ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
+  if (m->tp_on && !group_only && arena_mode != 1 && d_sum) {
+    // tensor parallel: the kernel pushes this launch's page list into the mailbox itself (kvb_tp.h); the ring
+    // must have a free slot before the launch, the host learns from the summary whether it was used
+    TpMailbox *tp = tp_mailbox(m->cfg.group_id);
+    if (tp && tp->device_ring()) {
+      int rc_room = tp->wait_room(1, m->tp_timeout_ms);
+      if (rc_room) return rc_room;
+      a.tp_ring = tp->device_ring();
+      a.tp_published = tp->device_published();
+      a.tp_pub = tp->pub();
+      a.tp_mask = kTpSlots - 1;
+      a.tp_slot_words = kTpSlotWords;
+      a.tp_flags = m->tp_flags_next;
+    }
+  }
   int rc = launch_step(m->st, a, m->stream);
   if (rc != 0) {
     set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -498,6 +548,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
 
   int64_t done = 0;
   bool first = true;
+  m->tp_flags_next = settle ? kTpFlagSettle : 0;
   while (done < n_ops) {
     volatile int64_t *vseq = &((Summary *)m->h_out)->seq;
     if (zc) *vseq = 0;
@@ -528,17 +579,9 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     m->last = *hs;
     m->d2h_bytes += zc ? (int64_t)(40 * 8 + hs->ev_inline_n * 8 + hs->ops_done * (int64_t)sizeof(kvb_res) + hs->out_used * 8)
                        : (int64_t)out_bytes;
-    // page map/unmap list of this launch -> VMM engine
-    if (hs->n_events > 0) {
-      if (hs->n_events <= hs->ev_inline_n) {
-        rc = apply_events(m, hs->ev_inline, hs->n_events, settle);
-      } else {
-        std::vector<int64_t> ev((size_t)hs->n_events);
-        CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev + hs->ev_begin, (size_t)hs->n_events * 8, cudaMemcpyDeviceToHost));
-        rc = apply_events(m, ev.data(), hs->n_events, settle);
-      }
-      if (rc) return rc;
-    }
+    // page map/unmap list of this launch -> the other TP ranks and this rank's VMM engine
+    rc = deliver_events(m, hs, settle);
+    if (rc) return rc;
     if (hs->ops_done <= 0) { set_error("step kernel made no progress at request %ld", (long)done); return KVB_ERR_STATE; }
     done += hs->ops_done;
     first = false;
@@ -696,6 +739,7 @@ static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg,
   if (rc) return rc;
   kvb_op op{kind, op_n, arg};
   memcpy(m->h_in, &op, sizeof(op));
+  m->tp_flags_next = 0;
   // order our launch after whatever produced the arrays on the caller's stream
   CUDA_TRY(cudaEventRecord(m->ev0, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev0, 0));
@@ -711,16 +755,8 @@ static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg,
   const Summary *hs = (const Summary *)m->h_out;
   m->last = *hs;
   m->d2h_bytes += (int64_t)(40 * 8 + hs->ev_inline_n * 8 + sizeof(kvb_res) + hs->out_used * 8);
-  if (hs->n_events > 0) {
-    if (hs->n_events <= hs->ev_inline_n) {
-      rc = apply_events(m, hs->ev_inline, hs->n_events);
-    } else {
-      std::vector<int64_t> ev((size_t)hs->n_events);
-      CUDA_TRY(cudaMemcpy(ev.data(), m->st.ev + hs->ev_begin, (size_t)hs->n_events * 8, cudaMemcpyDeviceToHost));
-      rc = apply_events(m, ev.data(), hs->n_events);
-    }
-    if (rc) return rc;
-  }
+  rc = deliver_events(m, hs, false);
+  if (rc) return rc;
   if (m->shm) {
     const int64_t per_page = m->cfg.num_layers * m->P * m->cfg.num_kv_buffers;
     const int64_t *sc = m->last.sc;
@@ -1132,39 +1168,160 @@ extern "C" int64_t kvb_group_indices_by_page(kvb_mgr *m, const int64_t *ids, int
   return D;
 }
 
-// ============================================================================================ TP export
-// [seq, n, e0 .. e(n-1)] in a fixed-size int64 device buffer: the payload of the one NCCL broadcast
-// that replaces kvcached/tp_ipc_util.py's per-rank socket round trips.
-static constexpr int64_t kTpWords = 2 + 1022;
+// ============================================================================================ tensor parallel
+// (1) The mailbox (kvb_tp.h): rank 0's kernel pushes each step's page list into a shared ring every rank polls.
+extern "C" int kvb_tp_init(const char *name, int rank, int world_size, int64_t group_id, kvb_mgr *m, int flags) {
+  if (rank == 0 && !m && (flags & 2)) {
+    // external producer: page lists come through kvb_tp_publish (a host that runs its bookkeeping elsewhere)
+    const double t_ms = env_f64("KVB200_TP_TIMEOUT_MS", 60000.0);
+    int rc0 = tp_open(name, 0, world_size, group_id, false, t_ms);
+    if (!rc0) rc0 = tp_mailbox(group_id)->wait_attached(t_ms);
+    return rc0;
+  }
+  if (rank == 0 && !m) { set_error("kvb_tp_init: rank 0 needs its block manager"); return KVB_ERR_INVALID; }
+  if (rank != 0 && m) { set_error("kvb_tp_init: only rank 0 drives a block manager"); return KVB_ERR_INVALID; }
+  const double timeout_ms = env_f64("KVB200_TP_TIMEOUT_MS", 60000.0);
+  const bool direct = !(flags & 1) && env_i64("KVB200_TP_DEVICE_DIRECT", 1) != 0;
+  if (rank != 0) return tp_open(name, rank, world_size, group_id, false, timeout_ms);
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  int rc = tp_open(name, 0, world_size, group_id, direct, timeout_ms);
+  if (rc) return rc;
+  TpMailbox *tp = tp_mailbox(group_id);
+  m->tp_timeout_ms = timeout_ms;
+  // every page this manager mapped before the mailbox existed (the null block's page) opens the ring
+  CUDA_TRY(cudaStreamSynchronize(m->stream));
+  std::vector<int32_t> mapped((size_t)m->max_pages);
+  CUDA_TRY(cudaMemcpy(mapped.data(), m->st.pg_mapped, mapped.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int64_t> ev;
+  for (int64_t p = 0; p < m->max_pages; ++p) if (mapped[(size_t)p]) ev.push_back(p * 2);
+  rc = tp->publish(m->seq, ev.data(), (int64_t)ev.size(), m->last.next_free, m->last.next_free_n, 0);
+  if (!rc) rc = tp->wait_attached(timeout_ms);
+  if (!rc) rc = tp->wait_applied(timeout_ms);
+  if (rc) { tp_close(group_id); return rc; }
+  m->tp_on = true;
+  return 0;
+}
+
+// rank 0: every rank that attached has applied everything published; other ranks: this rank has.
+extern "C" int kvb_tp_fence(int64_t group_id) {
+  TpMailbox *tp = tp_mailbox(group_id);
+  if (!tp) { set_error("kvb_tp_fence: group %ld has no mailbox", (long)group_id); return KVB_ERR_STATE; }
+  const double timeout_ms = env_f64("KVB200_TP_TIMEOUT_MS", 60000.0);
+  return tp->rank() == 0 ? tp->wait_applied(timeout_ms) : tp->wait_caught_up(timeout_ms);
+}
+
+extern "C" int kvb_tp_publish(int64_t group_id, int64_t seq, const int64_t *events, int64_t n, const int64_t *hints,
+                              int64_t n_hints, int flags) {
+  TpMailbox *tp = tp_mailbox(group_id);
+  if (!tp) { set_error("kvb_tp_publish: group %ld has no mailbox", (long)group_id); return KVB_ERR_STATE; }
+  if (n < 0 || (n > 0 && !events) || n_hints < 0 || (n_hints > 0 && !hints)) return KVB_ERR_INVALID;
+  int rc = tp->publish(seq, events, n, hints, n_hints, flags);
+  if (rc) return rc;
+  bool has_map = (flags & kTpFlagSettle) != 0;
+  for (int64_t i = 0; i < n && !has_map; ++i) has_map = !(events[i] & 1);
+  return has_map ? tp->wait_applied(env_f64("KVB200_TP_TIMEOUT_MS", 60000.0)) : 0;
+}
+
+extern "C" int kvb_tp_stats(int64_t group_id, int64_t *out8) {
+  TpMailbox *tp = tp_mailbox(group_id);
+  if (!tp || !out8) return KVB_ERR_STATE;
+  tp->stats(out8);
+  return 0;
+}
+
+extern "C" int kvb_tp_shutdown(int64_t group_id) { return tp_close(group_id); }
+
+extern "C" int kvb_mgr_tp_detach(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->tp_on = false;
+  return 0;
+}
+
+// (2) The collective path, kept as the checker of (1) and for multi-node groups: the page list as a fixed-size
+// int64 buffer [seq, n, e0 .. e(n-1), n_hints, hints ..., (last word) more] that the host side broadcasts with ONE
+// NCCL broadcast per chunk (torch.distributed).  Lists of any length travel in chunks: `more` = 1 says another
+// buffer of the same step follows (the reference ships page lists of any length, tp_ipc_util.py:173-267).
+static constexpr int64_t kTpWords = 1024;
+static constexpr int64_t kTpMaxEvents = kTpWords - 4 - 16;   // seq, n, n_hints, more + 16 hints
 extern "C" int64_t kvb_tp_buffer_words(void) { return kTpWords; }
 
+// packs the next chunk of `events[*cursor .. n)`; returns 1 if more chunks follow, 0 if this was the last
+extern "C" int kvb_tp_pack(int64_t seq, const int64_t *events, int64_t n, int64_t *cursor, const int64_t *hints,
+                           int64_t n_hints, int64_t *buf) {
+  if (!buf || !cursor || n < 0 || *cursor < 0 || *cursor > n || (n > 0 && !events)) return KVB_ERR_INVALID;
+  const int64_t k = std::min<int64_t>(n - *cursor, kTpMaxEvents);
+  const bool last = *cursor + k >= n;
+  int64_t nh = last ? std::max<int64_t>(0, std::min<int64_t>(n_hints, 16)) : 0;
+  memset(buf, 0, (size_t)kTpWords * 8);
+  buf[0] = seq;
+  buf[1] = k;
+  if (k) memcpy(buf + 2, events + *cursor, (size_t)k * 8);
+  buf[2 + k] = nh;
+  for (int64_t i = 0; i < nh; ++i) buf[3 + k + i] = hints[i];
+  buf[kTpWords - 1] = last ? 0 : 1;
+  *cursor += k;
+  return last ? 0 : 1;
+}
+
+// host buffer -> this rank's VMM engine; returns 1 if another chunk of the same step follows, 0 if complete
+extern "C" int kvb_tp_apply_host(int64_t group_id, const int64_t *buf, int64_t *seq_out, int64_t *n_out) {
+  if (!buf) return KVB_ERR_INVALID;
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g || !g->created()) { set_error("tp_apply: KV tensors of group %ld are not created", (long)group_id); return KVB_ERR_STATE; }
+  const int64_t n = buf[1], more = buf[kTpWords - 1];
+  if (seq_out) *seq_out = buf[0];
+  if (n_out) *n_out = n;
+  if (n < 0 || n > kTpMaxEvents || (more != 0 && more != 1)) { set_error("tp_apply: corrupt header n=%ld more=%ld", (long)n, (long)more); return KVB_ERR_INVALID; }
+  const int64_t *ev = buf + 2;
+  std::lock_guard<std::mutex> lk(g->mu);
+  int rc = 0;
+  if (n > 0) {
+    rc = g->enqueue_events(ev, n);
+    // maps wait only when the step's list is complete: chunks of one list are one batch for the engine
+    if (rc >= 0 && !more) rc = g->async() ? g->wait_maps() : g->fence();
+  } else if (!more) {
+    rc = g->async() ? g->wait_maps() : 0;
+  }
+  if (rc < 0) return rc;
+  const int64_t nh = ev[(size_t)n];
+  if (!more && nh >= 0 && nh <= 16) g->set_prefetch_hints(ev + n + 1, nh);
+  return (int)more;
+}
+
+// rank 0: next chunk of the manager's pending page events -> device buffer `dst`.  Returns 1 while more chunks
+// remain (call again after the broadcast), 0 when the list is drained.
 extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
   if (!m || !dst) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
-  int64_t n = (int64_t)m->pending_events.size();
-  int64_t nh = std::max<int64_t>(0, std::min<int64_t>(m->last.next_free_n, 16));
-  if (n + nh + 3 > kTpWords) { set_error("tp_export: %ld page events exceed the broadcast buffer (%ld)", (long)n, (long)(kTpWords - 3 - nh)); return KVB_ERR_OVERFLOW; }
-  size_t bytes = (size_t)(3 + n + nh) * 8;
-  int rc = ensure_io(m, bytes, 0);
+  int rc = ensure_io(m, (size_t)kTpWords * 8, 0);
   if (rc) return rc;
-  int64_t *h = (int64_t *)m->h_in;
-  h[0] = m->seq;
-  h[1] = n;
-  if (n) memcpy(h + 2, m->pending_events.data(), (size_t)n * 8);
-  h[2 + n] = nh;                       // map-ahead hints ride along: followers pre-map the same pages
-  for (int64_t i = 0; i < nh; ++i) h[3 + n + i] = m->last.next_free[i];
-  m->pending_events.clear();
-  CUDA_TRY(cudaMemcpyAsync((void *)(uintptr_t)dst, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  int64_t cursor = 0;
+  const int64_t n = (int64_t)m->pending_events.size();
+  int more = kvb_tp_pack(m->seq, m->pending_events.data(), n, &cursor, m->last.next_free, m->last.next_free_n, (int64_t *)m->h_in);
+  if (more < 0) return more;
+  m->pending_events.erase(m->pending_events.begin(), m->pending_events.begin() + cursor);
+  CUDA_TRY(cudaMemcpyAsync((void *)(uintptr_t)dst, m->h_in, (size_t)kTpWords * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  return 0;
+  return more;
+}
+// same, into a HOST buffer (gloo / CPU groups)
+extern "C" int kvb_mgr_tp_export_host(kvb_mgr *m, int64_t *dst) {
+  if (!m || !dst) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  int64_t cursor = 0;
+  const int64_t n = (int64_t)m->pending_events.size();
+  int more = kvb_tp_pack(m->seq, m->pending_events.data(), n, &cursor, m->last.next_free, m->last.next_free_n, dst);
+  if (more < 0) return more;
+  m->pending_events.erase(m->pending_events.begin(), m->pending_events.begin() + cursor);
+  return more;
 }
 
+// every other rank: device buffer -> pinned host (ONE copy + one stream synchronisation) -> kvb_tp_apply_host
 extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_t *seq_out, int64_t *n_out) {
   if (!src) return KVB_ERR_INVALID;
-  VmmGroup *g = vmm_group(group_id, false);
-  if (!g || !g->created()) { set_error("tp_apply: KV tensors of group %ld are not created", (long)group_id); return KVB_ERR_STATE; }
-  // ONE device->host copy of the whole (8 KB) buffer into pinned memory and one stream synchronisation per step
   static thread_local int64_t *pinned = nullptr;
   if (!pinned && cudaHostAlloc((void **)&pinned, (size_t)kTpWords * 8, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
@@ -1175,20 +1332,7 @@ extern "C" int kvb_tp_apply(int64_t group_id, uint64_t src, void *stream, int64_
   if (!buf) { pageable.resize((size_t)kTpWords); buf = pageable.data(); }
   CUDA_TRY(cudaMemcpyAsync(buf, (const void *)(uintptr_t)src, (size_t)kTpWords * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  const int64_t hdr[2] = {buf[0], buf[1]};
-  if (seq_out) *seq_out = hdr[0];
-  if (n_out) *n_out = hdr[1];
-  if (hdr[1] < 0 || hdr[1] > kTpWords - 3) { set_error("tp_apply: corrupt header n=%ld", (long)hdr[1]); return KVB_ERR_INVALID; }
-  const int64_t *ev = buf + 2;
-  std::lock_guard<std::mutex> lk(g->mu);
-  int rc = 0;
-  if (hdr[1] > 0) {
-    rc = g->enqueue_events(ev, hdr[1]);
-    if (rc >= 0) rc = g->async() ? g->wait_maps() : g->fence();
-  }
-  int64_t nh = ev[(size_t)hdr[1]];
-  if (nh >= 0 && nh <= 16 && hdr[1] + 1 + nh <= kTpWords - 2) g->set_prefetch_hints(ev + hdr[1] + 1, nh);
-  return rc < 0 ? rc : 0;
+  return kvb_tp_apply_host(group_id, buf, seq_out, n_out);
 }
 
 // ---- shm usage segment (kvctl / kvtop wire format) ---------------------------------------------------------

@@ -64,151 +64,12 @@ const Driver *driver() {
 }
 
 
-// ------------------------------------------------------------------------------------------ mock driver
-// A stand-in for the seven VMM driver calls that checks their legality (map only onto unmapped reserved space,
-// unmap / set-access only whole mappings, release only unmapped handles, no leaks) and counts them, so that the
-// engine's host logic — the part that decides WHICH calls are made — is testable without a GPU
-// (tests/test_vmm_engine_cpu.py).  Test infrastructure inside the library: installed only by kvb_vmm_mock_driver().
-namespace mock {
-struct Map { size_t size; CUmemGenericAllocationHandle h; bool access; };
-static std::mutex mu;
-static std::map<CUdeviceptr, size_t> reservations;
-static std::map<CUdeviceptr, Map> mappings;
-static std::map<CUmemGenericAllocationHandle, int> handles;   // handle -> live mappings
-static CUmemGenericAllocationHandle next_handle = 0x1000;
-static CUdeviceptr next_va = 0x7000000000ull;
-static int64_t n_create, n_release, n_map, n_unmap, n_access, n_violations;
-static double total_bytes = 64.0 * (1 << 30), other_bytes = 0, handle_bytes = 0;
-static int latency_us = 0;
-static char last_violation[256] = "";
-static bool installed = false;
-
-static void violate(const char *what) { n_violations++; snprintf(last_violation, sizeof(last_violation), "%s", what); }
-static void nap() { if (latency_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(latency_us)); }
-
-static CUresult AddressReserve(CUdeviceptr *p, size_t size, size_t, CUdeviceptr, unsigned long long) {
-  std::lock_guard<std::mutex> lk(mu);
-  *p = next_va;
-  next_va += (size + (1ull << 30)) & ~((1ull << 21) - 1);
-  reservations[*p] = size;
-  return CUDA_SUCCESS;
-}
-static CUresult AddressFree(CUdeviceptr p, size_t size) {
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = reservations.find(p);
-  if (it == reservations.end() || it->second != size) { violate("cuMemAddressFree of an unknown range"); return CUDA_ERROR_INVALID_VALUE; }
-  for (auto &m : mappings) if (m.first >= p && m.first < p + size) { violate("cuMemAddressFree with live mappings"); break; }
-  reservations.erase(it);
-  return CUDA_SUCCESS;
-}
-static CUresult Create(CUmemGenericAllocationHandle *h, size_t size, const CUmemAllocationProp *, unsigned long long) {
-  nap();
-  std::lock_guard<std::mutex> lk(mu);
-  if (handle_bytes + other_bytes + (double)size > total_bytes) return CUDA_ERROR_OUT_OF_MEMORY;
-  *h = next_handle++;
-  handles[*h] = 0;
-  handle_bytes += (double)size;
-  n_create++;
-  (void)size;
-  return CUDA_SUCCESS;
-}
-static std::map<CUmemGenericAllocationHandle, size_t> handle_size;
-static CUresult Release(CUmemGenericAllocationHandle h) {
-  nap();
-  std::lock_guard<std::mutex> lk(mu);
-  auto it = handles.find(h);
-  if (it == handles.end()) { violate("cuMemRelease of an unknown handle"); return CUDA_ERROR_INVALID_VALUE; }
-  if (it->second != 0) violate("cuMemRelease of a handle that is still mapped");
-  handle_bytes -= (double)handle_size[h];
-  handles.erase(it);
-  n_release++;
-  return CUDA_SUCCESS;
-}
-static CUresult MapFn(CUdeviceptr p, size_t size, size_t, CUmemGenericAllocationHandle h, unsigned long long) {
-  std::lock_guard<std::mutex> lk(mu);
-  n_map++;
-  if (!handles.count(h)) { violate("cuMemMap of an unknown handle"); return CUDA_ERROR_INVALID_VALUE; }
-  bool inside = false;
-  for (auto &r : reservations) if (p >= r.first && p + size <= r.first + r.second) inside = true;
-  if (!inside) { violate("cuMemMap outside any reservation"); return CUDA_ERROR_INVALID_VALUE; }
-  auto nx = mappings.lower_bound(p);
-  if (nx != mappings.end() && nx->first < p + size) { violate("cuMemMap over an existing mapping"); return CUDA_ERROR_INVALID_VALUE; }
-  if (nx != mappings.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second.size > p) { violate("cuMemMap over an existing mapping"); return CUDA_ERROR_INVALID_VALUE; } }
-  mappings[p] = Map{size, h, false};
-  handles[h]++;
-  return CUDA_SUCCESS;
-}
-static CUresult Unmap(CUdeviceptr p, size_t size) {
-  nap();
-  std::lock_guard<std::mutex> lk(mu);
-  n_unmap++;
-  // whole mappings inside [p, p+size) go; a partial overlap is an error
-  bool any = false;
-  for (auto it = mappings.lower_bound(p); it != mappings.end() && it->first < p + size;) {
-    if (it->first + it->second.size > p + size) { violate("cuMemUnmap splits a mapping"); return CUDA_ERROR_INVALID_VALUE; }
-    handles[it->second.h]--;
-    it = mappings.erase(it);
-    any = true;
-  }
-  if (!any && size < (1ull << 33)) { violate("cuMemUnmap of an unmapped range"); return CUDA_ERROR_INVALID_VALUE; }
-  return CUDA_SUCCESS;
-}
-static CUresult SetAccess(CUdeviceptr p, size_t size, const CUmemAccessDesc *, size_t) {
-  nap();
-  std::lock_guard<std::mutex> lk(mu);
-  n_access++;
-  size_t covered = 0;
-  for (auto it = mappings.lower_bound(p); it != mappings.end() && it->first < p + size; ++it) { it->second.access = true; covered += it->second.size; }
-  if (covered != size) { violate("cuMemSetAccess over a range that is not fully mapped"); return CUDA_ERROR_INVALID_VALUE; }
-  return CUDA_SUCCESS;
-}
-static CUresult Granularity(size_t *g, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) { *g = 2u << 20; return CUDA_SUCCESS; }
-static CUresult ErrorString(CUresult r, const char **s) { *s = r == CUDA_ERROR_OUT_OF_MEMORY ? "out of memory (mock)" : "invalid value (mock)"; return CUDA_SUCCESS; }
-}  // namespace mock
-
-int vmm_mock_driver(int64_t total_bytes, int latency_us) {
-  std::call_once(g_drv_once, [] {});   // the real resolution must not overwrite the mock later
-  {
-    std::lock_guard<std::mutex> lk(mock::mu);
-    mock::total_bytes = (double)total_bytes;
-    mock::latency_us = latency_us;
-    mock::other_bytes = 0;
-    mock::installed = true;
-  }
-  g_drv.MemAddressReserve = mock::AddressReserve;
-  g_drv.MemAddressFree = mock::AddressFree;
-  g_drv.MemCreate = [](CUmemGenericAllocationHandle *h, size_t size, const CUmemAllocationProp *p, unsigned long long f) {
-    CUresult r = mock::Create(h, size, p, f);
-    if (r == CUDA_SUCCESS) { std::lock_guard<std::mutex> lk(mock::mu); mock::handle_size[*h] = size; }
-    return r;
-  };
-  g_drv.MemRelease = mock::Release;
-  g_drv.MemMap = mock::MapFn;
-  g_drv.MemUnmap = mock::Unmap;
-  g_drv.MemSetAccess = mock::SetAccess;
-  g_drv.MemGetAllocationGranularity = mock::Granularity;
-  g_drv.GetErrorString = mock::ErrorString;
-  g_drv.ok = true;
-  return 0;
-}
-bool vmm_mock_installed() { return mock::installed; }
-void vmm_mock_set_other_bytes(int64_t bytes) { std::lock_guard<std::mutex> lk(mock::mu); mock::other_bytes = (double)bytes; }
-void vmm_mock_stats(int64_t *o) {
-  std::lock_guard<std::mutex> lk(mock::mu);
-  o[0] = mock::n_create; o[1] = mock::n_release; o[2] = mock::n_map; o[3] = mock::n_unmap; o[4] = mock::n_access;
-  o[5] = mock::n_violations; o[6] = (int64_t)mock::handles.size(); o[7] = (int64_t)mock::mappings.size();
-  int64_t leaked = 0;
-  for (auto &h : mock::handles) if (h.second < 0) leaked++;
-  o[8] = leaked; o[9] = (int64_t)mock::handle_bytes;
-}
-const char *vmm_mock_last_violation() { return mock::last_violation; }
-static bool mock_meminfo(size_t *fr, size_t *tot) {
-  std::lock_guard<std::mutex> lk(mock::mu);
-  double f = mock::total_bytes - mock::other_bytes - mock::handle_bytes;
-  *fr = (size_t)(f > 0 ? f : 0);
-  *tot = (size_t)mock::total_bytes;
-  return true;
-}
+#ifdef KVB_TEST_HOOKS
+#include "kvb_testhooks_mock.inc"   // libkvb200_test.so only: legality-checking stand-ins for the VMM driver calls
+#else
+namespace mock { static constexpr bool installed = false; }
+static bool mock_meminfo(size_t *, size_t *) { return false; }
+#endif
 
 static const char *cu_str(CUresult r) {
   const char *s = nullptr;
@@ -1019,220 +880,9 @@ int VmmGroup::raw_control(int64_t n_pages, int64_t iters, double *map_us, double
   return 0;
 }
 
-// Per-call driver costs (microseconds, averaged): out[0] cuMemCreate, [1] cuMemMap, [2] cuMemSetAccess per
-// unit, [3] cuMemSetAccess over the whole range (one call), [4] cuMemUnmap per unit, [5] cuMemUnmap of the
-// whole range (one call), [6] cuMemRelease, [7] remap cycle per unit (unmap + map + setaccess on a mapped unit)
-int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out) {
-  const Driver *d = driver();
-  if (!d) return KVB_ERR_CUDA_;
-  ensure_device(dev);
-  cudaFree(0);
-  CUmemAllocationProp prop{};
-  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  prop.location.id = dev;
-  CUmemAccessDesc acc{};
-  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  acc.location.id = dev;
-  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  size_t bytes = unit * (size_t)n;
-  CUdeviceptr base = 0;
-  CU_TRY(d->MemAddressReserve(&base, bytes, 2u << 20, 0, 0));
-  std::vector<CUmemGenericAllocationHandle> hs((size_t)n);
-  using clk = std::chrono::steady_clock;
-  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-  for (int k = 0; k < 8; ++k) out[k] = 0;
-  for (int64_t it = 0; it < iters; ++it) {
-    auto t0 = clk::now();
-    for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
-    auto t1 = clk::now();
-    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
-    auto t2 = clk::now();
-    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemSetAccess(base + u * unit, unit, &acc, 1));
-    auto t3 = clk::now();
-    for (int64_t u = 0; u < n; ++u) {   // remap cycle on live units
-      CU_TRY(d->MemUnmap(base + u * unit, unit));
-      CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
-      CU_TRY(d->MemSetAccess(base + u * unit, unit, &acc, 1));
-    }
-    auto t4 = clk::now();
-    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemUnmap(base + u * unit, unit));
-    auto t5 = clk::now();
-    for (int64_t u = 0; u < n; ++u) CU_TRY(d->MemMap(base + u * unit, unit, 0, hs[(size_t)u], 0));
-    auto t6 = clk::now();
-    CU_TRY(d->MemSetAccess(base, bytes, &acc, 1));
-    auto t7 = clk::now();
-    CU_TRY(d->MemUnmap(base, bytes));
-    auto t8 = clk::now();
-    for (auto h : hs) CU_TRY(d->MemRelease(h));
-    auto t9 = clk::now();
-    out[0] += us(t0, t1) / n;
-    out[1] += (us(t1, t2) + us(t5, t6)) / (2 * n);
-    out[2] += us(t2, t3) / n;
-    out[3] += us(t6, t7);
-    out[4] += us(t4, t5) / n;
-    out[5] += us(t7, t8);
-    out[6] += us(t8, t9) / n;
-    out[7] += us(t3, t4) / n;
-  }
-  for (int k = 0; k < 8; ++k) out[k] /= (double)iters;
-  d->MemAddressFree(base, bytes);
-  return 0;
-}
-
-// How do map/unmap cycles scale with the number of live mappings?  A reservation of M units is backed by
-// one zero handle (SetAccess per unit, or one call over the whole range when mode&1); 8 target units —
-// inside it, or in a separate 16-unit reservation when mode&2 — are then cycled zero->handle->zero.
-// out[0] = us per map cycle (unmap+map+setaccess), out[1] = us per unmap cycle, out[2] = init ms.
-int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out) {
-  const Driver *d = driver();
-  if (!d) return KVB_ERR_CUDA_;
-  ensure_device(dev);
-  cudaFree(0);
-  CUmemAllocationProp prop{};
-  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  prop.location.id = dev;
-  CUmemAccessDesc acc{};
-  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  acc.location.id = dev;
-  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  using clk = std::chrono::steady_clock;
-  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-  CUdeviceptr big = 0, small = 0;
-  CUmemGenericAllocationHandle zero;
-  CU_TRY(d->MemCreate(&zero, unit, &prop, 0));
-  auto t0 = clk::now();
-  CU_TRY(d->MemAddressReserve(&big, unit * (size_t)M, 2u << 20, 0, 0));
-  for (int64_t u = 0; u < M; ++u) {
-    CU_TRY(d->MemMap(big + u * unit, unit, 0, zero, 0));
-    if (!(mode & 1)) CU_TRY(d->MemSetAccess(big + u * unit, unit, &acc, 1));
-  }
-  if (mode & 1) CU_TRY(d->MemSetAccess(big, unit * (size_t)M, &acc, 1));
-  auto t1 = clk::now();
-  out[2] = us(t0, t1) / 1e3;
-  const int K = 8;
-  CUdeviceptr tgt[K];
-  if (mode & 2) {
-    CU_TRY(d->MemAddressReserve(&small, unit * 16, 2u << 20, 0, 0));
-    for (int u = 0; u < 16; ++u) {
-      CU_TRY(d->MemMap(small + u * unit, unit, 0, zero, 0));
-      CU_TRY(d->MemSetAccess(small + u * unit, unit, &acc, 1));
-    }
-    for (int k = 0; k < K; ++k) tgt[k] = small + (size_t)(2 * k) * unit;
-  } else {
-    for (int k = 0; k < K; ++k) tgt[k] = big + (size_t)((M / K) * k) * unit;
-  }
-  CUmemGenericAllocationHandle hs[K];
-  for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
-  double tm = 0, tu = 0;
-  for (int64_t it = 0; it < iters; ++it) {
-    auto a = clk::now();
-    for (int k = 0; k < K; ++k) {
-      CU_TRY(d->MemUnmap(tgt[k], unit));
-      CU_TRY(d->MemMap(tgt[k], unit, 0, hs[k], 0));
-      CU_TRY(d->MemSetAccess(tgt[k], unit, &acc, 1));
-    }
-    auto b = clk::now();
-    for (int k = 0; k < K; ++k) {
-      CU_TRY(d->MemUnmap(tgt[k], unit));
-      CU_TRY(d->MemMap(tgt[k], unit, 0, zero, 0));
-      CU_TRY(d->MemSetAccess(tgt[k], unit, &acc, 1));
-    }
-    auto c = clk::now();
-    tm += us(a, b) / K;
-    tu += us(b, c) / K;
-  }
-  out[0] = tm / iters;
-  out[1] = tu / iters;
-  d->MemUnmap(big, unit * (size_t)M);
-  d->MemAddressFree(big, unit * (size_t)M);
-  if (small) { d->MemUnmap(small, unit * 16); d->MemAddressFree(small, unit * 16); }
-  for (auto h : hs) d->MemRelease(h);
-  d->MemRelease(zero);
-  return 0;
-}
-
-// Does a map/unmap cycle get slower with the number of live PHYSICAL mappings, and is that per
-// reservation?  M distinct handles are mapped into one big reservation; 8 target units are cycled
-// (a) inside it, (b) in a separate small reservation, (c) in a small reservation placed directly behind
-// the big one at a fixed address.  out = {a_map, a_unmap, b_map, b_unmap, c_map, c_unmap, c_adjacent(0/1)}
-int vmm_probe3(int dev, size_t unit, int64_t M, int64_t iters, double *out) {
-  const Driver *d = driver();
-  if (!d) return KVB_ERR_CUDA_;
-  ensure_device(dev);
-  cudaFree(0);
-  CUmemAllocationProp prop{};
-  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  prop.location.id = dev;
-  CUmemAccessDesc acc{};
-  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  acc.location.id = dev;
-  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  using clk = std::chrono::steady_clock;
-  auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-  const int K = 8;
-  const CUdeviceptr hint = 0x3f0000000000ull;
-  CUdeviceptr big = 0, sep = 0, adj = 0;
-  size_t big_bytes = unit * (size_t)(M + 16);
-  CU_TRY(d->MemAddressReserve(&big, big_bytes, 2u << 20, hint, 0));
-  CU_TRY(d->MemAddressReserve(&adj, unit * 16, 2u << 20, big + big_bytes, 0));
-  CU_TRY(d->MemAddressReserve(&sep, unit * 16, 2u << 20, 0, 0));
-  out[6] = (adj == big + big_bytes) ? 1.0 : 0.0;
-  CUmemGenericAllocationHandle zero;
-  CU_TRY(d->MemCreate(&zero, unit, &prop, 0));
-  std::vector<CUmemGenericAllocationHandle> bg((size_t)M), hs(K);
-  for (auto &h : bg) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
-  for (auto &h : hs) CU_TRY(d->MemCreate(&h, unit, &prop, 0));
-  for (int64_t u = 0; u < M; ++u) {
-    CU_TRY(d->MemMap(big + u * unit, unit, 0, bg[(size_t)u], 0));
-    CU_TRY(d->MemSetAccess(big + u * unit, unit, &acc, 1));
-  }
-  for (int u = 0; u < 16; ++u) {
-    CU_TRY(d->MemMap(big + (M + u) * unit, unit, 0, zero, 0));
-    CU_TRY(d->MemSetAccess(big + (M + u) * unit, unit, &acc, 1));
-    CU_TRY(d->MemMap(sep + u * unit, unit, 0, zero, 0));
-    CU_TRY(d->MemSetAccess(sep + u * unit, unit, &acc, 1));
-    CU_TRY(d->MemMap(adj + u * unit, unit, 0, zero, 0));
-    CU_TRY(d->MemSetAccess(adj + u * unit, unit, &acc, 1));
-  }
-  CUdeviceptr bases[3] = {big + (size_t)M * unit, sep, adj};
-  for (int v = 0; v < 3; ++v) {
-    double tm = 0, tu = 0;
-    for (int64_t it = 0; it < iters; ++it) {
-      auto a = clk::now();
-      for (int k = 0; k < K; ++k) {
-        CUdeviceptr t = bases[v] + (size_t)(2 * k) * unit;
-        CU_TRY(d->MemUnmap(t, unit));
-        CU_TRY(d->MemMap(t, unit, 0, hs[k], 0));
-        CU_TRY(d->MemSetAccess(t, unit, &acc, 1));
-      }
-      auto b = clk::now();
-      for (int k = 0; k < K; ++k) {
-        CUdeviceptr t = bases[v] + (size_t)(2 * k) * unit;
-        CU_TRY(d->MemUnmap(t, unit));
-        CU_TRY(d->MemMap(t, unit, 0, zero, 0));
-        CU_TRY(d->MemSetAccess(t, unit, &acc, 1));
-      }
-      auto c2 = clk::now();
-      tm += us(a, b) / K;
-      tu += us(b, c2) / K;
-    }
-    out[2 * v] = tm / iters;
-    out[2 * v + 1] = tu / iters;
-  }
-  d->MemUnmap(big, big_bytes);
-  d->MemUnmap(sep, unit * 16);
-  d->MemUnmap(adj, unit * 16);
-  d->MemAddressFree(big, big_bytes);
-  d->MemAddressFree(sep, unit * 16);
-  d->MemAddressFree(adj, unit * 16);
-  for (auto h : bg) d->MemRelease(h);
-  for (auto h : hs) d->MemRelease(h);
-  d->MemRelease(zero);
-  return 0;
-}
+#ifdef KVB_TEST_HOOKS
+#include "kvb_testhooks_probe.inc"  // libkvb200_test.so only: per-call driver cost probes
+#endif
 
 // ------------------------------------------------------------------------------------------ registry
 struct Registry {

@@ -201,6 +201,7 @@ VmmGroup *vmm_group(int64_t group_id, bool create_if_missing);
 // cudaSetDevice only when the calling thread is on another device (cudaSetDevice itself costs tens of
 // microseconds on this stack; cudaGetDevice does not)
 int ensure_device(int dev);
+#ifdef KVB_TEST_HOOKS   // libkvb200_test.so only (kvb_testhooks_*.inc)
 // mock driver (host-logic tests without a GPU): legality-checking stand-ins for the VMM driver calls
 int vmm_mock_driver(int64_t total_bytes, int latency_us);
 bool vmm_mock_installed();
@@ -210,5 +211,7 @@ const char *vmm_mock_last_violation();
 int vmm_probe(int dev, size_t unit, int64_t n, int64_t iters, double *out8);
 int vmm_probe3(int dev, size_t unit, int64_t M, int64_t iters, double *out7);
 int vmm_probe2(int dev, size_t unit, int64_t M, int mode, int64_t iters, double *out3);
+
+#endif
 
 }  // namespace kvb

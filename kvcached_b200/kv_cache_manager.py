@@ -107,10 +107,10 @@ class _PageAllocatorView:
     def start_prealloc_thread(self) -> None:   # handle prefill replaces the prealloc thread
         pass
 
-    def stop_prealloc_thread(self) -> None:
+    def stop_prealloc_thread(self, timeout: Optional[float] = None) -> None:
         pass
 
-    _stop_prealloc_thread = stop_prealloc_thread   # the name kv_cache_manager.py:454 calls
+    _stop_prealloc_thread = stop_prealloc_thread   # the name kv_cache_manager.py:454 calls (with timeout=...)
 
 
 class KVCacheManager:
@@ -153,7 +153,6 @@ class KVCacheManager:
         self._h = None
         self.null_block: Optional[List[int]] = None
         self.page_allocator = _PageAllocatorView(self)
-        self._buf = np.empty(max(1024, min(num_blocks, 1 << 16)), dtype=np.int64)
         self._post_init_done = threading.Event()
         self._post_init_error: Optional[BaseException] = None
         # Like the reference (kv_cache_manager.py:190-227) the manager may be built before the KV
@@ -207,11 +206,12 @@ class KVCacheManager:
 
     def alloc_np(self, need_size: int) -> Optional[np.ndarray]:
         self._wait_post_init()
-        if need_size > self._buf.size:
-            self._buf = np.empty(int(need_size) * 2, dtype=np.int64)
-        rc = self._lib.kvb_mgr_alloc(self._h, need_size, _p64(self._buf), self._buf.size)
+        # a fresh array per call: ctypes releases the GIL during the C call, so a shared scratch buffer could be
+        # overwritten by a second thread's alloc() before it is copied (the reference is @synchronized)
+        buf = np.empty(max(int(need_size), 1), dtype=np.int64)
+        rc = self._lib.kvb_mgr_alloc(self._h, need_size, buf.ctypes.data, buf.size)
         if rc >= 0:
-            return self._buf[:rc].copy()
+            return buf[:rc]
         if rc == ST_NONE:
             return None
         if rc == ST_NO_PAGES:
@@ -229,7 +229,7 @@ class KVCacheManager:
                 if idx in rb:
                     raise ValueError(f"Freed index {idx} is in  reserved_blocks, which is not allowed.")
             bad0 = self.stats().bad_frees
-        _lib.check(self._lib.kvb_mgr_free(self._h, _p64(a), a.size), "free")
+        _lib.check(self._lib.kvb_mgr_free(self._h, a.ctypes.data, a.size), "free")
         if SANITY_CHECK and self.stats().bad_frees != bad0:
             raise ValueError("free(): some indices were not allocated (state inconsistency)")
 

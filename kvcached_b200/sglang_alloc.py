@@ -138,6 +138,7 @@ class ElasticPagedTokenToKVPoolAllocator:
         n_pages = C.c_int64(0)
         m = self.kvcached_allocator
         m._wait_post_init()
+        prefix_lens, seq_lens, last_loc = self._i64(prefix_lens), self._i64(seq_lens), self._i64(last_loc)
         rc = self._lib.kvb_mgr_alloc_extend(m._h, bs, prefix_lens.data_ptr(), seq_lens.data_ptr(), last_loc.data_ptr(),
                                             extend_num_tokens, out.data_ptr(), self._stream(), C.byref(n_pages))
         return self._result(rc, out)
@@ -152,9 +153,18 @@ class ElasticPagedTokenToKVPoolAllocator:
         n_pages = C.c_int64(0)
         m = self.kvcached_allocator
         m._wait_post_init()
+        seq_lens, last_loc = self._i64(seq_lens), self._i64(last_loc)
         rc = self._lib.kvb_mgr_alloc_decode(m._h, bs, seq_lens.data_ptr(), last_loc.data_ptr(), out.data_ptr(),
                                             self._stream(), C.byref(n_pages))
         return self._result(rc, out)
+
+    def _i64(self, t):
+        """The kernel reads contiguous int64 on the allocator's device; SGLang versions differ (int32 lengths,
+        views).  The reference's Triton kernels are dtype-agnostic, so normalise instead of asserting."""
+        torch = self._torch
+        if t.dtype != torch.int64 or not t.is_contiguous() or t.device != torch.device(self.device):
+            t = t.to(device=self.device, dtype=torch.int64).contiguous()
+        return t
 
     @staticmethod
     def _result(rc: int, out):

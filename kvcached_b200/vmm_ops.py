@@ -353,7 +353,9 @@ class PageAllocator:
     def start_prealloc_thread(self) -> None:
         pass
 
-    def stop_prealloc_thread(self) -> None:
+    def stop_prealloc_thread(self, timeout: Optional[float] = None) -> None:
         pass
 
+    # kv_cache_manager.py:454 calls the private name with a timeout; torch_bindings.cpp:212-213 binds only the public
+    # one, so the reference's own clear() raises AttributeError there.  Both names are served here.
     _stop_prealloc_thread = stop_prealloc_thread

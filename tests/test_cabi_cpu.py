@@ -15,8 +15,8 @@ from kvcached_b200 import trace as T
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_functions():
-    src = open(os.path.join(ROOT, "include", "kvb200.h")).read()
+def _header_functions(name="kvb200.h"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b(kvb_[a-z0-9_]+)\s*\(", src)
     return sorted(set(n for n in names if n not in ("kvb_mgr",)))
@@ -31,6 +31,21 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in kvcached_b200/_lib.py"
     assert lib.kvb_abi_version() == 1
     assert lib.kvb_total_launches() == 0 or lib.kvb_total_launches() > 0
+
+
+def test_product_library_carries_no_test_hooks():
+    """Mock driver and driver probes live in libkvb200_test.so (include/kvb200_test.h), not in the shipped library."""
+    lib = C.CDLL(_lib.LIB_PATH)
+    hooks = _header_functions("kvb200_test.h")
+    assert sorted(hooks) == sorted(_lib.TEST_SIGNATURES), hooks
+    for name in hooks:
+        assert not hasattr(lib, name), f"{name} (test hook) is exported by the product library"
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "mock" not in syms.lower() and "probe" not in syms.lower()
+    tlib = C.CDLL(_lib.TEST_LIB_PATH)
+    for name in hooks + _header_functions():
+        assert hasattr(tlib, name), f"{name} missing from libkvb200_test.so"
 
 
 def test_library_has_no_link_time_driver_dependency():

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Per-call CUDA VMM driver costs on this box (kvb_vmm_probe)."""
+import os
+os.environ.setdefault("KVB200_LIB", "test")   # the driver probes live in libkvb200_test.so
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

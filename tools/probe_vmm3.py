@@ -1,4 +1,6 @@
 #!/usr/bin/env python
+import os
+os.environ.setdefault("KVB200_LIB", "test")   # the driver probes live in libkvb200_test.so
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

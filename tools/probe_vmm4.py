@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Is a driver VMM call slower right after kernel activity?  map/unmap n pages with and without a
 kernel launch + sync in between; per-call attribution from kvb_vmm_timing."""
+import os
+os.environ.setdefault("KVB200_LIB", "test")   # the driver probes live in libkvb200_test.so
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
