@@ -109,27 +109,39 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- reference arm
-def run_reference(trace: dict, repeats: int, device: str = "cuda:0", prealloc: bool = True, timeout: int = 1500):
+REF_CORES = "0,1"     # BASELINE.md 3.3 pins the reference's scheduler thread; its prealloc thread gets the second core
+
+
+def run_reference(trace: dict, repeats: int, device: str = "cuda:0", prealloc: bool = True, timeout: int = 1500,
+                  contiguous: bool = True):
     """Replays through the unmodified reference (oracle/_ref) in a subprocess; returns its JSON or raises."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build_ref
+    import shutil
     if not build_ref.built():
         if not build_ref.build():
             raise RuntimeError("oracle/_ref is not built and /root/reference is not present")
-    tr = json.loads(json.dumps({"config": dict(trace["config"], prealloc=prealloc), "ops": trace["ops"]}))
+    tr = json.loads(json.dumps({"config": dict(trace["config"], prealloc=prealloc, contiguous=contiguous),
+                                "ops": trace["ops"]}))
     env = build_ref.ref_env(cpu_only=(device == "cpu" and not os.path.exists("/dev/nvidiactl")))
     env["KVCACHED_LOG_LEVEL"] = "ERROR"
     with tempfile.TemporaryDirectory() as d:
         tin, tout = os.path.join(d, "t.json"), os.path.join(d, "o.json")
         with open(tin, "w") as f:
             json.dump(tr, f)
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_replay.py"), tin, tout, "--time",
-                            "--device", device, "--repeat", str(repeats)],
-                           env=env, capture_output=True, text=True, timeout=timeout)
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_replay.py"), tin, tout, "--time",
+               "--device", device, "--repeat", str(repeats)]
+        pinned = False
+        if shutil.which("taskset") and (os.cpu_count() or 1) >= 2:
+            cmd = ["taskset", "-c", REF_CORES] + cmd
+            pinned = True
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
         if r.returncode != 0 or not os.path.isfile(tout):
             raise RuntimeError(f"reference replay failed (rc={r.returncode}): {r.stderr[-1500:]}")
         with open(tout) as f:
-            return json.load(f)
+            out = json.load(f)
+        out["pinned"] = f"taskset -c {REF_CORES}" if pinned else "not pinned (no taskset)"
+        return out
 
 
 def oracle_port_ops_per_s(trace: dict) -> dict:
@@ -144,30 +156,52 @@ def oracle_port_ops_per_s(trace: dict) -> dict:
             "sample": f"one replay of the full trace through oracle/kv_oracle.cpp ({n} calls, {dt:.3f} s, incl. Python glue)"}
 
 
+def reference_sample_trace(world: int):
+    """N > 1: the reference cannot create the 70B geometry's contiguous tensors (ftensor.cpp:161 asserts that its fixed
+    base address is a multiple of the 320 MiB compound page), so it runs its per-layer layout — 160 driver map loops
+    per page event — on a bounded sample of the workload: the same generator and distributions with 512 requests on
+    a pool 1/8 the size (same page events per call), so that K + W replays end within minutes."""
+    from kvcached_b200 import trace as T
+    cfg = T.make_config(f"llama70b_tp{world}", NUM_BLOCKS_TP // 8)
+    return cfg, T.decode_trace(cfg, N_REQUESTS // 8, seed=0)
+
+
 def reference_main(args, rank: int, world: int):
     if rank != 0:
         return
-    cfg, tr = build_trace(world)
-    n_calls = tr["meta"]["n_ops"]
     K, W = args.steps, args.warmup
-    try:
-        out = run_reference(tr, repeats=K + W, device="cuda:0", prealloc=True)
-        el = out["elapsed_all_s"][W:]
-        kind, dev = "reference", "cuda:0"
-    except Exception as e:   # reference could not run against the GPU: bookkeeping only on the CPU device
-        sys.stderr.write(f"[bench] reference on cuda:0 failed ({e}); falling back to the cpu device\n")
-        out = run_reference(tr, repeats=K + W, device="cpu", prealloc=False)
-        el = out["elapsed_all_s"][W:]
-        kind, dev = "reference", "cpu (bookkeeping only: map/unmap are no-ops)"
+    sample = "full replays of the trace"
+    if world == 1:
+        cfg, tr = build_trace(world)
+        attempts = [("cuda:0", True, True, "cuda:0, contiguous layout, prealloc thread on (shipping default)")]
+    else:
+        cfg, tr = reference_sample_trace(world)
+        sample = (f"replays of a bounded sample ({N_REQUESTS // 8} requests, pool {NUM_BLOCKS_TP // 8} blocks: same "
+                  "generator, distributions and page events per call as the full trace)")
+        attempts = [("cuda:0", True, False, "cuda:0, per-layer layout (the contiguous 70B geometry trips the reference's "
+                                            "own alignment assert, ftensor.cpp:161), prealloc thread on")]
+    attempts.append(("cpu", False, True, "cpu device (bookkeeping only: map/unmap are no-ops)"))
+    n_calls = tr["meta"]["n_ops"]
+    out = dev = None
+    for device, prealloc, contiguous, what in attempts:
+        try:
+            out = run_reference(tr, repeats=K + W, device=device, prealloc=prealloc, contiguous=contiguous)
+            dev = what
+            break
+        except Exception as e:
+            sys.stderr.write(f"[bench] reference on {what} failed ({e}); trying the next configuration\n")
+    if out is None:
+        raise RuntimeError("the reference could not replay the trace in any configuration")
+    el = out["elapsed_all_s"][W:]
     tot = sum(el)
     v = n_calls * len(el) / tot
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * tot / len(el), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(world),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
-                             "sample": f"{len(el)} full replays ({n_calls} calls each) of the trace through the "
-                                       f"unmodified reference KVCacheManager, device {dev}, single scheduler thread "
-                                       f"(+ its prealloc thread), host has {os.cpu_count()} cores"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 2, "kind": "reference",
+                             "sample": f"{len(el)} {sample} ({n_calls} calls each) through the unmodified reference "
+                                       f"KVCacheManager, {dev}; single scheduler thread + its prealloc thread, "
+                                       f"{out.get('pinned')}, host has {os.cpu_count()} cores"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -198,13 +232,20 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out = run_reference(tr, repeats=2, device="cuda:0", prealloc=True, timeout=600)
-            el = out["elapsed_all_s"][-1]
-            cpu_baseline = {"value": n_calls / el, "unit": UNIT, "cores": 1, "kind": "reference",
-                            "sample": f"1 warm-up + 1 timed full replay ({n_calls} calls, {el:.2f} s) through the "
+            out = run_reference(tr, repeats=1 + args.ref_replays, device="cuda:0", prealloc=True, timeout=900)
+            el = out["elapsed_all_s"][1:]
+            cpu_baseline = {"value": n_calls * len(el) / sum(el), "unit": UNIT, "cores": 2, "kind": "reference",
+                            "replays_s": el,
+                            "sample": f"1 warm-up + {len(el)} timed full replays ({n_calls} calls each) through the "
                                       f"unmodified reference KVCacheManager on cuda:0 (real cuMemMap work, prealloc "
-                                      f"thread on); host has {os.cpu_count()} cores, the scheduler path is single-threaded"}
-            try:
+                                      f"thread on = shipping default), {out.get('pinned')}; host has {os.cpu_count()} "
+                                      f"cores, the scheduler path is single-threaded"}
+            try:   # prealloc off = the deterministic parity mode
+                o3 = run_reference(tr, repeats=1, device="cuda:0", prealloc=False, timeout=600)
+                cpu_baseline["prealloc_off_value"] = n_calls / o3["elapsed_all_s"][-1]
+            except Exception as e:
+                cpu_baseline["prealloc_off_value"] = f"failed: {e}"[:200]
+            try:   # "cpu" device: map/unmap are no-ops, i.e. the reference's bookkeeping alone
                 o2 = run_reference(tr, repeats=2, device="cpu", prealloc=False, timeout=600)
                 cpu_baseline["bookkeeping_only_value"] = n_calls / o2["elapsed_all_s"][-1]
             except Exception:
@@ -246,6 +287,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             dev_ms.append(ms)
     assert m.stats().num_inuse_pages == 0, "trace must drain the pool"
     resident_launches = nl
+    page_events_per_replay = m.stats().events / (W + K)
     m.close()
     t_res = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -254,100 +296,168 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     value = n_calls * K / (res_ms_total * 1e-3)
 
     # ================= e2e: host buffers every scheduler step + real VMM ================================
+    # Two policies, both through KVCacheManager.run_ops per scheduler step with maps in place when a step returns
+    # and kvb_vmm_fence() inside the timed region:
+    #   strict   KVB200_VMM_RETAIN_MS=0: EVERY page event of the bookkeeping is applied to the device inside the
+    #            timed region (what the reference physically does per free, page_allocator.cpp:264-310, :648-686);
+    #            after the fence the physical mapping equals the bookkeeping's (+ <= 5 pages mapped ahead).  Headline.
+    #   default  retention on (bounded to 10 % of the device): pages the bookkeeping unmapped keep their handle for a
+    #            while, so most events cost no driver call.  Reported beside it with its physical overshoot.
     vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
     per_layer = cfg["num_blocks"] * cfg["block_size"] * cfg["cell_size"] * 2
     ranges = vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
     # attach_vmm=True (kvb_init was called).  Under TP only rank 0's manager is driven; the others follow its pages.
     mgr = R.manager_from_config(cfg, device_index=local_rank)
     plan = R.HostStepPlan(ct)
-    e2e_s = []
-    bytes0 = None
     tp = None
+    TP = None
     if world > 1:
         from kvcached_b200 import tp as TP
-        tp = TP.TpPageSync(mgr if rank == 0 else None, group_id=0, rank=rank, world=world, device=dev)
-    vt0 = None
-    for it in range(W + K):
-        if it == W:
-            s0 = mgr.stats()
-            bytes0 = (s0.h2d_bytes, s0.d2h_bytes)
-            vt0 = vmm_ops.vmm_timing()
-        flush_buf.fill_(it & 0xff)
+        if args.tp_transport == "nccl":
+            tp = TP.TpPageSync(mgr if rank == 0 else None, group_id=0, rank=rank, world=world, device=dev)
+        else:   # the step kernel pushes page lists into a shared ring; followers' threads apply them (kvb_tp.h)
+            tp = TP.TpMailbox(TP.mailbox_name(), rank, world, mgr=mgr if rank == 0 else None)
         barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            R.replay_host_steps(mgr, plan, keep_results=False)
-        else:
-            TP.replay_host_steps_tp(tp, mgr, plan, rank)
-        vmm_ops.fence()             # every queued unmap is applied inside the timed region
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+
+    def tp_fence():
+        """Every rank has applied every page list rank 0 produced so far (outside per-step paths)."""
+        if tp is None:
+            return
+        if args.tp_transport == "nccl":
+            tp.sync()
+            return
+        if rank == 0:
+            tp.fence()
+        barrier()                # rank 0 is done publishing
+        if rank != 0:
+            tp.fence()
+
+    def e2e_leg(strict: bool) -> dict:
+        vmm_ops.set_retention(0.0 if strict else 2000.0)
+        vmm_ops.settle()
         barrier()
-        if it >= W:
-            e2e_s.append(dt)
-    s1 = mgr.stats()
-    t_e2e = torch.tensor([sum(e2e_s)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_total = float(t_e2e.item())
-    e2e_value = n_calls * K / e2e_total
-    h2d = (s1.h2d_bytes - bytes0[0]) / K
-    d2h = (s1.d2h_bytes - bytes0[1]) / K
+        times, over_fence, over_peak, ret_peak = [], [], [], []
+        vt0 = b0 = None
+        for it in range(W + K):
+            if it == W:
+                s0 = mgr.stats()
+                b0 = (s0.h2d_bytes, s0.d2h_bytes)
+                vt0 = vmm_ops.vmm_timing()
+            flush_buf.fill_(it & 0xff)
+            vmm_ops.footprint()          # reset the peaks
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                R.replay_host_steps(mgr, plan, keep_results=False)
+            else:
+                TP.replay_host_steps_tp(tp, mgr, plan, rank)
+                tp_fence()               # every rank has applied everything rank 0 published
+            vmm_ops.fence()              # every queued unmap is applied inside the timed region
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            fp = vmm_ops.footprint()
+            if it >= W:
+                times.append(dt)
+                over_fence.append(fp["physical_pages"] - fp["wanted_pages"])
+                over_peak.append(fp["peak_overshoot_pages"])
+                ret_peak.append(fp["peak_retained_pages"])
+        s1 = mgr.stats()
+        vt1 = vmm_ops.vmm_timing()
+        t = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+        page_gib = vmm_ops.vmm_stats()["page_bytes"] / 2**30
+        leg = {"value": n_calls * K / total, "unit": UNIT, "ms_per_step": 1e3 * total / K,
+               "h2d_bytes_per_step": (s1.h2d_bytes - b0[0]) / K, "d2h_bytes_per_step": (s1.d2h_bytes - b0[1]) / K,
+               "page_transitions_per_replay": (vt1["unmap_calls"] - vt0["unmap_calls"]) / K,
+               "driver_ms_per_replay": sum(vt1[k] - vt0[k] for k in ("unmap_ms", "map_ms", "setaccess_ms", "create_ms",
+                                                                      "release_ms")) / K,
+               "physical_overshoot_pages_after_fence_max": max(over_fence),
+               "physical_overshoot_pages_peak_max": max(over_peak),
+               "physical_overshoot_pages_peak_mean": sum(over_peak) / len(over_peak),
+               "physical_overshoot_gib_peak_max": max(over_peak) * page_gib,
+               "retained_pages_peak_max": max(ret_peak)}
+        # the PHYSICAL mapping (everything mapped, not only what is wanted) against the bookkeeping
+        mapped_now = vmm_ops.mapped_pages()
+        phys_now = vmm_ops.vmm_stats()["mapped_pages"]
+        if rank == 0:
+            assert sorted(mapped_now) == mgr.mapped_pages(), "VMM mapping must equal the bookkeeping's mapped set"
+            if strict:
+                assert phys_now - len(mapped_now) <= 5, \
+                    f"strict mode: {phys_now} pages physically mapped, bookkeeping wants {len(mapped_now)}"
+        if dist is not None:   # every rank must hold exactly rank 0's mapped page set
+            h = torch.tensor([hash(tuple(mapped_now)) & 0x7fffffffffff, len(mapped_now)], dtype=torch.int64, device=dev)
+            hs = [torch.zeros_like(h) for _ in range(world)]
+            dist.all_gather(hs, h)
+            assert all(torch.equal(x, hs[0]) for x in hs), "ranks disagree on the mapped page set"
+            ph = torch.tensor([phys_now - len(mapped_now)], dtype=torch.int64, device=dev)
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+            leg["physical_overshoot_pages_after_fence_max_over_ranks"] = int(ph.item())
+            if strict:
+                assert int(ph.item()) <= 5, "strict mode: a rank holds pages the bookkeeping does not"
+        return leg
+
+    e2e_default = e2e_leg(strict=False)
+    e2e_strict = e2e_leg(strict=True)
+    vmm_ops.set_retention(2000.0)
+    e2e_value = e2e_strict["value"]
     vst = vmm_ops.vmm_stats()
     est = vmm_ops.engine_stats()
-    vt1 = vmm_ops.vmm_timing()
-    drv_ms = sum(vt1[k] - vt0[k] for k in ("unmap_ms", "map_ms", "setaccess_ms", "create_ms", "release_ms")) / K
-    transitions = (vt1["unmap_calls"] - vt0["unmap_calls"]) / K
-    mapped_now = vmm_ops.mapped_pages()
-    if rank == 0:
-        assert sorted(mapped_now) == mgr.mapped_pages(), "VMM mapping must equal the bookkeeping's mapped set"
-    if dist is not None:   # every rank must hold exactly rank 0's mapped page set
-        h = torch.tensor([hash(tuple(mapped_now)) & 0x7fffffffffff, len(mapped_now)], dtype=torch.int64, device=dev)
-        hs = [torch.zeros_like(h) for _ in range(world)]
-        dist.all_gather(hs, h)
-        assert all(torch.equal(x, hs[0]) for x in hs), "ranks disagree on the mapped page set"
+    tp_stats = tp.stats() if (tp is not None and args.tp_transport != "nccl") else None
 
     # ================= page map / unmap latency vs the raw driver loop ======================================
     map_unmap = {}
     if rank == 0:
         mgr.trim()
-        n_list = (1, 8, 64, 512) if world == 1 else (1, 8, 64)      # SURVEY 8(d); 512 compound pages = 64 GiB at TP1
-        lib.kvb_vmm_pool_config(0, 640)
-        lib.kvb_vmm_pool_prefill(0, 72)
-        for n in n_list:
+    tp_fence()             # rank 0's trim reaches the other ranks
+    vmm_ops.settle()       # every rank hands retained pages back: the leg below creates its own handles
+    barrier()
+    if rank == 0:
+        total_pages = int(mgr.stats().num_total_pages)
+        page_bytes = vst["page_bytes"]
+        free_b, _tot = torch.cuda.mem_get_info()
+        for n in (1, 8, 64, 512):      # SURVEY 8(d)
+            # n pages through the engine + n raw-control handles must fit the pool and the device
+            if n > total_pages or 2 * n * page_bytes > 0.7 * free_b:
+                map_unmap[f"n{n}"] = {"skipped": f"{n} pages of {page_bytes >> 20} MiB twice do not fit "
+                                                 f"(pool {total_pages} pages, {free_b >> 30} GiB free)"}
+                continue
             iters = 30 if n < 64 else (8 if n < 512 else 3)
-            if n == 512:
-                lib.kvb_vmm_pool_prefill(0, 512)
-            ids = np.arange(100, 100 + n, dtype=np.int64)
+            lib.kvb_vmm_pool_config(0, max(640, n + 16))
+            _lib.check(lib.kvb_vmm_pool_prefill(0, n + 8), "pool_prefill")
+            first = min(100, total_pages - n)
+            ids = np.arange(first, first + n, dtype=np.int64)
             p = ids.ctypes.data_as(_lib.p_i64)
             mm, uu = [], []
             for i in range(iters + 3):
                 t0 = time.perf_counter()
-                lib.kvb_map_pages(0, p, n)
+                rc_m = lib.kvb_map_pages(0, p, n)
                 t1 = time.perf_counter()
-                lib.kvb_unmap_pages(0, p, n)
+                rc_u = lib.kvb_unmap_pages(0, p, n)
                 t2 = time.perf_counter()
+                assert rc_m == 1 and rc_u == 1, f"map/unmap of {n} pages failed ({rc_m}, {rc_u}): {_lib.last_error()}"
                 if i >= 3:
                     mm.append((t1 - t0) * 1e6)
                     uu.append((t2 - t1) * 1e6)
+            lib.kvb_vmm_pool_config(0, 16)      # the control loop creates its own handles
             a = np.zeros(iters)
             b = np.zeros(iters)
-            rc = lib.kvb_vmm_raw_control(0, n, iters, 1, a.ctypes.data_as(_lib.p_f64), b.ctypes.data_as(_lib.p_f64))
-            assert rc == 0, _lib.last_error()
+            _lib.check(lib.kvb_vmm_raw_control(0, n, iters, 1, a.ctypes.data_as(_lib.p_f64), b.ctypes.data_as(_lib.p_f64)),
+                       "raw_control")
             map_unmap[f"n{n}"] = {"map_p50_us": pctl(mm, 0.5), "map_p99_us": pctl(mm, 0.99),
                                   "unmap_p50_us": pctl(uu, 0.5), "unmap_p99_us": pctl(uu, 0.99),
                                   "raw_map_p50_us": pctl(a.tolist(), 0.5), "raw_unmap_p50_us": pctl(b.tolist(), 0.5),
                                   "map_plus_unmap_vs_raw": (pctl(mm, 0.5) + pctl(uu, 0.5)) /
                                                            (pctl(a.tolist(), 0.5) + pctl(b.tolist(), 0.5))}
-        map_unmap["page_bytes"] = vst["page_bytes"]
+        map_unmap["page_bytes"] = page_bytes
         map_unmap["note"] = (f"one compound page = all {cfg['num_layers']} layers' K and V pages "
-                             f"({vst['page_bytes'] >> 20} MiB); raw = the same cuMemUnmap+cuMemMap+cuMemSetAccess calls on "
+                             f"({page_bytes >> 20} MiB); raw = the same cuMemUnmap+cuMemMap+cuMemSetAccess calls on "
                              "pre-created handles, same process")
         lib.kvb_vmm_pool_config(0, 16)
     barrier()
-    if tp is not None:
-        tp.sync()          # rank 0's trim reaches the other ranks
-    vmm_ops.settle()       # every rank hands its retained pages back before the KV buffers are allocated
+    vmm_ops.settle()
 
     # ================= fused KV scatter / gather through the mapped range ======================================
     L, bs, cell = cfg["num_layers"], cfg["block_size"], cfg["cell_size"]
@@ -361,7 +471,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             ids0 = mgr.alloc_np(Tn // bs)
             assert ids0 is not None
             ids_t.copy_(torch.from_numpy(ids0))
-        tp.sync()
+        tp_fence()
         dist.broadcast(ids_t, src=0)
         ids = ids_t.cpu().numpy()
     rng = np.random.default_rng(rank)
@@ -387,24 +497,34 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kv[name] = {"ms": float(t.item()), "gbs_per_gpu": alg_bytes / float(t.item()) / 1e6,
                     "gbs_total": world * alg_bytes / float(t.item()) / 1e6}
-    # end-to-end scatter from pinned host memory (smaller batch: PCIe bound)
+    # end-to-end scatter from pinned host memory (smaller batch: PCIe bound): device staging buffers allocated once,
+    # one untimed pass (the first touches lazily allocated pinned pages), median of 5
     Th = 2048
     kh = torch.empty((L, Th, cell // 2), dtype=torch.int16).random_().pin_memory()
     vh = torch.empty((L, Th, cell // 2), dtype=torch.int16).random_().pin_memory()
     sh = slots[:Th].cpu().pin_memory()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        kd, vd, sd = kh.to(dev, non_blocking=True), vh.to(dev, non_blocking=True), sh.to(dev, non_blocking=True)
+    kd, vd, sd = torch.empty_like(kh, device=dev), torch.empty_like(vh, device=dev), torch.empty_like(sh, device=dev)
+    hs_ms = []
+    for i in range(6):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        kd.copy_(kh, non_blocking=True)
+        vd.copy_(vh, non_blocking=True)
+        sd.copy_(sh, non_blocking=True)
         kv_ops.kv_scatter(lay, sd, kd, vd)
         chk = int(sd[0].item())     # device->host read closes the step
-    dt = (time.perf_counter() - t0) / 3
-    kv["scatter_from_pinned_host"] = {"tokens": Th, "ms": dt * 1e3, "gbs": (Th * L * 4 * cell) / dt / 1e9,
-                                      "h2d_bytes": 2 * kh.numel() * 2 + Th * 8, "d2h_bytes": 8}
+        if i:
+            hs_ms.append((time.perf_counter() - t0) * 1e3)
+    dt = statistics.median(hs_ms) / 1e3
+    h2d_b = 2 * kh.numel() * 2 + Th * 8
+    kv["scatter_from_pinned_host"] = {"tokens": Th, "ms": dt * 1e3, "ms_min_max": [min(hs_ms), max(hs_ms)],
+                                      "pcie_h2d_gbs": h2d_b / dt / 1e9, "gbs": (Th * L * 4 * cell) / dt / 1e9,
+                                      "h2d_bytes": h2d_b, "d2h_bytes": 8,
+                                      "note": "bound by the host->device copy (PCIe), not by the scatter kernel"}
+    del kd, vd, sd
     if rank == 0:
         mgr.free(ids)
-    if tp is not None:
-        tp.sync()
+    tp_fence()
     del k, v
     torch.cuda.empty_cache()
 
@@ -501,7 +621,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     if shard:
         for row in shard.values():
             row["frac_of_hbm_peak_scatter"] = row["scatter_gbs_per_gpu"] / peak
-    roofline = {"kernel": "kvb_kv_copy_kernel<scatter> (fused 32-layer paged KV scatter, T=65536 tokens)",
+    roofline = {"kernel": f"kvb_kv_copy_kernel<scatter> (fused {L}-layer paged KV scatter, cell {cell} B, T={Tn} tokens)",
                 "bound": "hbm", "achieved": kv["scatter"]["gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                 "frac": kv["scatter"]["gbs_per_gpu"] / peak,
                 "traffic": SCATTER_TRAFFIC_NCU if (world == 1 and Tn == SCATTER_T) else None,
@@ -517,26 +637,38 @@ def ours_main(args, rank: int, world: int, local_rank: int):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": res_ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int64", "data": "synthetic", "config": workload_config(world), "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": 1e3 * e2e_total / K, "scheduler_steps": len(plan.steps),
+                "e2e": {"value": e2e_value, "unit": UNIT,
+                        "h2d_bytes_per_step": e2e_strict["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": e2e_strict["d2h_bytes_per_step"],
+                        "ms_per_step": e2e_strict["ms_per_step"], "scheduler_steps": len(plan.steps),
+                        "policy": "strict (KVB200_VMM_RETAIN_MS=0): every page event of the bookkeeping is applied to "
+                                  "the device inside the timed region; map-ahead 5 pages",
+                        "page_events_per_replay": page_events_per_replay,
+                        "page_transitions_per_replay": e2e_strict["page_transitions_per_replay"],
+                        "driver_ms_per_replay": e2e_strict["driver_ms_per_replay"],
+                        "physical_overshoot_pages_after_fence_max": e2e_strict["physical_overshoot_pages_after_fence_max"],
+                        "strict": e2e_strict,
+                        "default_policy": dict(e2e_default, policy=(
+                            "retention: pages the bookkeeping unmapped keep their handle until the allocator is quiet "
+                            "for 2 s, never more than 10 % of the device (KVB200_RETAIN_MAX_FRACTION), leaving free the "
+                            "utilisation headroom + 2 % of the device, or 20 % while anybody else's footprint grows")),
                         "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"],
-                                "page_transitions_per_replay": transitions, "driver_ms_per_replay": drv_ms,
-                                "page_events_per_replay": 1744 if world == 1 else None,
                                 "map_ahead_hits": est["prefetch_hits"], "retention_hits": est["retention_hits"],
-                                "pages_retained_at_end": est["retained"],
-                                "policy": "async VMM thread; map-ahead 5 pages; unmapped pages keep their handle until the "
-                                          "allocator is quiet for 2 s, leaving free the utilisation headroom + 2% of the "
-                                          "device, or 20% while anybody else's footprint grows (KVB200_VMM_PREFETCH / "
-                                          "KVB200_VMM_RETAIN_MS / KVB200_RETAIN_FREE_FRACTION / KVB200_RETAIN_QUIET_MARGIN)"},
+                                "page_bytes": vst["page_bytes"]},
+                        "tp": tp_stats, "tp_transport": (args.tp_transport if world > 1 else None),
                         "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
-                               "place when a step returns, unmaps drain on the VMM thread, kvb_vmm_fence() closes the "
-                               "timed region"},
+                               "place (on every TP rank) when a step returns, unmaps drain on the VMM thread, "
+                               "kvb_vmm_fence() closes the timed region"},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "map_unmap": map_unmap, "kv_scatter": kv, "kv_scatter_tp_shards_on_one_gpu": shard,
                 "bitmap_sweep": sweep, "micro_alloc_free": micro,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+    if tp is not None and hasattr(tp, "close"):
+        tp.close()
     mgr.close()
     vmm_ops.shutdown_kvcached()
     if dist is not None:
@@ -551,14 +683,28 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-replays", type=int, default=3, help="timed replays of the cpu_baseline leg (N=1)")
+    ap.add_argument("--tp-transport", default="mailbox", choices=["mailbox", "nccl"],
+                    help="N>1: how rank 0's page lists reach the other ranks (mailbox = kernel push into a shared ring; "
+                         "nccl = one broadcast per scheduler step, the checker)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        reference_main(args, rank, world)
-    else:
-        ours_main(args, rank, world, local_rank)
+    try:
+        if args.impl == "reference":
+            reference_main(args, rank, world)
+        else:
+            ours_main(args, rank, world, local_rank)
+    except BaseException as e:
+        if isinstance(e, SystemExit) and not e.code:
+            raise
+        # the launcher keeps only its own wrapper's tail: say what failed, on which rank, before going down
+        import traceback
+        sys.stderr.write(f"[bench] rank {rank} of {world} failed:\n{traceback.format_exc()}\n")
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

@@ -124,6 +124,15 @@ int kvb_vmm_set_retention_ms(int64_t group_id, double ms);
  * KVB200_RETAIN_QUIET_MARGIN or 0.02 of the device; < 0 = keep), which a co-located model that wakes up sees as
  * available at once; taking any of it switches the larger reserve on within one poll (5-50 ms). */
 int kvb_vmm_set_retain_free_fraction(int64_t group_id, double fraction, double quiet_margin);
+/* Retained pages never hold more than `fraction` of the device (default KVB200_RETAIN_MAX_FRACTION or 0.10): at the
+ * cap a page the bookkeeping unmaps goes back to the zero page at once (the newest one — the FIFO free list needs it
+ * last).  The reference's count-based equivalent is max_reserved_pages (page_allocator.cpp:264-310). */
+int kvb_vmm_set_retain_max_fraction(int64_t group_id, double fraction);
+/* Physical footprint against the bookkeeping: out6 = {pages physically mapped now (wanted + mapped ahead + retained +
+ * unmap pending), pages the bookkeeping wants mapped, PEAK of the difference since the previous call, pages retained
+ * now, retention cap in pages, peak retained since the previous call}.  KVB200_VMM_RETAIN_MS=0 (strict): the
+ * difference is map-ahead pages plus unmaps still queued, and map-ahead pages only after kvb_vmm_fence. */
+int kvb_vmm_footprint(int64_t group_id, int64_t *out6);
 int kvb_vmm_settle(int64_t group_id);
 int64_t kvb_vmm_pending_unmaps(int64_t group_id);
 /* Map-ahead: the step kernel publishes the next pages its free list will hand out; the VMM thread maps up to `depth`

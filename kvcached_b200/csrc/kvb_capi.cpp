@@ -129,6 +129,19 @@ int kvb_vmm_set_retain_free_fraction(int64_t group_id, double f, double quiet_ma
   g->set_retain_free_fraction(f, quiet_margin);
   return 0;
 }
+int kvb_vmm_set_retain_max_fraction(int64_t group_id, double f) {
+  VmmGroup *g = vmm_group(group_id, true);
+  if (!g) return KVB_ERR_STATE;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->set_retain_max_fraction(f);
+  return 0;
+}
+int kvb_vmm_footprint(int64_t group_id, int64_t *out6) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g || !out6) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  g->footprint(out6);
+  return 0;
+}
 int kvb_vmm_set_async(int64_t group_id, int on) {
   VmmGroup *g = vmm_group(group_id, true);
   if (!g) return KVB_ERR_STATE;

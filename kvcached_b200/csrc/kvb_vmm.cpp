@@ -201,6 +201,18 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     quiet_margin_ = qm && *qm ? atof(qm) : 0.02;
     const char *fl = getenv("KVB200_POOL_FLOOR");
     pool_floor_ = fl && *fl ? atoll(fl) : 16;
+    const char *mx = getenv("KVB200_RETAIN_MAX_FRACTION");
+    retain_max_frac_ = mx && *mx ? atof(mx) : 0.10;
+    if (retain_max_frac_ < 0) retain_max_frac_ = 0;
+    if (retain_max_frac_ > 1) retain_max_frac_ = 1;
+    // the cap needs the device size before the VMM thread's first sample
+    size_t fr = 0, tot = 0;
+    if (mock::installed ? mock_meminfo(&fr, &tot) : (cudaMemGetInfo(&fr, &tot) == cudaSuccess)) {
+      mem_free_ = (double)fr;
+      mem_total_ = (double)tot;
+    } else {
+      cudaGetLastError();
+    }
   }
   {
     // pages mapped ahead of demand; the reference keeps KVCACHED_MIN_RESERVED_PAGES (5) pre-mapped by default
@@ -271,6 +283,7 @@ void VmmGroup::update(int64_t p, int want, int spec, int phys, int force) {
   if (phys >= 0 && ph != (phys != 0)) { ph = phys != 0; n_mapped_ += ph ? 1 : -1; }
   if (force >= 0) f = force != 0;
   if (w || sp || !ph) f = false;
+  n_want_ += (int)w - (int)want_[(size_t)p];
   want_[(size_t)p] = w;
   spec_[(size_t)p] = sp;
   mapped_[(size_t)p] = ph;
@@ -280,12 +293,16 @@ void VmmGroup::update(int64_t p, int want, int spec, int phys, int force) {
   n_retained_ += (ph && !w && !sp && !f);
   need_spec_ += (sp && !w && !ph);
   n_spec_mapped_ += (sp && !w && ph);
+  if (n_mapped_ - n_want_ > peak_over_) peak_over_ = n_mapped_ - n_want_;
+  if (n_retained_ > peak_retained_) peak_retained_ = n_retained_;
 }
 
 // A mapped page that is neither wanted nor hinted any more.
 void VmmGroup::make_unwanted(int64_t p) {
   if (!mapped_[(size_t)p] || want_[(size_t)p] || spec_[(size_t)p]) return;
-  if (async_ && retention_ms_ > 0 && !force_[(size_t)p]) {
+  if (async_ && retention_ms_ > 0 && !force_[(size_t)p] && n_retained_ <= retain_cap_pages()) {
+    // (the page counts as retained from the moment it became unwanted, hence <=: at the cap it goes back at once —
+    // the newest page is the one the FIFO free list needs last)
     retained_.push_back(Retained{p, ++ret_seq_[(size_t)p], now_ms()});
     // the pool cap bounds idle handles, retained ones included
     while ((int64_t)pool_.size() / n_sub_ + n_retained_ > pool_cap_pages_ && force_one_retained(false)) {}
@@ -293,6 +310,29 @@ void VmmGroup::make_unwanted(int64_t p) {
     update(p, -1, -1, -1, 1);
     qu_.push_back(p);
   }
+}
+
+// Retained pages are a cache nobody asked for: never more than retain_max_frac_ of the device.
+int64_t VmmGroup::retain_cap_pages() const {
+  if (mem_total_ <= 0) return n_pages_;
+  return (int64_t)(mem_total_ * retain_max_frac_ / ((double)unit_ * n_sub_));
+}
+void VmmGroup::set_retain_max_fraction(double f) {
+  Lock lk(qmu_);
+  retain_max_frac_ = f < 0 ? 0 : (f > 1 ? 1 : f);
+  while (n_retained_ > retain_cap_pages() && force_one_retained(true)) {}
+  if (async_ && need_unmap_ > 0) ensure_worker(lk);
+}
+void VmmGroup::footprint(int64_t *o) {
+  Lock lk(qmu_);
+  o[0] = n_mapped_;
+  o[1] = n_want_;
+  o[2] = peak_over_;
+  o[3] = n_retained_;
+  o[4] = retain_cap_pages();
+  o[5] = peak_retained_;
+  peak_over_ = n_mapped_ - n_want_;
+  peak_retained_ = n_retained_;
 }
 
 bool VmmGroup::force_one_retained(bool newest) {

@@ -89,6 +89,12 @@ class VmmGroup {
   // the utilisation headroom plus KVB200_RETAIN_QUIET_MARGIN (0.02 of the device): a co-located model that wakes up
   // always sees that margin as available, and taking any of it switches the larger reserve on within one poll.
   void set_retain_free_fraction(double f, double quiet_margin = -1);
+  // Retained pages never hold more than this fraction of the device (default KVB200_RETAIN_MAX_FRACTION or 0.10): a
+  // page unmapped by the bookkeeping while the cap is reached goes back to the zero page at once.
+  void set_retain_max_fraction(double f);
+  // out6 = {pages physically mapped (wanted + mapped ahead + retained + unmap pending), pages the bookkeeping wants
+  // mapped, peak of the difference since the last call, pages retained now, retention cap in pages, peak retained}
+  void footprint(int64_t *out6);
   int settle();       // fence + every retained page back on the zero page (trim / clear / resize / kvctl limit)
   void set_prefetch_hints(const int64_t *pages, int64_t n);
   void set_prefetch_depth(int depth);
@@ -165,6 +171,9 @@ class VmmGroup {
   struct PoolEnt { CUmemGenericAllocationHandle h; double t_ms; };
   double retention_ms_ = 0;
   int64_t n_retained_ = 0, n_retention_hits_ = 0, release_debt_ = 0, pool_floor_ = 16;
+  int64_t n_want_ = 0, peak_over_ = 0, peak_retained_ = 0;
+  double retain_max_frac_ = 0.10;
+  int64_t retain_cap_pages() const;
   double mem_t_ms_ = -1e18, gpu_util_ = 0.95, retain_free_frac_ = 0.20, last_map_ms_ = -1e18;
   double mem_free_ = 0, mem_total_ = 0;     // bytes, as of mem_t_ms_ (adjusted by our own creates / releases)
   double quiet_margin_ = 0.02, others_base_ = -1, contended_until_ms_ = -1e18;

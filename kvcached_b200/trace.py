@@ -51,16 +51,23 @@ def blocks_per_page(cfg: dict) -> int:
 
 # --------------------------------------------------------------------------- random mix
 def random_trace(cfg: dict, seed: int, n_ops: int = 300, max_alloc: int = 200,
-                 p_free: float = 0.45, extra: bool = True) -> dict:
+                 p_free: float = 0.45, extra: bool = True, p_clear: float = 0.0) -> dict:
     """Random allocs, partial/whole/concatenated frees and (optionally) resize / trim /
     reserve events.  Sizes are chosen against a block-count model so most allocs succeed
-    and some deliberately over-ask (-> None)."""
+    and some deliberately over-ask (-> None).  p_clear > 0 also emits KVCacheManager.clear()
+    (kv_cache_manager.py:444-489): everything is freed, ids held from before are never freed again.
+    (The extra random draw happens only then, so traces with p_clear = 0 are what they always were.)"""
     rng = np.random.default_rng(seed)
     ops: List[list] = []
     live: List[list] = []          # [op_index, lo, hi] un-freed ranges, assuming the alloc succeeded
     used = 1 if cfg.get("reserve_null_block") else 0
     cap = cfg["num_blocks"]
     for _ in range(n_ops):
+        if p_clear > 0 and rng.random() < p_clear:
+            ops.append(["clear"])
+            live = []
+            used = 1 if cfg.get("reserve_null_block") else 0
+            continue
         u = rng.random()
         if extra and u < 0.03:
             ops.append(["avail"])

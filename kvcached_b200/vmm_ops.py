@@ -119,6 +119,20 @@ def set_retain_free_fraction(fraction: float, quiet_margin: float = -1.0, group_
                "vmm set_retain_free_fraction")
 
 
+def set_retain_max_fraction(fraction: float, group_id: int = 0) -> None:
+    """Retained pages never hold more than this fraction of the device (default 0.10)."""
+    _lib.check(_lib.load().kvb_vmm_set_retain_max_fraction(group_id, float(fraction)), "vmm set_retain_max_fraction")
+
+
+def footprint(group_id: int = 0) -> Dict[str, int]:
+    """Physical footprint against the bookkeeping (peaks are since the previous call)."""
+    o = np.zeros(6, dtype=np.int64)
+    _lib.check(_lib.load().kvb_vmm_footprint(group_id, o.ctypes.data_as(_lib.p_i64)), "vmm footprint")
+    keys = ["physical_pages", "wanted_pages", "peak_overshoot_pages", "retained_pages", "retain_cap_pages",
+            "peak_retained_pages"]
+    return dict(zip(keys, o.tolist()))
+
+
 def wait_maps(group_id: int = 0) -> None:
     _lib.check(_lib.load().kvb_vmm_wait_maps(group_id), "vmm wait_maps")
 

@@ -17,6 +17,7 @@ Trace format (shared with oracle/oracle.py and kvcached_b200/trace.py):
     ["try_reserve", n]      -> bool                   kv_cache_manager.py:363
     ["free_reserved"]                                 kv_cache_manager.py:375
     ["avail"]               -> int                    kv_cache_manager.py:412
+    ["clear"]                                         kv_cache_manager.py:444  (see the note in run())
     ["step"]                scheduler-step boundary (no-op for the reference)
 
 After every op a snapshot is recorded: available_size, page counters, the
@@ -75,6 +76,13 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: in
                          reserve_null_block=cfg.get("reserve_null_block", False),
                          num_kv_buffers=nkv)
     mgr._post_init_done.wait(timeout=15.0)
+    # KVCacheManager.clear() calls page_allocator._stop_prealloc_thread(timeout=...) (kv_cache_manager.py:454), a name
+    # csrc/torch_bindings.cpp:212-213 does not bind (only stop_prealloc_thread() is) — the reference's own clear()
+    # raises AttributeError in this snapshot.  The ONE addition made here is that missing alias onto the reference's
+    # own bound method; every line of clear() that follows runs unmodified, which is what pins clear() parity.
+    pa_cls = type(mgr.page_allocator)
+    if not hasattr(pa_cls, "_stop_prealloc_thread"):
+        pa_cls._stop_prealloc_thread = lambda self, timeout=None: self.stop_prealloc_thread()
 
     mapped: set[int] = set()
     per_page = P * L * nkv if contiguous else P
@@ -168,6 +176,8 @@ def _one_pass(trace, mgr, snap, timing_only):
             mgr.free_reserved()
         elif kind == "avail":
             r = mgr.available_size()
+        elif kind == "clear":
+            mgr.clear()
         elif kind == "step":
             pass
         else:

@@ -71,6 +71,18 @@ def cases() -> dict:
                                             n_requests=128, seed=1, tokens_per_step=16)
     c["decode_mla"] = T.decode_trace(T.make_config("mla_p64", 2000, reserve_null_block=True), n_requests=64, seed=2,
                                      tokens_per_step=8)
+    # KVCacheManager.clear() (kv_cache_manager.py:444-489) between random traffic; oracle/ref_replay.py binds the one
+    # missing private name the reference's clear() trips over, the method body runs unmodified
+    c["clear_basic"] = {"config": nb, "ops": [
+        ["alloc", 300], ["alloc", 70], ["free_slice", 0, 10, 200], ["try_reserve", 20], ["clear"], ["avail"],
+        ["alloc", 130], ["resize", 6 * 2 * MiB], ["clear"], ["alloc", 5], ["free_cat", [9]], ["clear"], ["clear"],
+        ["avail"]]}
+    c["clear_rand0"] = T.random_trace(small, 800, n_ops=320, p_clear=0.03)
+    c["clear_null_rand0"] = T.random_trace(nb, 801, n_ops=320, p_clear=0.03)
+    c["clear_null_rand1"] = T.random_trace(nb, 802, n_ops=320, p_clear=0.05)
+    c["clear_mla_p1"] = T.random_trace(T.make_config("mla_p1", 30000, reserve_null_block=True), 803, n_ops=250,
+                                       max_alloc=4000, p_clear=0.03)
+    c["clear_tp8"] = T.random_trace(T.make_config("llama70b_tp8", 8192), 804, n_ops=250, max_alloc=1500, p_clear=0.03)
     # micro pairs (bench_alloc pattern)
     c["micro_churn_k16"] = T.micro_trace(small, 16, 40, churn=True)
     c["micro_pinned_k4"] = T.micro_trace(small, 4, 40, churn=False)

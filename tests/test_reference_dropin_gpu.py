@@ -75,7 +75,10 @@ def test_unmodified_reference_manager_runs_on_our_extension(reference_manager_mo
         (flat,) = our_vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", cfg["num_layers"])
         mgr = mod.KVCacheManager(cfg["num_blocks"], cfg["block_size"], cfg["cell_size"], cfg["num_layers"])
         assert mgr._post_init_done.wait(timeout=15.0)
-        trace = T.random_trace(cfg, 77, n_ops=150, extra=False)
+        # clear() included: the unmodified reference clear() calls page_allocator._stop_prealloc_thread(timeout=...),
+        # which our PageAllocator binds (the reference's own extension does not, torch_bindings.cpp:212-213)
+        trace = T.random_trace(cfg, 77, n_ops=220, extra=False, p_clear=0.03)
+        assert sum(1 for o in trace["ops"] if o[0] == "clear") >= 3
         want = oracle.replay(trace)
         results = []
         for i, (op, w) in enumerate(zip(trace["ops"], want["records"])):

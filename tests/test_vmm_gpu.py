@@ -373,3 +373,60 @@ def test_per_layer_and_unified_pool_mapping(unified):
         assert vmm_ops.mapped_pages() == [] and int(tens[0][2 * epp + 7]) == 0
     finally:
         vmm_ops.shutdown_kvcached()
+
+
+@pytest.mark.parametrize("cell", [256, 512, 1024])
+@pytest.mark.parametrize("T_tokens", [5, 4096])
+def test_kv_scatter_gather_tp_shard_cells_80_layers(cell, T_tokens):
+    """The per-rank shapes of Llama-3.3-70B under TP 8 / 4 / 2 (BASELINE configs[4]: 80 layers, 1 / 2 / 4 KV heads per
+    rank -> cell 256 / 512 / 1024 B): several cells share a warp in the kernel, so these sizes take other code paths
+    than the 2 KiB cell.  Also: padding slots (-1) move nothing, and per-layer scatter launches == the fused launch."""
+    import torch
+    torch.cuda.init()
+    vmm_ops.init_kvcached("cuda:0", PAGE, True)
+    try:
+        L, bs, blocks = 80, 16, 1024
+        per_layer = -(-blocks * bs * cell * 2 // (2 * PAGE)) * 2 * PAGE
+        ranges = vmm_ops.create_kv_tensors_raw(per_layer, L, 2)
+        tens = vmm_ops.create_kv_tensors(per_layer, 2, "cuda:0", L, 2)
+        m = KVCacheManager(blocks, bs, cell, L)
+        ids = np.asarray(m.alloc(-(-T_tokens // bs) + 2), dtype=np.int64)
+        rng = np.random.default_rng(cell + T_tokens)
+        slots_np = rng.choice((ids[:, None] * bs + np.arange(bs)[None, :]).reshape(-1), size=T_tokens, replace=False)
+        pad = rng.random(T_tokens) < 0.2                      # every fifth token is padding
+        slots_np = np.where(pad, -1, slots_np)
+        slots = torch.from_numpy(slots_np).cuda()
+        live = torch.from_numpy(~pad).cuda()
+        lslots = slots[live]
+        g = torch.Generator(device="cuda").manual_seed(3)
+        k_src = torch.randint(-32768, 32767, (L, T_tokens, cell // 2), dtype=torch.int16, device="cuda", generator=g)
+        v_src = torch.randint(-32768, 32767, (L, T_tokens, cell // 2), dtype=torch.int16, device="cuda", generator=g)
+        lay = kv_ops.layout_vllm_contiguous(ranges[0][0], L, bs, cell, 2)
+        view = tens[0].view(torch.int16).view(-1, L, 2, bs, cell // 2)
+        before = view[ids[0]].clone()
+        kv_ops.kv_scatter(lay, slots, k_src, v_src)
+        torch.cuda.synchronize()
+        for l in (0, 1, 39, 79):
+            assert torch.equal(view[lslots // bs, l, 0, lslots % bs], k_src[l][live])
+            assert torch.equal(view[lslots // bs, l, 1, lslots % bs], v_src[l][live])
+        # every layer at once, bytewise
+        got_k = view[lslots // bs, :, 0, lslots % bs].transpose(0, 1)
+        assert torch.equal(got_k, k_src[:, live])
+        # gather: padding rows stay untouched
+        k_out = torch.full_like(k_src, 7)
+        v_out = torch.full_like(v_src, 7)
+        kv_ops.kv_gather(lay, slots, k_out, v_out)
+        torch.cuda.synchronize()
+        assert torch.equal(k_out[:, live], k_src[:, live]) and torch.equal(v_out[:, live], v_src[:, live])
+        assert bool((k_out[:, ~live] == 7).all()) and bool((v_out[:, ~live] == 7).all())
+        # per-layer scatter launches (the engine's own call shape [T, H, D] per layer) == the fused launch
+        k2, v2 = k_src.flip(1).contiguous(), v_src.flip(1).contiguous()
+        for l in range(L):
+            kv_ops.kv_scatter(lay, slots, k2[l], v2[l], l, l + 1)
+        k_out.zero_(); v_out.zero_()
+        kv_ops.kv_gather(lay, slots, k_out, v_out)
+        torch.cuda.synchronize()
+        assert torch.equal(k_out[:, live], k2[:, live]) and torch.equal(v_out[:, live], v2[:, live])
+        m.close()
+    finally:
+        vmm_ops.shutdown_kvcached()

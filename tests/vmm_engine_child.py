@@ -55,6 +55,7 @@ def setup(total_gib=64, latency_us=0, n_pages=64, layers=4, contiguous=True):
     # zero page: one handle, mapped over every unit, access granted
     units = n_pages * (1 if contiguous else layers * 2)
     assert st["creates"] == 1 and st["maps"] == units and st["access"] == units and st["mappings"] == units
+    vmm_ops.set_retain_max_fraction(1.0)     # the cases below model tiny devices; case_retention_cap tests the cap
     return unit, rngs
 
 
@@ -129,6 +130,45 @@ def case_cancel_and_retention():
     vmm_ops.shutdown_kvcached()
     f = no_violations()
     assert f["handles"] == 0 and f["mappings"] == 0
+
+
+def case_retention_cap():
+    """Retained pages never hold more than the cap (a fraction of the device): the page unmapped at the cap goes back
+    to the zero page at once, and the footprint counters say what is physically held beyond the bookkeeping."""
+    layers = 4
+    unit = PAGE * layers * 2
+    setup(total_gib=100 * unit / (1 << 30), n_pages=200, layers=layers)
+    vmm_ops.set_prefetch(0)
+    vmm_ops.set_retention(600_000)
+    vmm_ops.set_retain_free_fraction(0.0, 0.0)
+    vmm_ops.set_retain_max_fraction(0.10)                   # 10 of 100 units
+    events(range(40), False)
+    vmm_ops.wait_maps()
+    fp = vmm_ops.footprint()
+    assert fp["physical_pages"] == 40 and fp["wanted_pages"] == 40 and fp["retain_cap_pages"] == 10
+    events(range(40), True)
+    vmm_ops.fence()
+    st = no_violations()
+    fp = vmm_ops.footprint()
+    assert vmm_ops.engine_stats()["retained"] == 10 and fp["retained_pages"] == 10
+    assert fp["physical_pages"] == 10 and fp["wanted_pages"] == 0 and fp["peak_overshoot_pages"] >= 10
+    assert st["mappings"] == 200                            # 190 units on the zero page + 10 retained
+    # the FIRST ten pages freed are the ones kept (the FIFO free list hands them out first)
+    events(range(10), False)
+    vmm_ops.wait_maps()
+    assert vmm_ops.engine_stats()["retention_hits"] == 10
+    # lowering the cap hands pages back; strict mode = cap irrelevant, nothing retained
+    events(range(10), True)
+    vmm_ops.set_retain_max_fraction(0.03)
+    vmm_ops.fence()
+    assert vmm_ops.engine_stats()["retained"] == 3
+    vmm_ops.set_retention(0)
+    vmm_ops.fence()
+    fp = vmm_ops.footprint()
+    assert fp["physical_pages"] == 0 and fp["retained_pages"] == 0
+    vmm_ops.shutdown_kvcached()
+    e = no_violations()
+    assert e["handles"] == 0 and e["mappings"] == 0
 
 
 def case_steal_and_reserve():
