@@ -296,13 +296,14 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     value = n_calls * K / (res_ms_total * 1e-3)
 
     # ================= e2e: host buffers every scheduler step + real VMM ================================
-    # Two policies, both through KVCacheManager.run_ops per scheduler step with maps in place when a step returns
-    # and kvb_vmm_fence() inside the timed region:
-    #   strict   KVB200_VMM_RETAIN_MS=0: EVERY page event of the bookkeeping is applied to the device inside the
-    #            timed region (what the reference physically does per free, page_allocator.cpp:264-310, :648-686);
-    #            after the fence the physical mapping equals the bookkeeping's (+ <= 5 pages mapped ahead).  Headline.
-    #   default  retention on (bounded to 10 % of the device): pages the bookkeeping unmapped keep their handle for a
-    #            while, so most events cost no driver call.  Reported beside it with its physical overshoot.
+    # KVCacheManager.run_ops per scheduler step with HOST buffers; maps in place (on every TP rank) when a step returns,
+    # kvb_vmm_fence() inside the timed region.  Two legs:
+    #   e2e (headline)      the library's DEFAULT policy: retention off — EVERY page event of the bookkeeping is applied
+    #                       to the device inside the timed region (what the reference physically does per free,
+    #                       page_allocator.cpp:264-310, :648-686); after the fence the physical mapping equals the
+    #                       bookkeeping's (+ <= 5 pages mapped ahead).  Unmapped handles wait in the bounded pool.
+    #   e2e.with_retention  opt-in KVB200_VMM_RETAIN_MS=2000: unmapped pages keep their handle for a while (<= 10 % of
+    #                       the device), most events cost no driver call; reported with its physical overshoot.
     vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
     per_layer = cfg["num_blocks"] * cfg["block_size"] * cfg["cell_size"] * 2
     ranges = vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
@@ -334,6 +335,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
 
     def e2e_leg(strict: bool) -> dict:
         vmm_ops.set_retention(0.0 if strict else 2000.0)
+        pooled_peak = 0
         vmm_ops.settle()
         barrier()
         times, over_fence, over_peak, ret_peak = [], [], [], []
@@ -357,6 +359,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             dt = time.perf_counter() - t0
             barrier()
             fp = vmm_ops.footprint()
+            pooled_peak = max(pooled_peak, fp["pooled_pages"])
             if it >= W:
                 times.append(dt)
                 over_fence.append(fp["physical_pages"] - fp["wanted_pages"])
@@ -378,7 +381,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                "physical_overshoot_pages_peak_max": max(over_peak),
                "physical_overshoot_pages_peak_mean": sum(over_peak) / len(over_peak),
                "physical_overshoot_gib_peak_max": max(over_peak) * page_gib,
-               "retained_pages_peak_max": max(ret_peak)}
+               "retained_pages_peak_max": max(ret_peak),
+               "pooled_unmapped_handles_pages_after_fence_max": pooled_peak, "pool_cap_pages": fp["pool_cap_pages"]}
         # the PHYSICAL mapping (everything mapped, not only what is wanted) against the bookkeeping
         mapped_now = vmm_ops.mapped_pages()
         phys_now = vmm_ops.vmm_stats()["mapped_pages"]
@@ -399,9 +403,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 assert int(ph.item()) <= 5, "strict mode: a rank holds pages the bookkeeping does not"
         return leg
 
-    e2e_default = e2e_leg(strict=False)
-    e2e_strict = e2e_leg(strict=True)
-    vmm_ops.set_retention(2000.0)
+    e2e_retain = e2e_leg(strict=False)
+    e2e_strict = e2e_leg(strict=True)     # the default policy; last, so the state the later legs see is the default one
     e2e_value = e2e_strict["value"]
     vst = vmm_ops.vmm_stats()
     est = vmm_ops.engine_stats()
@@ -641,17 +644,19 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                         "h2d_bytes_per_step": e2e_strict["h2d_bytes_per_step"],
                         "d2h_bytes_per_step": e2e_strict["d2h_bytes_per_step"],
                         "ms_per_step": e2e_strict["ms_per_step"], "scheduler_steps": len(plan.steps),
-                        "policy": "strict (KVB200_VMM_RETAIN_MS=0): every page event of the bookkeeping is applied to "
-                                  "the device inside the timed region; map-ahead 5 pages",
+                        "policy": "library default (retention off): every page event of the bookkeeping is applied to the "
+                                  "device inside the timed region; map-ahead 5 pages; unmapped handles pooled, <= 10 % "
+                                  "of the device, released after 2 s without a map",
                         "page_events_per_replay": page_events_per_replay,
                         "page_transitions_per_replay": e2e_strict["page_transitions_per_replay"],
                         "driver_ms_per_replay": e2e_strict["driver_ms_per_replay"],
                         "physical_overshoot_pages_after_fence_max": e2e_strict["physical_overshoot_pages_after_fence_max"],
                         "strict": e2e_strict,
-                        "default_policy": dict(e2e_default, policy=(
-                            "retention: pages the bookkeeping unmapped keep their handle until the allocator is quiet "
-                            "for 2 s, never more than 10 % of the device (KVB200_RETAIN_MAX_FRACTION), leaving free the "
-                            "utilisation headroom + 2 % of the device, or 20 % while anybody else's footprint grows")),
+                        "with_retention": dict(e2e_retain, policy=(
+                            "opt-in KVB200_VMM_RETAIN_MS=2000: pages the bookkeeping unmapped keep their handle until the "
+                            "allocator is quiet for 2 s, never more than 10 % of the device (KVB200_RETAIN_MAX_FRACTION), "
+                            "leaving free the utilisation headroom + 2 % of the device, or 20 % while anybody else's "
+                            "footprint grows")),
                         "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"],
                                 "map_ahead_hits": est["prefetch_hits"], "retention_hits": est["retention_hits"],
                                 "page_bytes": vst["page_bytes"]},

@@ -108,15 +108,18 @@ int kvb_vmm_enqueue_page_events(int64_t group_id, const int64_t *events, int64_t
 int kvb_vmm_wait_maps(int64_t group_id);
 int kvb_vmm_fence(int64_t group_id);
 int kvb_vmm_set_async(int64_t group_id, int on);
-/* Retention: a page the bookkeeping unmapped keeps its physical handle mapped until the allocator has been quiet (no
- * map event) for `ms` milliseconds (default KVB200_VMM_RETAIN_MS or 2000; 0 = unmap at once).  Mapped again before
- * that it costs nothing.  It goes back to the
- * zero page and its memory to the device earlier when a map needs a handle that can neither come from the pool nor
- * be created within the KVCACHED_GPU_UTILIZATION headroom (the page retained last goes first: the free page list is
- * a FIFO), when the pool cap is exceeded, under memory pressure and at settle points (trim / clear / resize /
- * kvctl limit, kvb_vmm_settle).  Idle pooled handles above KVB200_POOL_FLOOR (16) are released after the same
- * time.  The reference's hysteresis is count-based: max_reserved_pages stay mapped (page_allocator.cpp:264-310). */
-int kvb_vmm_set_retention_ms(int64_t group_id, double ms);
+/* Retention (OPT-IN; default KVB200_VMM_RETAIN_MS or 0 = off: the physical mapping follows the bookkeeping, a page
+ * unmapped there goes back to the zero page).  With ms > 0 a page the bookkeeping unmapped keeps its physical handle
+ * mapped until the allocator has been quiet (no map event) for `ms` milliseconds; mapped again before that it costs
+ * nothing.  Retained pages never hold more than KVB200_RETAIN_MAX_FRACTION (0.10) of the device, and go back earlier
+ * when a map needs a handle that can neither come from the pool nor be created within the KVCACHED_GPU_UTILIZATION
+ * headroom (the page retained last goes first: the free page list is a FIFO), under memory pressure and at settle
+ * points (trim / clear / resize / kvctl limit, kvb_vmm_settle).
+ * Independently of retention, UNMAPPED handles wait in a pool for the next map instead of cuMemRelease + cuMemCreate
+ * per transition (page.cpp:10-25): at most KVB200_POOL_MAX_FRACTION (0.10) of the device, released after
+ * KVB200_POOL_IDLE_MS (2000) without a map down to KVB200_POOL_FLOOR (16) handles.  The reference's hysteresis is
+ * count-based: max_reserved_pages stay mapped (page_allocator.cpp:264-310) — mirrored exactly in the bookkeeping. */
+int kvb_vmm_set_retention_ms(int64_t group_id, double ms);   /* default: KVB200_VMM_RETAIN_MS or 0 = retention off */
 /* The reserve retained pages must leave free.  While somebody else's footprint on the device is growing (another
  * process, or this process's own allocations) and for 10 s after it last grew: `fraction` of the device (default
  * KVB200_RETAIN_FREE_FRACTION or 0.20) — the VMM thread hands retained pages back (newest first) until it is whole.
@@ -128,11 +131,12 @@ int kvb_vmm_set_retain_free_fraction(int64_t group_id, double fraction, double q
  * cap a page the bookkeeping unmaps goes back to the zero page at once (the newest one — the FIFO free list needs it
  * last).  The reference's count-based equivalent is max_reserved_pages (page_allocator.cpp:264-310). */
 int kvb_vmm_set_retain_max_fraction(int64_t group_id, double fraction);
-/* Physical footprint against the bookkeeping: out6 = {pages physically mapped now (wanted + mapped ahead + retained +
+/* Physical footprint against the bookkeeping: out8 = {pages physically mapped now (wanted + mapped ahead + retained +
  * unmap pending), pages the bookkeeping wants mapped, PEAK of the difference since the previous call, pages retained
- * now, retention cap in pages, peak retained since the previous call}.  KVB200_VMM_RETAIN_MS=0 (strict): the
- * difference is map-ahead pages plus unmaps still queued, and map-ahead pages only after kvb_vmm_fence. */
-int kvb_vmm_footprint(int64_t group_id, int64_t *out6);
+ * now, retention cap in pages, peak retained since the previous call, pages' worth of unmapped handles in the pool,
+ * pool cap in pages}.  With retention off (the default) the difference is map-ahead pages plus unmaps still queued,
+ * and map-ahead pages only after kvb_vmm_fence. */
+int kvb_vmm_footprint(int64_t group_id, int64_t *out8);
 int kvb_vmm_settle(int64_t group_id);
 int64_t kvb_vmm_pending_unmaps(int64_t group_id);
 /* Map-ahead: the step kernel publishes the next pages its free list will hand out; the VMM thread maps up to `depth`
@@ -292,7 +296,11 @@ int64_t kvb_mgr_step(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const int64_t
 /* ---- single-request entry points (the reference's method set) ---------------------------- */
 /* alloc(n): returns n (ids in out), KVB_ST_NONE, KVB_ST_NO_PAGES, or <= KVB_ERR_* - 100 */
 int64_t kvb_mgr_alloc(kvb_mgr *m, int64_t n, int64_t *out, int64_t cap);
+/* free(ids) returns nothing, so it does not wait for its kernel: stream order keeps the sequence, and the launch's
+ * results (counters, page unmaps) are consumed by the next call on this manager — or, when the engine goes idle, by the
+ * VMM thread within 50 ms.  KVB200_ASYNC_FREE=0 makes it wait.  kvb_mgr_sync waits for everything launched so far. */
 int kvb_mgr_free(kvb_mgr *m, const int64_t *ids, int64_t n);
+int kvb_mgr_sync(kvb_mgr *m);
 int kvb_mgr_resize(kvb_mgr *m, int64_t new_mem_size);      /* 1 True, 0 False, KVB_ST_ASSERT */
 int kvb_mgr_trim(kvb_mgr *m);
 int kvb_mgr_try_to_reserve(kvb_mgr *m, int64_t n);         /* 1 / 0 / KVB_ST_NO_PAGES */

@@ -113,6 +113,7 @@ SIGNATURES = {
     "kvb_mgr_step": (i64, [C.c_void_p, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, i64]),
     "kvb_mgr_alloc": (i64, [C.c_void_p, i64, C.c_void_p, i64]),
     "kvb_mgr_free": (C.c_int, [C.c_void_p, C.c_void_p, i64]),
+    "kvb_mgr_sync": (C.c_int, [C.c_void_p]),
     "kvb_mgr_resize": (C.c_int, [C.c_void_p, i64]),
     "kvb_mgr_trim": (C.c_int, [C.c_void_p]),
     "kvb_mgr_try_to_reserve": (C.c_int, [C.c_void_p, i64]),

@@ -136,10 +136,10 @@ int kvb_vmm_set_retain_max_fraction(int64_t group_id, double f) {
   g->set_retain_max_fraction(f);
   return 0;
 }
-int kvb_vmm_footprint(int64_t group_id, int64_t *out6) {
+int kvb_vmm_footprint(int64_t group_id, int64_t *out8) {
   VmmGroup *g = vmm_group(group_id, false);
-  if (!g || !out6) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
-  g->footprint(out6);
+  if (!g || !out8) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  g->footprint(out8);
   return 0;
 }
 int kvb_vmm_set_async(int64_t group_id, int on) {

@@ -129,7 +129,14 @@ struct LaunchArgs {
   int64_t *tp_published;  // header word: records published so far
   int64_t tp_pub;         // record number this launch may write
   int32_t tp_mask, tp_slot_words, tp_flags, tp_pad;
+  // single-request launches (kvb_mgr_alloc / kvb_mgr_free): the request — and up to kInlineIds ids of a free — ride in
+  // the kernel parameters, so the kernel starts without a PCIe read of the host's request buffer
+  int32_t inline_on;      // 0 = requests at `ops`; 1 = inline_op with ids in inline_ids; 2 = inline_op with ids at `ids`
+  int32_t inline_pad;
+  kvb_op inline_op;
+  int64_t inline_ids[256];
 };
+constexpr int kInlineIds = 256;
 
 #ifndef KVB_STEP_THREADS
 #define KVB_STEP_THREADS 512

@@ -1678,7 +1678,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   while (op < a.op_end && !s.misc[MI_STOP]) {
     const int chunk_base = op;
     const int chunk_n = (a.op_end - op) < OPS_CHUNK ? (a.op_end - op) : OPS_CHUNK;
-    if (tid < chunk_n) s.ops[tid] = a.ops[chunk_base + tid];
+    if (tid < chunk_n) s.ops[tid] = a.inline_on ? a.inline_op : a.ops[chunk_base + tid];
     __syncthreads();
     while (op < chunk_base + chunk_n && !s.misc[MI_STOP]) {
       const kvb_op o = s.ops[op - chunk_base];
@@ -1734,7 +1734,8 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           int n = 0;
           if (o.kind == KVB_OP_FREE_IDS) {
             n = o.n;
-            for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j];
+            if (a.inline_on == 1) { for (int j = tid; j < n; j += NT) c.fids[j] = a.inline_ids[j]; }
+            else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
           } else if (o.kind == KVB_OP_FREE_REF) {
             n = gather_refs(c, s, a, o.arg, o.n);
           } else {

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -37,6 +38,16 @@ namespace std { namespace __detail { extern const unsigned long __prime_list[]; 
   } while (0)
 
 namespace kvb { std::atomic<int64_t> g_total_launches{0}; }
+
+constexpr int kFastSlots = 4;
+constexpr int kFastOut = 2048;             // ids one fast alloc can return
+constexpr int kFastIn = 8192;              // ids one fast free can take beyond the inline parameter block
+struct FastSlot {
+  kvb::Summary sum;
+  kvb_res res;
+  int64_t out[kFastOut];
+  int64_t in_ids[kFastIn];
+};
 
 namespace {
 constexpr int kNumPrimes = 256 + 48;   // entries of libstdc++'s __prime_list before the sentinel (64-bit)
@@ -107,6 +118,18 @@ struct kvb_mgr {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::unique_ptr<ShmUsage> shm;   // usage publishing + limit (mem_info_tracker.hpp); null = off
   int64_t shm_publishes = 0;
+  // single-request fast path: a ring of pinned slots; kvb_mgr_free launches and returns, its summary is collected by
+  // the next call (or the VMM thread's idle hook)
+  struct FastSlot *fast = nullptr;         // pinned host, kFastSlots entries
+  kvb_res *d_fast_res = nullptr;           // device scratch the kernel writes before mirroring to the slot
+  int64_t *d_fast_out = nullptr;
+  struct Pending { int64_t seq; int slot; };
+  std::deque<Pending> pending;             // launched, summary not yet consumed (oldest first)
+  int fast_next = 0;
+  bool fast_on = true;                     // KVB200_FAST_PATH=0 disables
+  bool async_free = true;                  // KVB200_ASYNC_FREE=0: kvb_mgr_free waits for its kernel
+  int64_t n_fast = 0, n_async_free = 0;
+  bool in_hook = false;                    // collect_pending runs on the VMM thread (idle hook)
   bool tp_on = false;              // kvb_tp_init attached this manager (rank 0) to the group's TP mailbox
   int tp_flags_next = 0;           // flags of the record the next launch may push (kTpFlagSettle)
   double tp_timeout_ms = 60000.0;
@@ -194,7 +217,8 @@ int apply_events(kvb_mgr *m, const int64_t *ev, int64_t n, bool settle = false) 
   std::lock_guard<std::mutex> lk(g->mu);
   g->set_sync_before_unmap(m->cfg.async_sched != 0);
   int rc = g->enqueue_events(ev, n);
-  if (rc >= 0) rc = (g->async() && !settle) ? g->wait_maps() : (settle ? g->settle() : g->fence());
+  if (rc >= 0 && !(m->in_hook && g->async()))   // the VMM thread's own hook only queues (it cannot wait for itself)
+    rc = (g->async() && !settle) ? g->wait_maps() : (settle ? g->settle() : g->fence());
   m->phys_cached = -1;   // physical memory just changed hands
   return rc < 0 ? rc : 0;
 }
@@ -283,6 +307,141 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
   g_total_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }
+
+
+// What every completed launch owes the host side: the summary becomes the stats cache, its page list goes to the
+// other TP ranks and the VMM engine, usage is published, map-ahead hints are refreshed.
+int after_launch(kvb_mgr *m, const Summary *hs, bool settle) {
+  m->last = *hs;
+  int rc = deliver_events(m, hs, settle);
+  if (rc) return rc;
+  if (m->shm) {   // PageAllocator::update_memory_usage (page_allocator.cpp:688-701), once per launch
+    const int64_t per_page = m->cfg.num_layers * m->P * m->cfg.num_kv_buffers;
+    const int64_t *sc = m->last.sc;
+    m->shm_publishes += m->shm->publish((sc[SC_NTOTAL] - sc[SC_NFREE]) * per_page, sc[SC_RL_SIZE] * per_page);
+  }
+  if (m->cfg.attach_vmm) {
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g && g->created()) {
+      std::lock_guard<std::mutex> lk(g->mu);
+      if (settle) {   // memory goes back on purpose: nothing stays mapped ahead, and earlier queued unmaps settle too
+        g->set_prefetch_hints(nullptr, 0);
+        rc = g->settle();
+        if (rc) return rc;
+      } else {        // map-ahead hints: the pages the free list will hand out next
+        g->set_prefetch_hints(hs->next_free, hs->next_free_n);
+      }
+    }
+  }
+  return 0;
+}
+
+// Wait (spinning on the pinned sequence word the kernel writes last) for launch `want`.
+int wait_seq(kvb_mgr *m, volatile int64_t *vseq, int64_t want) {
+  uint64_t spins = 0;
+  while (*vseq != want) {
+    if ((++spins & 0x3ff) == 0) {   // every ~1k polls make sure the kernel is still alive
+      cudaError_t q = cudaStreamQuery(m->stream);
+      if (q == cudaSuccess) {
+        if (*vseq == want) break;
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        if (*vseq != want) { set_error("step kernel finished without publishing its summary"); return KVB_ERR_STATE; }
+        break;
+      }
+      if (q != cudaErrorNotReady) { set_error("step kernel failed: %s", cudaGetErrorString(q)); return KVB_ERR_CUDA; }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return 0;
+}
+
+// Consume the summaries of launches that returned before their kernel finished (asynchronous frees), oldest first.
+// block = false: only those that have landed already (the VMM thread's idle hook).
+int collect_pending(kvb_mgr *m, bool block = true) {
+  while (!m->pending.empty()) {
+    kvb_mgr::Pending p = m->pending.front();
+    FastSlot *sl = m->fast + p.slot;
+    volatile int64_t *vseq = &sl->sum.seq;
+    if (!block && *vseq != p.seq) return 0;
+    int rc = wait_seq(m, vseq, p.seq);
+    m->pending.pop_front();
+    if (rc) return rc;
+    m->d2h_bytes += (int64_t)(40 * 8 + sl->sum.ev_inline_n * 8 + sizeof(kvb_res) + sl->sum.out_used * 8);
+    rc = after_launch(m, &sl->sum, false);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int fast_init(kvb_mgr *m) {
+  if (m->fast) return 0;
+  CUDA_TRY(cudaHostAlloc((void **)&m->fast, sizeof(FastSlot) * kFastSlots, cudaHostAllocDefault));
+  memset(m->fast, 0, sizeof(FastSlot) * kFastSlots);
+  CUDA_TRY(cudaMalloc((void **)&m->d_fast_res, sizeof(kvb_res) * 2));
+  CUDA_TRY(cudaMalloc((void **)&m->d_fast_out, (size_t)kFastOut * 8));
+  return 0;
+}
+
+// One request, in the kernel parameters.  wait = false (free): returns once the kernel is launched.
+// Returns <0, or 0 with *res filled (wait) / untouched (no wait).
+int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_res *res, int64_t *out, int64_t cap) {
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  int rc = fast_init(m);
+  if (rc) return rc;
+  if ((int)m->pending.size() >= kFastSlots - 1) {   // the slot about to be reused must have been consumed
+    rc = collect_pending(m);
+    if (rc) return rc;
+  }
+  const int slot = m->fast_next;
+  m->fast_next = (m->fast_next + 1) % kFastSlots;
+  FastSlot *sl = m->fast + slot;
+  LaunchArgs a{};
+  a.inline_op = kvb_op{kind, n, 0};
+  if (kind == KVB_OP_FREE_IDS) {
+    if (n <= kInlineIds) {
+      a.inline_on = 1;
+      memcpy(a.inline_ids, ids, (size_t)n * 8);
+    } else {
+      a.inline_on = 2;
+      memcpy(sl->in_ids, ids, (size_t)n * 8);
+      a.ids = sl->in_ids;   // pinned host memory: the kernel reads it over PCIe
+    }
+    m->h2d_bytes += (int64_t)n * 8 + (int64_t)sizeof(kvb_op);
+  } else {
+    a.inline_on = 1;
+    m->h2d_bytes += (int64_t)sizeof(kvb_op);
+  }
+  a.op_begin = 0;
+  a.op_end = 1;
+  a.res = m->d_fast_res;
+  a.out_ids = m->d_fast_out;
+  a.out_cap = kFastOut;
+  a.phys_free = phys_free_pages(m);
+  a.summary = &sl->sum;
+  a.seq = ++m->seq;
+  a.arena_mode = 0;
+  a.host_res = &sl->res;
+  a.host_out = sl->out;
+  a.resize_target = m->shm ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
+  reinterpret_cast<volatile int64_t &>(sl->sum.seq) = 0;
+  int lrc = launch_step(m->st, a, m->stream);
+  if (lrc != 0) { set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); return KVB_ERR_CUDA; }
+  m->launches++;
+  m->n_fast++;
+  g_total_launches.fetch_add(1, std::memory_order_relaxed);
+  m->pending.push_back(kvb_mgr::Pending{a.seq, slot});
+  if (!wait) { m->n_async_free++; return 0; }
+  rc = collect_pending(m);     // earlier frees first, then this launch
+  if (rc) return rc;
+  *res = sl->res;
+  if (out && sl->res.status == KVB_ST_OK && sl->res.n > 0) {
+    if (sl->res.n > cap) { set_error("alloc: caller buffer holds %ld ids, %d returned", (long)cap, sl->res.n); return KVB_ERR_OVERFLOW; }
+    memcpy(out, sl->out + sl->res.off, (size_t)sl->res.n * 8);
+  }
+  return 0;
+}
+
+bool fast_ok(const kvb_mgr *m) { return m->fast_on && !m->tp_on; }
 
 }  // namespace
 
@@ -446,6 +605,21 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
     }
   }
 
+  m->fast_on = env_i64("KVB200_FAST_PATH", 1) != 0;
+  m->async_free = env_i64("KVB200_ASYNC_FREE", 1) != 0;
+  if (c.attach_vmm && vmm_initialized()) {
+    // a free() that returned before its kernel finished leaves its page list to the next manager call; when the
+    // engine goes idle instead, the VMM thread picks it up on its next timer wake-up (<= 50 ms)
+    VmmGroup *g = vmm_group(c.group_id, false);
+    if (g) g->set_idle_hook([m] {
+      if (m->pending.empty() || !m->mu.try_lock()) return;
+      m->in_hook = true;
+      collect_pending(m, false);
+      m->in_hook = false;
+      m->mu.unlock();
+    });
+  }
+
   // _post_init: reserve the null block (kv_cache_manager.py:233-243)
   if (c.reserve_null_block) {
     int64_t id = -1;
@@ -463,12 +637,23 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
 extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
   if (!m) return 0;
   cudaSetDevice(m->dev);
+  if (m->cfg.attach_vmm && vmm_initialized()) {
+    VmmGroup *g = vmm_group(m->cfg.group_id, false);
+    if (g) g->set_idle_hook(nullptr);   // returns once a running hook has finished
+  }
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    collect_pending(m);
+  }
   if (m->stream) cudaStreamSynchronize(m->stream);
   if (m->cfg.attach_vmm && vmm_initialized()) {
     VmmGroup *g = vmm_group(m->cfg.group_id, false);
     if (g && g->created()) g->fence();
   }
   if (m->d_block) cudaFree(m->d_block);
+  if (m->fast) cudaFreeHost(m->fast);
+  if (m->d_fast_res) cudaFree(m->d_fast_res);
+  if (m->d_fast_out) cudaFree(m->d_fast_out);
   if (m->h_in) cudaFreeHost(m->h_in);
   if (m->d_in) cudaFree(m->d_in);
   if (m->h_out) cudaFreeHost(m->h_out);
@@ -497,6 +682,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
                            const kvb_ref *refs, int64_t n_refs, kvb_res *res, int64_t *out_ids, int64_t out_cap) {
   if (n_ops <= 0) return 0;
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t need_out = 0;
   for (int64_t i = 0; i < n_ops; ++i) {
     if (ops[i].kind == KVB_OP_ALLOC && ops[i].n > 0) need_out += ops[i].n;
@@ -632,7 +818,13 @@ static int one_op(kvb_mgr *m, int kind, int32_t n, int64_t arg, const int64_t *i
 extern "C" int64_t kvb_mgr_alloc(kvb_mgr *m, int64_t n, int64_t *out, int64_t cap) {
   if (!m || n < 0 || n > INT32_MAX) { set_error("kvb_mgr_alloc: bad argument"); return KVB_ERR_INVALID - 100; }
   kvb_res r{};
-  int rc = one_op(m, KVB_OP_ALLOC, (int32_t)n, 0, nullptr, 0, &r, out, cap);
+  int rc;
+  if (n <= kFastOut && fast_ok(m)) {   // one request in the kernel parameters, result straight into a pinned slot
+    std::lock_guard<std::mutex> lk(m->mu);
+    rc = fast_op(m, KVB_OP_ALLOC, (int32_t)n, nullptr, true, &r, out, cap);
+  } else {
+    rc = one_op(m, KVB_OP_ALLOC, (int32_t)n, 0, nullptr, 0, &r, out, cap);
+  }
   if (rc) return rc - 100;
   if (r.status == KVB_ST_OK) return r.n;
   return r.status;
@@ -641,6 +833,12 @@ extern "C" int kvb_mgr_free(kvb_mgr *m, const int64_t *ids, int64_t n) {
   if (!m || n < 0 || (n > 0 && !ids)) { set_error("kvb_mgr_free: bad argument"); return KVB_ERR_INVALID; }
   if (n == 0) return 0;   // kv_cache_manager.py:310-311
   kvb_res r{};
+  if (n <= kFastIn && n <= m->f_cap && fast_ok(m)) {
+    // free() returns nothing, so it does not wait for its kernel (stream order keeps the sequence); the launch's
+    // summary — counters, page unmaps — is consumed by the next call on this manager, or by the VMM thread when idle
+    std::lock_guard<std::mutex> lk(m->mu);
+    return fast_op(m, KVB_OP_FREE_IDS, (int32_t)n, ids, !m->async_free, &r, nullptr, 0);
+  }
   return one_op(m, KVB_OP_FREE_IDS, (int32_t)n, 0, ids, n, &r, nullptr, 0);
 }
 extern "C" int kvb_mgr_resize(kvb_mgr *m, int64_t new_mem_size) {
@@ -684,6 +882,7 @@ extern "C" int kvb_mgr_clear(kvb_mgr *m) {
 extern "C" int64_t kvb_mgr_available_size(kvb_mgr *m) {
   if (!m) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   const int64_t *sc = m->last.sc;
   int64_t a = sc[SC_NAB] + sc[SC_NRB];
   if (sc[SC_INSHRINK]) return a;
@@ -695,6 +894,7 @@ extern "C" int64_t kvb_mgr_available_size(kvb_mgr *m) {
 extern "C" int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *o) {
   if (!m || !o) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   const int64_t *sc = m->last.sc;
   o->num_free_pages = sc[SC_NFREE];
   o->num_total_pages = sc[SC_NTOTAL];
@@ -722,9 +922,19 @@ extern "C" int kvb_mgr_get_stats(kvb_mgr *m, kvb_mgr_stats *o) {
   return 0;
 }
 
+// Everything launched so far has completed and its page list has reached the VMM engine (kvb_mgr_free returns before
+// its kernel does).
+extern "C" int kvb_mgr_sync(kvb_mgr *m) {
+  if (!m) return KVB_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(m->mu);
+  if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  return collect_pending(m);
+}
+
 extern "C" int kvb_mgr_set_phys_free_pages(kvb_mgr *m, int64_t n) {
   if (!m) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   m->phys_override = n;
   return 0;
 }
@@ -735,7 +945,9 @@ static int slots_locked(kvb_mgr *m, int kind, const LaunchArgs &sl, int64_t arg,
                         int32_t op_n = 0) {
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   size_t o_res = align_up(sizeof(Summary), 16), o_ids = o_res + 64;
-  int rc = ensure_io(m, sizeof(kvb_op), o_ids + (size_t)arena_cap * 8);
+  int rc = collect_pending(m);
+  if (rc) return rc;
+  rc = ensure_io(m, sizeof(kvb_op), o_ids + (size_t)arena_cap * 8);
   if (rc) return rc;
   kvb_op op{kind, op_n, arg};
   memcpy(m->h_in, &op, sizeof(op));
@@ -851,6 +1063,7 @@ extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops
   if (!m || !ops || n_ops <= 0 || !step_offsets || n_steps <= 0) { set_error("trace_upload: bad argument"); return KVB_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   for (void *p : {(void *)m->t_ops, (void *)m->t_ids, (void *)m->t_refs, (void *)m->t_res, (void *)m->t_out})
     if (p) cudaFree(p);
   m->t_ops = nullptr; m->t_ids = nullptr; m->t_refs = nullptr; m->t_res = nullptr; m->t_out = nullptr;
@@ -874,6 +1087,7 @@ extern "C" int kvb_mgr_trace_reset_cursor(kvb_mgr *m) {
   if (!m) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_OUT_CURSOR, 0, 8, m->stream));
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
   CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -888,6 +1102,7 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
   if (step_begin < 0 || step_end > n_steps || step_begin > step_end) { set_error("trace_run: bad step range"); return KVB_ERR_INVALID; }
   if (steps_per_launch <= 0) steps_per_launch = 1;
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t launches0 = m->launches;
   // events of the whole range accumulate in the device log
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
@@ -922,6 +1137,7 @@ extern "C" int kvb_mgr_trace_results(kvb_mgr *m, kvb_res *res, int64_t n_ops, in
   if (!m || !m->t_ops) { set_error("trace_results: no trace uploaded"); return KVB_ERR_STATE; }
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   if (n_ops > m->t_nops) n_ops = m->t_nops;
   if (res && n_ops > 0) CUDA_TRY(cudaMemcpy(res, m->t_res, (size_t)n_ops * sizeof(kvb_res), cudaMemcpyDeviceToHost));
   int64_t cur = 0;
@@ -948,6 +1164,7 @@ extern "C" int64_t kvb_mgr_dump_list(kvb_mgr *m, int which, int64_t *out, int64_
   if (!m || !out) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   int64_t sc[SC_COUNT];
   CUDA_TRY(cudaMemcpy(sc, m->st.sc, sizeof(sc), cudaMemcpyDeviceToHost));
@@ -1006,6 +1223,7 @@ extern "C" int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t p, int64_t *out,
   if (!m || p < 0 || p >= m->max_pages) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   CUDA_TRY(cudaStreamSynchronize(m->stream));
   int32_t st = 0, cnt = 0, head = 0;
   CUDA_TRY(cudaMemcpy(&st, m->st.pg_state + p, 4, cudaMemcpyDeviceToHost));
@@ -1023,6 +1241,7 @@ extern "C" int64_t kvb_mgr_page_free_blocks(kvb_mgr *m, int64_t p, int64_t *out,
 extern "C" int64_t kvb_mgr_drain_events(kvb_mgr *m, int64_t *out, int64_t cap) {
   if (!m) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t n = (int64_t)m->pending_events.size();
   if (n > cap) return KVB_ERR_OVERFLOW;
   if (n) memcpy(out, m->pending_events.data(), (size_t)n * 8);
@@ -1034,6 +1253,7 @@ extern "C" int kvb_mgr_audit(kvb_mgr *m, int64_t *out4, float *device_ms) {
   if (!m || !out4) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
   g_total_launches.fetch_add(1, std::memory_order_relaxed);
   if (launch_audit(m->st, m->d_scratch + 8, m->stream) != 0) { set_error("audit kernel launch failed: %s", cudaGetErrorString(cudaGetLastError())); return KVB_ERR_CUDA; }
@@ -1146,6 +1366,7 @@ extern "C" int64_t kvb_group_indices_by_page(kvb_mgr *m, const int64_t *ids, int
   if (n > m->f_cap) { set_error("group_indices_by_page: %ld ids exceed the pool's block count", (long)n); return KVB_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   kvb_op op{KVB_OP_FREE_IDS, (int32_t)n, 0};
   size_t b_ops = sizeof(kvb_op), b_ids = (size_t)n * 8;
   size_t o_res = align_up(sizeof(Summary), 16), o_pg = o_res + 64, o_ct = o_pg + b_ids, o_gr = o_ct + b_ids;
@@ -1185,7 +1406,9 @@ extern "C" int kvb_tp_init(const char *name, int rank, int world_size, int64_t g
   if (rank != 0) return tp_open(name, rank, world_size, group_id, false, timeout_ms);
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
-  int rc = tp_open(name, 0, world_size, group_id, direct, timeout_ms);
+  int rc = collect_pending(m);
+  if (rc) return rc;
+  rc = tp_open(name, 0, world_size, group_id, direct, timeout_ms);
   if (rc) return rc;
   TpMailbox *tp = tp_mailbox(group_id);
   m->tp_timeout_ms = timeout_ms;
@@ -1296,6 +1519,7 @@ extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
   if (!m || !dst) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int rc = ensure_io(m, (size_t)kTpWords * 8, 0);
   if (rc) return rc;
   int64_t cursor = 0;
@@ -1311,6 +1535,7 @@ extern "C" int kvb_mgr_tp_export(kvb_mgr *m, uint64_t dst, void *stream) {
 extern "C" int kvb_mgr_tp_export_host(kvb_mgr *m, int64_t *dst) {
   if (!m || !dst) return KVB_ERR_INVALID;
   std::lock_guard<std::mutex> lk(m->mu);
+  { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t cursor = 0;
   const int64_t n = (int64_t)m->pending_events.size();
   int more = kvb_tp_pack(m->seq, m->pending_events.data(), n, &cursor, m->last.next_free, m->last.next_free_n, dst);

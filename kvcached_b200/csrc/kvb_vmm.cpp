@@ -191,8 +191,13 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   {
     // how long an unmapped page keeps its physical handle / an idle handle stays pooled (0 = not at all)
     const char *e = getenv("KVB200_VMM_RETAIN_MS");
-    retention_ms_ = e && *e ? atof(e) : 2000.0;
+    // default 0: the physical mapping follows the bookkeeping (what is unmapped there goes back to the zero page);
+    // retention is an opt-in cache for boxes whose driver round trip is slow
+    retention_ms_ = e && *e ? atof(e) : 0.0;
     if (retention_ms_ < 0) retention_ms_ = 0;
+    const char *pi = getenv("KVB200_POOL_IDLE_MS");
+    pool_idle_ms_ = pi && *pi ? atof(pi) : 2000.0;
+    if (pool_idle_ms_ < 0) pool_idle_ms_ = 0;
     const char *u = getenv("KVCACHED_GPU_UTILIZATION");
     gpu_util_ = u && *u ? atof(u) : 0.95;
     const char *rf = getenv("KVB200_RETAIN_FREE_FRACTION");
@@ -231,7 +236,14 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     // (expire()), all of them when the device runs short (phys_free_pages -> pool_release) or on pool_config.
     const char *e = getenv("KVB200_HANDLE_POOL_PAGES");
     int64_t pages = e ? atoll(e) : -1;
-    if (pages < 0) pages = n_pages_;   // recycle everything; memory goes back on pressure (pool_release) or trim
+    if (pages < 0) {
+      // unmapped handles waiting for the next map: never more than KVB200_POOL_MAX_FRACTION (0.10) of the device —
+      // beyond that an unmap releases its handle (cuMemRelease) like the reference does on every unmap
+      const char *pf = getenv("KVB200_POOL_MAX_FRACTION");
+      double frac = pf && *pf ? atof(pf) : 0.10;
+      pages = n_pages_;
+      if (mem_total_ > 0 && frac >= 0 && frac < 1) pages = std::min<int64_t>(pages, std::max<int64_t>(pool_floor_, (int64_t)(mem_total_ * frac / ((double)unit_ * n_sub_))));
+    }
     pool_cap_pages_ = pages;
   }
   created_ = true;
@@ -323,7 +335,7 @@ void VmmGroup::set_retain_max_fraction(double f) {
   while (n_retained_ > retain_cap_pages() && force_one_retained(true)) {}
   if (async_ && need_unmap_ > 0) ensure_worker(lk);
 }
-void VmmGroup::footprint(int64_t *o) {
+void VmmGroup::footprint(int64_t *o) {   // out8
   Lock lk(qmu_);
   o[0] = n_mapped_;
   o[1] = n_want_;
@@ -331,6 +343,8 @@ void VmmGroup::footprint(int64_t *o) {
   o[3] = n_retained_;
   o[4] = retain_cap_pages();
   o[5] = peak_retained_;
+  o[6] = n_sub_ ? (int64_t)pool_.size() / n_sub_ : 0;
+  o[7] = pool_cap_pages_;
   peak_over_ = n_mapped_ - n_want_;
   peak_retained_ = n_retained_;
 }
@@ -374,7 +388,7 @@ void VmmGroup::expire(double now) {
   }
   // idle pooled handles above the floor go back to the device too (oldest first, a few per wake-up)
   for (int k = 0; k < 8 && (int64_t)pool_.size() > pool_floor_ * n_sub_ &&
-                  now - std::max(pool_.front().t_ms, last_map_ms_) >= retention_ms_; ++k) {
+                  now - std::max(pool_.front().t_ms, last_map_ms_) >= pool_idle_ms_; ++k) {
     g_drv.MemRelease(pool_.front().h);
     pool_.pop_front();
     n_released_++; mem_free_ += (double)unit_;
@@ -575,7 +589,15 @@ void VmmGroup::worker_main() {
     if (stop_ && need_map_ == 0 && need_unmap_ == 0) break;
     if (now_ms() - mem_t_ms_ > 5.0) poll_meminfo(lk);
     expire(now_ms());
-    if (need_map_ == 0 && need_unmap_ == 0 && need_spec_ == 0) continue;   // timer wake-up, nothing due
+    if (need_map_ == 0 && need_unmap_ == 0 && need_spec_ == 0) {   // timer wake-up, nothing due
+      lk.unlock();
+      {
+        std::lock_guard<std::mutex> hk(hook_mu_);
+        if (idle_hook_) idle_hook_();
+      }
+      lk.lock();
+      continue;
+    }
     bool did = process_next(lk);
     cv_done_.notify_all();
     if (!did) {
@@ -592,6 +614,11 @@ void VmmGroup::worker_main() {
   }
   worker_running_ = false;
   cv_done_.notify_all();
+}
+
+void VmmGroup::set_idle_hook(std::function<void()> fn) {
+  std::lock_guard<std::mutex> hk(hook_mu_);
+  idle_hook_ = std::move(fn);
 }
 
 void VmmGroup::set_async(bool on) {

@@ -9,6 +9,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -92,9 +93,10 @@ class VmmGroup {
   // Retained pages never hold more than this fraction of the device (default KVB200_RETAIN_MAX_FRACTION or 0.10): a
   // page unmapped by the bookkeeping while the cap is reached goes back to the zero page at once.
   void set_retain_max_fraction(double f);
-  // out6 = {pages physically mapped (wanted + mapped ahead + retained + unmap pending), pages the bookkeeping wants
-  // mapped, peak of the difference since the last call, pages retained now, retention cap in pages, peak retained}
-  void footprint(int64_t *out6);
+  // out8 = {pages physically mapped (wanted + mapped ahead + retained + unmap pending), pages the bookkeeping wants
+  // mapped, peak of the difference since the last call, pages retained now, retention cap in pages, peak retained,
+  // pages' worth of unmapped handles in the pool, pool cap in pages}
+  void footprint(int64_t *out8);
   int settle();       // fence + every retained page back on the zero page (trim / clear / resize / kvctl limit)
   void set_prefetch_hints(const int64_t *pages, int64_t n);
   void set_prefetch_depth(int depth);
@@ -104,6 +106,10 @@ class VmmGroup {
   bool async() const { return async_; }
   void set_sync_before_unmap(bool on) { sync_before_unmap_ = on; }
   int64_t pending_unmaps();
+  // Called by the VMM thread on its timer wake-ups (<= 50 ms apart) with no engine lock held: the block manager hangs
+  // the collection of launches that returned before their kernel finished (asynchronous frees) on it.
+  // set_idle_hook returns once a hook that is running has finished.
+  void set_idle_hook(std::function<void()> fn);
   // Free / total device memory as last seen by the VMM thread (it polls every few milliseconds while it works and
   // at every idle wake-up, and accounts for its own cuMemCreate / cuMemRelease in between), so that the scheduler
   // thread never enters the driver for available_size().  False if there is no recent sample.
@@ -169,7 +175,7 @@ class VmmGroup {
   struct Retained { int64_t p; uint32_t seq; double t_ms; };
   std::deque<Retained> retained_; // oldest first
   struct PoolEnt { CUmemGenericAllocationHandle h; double t_ms; };
-  double retention_ms_ = 0;
+  double retention_ms_ = 0, pool_idle_ms_ = 2000.0;
   int64_t n_retained_ = 0, n_retention_hits_ = 0, release_debt_ = 0, pool_floor_ = 16;
   int64_t n_want_ = 0, peak_over_ = 0, peak_retained_ = 0;
   double retain_max_frac_ = 0.10;
@@ -183,7 +189,8 @@ class VmmGroup {
   int prefetch_depth_ = 0;
   int64_t need_map_ = 0, need_unmap_ = 0, need_spec_ = 0, n_spec_mapped_ = 0, n_prefetch_hits_ = 0, inflight_ = -1;
   bool inflight_to_mapped_ = false;
-  std::mutex qmu_;
+  std::mutex qmu_, hook_mu_;
+  std::function<void()> idle_hook_;
   std::condition_variable cv_work_, cv_done_;
   std::thread worker_;
   bool worker_running_ = false, stop_ = false, async_ = false, sync_before_unmap_ = false;

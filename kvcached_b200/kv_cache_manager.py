@@ -233,6 +233,11 @@ class KVCacheManager:
         if SANITY_CHECK and self.stats().bad_frees != bad0:
             raise ValueError("free(): some indices were not allocated (state inconsistency)")
 
+    def sync(self) -> None:
+        """free() returns before its kernel does; sync() waits for everything launched so far."""
+        self._wait_post_init()
+        _lib.check(self._lib.kvb_mgr_sync(self._h), "sync")
+
     def try_to_reserve(self, need_size: int) -> bool:
         self._wait_post_init()
         rc = self._lib.kvb_mgr_try_to_reserve(self._h, need_size)

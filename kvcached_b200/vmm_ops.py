@@ -126,10 +126,10 @@ def set_retain_max_fraction(fraction: float, group_id: int = 0) -> None:
 
 def footprint(group_id: int = 0) -> Dict[str, int]:
     """Physical footprint against the bookkeeping (peaks are since the previous call)."""
-    o = np.zeros(6, dtype=np.int64)
+    o = np.zeros(8, dtype=np.int64)
     _lib.check(_lib.load().kvb_vmm_footprint(group_id, o.ctypes.data_as(_lib.p_i64)), "vmm footprint")
     keys = ["physical_pages", "wanted_pages", "peak_overshoot_pages", "retained_pages", "retain_cap_pages",
-            "peak_retained_pages"]
+            "peak_retained_pages", "pooled_pages", "pool_cap_pages"]
     return dict(zip(keys, o.tolist()))
 
 

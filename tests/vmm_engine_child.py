@@ -56,6 +56,7 @@ def setup(total_gib=64, latency_us=0, n_pages=64, layers=4, contiguous=True):
     units = n_pages * (1 if contiguous else layers * 2)
     assert st["creates"] == 1 and st["maps"] == units and st["access"] == units and st["mappings"] == units
     vmm_ops.set_retain_max_fraction(1.0)     # the cases below model tiny devices; case_retention_cap tests the cap
+    lib.kvb_vmm_pool_config(0, n_pages)      # ... and so does the handle pool's default cap (10 % of the device)
     return unit, rngs
 
 
