@@ -20,9 +20,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
-LIB = os.path.join(HERE, "libkvb200.so")
-LIB_TEST = os.path.join(HERE, "libkvb200_test.so")
+# KVB200_BUILD_SUFFIX=_prof KVB200_NVCC_FLAGS=-DKVB_PROFILE builds libkvb200_prof.so beside the product (tuning builds)
+SUFFIX = os.environ.get("KVB200_BUILD_SUFFIX", "")
+OBJ = os.path.join(HERE, "_obj" + SUFFIX)
+LIB = os.path.join(HERE, f"libkvb200{SUFFIX}.so")
+LIB_TEST = os.path.join(HERE, f"libkvb200{SUFFIX}_test.so")
 SOURCES = ["kvb_kernels.cu", "kvb_manager.cpp", "kvb_vmm.cpp", "kvb_capi.cpp", "kvb_shm.cpp", "kvb_tp.cpp"]
 HOOKED = ["kvb_vmm.cpp", "kvb_capi.cpp"]            # recompiled with -DKVB_TEST_HOOKS for the test library
 HEADERS = ["kvb_internal.h", "kvb_vmm.h", "kvb_shm.h", "kvb_tp.h", "kvb_testhooks_mock.inc", "kvb_testhooks_probe.inc",

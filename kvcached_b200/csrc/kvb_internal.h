@@ -132,7 +132,7 @@ struct LaunchArgs {
   // single-request launches (kvb_mgr_alloc / kvb_mgr_free): the request — and up to kInlineIds ids of a free — ride in
   // the kernel parameters, so the kernel starts without a PCIe read of the host's request buffer
   int32_t inline_on;      // 0 = requests at `ops`; 1 = inline_op with ids in inline_ids; 2 = inline_op with ids at `ids`
-  int32_t inline_pad;
+  int32_t out_on_host;    // res / out_ids / summary ARE pinned host memory (single-request path): fence before seq
   kvb_op inline_op;
   int64_t inline_ids[256];
 };

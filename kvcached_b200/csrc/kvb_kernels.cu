@@ -2048,19 +2048,16 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         const int64_t fls = sc[SC_FL_SIZE];
         slot[8 + tid] = tid < fls ? c.fl[(int)((sc[SC_FL_HEAD] + tid) & c.q_mask)] : -1;
       }
-      __threadfence_system();
     }
+    const bool to_host = a.host_res != nullptr || a.out_on_host;
     if (a.host_res) {
-      // zero-copy step: results go straight to the caller's pinned host buffers over PCIe; the
-      // summary's sequence number (written last, after a system-scope fence) is what the host polls.
+      // zero-copy step: results go straight to the caller's pinned host buffers over PCIe
       const kvb_res *dr = a.res + a.op_begin;
       kvb_res *hr = a.host_res + a.op_begin;
       for (int i = tid; i < op - a.op_begin; i += NT) hr[i] = dr[i];
       const int64_t o0 = out_begin, o1 = sc[SC_OUT_CURSOR];
       for (int64_t i = o0 + tid; i < o1; i += NT) a.host_out[i] = a.out_ids[i];
-      __threadfence_system();
     }
-    __syncthreads();
     if (tid == 0) {
       if (tp_push) {
         int64_t *slot = a.tp_ring + (size_t)(a.tp_pub & a.tp_mask) * a.tp_slot_words;
@@ -2070,9 +2067,6 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         slot[3] = 0;                                   // no continuation
         slot[4] = (a.tp_flags & 1) ? 0 : (fls < 16 ? fls : 16);
         slot[5] = a.tp_flags;
-        __threadfence_system();
-        *reinterpret_cast<volatile int64_t *>(slot) = a.tp_pub + 1;   // followers poll this word
-        *reinterpret_cast<volatile int64_t *>(a.tp_published) = a.tp_pub + 1;
       }
       sm->tp_published = tp_push ? 1 : 0;
       sm->ops_done = op - a.op_begin;
@@ -2080,8 +2074,19 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
       sm->n_events = nev;
       sm->ev_begin = ev_begin;
       sm->ev_inline_n = nin;
-      __threadfence_system();
-      sm->seq = a.seq;   // written last: the host may poll it
+    }
+    // ONE system-scope fence per thread after everything it wrote for the host (results, ids, summary, mailbox
+    // slot), then the barrier: when thread 0 passes it, all of that is visible system-wide, and the sequence words
+    // the host / the TP followers poll can follow without a second fence.
+    if (to_host || tp_push) __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      if (tp_push) {
+        int64_t *slot = a.tp_ring + (size_t)(a.tp_pub & a.tp_mask) * a.tp_slot_words;
+        *reinterpret_cast<volatile int64_t *>(slot) = a.tp_pub + 1;   // followers poll this word
+        *reinterpret_cast<volatile int64_t *>(a.tp_published) = a.tp_pub + 1;
+      }
+      *reinterpret_cast<volatile int64_t *>(&sm->seq) = a.seq;        // written last: the host polls it
     }
   }
   KVB_PROF(10);
@@ -2310,58 +2315,93 @@ __global__ void kvb_dump_avail_kernel(DevState c, int64_t *out, int64_t *n_out) 
 }
 
 // ==================================================================================== KV scatter / gather
-// One warp moves one token's K (or V) cell of one layer: cell_bytes contiguous bytes between the
-// dense source [kv][layer][T][cell] and the paged destination
+// Moves token K / V cells between the dense buffers [layer][T][cell] (K and V separately) and the paged range
 //   base + block*stride_block + in_block*stride_token + layer*stride_layer + kv*stride_kv
-// (kvcached/integration/vllm/interfaces.py:281-298, integration/sglang/interfaces.py:132-173).
-// Every lane keeps UNROLL independent 16-byte loads in flight before the first store; loads bypass
-// L1 (streaming, no reuse) and stores are full 128-byte lines.  Grid = persistent CTAs, a multiple
-// of the SM count; work items are (token, layer, kv) cells, token-fastest inside a layer so that a
-// CTA's concurrent source reads are contiguous.
-// `g` lanes (a power of two, chosen by the launcher so that a lane moves ~4 vectors) serve one cell;
-// a warp serves 32/g cells at once, so small cells (TP shards, 256 B) keep every lane busy.
-template <int GATHER>
+// (kvcached/integration/vllm/interfaces.py:281-298, integration/sglang/interfaces.py:132-173).  HBM-bound:
+// 2*cell read + 2*cell written per token and layer, nothing is touched twice.
+//   * `g` lanes (a power of two chosen by the launcher) serve one cell, a warp serves 32/g cells side by side;
+//   * every lane keeps V*U independent 128-bit loads in flight before its first store: V vectors of each of U cells
+//     (2 KiB cell: V=4, U=1 as two passes; 512 B: V=2, U=2; 256 B: V=1, U=4) — with one cell per pass a 256-byte
+//     cell leaves a lane a single load in flight and the kernel waits on latency instead of streaming;
+//   * loads bypass L1 (no reuse), stores are whole 128-byte lines;
+//   * a warp owns a CONTIGUOUS run of the flattened (kv, layer, token) space, token fastest: its dense-side
+//     traffic is one contiguous stream, and (kv, layer, token) advance incrementally — one 64-bit division per
+//     warp instead of three per cell;
+//   * grid = persistent CTAs, SM count x CTAs resident at once.
+// A negative slot is padding and moves nothing.
+template <int GATHER, int V, int U>
 __global__ void __launch_bounds__(256) kvb_kv_copy_kernel(kvb_kv_layout lay, const int64_t *__restrict__ slots,
                                                           int64_t T, unsigned char *kbuf, unsigned char *vbuf,
-                                                          int32_t l0, int32_t l1, int32_t g) {
+                                                          int32_t l0, int32_t l1, int32_t g, int32_t bs_shift, int32_t chunked) {
   const int lane = threadIdx.x & 31;
   const int gl = lane & (g - 1);            // lane inside its group
-  const int cpw = 32 / g;                   // cells per warp
+  const int sub = lane / g;                 // which of the warp's cells this group serves
+  const int cpw = 32 / g;                   // cells per warp and pass
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int nl = l1 - l0;
-  const int64_t cells = T * nl * lay.num_kv;
+  const int64_t items = T * nl * lay.num_kv;
+  const int per_iter = cpw * U;
+  // chunked: a warp owns one contiguous run; strided: pass p of warp w covers cells [(p*nwarps + w) * per_iter, +per_iter)
+  // so that neighbouring warps stream neighbouring addresses at the same time
+  int64_t begin, end, step;
+  if (chunked) {
+    int64_t chunk = (items + nwarps - 1) / nwarps;
+    chunk = (chunk + per_iter - 1) / per_iter * per_iter;
+    begin = warp * chunk;
+    end = begin + chunk < items ? begin + chunk : items;
+    step = per_iter;
+  } else {
+    begin = warp * per_iter;
+    end = items;
+    step = nwarps * per_iter;
+  }
+  if (begin >= items) return;
   const int vec = (int)(lay.cell_bytes >> 4);   // 16-byte vectors per cell
-  for (int64_t it = warp * cpw + lane / g; it < cells; it += nwarps * cpw) {
-    // it = (kv * nl + layer) * T + token
-    int64_t tok = it % T;
-    int64_t rest = it / T;
-    int layer = (int)(rest % nl);
-    int kv = (int)(rest / nl);
-    int64_t slot = slots[tok];
-    if (slot < 0) continue;                   // padding entries (engines pad slot mappings with -1) move nothing
-    int64_t blk = slot / lay.block_size;
-    int inb = (int)(slot - blk * lay.block_size);
-    unsigned char *paged = reinterpret_cast<unsigned char *>(lay.base) + blk * lay.stride_block +
-                           inb * lay.stride_token + (int64_t)(l0 + layer) * lay.stride_layer + kv * lay.stride_kv;
-    unsigned char *dense = (kv ? vbuf : kbuf) + ((int64_t)layer * T + tok) * lay.cell_bytes;
-    const uint4 *src = reinterpret_cast<const uint4 *>(GATHER ? paged : dense);
-    uint4 *dst = reinterpret_cast<uint4 *>(GATHER ? dense : paged);
-    int v = gl;
-    for (; v + 3 * g < vec; v += 4 * g) {
-      uint4 a0 = ld_stream(src + v), a1 = ld_stream(src + v + g), a2 = ld_stream(src + v + 2 * g),
-            a3 = ld_stream(src + v + 3 * g);
-      st_stream(dst + v, a0);
-      st_stream(dst + v + g, a1);
-      st_stream(dst + v + 2 * g, a2);
-      st_stream(dst + v + 3 * g, a3);
+  int64_t lk = begin / T;                       // (kv * nl + layer) of the pass's first cell
+  int64_t tok = begin - lk * T;
+  for (int64_t base = begin; base < end; base += step) {
+    const uint4 *src[U];
+    uint4 *dst[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int off = k * cpw + sub;
+      src[k] = nullptr;
+      dst[k] = nullptr;
+      if (base + off < end) {   // (strided: end = items)
+        int64_t t = tok + off, q = lk;
+        if (t >= T) { const int64_t w = t / T; q += w; t -= w * T; }
+        const int64_t slot = slots[t];
+        if (slot >= 0) {
+          const int kv = (int)(q / nl);
+          const int layer = (int)(q - (int64_t)kv * nl);
+          int64_t blk;
+          int inb;
+          if (bs_shift >= 0) { blk = slot >> bs_shift; inb = (int)(slot & ((1 << bs_shift) - 1)); }
+          else { blk = slot / lay.block_size; inb = (int)(slot - blk * lay.block_size); }
+          unsigned char *paged = reinterpret_cast<unsigned char *>(lay.base) + blk * lay.stride_block +
+                                 inb * lay.stride_token + (int64_t)(l0 + layer) * lay.stride_layer + kv * lay.stride_kv;
+          unsigned char *dense = (kv ? vbuf : kbuf) + ((int64_t)layer * T + t) * lay.cell_bytes;
+          src[k] = reinterpret_cast<const uint4 *>(GATHER ? paged : dense);
+          dst[k] = reinterpret_cast<uint4 *>(GATHER ? dense : paged);
+        }
+      }
     }
-    for (; v + g < vec; v += 2 * g) {
-      uint4 a0 = ld_stream(src + v), a1 = ld_stream(src + v + g);
-      st_stream(dst + v, a0);
-      st_stream(dst + v + g, a1);
+    for (int v0 = gl; v0 < vec; v0 += g * V) {
+      uint4 a[U][V];
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (src[k] && v0 + j * g < vec) a[k][j] = ld_stream(src[k] + v0 + j * g);
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (src[k] && v0 + j * g < vec) st_stream(dst[k] + v0 + j * g, a[k][j]);
     }
-    for (; v < vec; v += g) st_stream(dst + v, ld_stream(src + v));
+    tok += step;
+    if (tok >= T) { const int64_t w = tok / T; lk += w; tok -= w * T; }
   }
 }
 
@@ -2439,31 +2479,50 @@ int launch_dump_avail(const DevState &st, int64_t *d_out, int64_t *d_n, void *st
   return (int)cudaGetLastError();
 }
 
+template <int GATHER, int V, int U>
+static int launch_kv_copy_t(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, void *k, void *v, int32_t l0,
+                            int32_t l1, int g, int bs_shift, int chunked, int64_t cells, void *stream) {
+  static int grid_cache[kMaxDev];
+  int64_t grid = resident_grid(kvb_kv_copy_kernel<GATHER, V, U>, 256, grid_cache);
+  const int64_t want = (cells * g + 255) / 256;   // one group of g lanes per cell
+  if (want < grid) grid = want;
+  kvb_kv_copy_kernel<GATHER, V, U><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      lay, slots, T, (unsigned char *)k, (unsigned char *)v, l0, l1, g, bs_shift, chunked);
+  return (int)cudaGetLastError();
+}
+
 int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, void *k, void *v, int32_t l0,
                    int32_t l1, int gather, void *stream) {
   if (T <= 0 || l1 <= l0) return 0;
-  int64_t cells = T * (int64_t)(l1 - l0) * lay.num_kv;
-  int vec = (int)(lay.cell_bytes >> 4);
+  const int64_t cells = T * (int64_t)(l1 - l0) * lay.num_kv;
+  const int vec = (int)(lay.cell_bytes >> 4);
   // lanes per cell: the largest power of two that leaves every lane 4 vectors, but never fewer than 8 lanes (gather)
   // / 16 lanes (scatter) as long as a lane keeps 2 vectors: a store instruction then writes whole 128-byte lines of a
-  // cell instead of half lines.  Measured per cell size (tools/probe_scatter.py, 80 layers, T = 65 536, TB/s
-  // scatter / gather): 2048 B 5.93 / 5.98, 1024 B 5.84 / 5.90, 512 B 5.45 / 5.73 (was 5.07 / 5.73), 256 B
-  // 5.30 / 5.45 (was 4.29 / 5.19).
+  // cell instead of half lines.
   const int min_lanes = gather ? 8 : 16;
   int g = 32;
   while (g > 1 && g * 4 > vec) g >>= 1;
   while (g < min_lanes && g * 4 <= vec) g <<= 1;   // doubling keeps >= 2 vectors per lane
-  int64_t want = (cells * g + 255) / 256;
-  static int grid_sc[kMaxDev], grid_ga[kMaxDev];
-  int64_t grid = gather ? resident_grid(kvb_kv_copy_kernel<1>, 256, grid_ga) : resident_grid(kvb_kv_copy_kernel<0>, 256, grid_sc);
-  if (want < grid) grid = want;
-  if (gather)
-    kvb_kv_copy_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,
-                                                                            (unsigned char *)v, l0, l1, g);
-  else
-    kvb_kv_copy_kernel<0><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(lay, slots, T, (unsigned char *)k,
-                                                                            (unsigned char *)v, l0, l1, g);
-  return (int)cudaGetLastError();
+  if (g > vec) g = vec >= 1 ? (1 << (31 - __builtin_clz((unsigned)vec))) : 1;   // never more lanes than vectors
+  // vectors per lane and cell, and cells per lane group and pass: V * U loads in flight per lane (KVB200_COPY_MLP: 4 or 8)
+  static int mlp = 0, chunked = 0;
+  if (!mlp) {
+    const char *e = getenv("KVB200_COPY_MLP");
+    const char *o = getenv("KVB200_COPY_ORDER");
+    chunked = (o && o[0] == 'c') ? 1 : 0;
+    mlp = (e && atoi(e) == 8) ? 8 : 4;
+  }
+  const int per_lane = (vec + g - 1) / g;
+  const int V = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+  int bs_shift = -1;
+  if (lay.block_size > 0 && (lay.block_size & (lay.block_size - 1)) == 0) bs_shift = __builtin_ctz((unsigned)lay.block_size);
+#define KVB_COPY(GA, VV, UU) launch_kv_copy_t<GA, VV, UU>(lay, slots, T, k, v, l0, l1, g, bs_shift, chunked, cells, stream)
+#define KVB_COPY_V(GA)                                                                  \
+  (mlp == 8 ? (V == 4 ? KVB_COPY(GA, 4, 2) : V == 2 ? KVB_COPY(GA, 2, 4) : KVB_COPY(GA, 1, 8)) \
+            : (V == 4 ? KVB_COPY(GA, 4, 1) : V == 2 ? KVB_COPY(GA, 2, 2) : KVB_COPY(GA, 1, 4)))
+  return gather ? KVB_COPY_V(1) : KVB_COPY_V(0);
+#undef KVB_COPY_V
+#undef KVB_COPY
 }
 
 }  // namespace kvb

@@ -121,8 +121,6 @@ struct kvb_mgr {
   // single-request fast path: a ring of pinned slots; kvb_mgr_free launches and returns, its summary is collected by
   // the next call (or the VMM thread's idle hook)
   struct FastSlot *fast = nullptr;         // pinned host, kFastSlots entries
-  kvb_res *d_fast_res = nullptr;           // device scratch the kernel writes before mirroring to the slot
-  int64_t *d_fast_out = nullptr;
   struct Pending { int64_t seq; int slot; };
   std::deque<Pending> pending;             // launched, summary not yet consumed (oldest first)
   int fast_next = 0;
@@ -377,8 +375,6 @@ int fast_init(kvb_mgr *m) {
   if (m->fast) return 0;
   CUDA_TRY(cudaHostAlloc((void **)&m->fast, sizeof(FastSlot) * kFastSlots, cudaHostAllocDefault));
   memset(m->fast, 0, sizeof(FastSlot) * kFastSlots);
-  CUDA_TRY(cudaMalloc((void **)&m->d_fast_res, sizeof(kvb_res) * 2));
-  CUDA_TRY(cudaMalloc((void **)&m->d_fast_out, (size_t)kFastOut * 8));
   return 0;
 }
 
@@ -413,15 +409,16 @@ int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_
   }
   a.op_begin = 0;
   a.op_end = 1;
-  a.res = m->d_fast_res;
-  a.out_ids = m->d_fast_out;
+  // results and ids are written by the kernel straight into the pinned slot (plain ALLOC / FREE_IDS never read
+  // them back), index 0 = this request
+  a.res = &sl->res;
+  a.out_ids = sl->out;
   a.out_cap = kFastOut;
+  a.out_on_host = 1;
   a.phys_free = phys_free_pages(m);
   a.summary = &sl->sum;
   a.seq = ++m->seq;
   a.arena_mode = 0;
-  a.host_res = &sl->res;
-  a.host_out = sl->out;
   a.resize_target = m->shm ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
   reinterpret_cast<volatile int64_t &>(sl->sum.seq) = 0;
   int lrc = launch_step(m->st, a, m->stream);
@@ -652,8 +649,6 @@ extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
   }
   if (m->d_block) cudaFree(m->d_block);
   if (m->fast) cudaFreeHost(m->fast);
-  if (m->d_fast_res) cudaFree(m->d_fast_res);
-  if (m->d_fast_out) cudaFree(m->d_fast_out);
   if (m->h_in) cudaFreeHost(m->h_in);
   if (m->d_in) cudaFree(m->d_in);
   if (m->h_out) cudaFreeHost(m->h_out);
