@@ -207,6 +207,133 @@ def reference_main(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------- extra legs (rank 0)
+MICRO_KS = ((1, 3000), (4, 3000), (16, 3000), (64, 2000), (256, 1000))
+
+
+def micro_alloc_free_leg(cfg: dict, local_rank: int, with_reference: bool) -> dict:
+    from kvcached_b200 import replay as R
+    out = {"unit": "us per alloc(k)+free pair", "api": "KVCacheManager.alloc(k) -> list, KVCacheManager.free(list)"}
+    mm = R.manager_from_config(cfg, attach_vmm=False, device_index=local_rank)
+    mm.set_phys_free_pages(1 << 40)
+    for variant in ("churn", "no_churn"):
+        pinned = mm.alloc(1) if variant == "no_churn" else None
+        for kk, iters in MICRO_KS:
+            for _ in range(100):
+                mm.free(mm.alloc(kk))
+            mm.sync()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                mm.free(mm.alloc(kk))
+            mm.sync()
+            out[f"{variant}_k{kk}"] = (time.perf_counter() - t0) / iters * 1e6
+        if pinned:
+            mm.free(pinned)
+    mm.close()
+    if with_reference:
+        try:
+            ops, sections = [], []
+            for variant in ("churn", "no_churn"):
+                if variant == "no_churn":
+                    ops.append(["alloc", 1])
+                for kk, iters in MICRO_KS:
+                    for _ in range(100):
+                        ops.append(["alloc", kk])
+                        ops.append(["free_cat", [len(ops) - 1]])
+                    ops.append(["mark"])
+                    for _ in range(iters):
+                        ops.append(["alloc", kk])
+                        ops.append(["free_cat", [len(ops) - 1]])
+                    ops.append(["mark"])
+                    sections.append((f"{variant}_k{kk}", iters))
+            ref = {}
+            for dev, key in (("cuda:0", "reference_cuda0"), ("cpu", "reference_bookkeeping_only")):
+                o = run_reference({"config": cfg, "ops": ops}, repeats=1, device=dev, prealloc=(dev != "cpu"), timeout=600)
+                mk = o["marks"]
+                ref[key] = {name: (mk[2 * i + 1] - mk[2 * i]) / iters * 1e6 for i, (name, iters) in enumerate(sections)}
+                ref[key]["pinned"] = o.get("pinned")
+            out.update(ref)
+            out["ours_vs_reference_cuda0"] = {name: out[name] / ref["reference_cuda0"][name] for name, _ in sections}
+        except Exception as e:
+            out["reference_error"] = str(e)[:300]
+    return out
+
+
+def per_call_e2e_leg(mgr, tr: dict, n_calls: int, vmm_ops) -> dict:
+    """The decode trace, one alloc()/free() call per request with Python lists in and out (replay.replay_per_op)."""
+    from kvcached_b200 import replay as R
+    times = []
+    for it in range(3):
+        vmm_ops.settle()
+        t0 = time.perf_counter()
+        R.replay_per_op(mgr, tr, snapshots=False)
+        mgr.sync()
+        vmm_ops.fence()
+        times.append(time.perf_counter() - t0)
+    assert mgr.stats().num_inuse_pages == 0
+    dt = sum(times[1:]) / len(times[1:])
+    return {"value": n_calls / dt, "unit": UNIT, "ms_per_replay": dt * 1e3, "replays_s": times,
+            "api": "KVCacheManager.alloc(n) / free(ids) once per request (lists), attach_vmm=True, default policy; "
+                   "free() does not wait for its kernel, alloc() does; fence inside the timed region"}
+
+
+def mla_pin_leg(local_rank: int, with_reference: bool) -> dict:
+    """ElasticBlockPool (prefix-cache pinning on the device, kvcached_b200/block_pool.py) vs the unmodified reference
+    pool over the unmodified reference manager, same scenario, bookkeeping only on both sides (the reference cannot
+    create the 61-layer contiguous tensors: ftensor.cpp:161 asserts that its base address is a multiple of the 122 MiB
+    compound page)."""
+    from kvcached_b200 import pool_trace as PT
+    from kvcached_b200 import trace as T
+    from kvcached_b200.block_pool import ElasticBlockPool
+    from kvcached_b200.kv_cache_manager import KVCacheManager
+    out = {"unit": "pool events/s (arrive / decode / finish / evict / reset of the vLLM-style flow)"}
+    for name, layout, bs, blocks, reqs, pre, suf, dec in (
+            ("page64", "mla_p64", 64, 28 * 400, 1500, (2, 24), (0, 12), (0, 6)),
+            ("page1", "mla_p1", 1, 1820 * 40, 400, (64, 768), (0, 256), (0, 64))):
+        cfg = T.make_config(layout, blocks)
+        cap = 16000 // bs
+        sc = PT.make_scenario(seed=0, n_requests=reqs, n_prefixes=20, zipf_a=1.1, prefix_blocks=pre, suffix_blocks=suf,
+                              decode_blocks=dec, concurrency=32, block_size=bs)
+        pm = KVCacheManager(blocks, bs, cfg["cell_size"], cfg["num_layers"], num_kv_buffers=1, attach_vmm=False,
+                            max_cached_blocks=cap, device_index=local_rank)
+        pm.set_phys_free_pages(1 << 40)
+        pool = ElasticBlockPool(blocks, bs, cfg["cell_size"], cfg["num_layers"], True, num_kv_buffers=1,
+                                max_cached_blocks=cap, kv_cache_manager=pm)
+        t0 = time.perf_counter()
+        recs = PT.drive_pool(pool, sc, lambda p: {})
+        dt = time.perf_counter() - t0
+        row = {"events": len(recs), "ours_events_per_s": len(recs) / dt, "ours_s": dt, "block_size": bs, "cap_blocks": cap,
+               "refused": sum(1 for r in recs if r["r"] == "ERR:ValueError"),
+               "evictable_at_end": len(pool.evictable_ids())}
+        pm.close()
+        if with_reference:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import build_ref
+                env = build_ref.ref_env(cpu_only=not os.path.exists("/dev/nvidiactl"))
+                env["KVCACHED_LOG_LEVEL"] = "ERROR"
+                fix = {"config": dict(cfg, enable_caching=True, max_cached_blocks=cap), "scenario": sc, "timing": True}
+                with tempfile.TemporaryDirectory() as d:
+                    tin, tout = os.path.join(d, "s.json"), os.path.join(d, "o.json")
+                    with open(tin, "w") as f:
+                        json.dump(fix, f)
+                    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_pool_replay.py"), tin, tout],
+                                       env=env, capture_output=True, text=True, timeout=600)
+                    if r.returncode != 0:
+                        raise RuntimeError(r.stderr[-400:])
+                    with open(tout) as f:
+                        o = json.load(f)
+                row["reference_events_per_s"] = o["n_events"] / o["elapsed_s"]
+                row["reference_s"] = o["elapsed_s"]
+                row["same_outcome"] = (o["n_events"] == len(recs) and o["n_errors"] == row["refused"]
+                                       and o["evictable_at_end"] == row["evictable_at_end"])
+                row["ours_vs_reference"] = row["ours_events_per_s"] / row["reference_events_per_s"]
+            except Exception as e:
+                row["reference_error"] = str(e)[:300]
+        out[name] = row
+    return out
+
+
 # --------------------------------------------------------------------------------------- our arm
 def pctl(xs, q):
     xs = sorted(xs)
@@ -578,7 +705,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
 
     # ================= bitmap sweep on a stress size (2^30 blocks = 128 MiB bitmap streams HBM) ===
     sweep = None
-    micro = None
+    micro = per_call = mla_pin = None
     if rank == 0:
         o4 = np.zeros(4)
         o5 = np.zeros(4)
@@ -597,20 +724,16 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else sweep["gbs"] / 6650.0
         else:
             sweep = {"error": _lib.last_error()}
-        # T-micro (benchmarks/bench_alloc/bench_alloc.py:57-62): alloc(k); free(h) pairs through the single-request API
-        micro = {}
-        mm = R.manager_from_config(cfg, attach_vmm=False, device_index=local_rank)
-        mm.set_phys_free_pages(1 << 40)
-        pinned = mm.alloc(1)                                   # no-churn variant: one pinned block keeps the page
-        for kk, iters in ((1, 2000), (16, 2000), (256, 1000)):
-            for _ in range(50):
-                mm.free(mm.alloc_np(kk))
-            t0 = time.perf_counter()
-            for _ in range(iters):
-                mm.free(mm.alloc_np(kk))
-            micro[f"k{kk}_pair_us"] = (time.perf_counter() - t0) / iters * 1e6
-        mm.free(pinned)
-        mm.close()
+        # ---- T-micro (benchmarks/bench_alloc/bench_alloc.py:57-62): alloc(k); free(h) pairs through the single-request
+        # API the unmodified integration patches call, page-churn (pool empty between pairs) and no-churn (one pinned
+        # block keeps the page), the unmodified reference timed beside it in the same run on the same sections.
+        micro = micro_alloc_free_leg(cfg, local_rank, with_reference=not args.no_cpu_baseline)
+        # ---- T-decode-4096 through the PER-CALL API (one alloc()/free() per request, what unmodified patches.py does),
+        # real VMM, default policy; kvb_vmm_fence inside the timed region
+        per_call = per_call_e2e_leg(mgr, tr, n_calls, vmm_ops)
+        # ---- T-mla-pin (BASELINE configs[3]): DeepSeek-V3 MLA latent KV (61 layers, cell 1152 B, one buffer), prefix-cache
+        # pinning with 20 shared prefixes x Zipf(1.1), cap 16 000 tokens, page size 64 and 1
+        mla_pin = mla_pin_leg(local_rank, with_reference=not args.no_cpu_baseline)
     clk = clocks.stop()
 
     peaks = {}
@@ -666,7 +789,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                "kvb_vmm_fence() closes the timed region"},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "map_unmap": map_unmap, "kv_scatter": kv, "kv_scatter_tp_shards_on_one_gpu": shard,
-                "bitmap_sweep": sweep, "micro_alloc_free": micro,
+                "bitmap_sweep": sweep, "micro_alloc_free": micro, "e2e_per_call_api": per_call, "mla_pin": mla_pin,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)

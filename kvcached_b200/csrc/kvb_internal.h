@@ -135,8 +135,22 @@ struct LaunchArgs {
   int32_t out_on_host;    // res / out_ids / summary ARE pinned host memory (single-request path): fence before seq
   kvb_op inline_op;
   int64_t inline_ids[256];
+  // keep_events: the page event log continues from the previous launch (it published nothing: a free() whose summary
+  // is left to the next launch) and this launch reports the log from its start.
+  int32_t keep_events;
+  // Flagged publish of a single-request launch: every 64-bit word of `ll` carries 32 bits of payload and the launch's
+  // 32-bit flag, so the host validates each word on its own and the kernel needs NO system-scope fence between
+  // payload and sequence word (8-byte stores are single-copy atomic over PCIe).  Layout: LlWord below.
+  uint32_t ll_flag;
+  uint64_t *ll;
 };
 constexpr int kInlineIds = 256;
+// 32-bit payload slots of the flagged record (64-bit values take two: lo, hi)
+enum LlWord : int {
+  LL_STATUS = 0, LL_N, LL_AVAIL, LL_AUX = LL_AVAIL + 2, LL_NEV = LL_AUX + 2, LL_NHINT, LL_HINT,
+  LL_SC = LL_HINT + 16, LL_EV = LL_SC + 2 * SC_COUNT, LL_IDS = LL_EV + 2 * 16
+};
+constexpr int kLlEvents = 16;    // page events carried inline (more: the host reads the device log)
 
 #ifndef KVB_STEP_THREADS
 #define KVB_STEP_THREADS 512

@@ -1665,10 +1665,10 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
     sc[SC_PHYS] = a.phys_free;
     sc[SC_LAUNCHES] += 1;
     if (a.arena_mode == 0) sc[SC_OUT_CURSOR] = 0;
-    if (a.arena_mode != 1) sc[SC_NEV] = 0;
+    if (a.arena_mode != 1 && !a.keep_events) sc[SC_NEV] = 0;
   }
   __syncthreads();
-  const int64_t ev_begin = sc[SC_NEV];
+  const int64_t ev_begin = a.keep_events ? 0 : sc[SC_NEV];
   const int64_t out_begin = sc[SC_OUT_CURSOR];
 #ifdef KVB_PROFILE
   if (tid == 0) s.prof_t = clock64();
@@ -2026,6 +2026,39 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   __syncthreads();
   KVB_PROF(9);
   if (tid < SC_COUNT) c.sc[tid] = sc[tid];
+  if (a.ll) {
+    // Single request, flagged publish: payload and flag travel in the same 8-byte store, so no fence orders them.
+    // (res and ids were written to device scratch by the request; the block barrier above made them visible.)
+    const kvb_res r = a.res[a.op_begin];
+    const int64_t nev = sc[SC_NEV] - ev_begin;
+    const int nids = (r.status == KVB_ST_OK && r.n > 0 && sc[SC_OUT_CURSOR] > out_begin) ? (int)(sc[SC_OUT_CURSOR] - out_begin) : 0;
+    const int nevin = nev < kLlEvents ? (int)nev : kLlEvents;
+    const int total = LL_IDS + nids;
+    const uint64_t flag = (uint64_t)a.ll_flag << 32;
+    const int64_t fls = sc[SC_FL_SIZE];
+    for (int wd = tid; wd < total; wd += NT) {
+      uint32_t v = 0;
+      if (wd == LL_STATUS) v = (uint32_t)r.status;
+      else if (wd == LL_N) v = (uint32_t)r.n;
+      else if (wd < LL_AUX) v = (uint32_t)((uint64_t)r.avail >> (32 * (wd - LL_AVAIL)));
+      else if (wd < LL_NEV) v = (uint32_t)((uint64_t)r.aux >> (32 * (wd - LL_AUX)));
+      else if (wd == LL_NEV) v = (uint32_t)nev;
+      else if (wd == LL_NHINT) v = (uint32_t)(fls < 16 ? fls : 16);
+      else if (wd < LL_SC) {
+        const int h = wd - LL_HINT;
+        v = h < fls ? (uint32_t)c.fl[(int)((sc[SC_FL_HEAD] + h) & c.q_mask)] : 0xffffffffu;
+      } else if (wd < LL_EV) {
+        const int q = wd - LL_SC;
+        v = (uint32_t)((uint64_t)sc[q >> 1] >> (32 * (q & 1)));
+      } else if (wd < LL_IDS) {
+        const int q = wd - LL_EV;
+        v = (q >> 1) < nevin ? (uint32_t)((uint64_t)c.ev[ev_begin + (q >> 1)] >> (32 * (q & 1))) : 0u;
+      } else {
+        v = (uint32_t)a.out_ids[out_begin + (wd - LL_IDS)];     // block ids are < 2^31
+      }
+      a.ll[wd] = flag | v;
+    }
+  }
   Summary *sm = a.summary;
   if (sm) {
     int64_t nev = sc[SC_NEV] - ev_begin;
@@ -2504,13 +2537,17 @@ int launch_kv_copy(const kvb_kv_layout &lay, const int64_t *slots, int64_t T, vo
   while (g > 1 && g * 4 > vec) g >>= 1;
   while (g < min_lanes && g * 4 <= vec) g <<= 1;   // doubling keeps >= 2 vectors per lane
   if (g > vec) g = vec >= 1 ? (1 << (31 - __builtin_clz((unsigned)vec))) : 1;   // never more lanes than vectors
-  // vectors per lane and cell, and cells per lane group and pass: V * U loads in flight per lane (KVB200_COPY_MLP: 4 or 8)
+  // vectors per lane and cell, and cells per lane group and pass: V * U loads in flight per lane (KVB200_COPY_MLP: 4 or 8;
+  // KVB200_COPY_ORDER: chunked or strided — tuning switches, the defaults are the measured best)
   static int mlp = 0, chunked = 0;
   if (!mlp) {
     const char *e = getenv("KVB200_COPY_MLP");
     const char *o = getenv("KVB200_COPY_ORDER");
-    chunked = (o && o[0] == 'c') ? 1 : 0;
-    mlp = (e && atoi(e) == 8) ? 8 : 4;
+    // measured on B200 (tools/probe_scatter.py, 80 layers, T = 65 536, scatter GB/s at cell 2048 / 1024 / 512 / 256 B):
+    //   4 loads in flight, strided 6128 / 6038 / 5655 / 5515     chunked 6132 / 6051 / 5683 / 5578
+    //   8 loads in flight, strided 6165 / 5940 / 5584 / 5245     chunked 6215 / 6095 / 6045 / 5835   <- default
+    chunked = (o && o[0] == 's') ? 0 : 1;
+    mlp = (e && atoi(e) == 4) ? 4 : 8;
   }
   const int per_lane = (vec + g - 1) / g;
   const int V = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);

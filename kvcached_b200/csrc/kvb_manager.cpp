@@ -43,10 +43,10 @@ constexpr int kFastSlots = 4;
 constexpr int kFastOut = 2048;             // ids one fast alloc can return
 constexpr int kFastIn = 8192;              // ids one fast free can take beyond the inline parameter block
 struct FastSlot {
-  kvb::Summary sum;
+  kvb::Summary sum;                       // summary-carrying launches (a free of more than kInlineIds ids)
   kvb_res res;
-  int64_t out[kFastOut];
   int64_t in_ids[kFastIn];
+  uint64_t ll[kvb::LL_IDS + kFastOut];    // flagged record of a single-request launch (kvb_internal.h: LlWord)
 };
 
 namespace {
@@ -123,6 +123,10 @@ struct kvb_mgr {
   struct FastSlot *fast = nullptr;         // pinned host, kFastSlots entries
   struct Pending { int64_t seq; int slot; };
   std::deque<Pending> pending;             // launched, summary not yet consumed (oldest first)
+  kvb_res *d_fast_res = nullptr;           // device scratch of single-request launches
+  int64_t *d_fast_out = nullptr;
+  bool log_open = false;                   // silent launches (frees that published nothing) since the last publishing one
+  int silent_count = 0;
   int fast_next = 0;
   bool fast_on = true;                     // KVB200_FAST_PATH=0 disables
   bool async_free = true;                  // KVB200_ASYNC_FREE=0: kvb_mgr_free waits for its kernel
@@ -353,8 +357,11 @@ int wait_seq(kvb_mgr *m, volatile int64_t *vseq, int64_t want) {
   return 0;
 }
 
-// Consume the summaries of launches that returned before their kernel finished (asynchronous frees), oldest first.
-// block = false: only those that have landed already (the VMM thread's idle hook).
+int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_res *res, int64_t *out, int64_t cap);
+
+// Launches that returned before their kernel finished: summary-carrying ones are consumed oldest first; frees that
+// published nothing (log_open) are flushed by one tiny publishing request whose record carries their page events.
+// block = false (the VMM thread's idle hook): summary-carrying launches only if they have landed.
 int collect_pending(kvb_mgr *m, bool block = true) {
   while (!m->pending.empty()) {
     kvb_mgr::Pending p = m->pending.front();
@@ -368,6 +375,11 @@ int collect_pending(kvb_mgr *m, bool block = true) {
     rc = after_launch(m, &sl->sum, false);
     if (rc) return rc;
   }
+  if (m->log_open) {
+    kvb_res r{};
+    int rc = fast_op(m, KVB_OP_AVAIL, 0, nullptr, true, &r, nullptr, 0);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -375,66 +387,142 @@ int fast_init(kvb_mgr *m) {
   if (m->fast) return 0;
   CUDA_TRY(cudaHostAlloc((void **)&m->fast, sizeof(FastSlot) * kFastSlots, cudaHostAllocDefault));
   memset(m->fast, 0, sizeof(FastSlot) * kFastSlots);
+  CUDA_TRY(cudaMalloc((void **)&m->d_fast_res, sizeof(kvb_res) * 2));
+  CUDA_TRY(cudaMalloc((void **)&m->d_fast_out, (size_t)kFastOut * 8));
   return 0;
 }
 
-// One request, in the kernel parameters.  wait = false (free): returns once the kernel is launched.
+// One request, in the kernel parameters.
+//   wait:                 the record comes back as flagged 8-byte words (payload + launch flag in one store, no
+//                         system fence in the kernel); the host validates every word.
+//   !wait, n <= kInlineIds: a free() that publishes NOTHING — its page events stay in the device log, which the
+//                         next publishing launch reports from its start (keep_events).
+//   !wait, larger:        summary-carrying launch, waited for (its ids travel through the slot's pinned buffer).
 // Returns <0, or 0 with *res filled (wait) / untouched (no wait).
 int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_res *res, int64_t *out, int64_t cap) {
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   int rc = fast_init(m);
   if (rc) return rc;
-  if ((int)m->pending.size() >= kFastSlots - 1) {   // the slot about to be reused must have been consumed
-    rc = collect_pending(m);
-    if (rc) return rc;
-  }
+  const bool big_free = kind == KVB_OP_FREE_IDS && n > kInlineIds;
+  if (big_free) wait = true;
+  // the event log of unpublished frees must never come near its capacity
+  if (!wait && m->log_open && (int64_t)m->silent_count * (2 * m->max_pages + 8) > m->st.ev_cap / 2) wait = true;
   const int slot = m->fast_next;
   m->fast_next = (m->fast_next + 1) % kFastSlots;
   FastSlot *sl = m->fast + slot;
   LaunchArgs a{};
   a.inline_op = kvb_op{kind, n, 0};
+  a.inline_on = 1;
   if (kind == KVB_OP_FREE_IDS) {
-    if (n <= kInlineIds) {
-      a.inline_on = 1;
+    if (!big_free) {
       memcpy(a.inline_ids, ids, (size_t)n * 8);
     } else {
       a.inline_on = 2;
       memcpy(sl->in_ids, ids, (size_t)n * 8);
       a.ids = sl->in_ids;   // pinned host memory: the kernel reads it over PCIe
     }
-    m->h2d_bytes += (int64_t)n * 8 + (int64_t)sizeof(kvb_op);
-  } else {
-    a.inline_on = 1;
-    m->h2d_bytes += (int64_t)sizeof(kvb_op);
+    m->h2d_bytes += (int64_t)n * 8;
   }
+  m->h2d_bytes += (int64_t)sizeof(kvb_op);
   a.op_begin = 0;
   a.op_end = 1;
-  // results and ids are written by the kernel straight into the pinned slot (plain ALLOC / FREE_IDS never read
-  // them back), index 0 = this request
-  a.res = &sl->res;
-  a.out_ids = sl->out;
+  a.res = m->d_fast_res;
+  a.out_ids = m->d_fast_out;
   a.out_cap = kFastOut;
-  a.out_on_host = 1;
   a.phys_free = phys_free_pages(m);
-  a.summary = &sl->sum;
   a.seq = ++m->seq;
   a.arena_mode = 0;
+  a.keep_events = m->log_open ? 1 : 0;
   a.resize_target = m->shm ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
-  reinterpret_cast<volatile int64_t &>(sl->sum.seq) = 0;
+  const uint32_t flag = (uint32_t)(a.seq & 0x7fffffff) | 0x80000000u;
+  if (big_free) {
+    a.summary = &sl->sum;
+    a.host_res = &sl->res;
+    reinterpret_cast<volatile int64_t &>(sl->sum.seq) = 0;
+  } else if (wait) {
+    a.ll = sl->ll;
+    a.ll_flag = flag;
+  }
   int lrc = launch_step(m->st, a, m->stream);
   if (lrc != 0) { set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); return KVB_ERR_CUDA; }
   m->launches++;
   m->n_fast++;
   g_total_launches.fetch_add(1, std::memory_order_relaxed);
-  m->pending.push_back(kvb_mgr::Pending{a.seq, slot});
-  if (!wait) { m->n_async_free++; return 0; }
-  rc = collect_pending(m);     // earlier frees first, then this launch
-  if (rc) return rc;
-  *res = sl->res;
-  if (out && sl->res.status == KVB_ST_OK && sl->res.n > 0) {
-    if (sl->res.n > cap) { set_error("alloc: caller buffer holds %ld ids, %d returned", (long)cap, sl->res.n); return KVB_ERR_OVERFLOW; }
-    memcpy(out, sl->out + sl->res.off, (size_t)sl->res.n * 8);
+  if (!wait) {          // silent: nothing to wait for, nothing to read
+    m->log_open = true;
+    m->silent_count++;
+    m->n_async_free++;
+    return 0;
   }
+  m->log_open = false;  // this launch reports the whole log
+  m->silent_count = 0;
+  if (big_free) {
+    rc = wait_seq(m, &sl->sum.seq, a.seq);
+    if (rc) return rc;
+    m->d2h_bytes += (int64_t)(40 * 8 + sl->sum.ev_inline_n * 8 + sizeof(kvb_res));
+    rc = after_launch(m, &sl->sum, false);
+    if (rc) return rc;
+    *res = sl->res;
+    return 0;
+  }
+  // ---- flagged record: word 0 first (with the liveness checks), then every word on its own
+  volatile uint64_t *ll = sl->ll;
+  {
+    uint64_t spins = 0;
+    while ((uint32_t)(ll[0] >> 32) != flag) {
+      if ((++spins & 0x3ff) == 0) {
+        cudaError_t q = cudaStreamQuery(m->stream);
+        if (q == cudaSuccess) {
+          if ((uint32_t)(ll[0] >> 32) == flag) break;
+          CUDA_TRY(cudaStreamSynchronize(m->stream));
+          if ((uint32_t)(ll[0] >> 32) != flag) { set_error("step kernel finished without publishing its record"); return KVB_ERR_STATE; }
+          break;
+        }
+        if (q != cudaErrorNotReady) { set_error("step kernel failed: %s", cudaGetErrorString(q)); return KVB_ERR_CUDA; }
+      }
+    }
+  }
+  auto word = [&](int i) -> uint32_t {
+    uint64_t v = ll[i];
+    uint64_t spins = 0;
+    while ((uint32_t)(v >> 32) != flag) {
+      if ((++spins & 0xfffff) == 0 && cudaStreamQuery(m->stream) != cudaErrorNotReady) {
+        v = ll[i];
+        if ((uint32_t)(v >> 32) == flag) break;
+        return 0xdeadbeefu;   // kernel gone, word never arrived: caught by the status check below
+      }
+      v = ll[i];
+    }
+    return (uint32_t)v;
+  };
+  auto word64 = [&](int i) -> int64_t { return (int64_t)((uint64_t)word(i) | ((uint64_t)word(i + 1) << 32)); };
+  Summary hs{};
+  hs.seq = a.seq;
+  hs.ops_done = 1;
+  kvb_res r{};
+  r.status = (int32_t)word(LL_STATUS);
+  r.n = (int32_t)word(LL_N);
+  r.off = 0;
+  r.avail = word64(LL_AVAIL);
+  r.aux = word64(LL_AUX);
+  hs.n_events = (int64_t)word(LL_NEV);
+  hs.ev_begin = 0;
+  hs.ev_inline_n = std::min<int64_t>(hs.n_events, kLlEvents);
+  for (int i = 0; i < hs.ev_inline_n; ++i) hs.ev_inline[i] = word64(LL_EV + 2 * i);
+  hs.next_free_n = (int64_t)word(LL_NHINT);
+  for (int i = 0; i < 16; ++i) { uint32_t h = word(LL_HINT + i); hs.next_free[i] = h == 0xffffffffu ? -1 : (int64_t)h; }
+  for (int i = 0; i < SC_COUNT; ++i) hs.sc[i] = word64(LL_SC + 2 * i);
+  const int nids = (r.status == KVB_ST_OK && r.n > 0 && kind == KVB_OP_ALLOC) ? r.n : 0;
+  hs.out_used = nids;
+  m->d2h_bytes += (int64_t)(LL_IDS + nids) * 8;
+  if (nids > 0) {
+    if (!out || nids > cap) { set_error("alloc: caller buffer holds %ld ids, %d returned", (long)cap, nids); return KVB_ERR_OVERFLOW; }
+    for (int i = 0; i < nids; ++i) out[i] = (int64_t)word(LL_IDS + i);
+  }
+  if (hs.n_events > hs.ev_inline_n) CUDA_TRY(cudaStreamSynchronize(m->stream));   // the device log is read below
+  rc = after_launch(m, &hs, false);
+  if (rc) return rc;
+  *res = r;
   return 0;
 }
 
@@ -609,7 +697,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
     // engine goes idle instead, the VMM thread picks it up on its next timer wake-up (<= 50 ms)
     VmmGroup *g = vmm_group(c.group_id, false);
     if (g) g->set_idle_hook([m] {
-      if (m->pending.empty() || !m->mu.try_lock()) return;
+      if ((m->pending.empty() && !m->log_open) || !m->mu.try_lock()) return;
       m->in_hook = true;
       collect_pending(m, false);
       m->in_hook = false;
@@ -649,6 +737,8 @@ extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
   }
   if (m->d_block) cudaFree(m->d_block);
   if (m->fast) cudaFreeHost(m->fast);
+  if (m->d_fast_res) cudaFree(m->d_fast_res);
+  if (m->d_fast_out) cudaFree(m->d_fast_out);
   if (m->h_in) cudaFreeHost(m->h_in);
   if (m->d_in) cudaFree(m->d_in);
   if (m->h_out) cudaFreeHost(m->h_out);

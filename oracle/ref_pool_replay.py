@@ -3,7 +3,8 @@
 (kvcached/integration/vllm/patches.py:308-614) sitting on the UNMODIFIED reference KVCacheManager
 ("cpu" device: bookkeeping exact, map/unmap no-ops).
 
-TEST INFRASTRUCTURE ONLY (golden generation).  Own process, oracle/_ref/pkg on PYTHONPATH:
+TEST INFRASTRUCTURE ONLY (golden generation; with "timing": true in the input, the reference side of bench.py's
+T-mla-pin leg).  Own process, oracle/_ref/pkg on PYTHONPATH:
 
     python oracle/ref_pool_replay.py scenario.json out.json
 
@@ -80,8 +81,16 @@ def run(fix: dict) -> dict:
             "ap": list(mgr.avail_pages.keys()),
         }
 
-    out = {"null_block": pool.null_block.block_id, "init": snap(pool),
-           "records": drive_pool(pool, fix["scenario"], snap)}
+    if fix.get("timing"):      # bench.py's T-mla-pin leg: the scenario once, no snapshots, wall time
+        import time
+        t0 = time.perf_counter()
+        recs = drive_pool(pool, fix["scenario"], lambda p: {})
+        out = {"elapsed_s": time.perf_counter() - t0, "n_events": len(recs),
+               "n_errors": sum(1 for r in recs if r["r"] == "ERR:ValueError"),
+               "free_at_end": pool.get_num_free_blocks(), "evictable_at_end": len(pool._evictable_blocks)}
+    else:
+        out = {"null_block": pool.null_block.block_id, "init": snap(pool),
+               "records": drive_pool(pool, fix["scenario"], snap)}
     vmm_ops.shutdown_kvcached()
     return out
 

@@ -19,6 +19,7 @@ Trace format (shared with oracle/oracle.py and kvcached_b200/trace.py):
     ["avail"]               -> int                    kv_cache_manager.py:412
     ["clear"]                                         kv_cache_manager.py:444  (see the note in run())
     ["step"]                scheduler-step boundary (no-op for the reference)
+    ["mark"]                records a timestamp (out["marks"]): section boundaries of bench.py's T-micro leg
 
 After every op a snapshot is recorded: available_size, page counters, the
 avail_pages / full_pages keys in dict order, reserved_blocks, in_shrink and the
@@ -125,13 +126,16 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: in
         elapsed_all.append(elapsed)
     out = {"elapsed_s": elapsed_all[-1], "elapsed_all_s": elapsed_all, "n_calls": n_calls, "n_blocks": n_blocks,
            "null_block": mgr.null_block, "nproc": os.cpu_count(), "device": device,
-           "prealloc": bool(cfg.get("prealloc", False))}
+           "prealloc": bool(cfg.get("prealloc", False)), "marks": MARKS}
     if not timing_only:
         out["records"] = records
     else:
         out["final"] = {"avail": mgr.available_size()}
     vmm_ops.shutdown_kvcached()
     return out
+
+
+MARKS: list = []
 
 
 def _one_pass(trace, mgr, snap, timing_only):
@@ -180,6 +184,8 @@ def _one_pass(trace, mgr, snap, timing_only):
             mgr.clear()
         elif kind == "step":
             pass
+        elif kind == "mark":              # timing aid of bench.py's T-micro leg: a timestamp between trace sections
+            MARKS.append(time.perf_counter())
         else:
             raise ValueError(f"unknown op {op}")
         results.append(r)

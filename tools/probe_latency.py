@@ -42,7 +42,10 @@ for i in range(2000):
 t1 = time.perf_counter()
 for g in got:
     lib.kvb_mgr_free(m._h, g.ctypes.data, 16)
+t2a = time.perf_counter()
+lib.kvb_mgr_sync(m._h)
 t2 = time.perf_counter()
+out["k16_free_host_side_us"] = (t2a - t1) / 2000 * 1e6
 out["k16_alloc_only_us"] = (t1 - t0) / 2000 * 1e6
 out["k16_free_only_us"] = (t2 - t1) / 2000 * 1e6
 out["available_size_us"] = bench(lambda: m.available_size(), 5000)
