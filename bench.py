@@ -334,6 +334,190 @@ def mla_pin_leg(local_rank: int, with_reference: bool) -> dict:
     return out
 
 
+# --------------------------------------------------------------------------------------- T-two-model (C3)
+TWO_MODELS = {"A": ("llama8b", NUM_BLOCKS), "B": ("qwen7b", 192000)}     # Llama-3.1-8B + Qwen2.5-7B (BASELINE configs[2])
+
+
+def _wait_file(path: str, timeout: float = 300.0) -> None:
+    t_end = time.time() + timeout
+    while not os.path.exists(path):
+        if time.time() > t_end:
+            raise TimeoutError(f"timed out waiting for {path}")
+        time.sleep(0.0005)
+
+
+def two_model_worker(role: str, d: str, local_rank: int) -> None:
+    """One engine PROCESS of the co-location scenario (examples/01_simple_two_models of the reference): its own virtual
+    KV tensors, manager, VMM thread and usage segment; the only coupling with the other process is the device's free
+    memory as cudaMemGetInfo reports it (page_allocator.cpp:442-455) — nothing is injected."""
+    import numpy as np
+    import torch
+    from kvcached_b200 import replay as R
+    from kvcached_b200 import trace as T
+    from kvcached_b200 import vmm_ops
+    from kvcached_b200.kv_cache_manager import shm_read
+    torch.cuda.set_device(local_rank)
+    torch.cuda.init()
+    layout, blocks = TWO_MODELS[role]
+    cfg = T.make_config(layout, blocks)
+    vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
+    per_layer = cfg["num_blocks"] * cfg["block_size"] * cfg["cell_size"] * 2
+    vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
+    ipc = f"kvb_two_{os.getpid()}_{role}"
+    mgr = R.manager_from_config(cfg, device_index=local_rank, ipc_name=ipc, publish_shm=True)
+    tr = T.decode_trace(cfg, 2048, seed=1 if role == "A" else 2, target_peak=0.35)
+    ct = R.compile_trace(tr)
+    plan = R.HostStepPlan(ct)
+    out = {"role": role, "layout": layout, "num_blocks": blocks, "ipc_name": mgr.shm_name(), "calls": tr["meta"]["n_ops"],
+           "page_mib": vmm_ops.vmm_stats()["page_bytes"] >> 20}
+    R.replay_host_steps(mgr, plan, keep_results=False)          # warm-up replay, alone-ish
+    vmm_ops.fence()
+    open(os.path.join(d, f"ready_{role}"), "w").close()
+    _wait_file(os.path.join(d, "go1"))
+    # ---- phase 1: both models replay their decode trace at the same time
+    times, nones = [], 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res_all, _held = R.replay_host_steps(mgr, plan, keep_results=True)
+        vmm_ops.fence()
+        times.append(time.perf_counter() - t0)
+        nones += int((res_all["status"] == -1).sum())
+    out["corun_ops_per_s"] = tr["meta"]["n_ops"] * len(times) / sum(times)
+    out["corun_replays_s"] = times
+    out["corun_allocs_refused"] = nones
+    assert mgr.stats().num_inuse_pages == 0
+    # ---- kvctl limit: the parent writes a smaller total into this model's usage segment; the next alloc applies it
+    open(os.path.join(d, f"phase1_{role}"), "w").close()
+    _wait_file(os.path.join(d, f"limited_{role}"))
+    total0 = mgr.stats().num_total_pages
+    ids = mgr.alloc(1)
+    mgr.free(ids)
+    out["limit"] = {"total_pages_before": int(total0), "total_pages_after": int(mgr.stats().num_total_pages),
+                    "segment": shm_read(mgr.shm_name())}
+    open(os.path.join(d, f"limit_seen_{role}"), "w").close()
+    _wait_file(os.path.join(d, f"unlimited_{role}"))
+    ids = mgr.alloc(1)
+    mgr.free(ids)
+    out["limit"]["total_pages_restored"] = int(mgr.stats().num_total_pages)
+    # ---- phase 2: memory freed by A becomes allocatable by B
+    bpp = mgr.stats().blocks_per_page
+    if role == "A":
+        want_pages = int(0.55 * torch.cuda.mem_get_info()[1] / vmm_ops.vmm_stats()["page_bytes"])
+        ids = mgr.alloc_np(want_pages * bpp)
+        assert ids is not None
+        vmm_ops.fence()
+        out["handover"] = {"held_pages": want_pages, "held_gib": want_pages * vmm_ops.vmm_stats()["page_bytes"] / 2**30}
+        open(os.path.join(d, "A_holds"), "w").close()
+        _wait_file(os.path.join(d, "B_polling"))
+        time.sleep(0.3)
+        t0 = time.time()
+        mgr.free(ids)
+        mgr.trim()                   # settle point: every page goes back to the device before trim returns
+        vmm_ops.fence()
+        t1 = time.time()
+        out["handover"].update(t_free_start=t0, t_free_done=t1, free_trim_fence_ms=(t1 - t0) * 1e3)
+        with open(os.path.join(d, "A_freed"), "w") as f:
+            json.dump({"t0": t0, "t1": t1, "pages": want_pages}, f)
+    else:
+        _wait_file(os.path.join(d, "A_holds"))
+        a_before = mgr.available_size()
+        open(os.path.join(d, "B_polling"), "w").close()
+        series = []
+        t_end = time.time() + 60
+        while time.time() < t_end:
+            series.append((time.time(), mgr.available_size()))
+            if os.path.exists(os.path.join(d, "A_freed")) and len(series) > 50 and series[-1][1] == series[-50][1] \
+                    and series[-1][1] > a_before:
+                break
+            time.sleep(0.0002)
+        time.sleep(0.05)
+        with open(os.path.join(d, "A_freed")) as f:
+            af = json.load(f)
+        a_after = mgr.available_size()
+        gained = a_after - a_before
+        t_half = next((t for t, a in series if a >= a_before + 0.5 * gained), None)
+        t_90 = next((t for t, a in series if a >= a_before + 0.9 * gained), None)
+        # ... and B can really take it: allocate (and map) 90 % of what appeared
+        n_take = int(0.9 * gained)
+        t0 = time.perf_counter()
+        ids = mgr.alloc_np(n_take) if n_take > 0 else None
+        vmm_ops.fence()
+        t_alloc = time.perf_counter() - t0
+        out["handover"] = {"available_blocks_before": int(a_before), "available_blocks_after": int(a_after),
+                           "gained_gib": gained / bpp * vmm_ops.vmm_stats()["page_bytes"] / 2**30,
+                           "ms_from_A_free_start_to_half_visible": None if t_half is None else (t_half - af["t0"]) * 1e3,
+                           "ms_from_A_free_start_to_90pct_visible": None if t_90 is None else (t_90 - af["t0"]) * 1e3,
+                           "ms_from_A_free_done_to_90pct_visible": None if t_90 is None else (t_90 - af["t1"]) * 1e3,
+                           "B_alloc_and_map_of_90pct_ok": ids is not None, "B_alloc_and_map_ms": t_alloc * 1e3,
+                           "polls": len(series)}
+        if ids is not None:
+            mgr.free(ids)
+            mgr.trim()
+    with open(os.path.join(d, f"result_{role}.json"), "w") as f:
+        json.dump(out, f)
+    mgr.close()
+    vmm_ops.shutdown_kvcached()
+
+
+def two_model_leg(local_rank: int) -> dict:
+    """T-two-model: two engine processes on ONE GPU, live cudaMemGetInfo, `kvctl limit` through the usage segment, and
+    the time for memory freed by one model to become allocatable by the other (default policy: retention off)."""
+    from kvcached_b200.kv_cache_manager import shm_read, shm_set_limit
+    d = tempfile.mkdtemp(prefix="kvb_two_")
+    procs = {}
+    errs = {}
+    try:
+        for role in ("A", "B"):
+            errs[role] = open(os.path.join(d, f"err_{role}.log"), "w")
+            procs[role] = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--two-model-worker", role, d,
+                                            str(local_rank)], stdout=errs[role], stderr=subprocess.STDOUT)
+
+        def alive_wait(path, timeout=300.0):
+            t_end = time.time() + timeout
+            while not os.path.exists(path):
+                for r, p in procs.items():
+                    if p.poll() not in (None, 0):
+                        raise RuntimeError(f"worker {r} exited {p.returncode}: " + open(os.path.join(d, f"err_{r}.log")).read()[-1500:])
+                if time.time() > t_end:
+                    raise TimeoutError(path)
+                time.sleep(0.01)
+
+        for role in ("A", "B"):
+            alive_wait(os.path.join(d, f"ready_{role}"))
+        open(os.path.join(d, "go1"), "w").close()
+        for role in ("A", "B"):
+            alive_wait(os.path.join(d, f"phase1_{role}"))
+        # kvctl limit (kvcached/cli/utils.py:116-141 writes total_size into the segment): a quarter of the pool, then back
+        import glob
+        for role in ("A", "B"):
+            seg = [os.path.basename(x) for x in glob.glob(f"/dev/shm/kvb_two_{procs[role].pid}_{role}*")]
+            name = seg[0]
+            total = shm_read(name)[0]
+            shm_set_limit(name, total // 4)
+            open(os.path.join(d, f"limited_{role}"), "w").close()
+            alive_wait(os.path.join(d, f"limit_seen_{role}"))
+            shm_set_limit(name, total)
+            open(os.path.join(d, f"unlimited_{role}"), "w").close()
+        for role in ("A", "B"):
+            alive_wait(os.path.join(d, f"result_{role}.json"), timeout=300)
+        out = {}
+        for role in ("A", "B"):
+            with open(os.path.join(d, f"result_{role}.json")) as f:
+                out[role] = json.load(f)
+        for p in procs.values():
+            p.wait(timeout=60)
+        out["coupling"] = "two processes, one GPU; each reads the device's free memory live (VMM thread sample, <= 5 ms old)"
+        return out
+    except Exception as e:
+        return {"error": str(e)[:1500]}
+    finally:
+        for p in procs.values():
+            if p.poll() is None:
+                p.kill()
+        for f in errs.values():
+            f.close()
+
+
 # --------------------------------------------------------------------------------------- our arm
 def pctl(xs, q):
     xs = sorted(xs)
@@ -759,6 +943,13 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                         "(11 KB bitmap, 366 KB rings at this size): no HBM roofline applies"}}
     total_launches = lib.kvb_total_launches() - launches0
 
+    two_model = None
+    if rank == 0 and world == 1 and not args.no_two_model:
+        # the two engine processes need the device: this process lets go of its own mappings first
+        mgr.trim()
+        vmm_ops.settle()
+        torch.cuda.empty_cache()
+        two_model = two_model_leg(local_rank)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": res_ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -790,6 +981,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "map_unmap": map_unmap, "kv_scatter": kv, "kv_scatter_tp_shards_on_one_gpu": shard,
                 "bitmap_sweep": sweep, "micro_alloc_free": micro, "e2e_per_call_api": per_call, "mla_pin": mla_pin,
+                "two_model": two_model,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)
@@ -811,6 +1003,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-two-model", action="store_true")
+    ap.add_argument("--two-model-worker", nargs=3, metavar=("ROLE", "DIR", "LOCAL_RANK"), help=argparse.SUPPRESS)
     ap.add_argument("--ref-replays", type=int, default=3, help="timed replays of the cpu_baseline leg (N=1)")
     ap.add_argument("--tp-transport", default="mailbox", choices=["mailbox", "nccl"],
                     help="N>1: how rank 0's page lists reach the other ranks (mailbox = kernel push into a shared ring; "
@@ -819,6 +1013,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.two_model_worker:
+        role, d, lr = args.two_model_worker
+        two_model_worker(role, d, int(lr))
+        return
     try:
         if args.impl == "reference":
             reference_main(args, rank, world)

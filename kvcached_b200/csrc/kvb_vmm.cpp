@@ -433,7 +433,10 @@ double VmmGroup::reserve_fraction(double now) const {
 
 bool VmmGroup::cached_meminfo(size_t *free_bytes, size_t *total_bytes) {
   Lock lk(qmu_);
-  if (!worker_running_ || now_ms() - mem_t_ms_ > 250.0 || mem_total_ <= 0) return false;
+  // the VMM thread samples every 5 ms while it works but only every 50 ms while idle: an older sample is not served
+  // (the caller then asks the driver itself, at most once per KVB200_MEMINFO_REFRESH_US), so that memory another
+  // process just released is seen within milliseconds
+  if (!worker_running_ || now_ms() - mem_t_ms_ > 10.0 || mem_total_ <= 0) return false;
   *free_bytes = (size_t)(mem_free_ > 0 ? mem_free_ : 0);
   *total_bytes = (size_t)mem_total_;
   return true;
