@@ -334,6 +334,87 @@ def mla_pin_leg(local_rank: int, with_reference: bool) -> dict:
     return out
 
 
+# --------------------------------------------------------------------------------------- init time and the per-layer layout
+def init_and_layout_leg(local_rank: int, cfg: dict, ref_create_s) -> dict:
+    """create_kv_tensors wall time (VA reservation + zero-page init, ftensor.cpp:160-176) for the contiguous and the
+    per-layer layout, eager and background; and page map / unmap of the per-layer layout (64 driver units per page)
+    against the raw driver loop.  The caller has shut the main group down."""
+    import numpy as np
+    from kvcached_b200 import _lib, vmm_ops
+    lib = _lib.load()
+    L = cfg["num_layers"]
+    per_layer_full = cfg["num_blocks"] * cfg["block_size"] * cfg["cell_size"] * 2
+    out = {"reference_contiguous_create_s": ref_create_s}
+
+    def create(contiguous: bool, per_layer: int, background: bool) -> dict:
+        vmm_ops.zero_init_mode(1 if background else 0)
+        vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, contiguous)
+        t0 = time.perf_counter()
+        vmm_ops.create_kv_tensors_raw(per_layer, L, 2)
+        t_create = time.perf_counter() - t0
+        row = {"create_s": t_create, "units": vmm_ops.init_progress()["units"]}
+        if background:
+            # the first pages are usable long before the init is through
+            ids = np.arange(40, 44, dtype=np.int64)
+            t0 = time.perf_counter()
+            _lib.check(lib.kvb_map_pages(0, ids.ctypes.data_as(_lib.p_i64), ids.size), "map_pages")
+            row["first_4_pages_mapped_after_s"] = t_create + time.perf_counter() - t0
+            t0 = time.perf_counter()
+            vmm_ops.wait_init()
+            row["fully_backed_after_s"] = t_create + time.perf_counter() - t0 + row["first_4_pages_mapped_after_s"] - t_create
+            _lib.check(lib.kvb_unmap_pages(0, ids.ctypes.data_as(_lib.p_i64), ids.size), "unmap_pages")
+        row["us_per_unit"] = vmm_ops.init_progress()["init_ms"] * 1e3 / max(row["units"], 1)
+        return row
+
+    try:
+        out["contiguous_eager"] = create(True, per_layer_full, False)
+        vmm_ops.shutdown_kvcached()
+        out["contiguous_background"] = create(True, per_layer_full, True)
+        vmm_ops.shutdown_kvcached()
+        # per-layer: 64 units per page; an eighth of the pool keeps the eager leg at a few seconds (the cost is per unit)
+        pl = per_layer_full // 8 // (2 * PAGE) * (2 * PAGE)
+        out["per_layer_eager_eighth_pool"] = create(False, pl, False)
+        out["per_layer_eager_full_pool_extrapolated_s"] = out["per_layer_eager_eighth_pool"]["create_s"] * per_layer_full / pl
+        # page map / unmap in the per-layer layout vs the raw loop (same 64 driver units per page)
+        mu = {}
+        for n in (1, 8):
+            iters = 10 if n == 1 else 4
+            lib.kvb_vmm_pool_config(0, 64)
+            _lib.check(lib.kvb_vmm_pool_prefill(0, n + 2), "pool_prefill")
+            ids = np.arange(10, 10 + n, dtype=np.int64)
+            p = ids.ctypes.data_as(_lib.p_i64)
+            mm, uu = [], []
+            for i in range(iters + 2):
+                t0 = time.perf_counter()
+                rc_m = lib.kvb_map_pages(0, p, n)
+                t1 = time.perf_counter()
+                rc_u = lib.kvb_unmap_pages(0, p, n)
+                t2 = time.perf_counter()
+                assert rc_m == 1 and rc_u == 1, _lib.last_error()
+                if i >= 2:
+                    mm.append((t1 - t0) * 1e6)
+                    uu.append((t2 - t1) * 1e6)
+            lib.kvb_vmm_pool_config(0, 16)
+            a, b = np.zeros(iters), np.zeros(iters)
+            _lib.check(lib.kvb_vmm_raw_control(0, n, iters, 0, a.ctypes.data_as(_lib.p_f64), b.ctypes.data_as(_lib.p_f64)), "raw")
+            mu[f"n{n}"] = {"map_p50_us": pctl(mm, 0.5), "unmap_p50_us": pctl(uu, 0.5), "raw_map_p50_us": pctl(a.tolist(), 0.5),
+                           "raw_unmap_p50_us": pctl(b.tolist(), 0.5),
+                           "map_plus_unmap_vs_raw": (pctl(mm, 0.5) + pctl(uu, 0.5)) / (pctl(a.tolist(), 0.5) + pctl(b.tolist(), 0.5)),
+                           "driver_units_per_page": 2 * L}
+        out["per_layer_map_unmap"] = mu
+        vmm_ops.shutdown_kvcached()
+        out["per_layer_background_eighth_pool"] = create(False, pl, True)
+        vmm_ops.shutdown_kvcached()
+    except Exception as e:
+        out["error"] = str(e)[:500]
+        try:
+            vmm_ops.shutdown_kvcached()
+        except Exception:
+            pass
+    vmm_ops.zero_init_mode(-1)
+    return out
+
+
 # --------------------------------------------------------------------------------------- T-two-model (C3)
 TWO_MODELS = {"A": ("llama8b", NUM_BLOCKS), "B": ("qwen7b", 192000)}     # Llama-3.1-8B + Qwen2.5-7B (BASELINE configs[2])
 
@@ -546,7 +627,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             out = run_reference(tr, repeats=1 + args.ref_replays, device="cuda:0", prealloc=True, timeout=900)
             el = out["elapsed_all_s"][1:]
             cpu_baseline = {"value": n_calls * len(el) / sum(el), "unit": UNIT, "cores": 2, "kind": "reference",
-                            "replays_s": el,
+                            "replays_s": el, "create_kv_tensors_s": out.get("create_kv_tensors_s"),
                             "sample": f"1 warm-up + {len(el)} timed full replays ({n_calls} calls each) through the "
                                       f"unmodified reference KVCacheManager on cuda:0 (real cuMemMap work, prealloc "
                                       f"thread on = shipping default), {out.get('pinned')}; host has {os.cpu_count()} "
@@ -845,6 +926,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     # ================= the per-rank scatter at the TP shard shapes, on this GPU (ranks do not interact) ==========
     # Llama-3.3-70B: 80 layers, 8 KV heads sharded over TP ranks -> cell 2048 / 1024 / 512 / 256 B (BASELINE configs[4])
     shard = None
+    init_leg = None
     if rank == 0 and world == 1:
         shard = {}
         mgr.close()
@@ -882,6 +964,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             ms_.close()
             vmm_ops.shutdown_kvcached()
             torch.cuda.empty_cache()
+        init_leg = init_and_layout_leg(local_rank, cfg, (cpu_baseline or {}).get("create_kv_tensors_s"))
         # the rest of the bench needs the original group again
         vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
         vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
@@ -981,7 +1064,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "map_unmap": map_unmap, "kv_scatter": kv, "kv_scatter_tp_shards_on_one_gpu": shard,
                 "bitmap_sweep": sweep, "micro_alloc_free": micro, "e2e_per_call_api": per_call, "mla_pin": mla_pin,
-                "two_model": two_model,
+                "two_model": two_model, "init_and_layout": init_leg,
                 "ops_per_replay": n_calls, "scheduler_steps": int(n_sched_steps),
                 "resident_launches_per_replay": int(resident_launches)}
         print(json.dumps(line), flush=True)

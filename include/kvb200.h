@@ -79,6 +79,18 @@ int kvb_contiguous_layout(void);
 int kvb_create_kv_tensors(int64_t group_id, int64_t size_per_layer, int64_t num_layers,
                           int64_t num_kv_buffers, int unified_pool,
                           uint64_t *out_ptrs, int64_t *out_bytes, int cap);
+/* Zero-page init.  Eager (default, like ftensor.cpp:160-176): every unit of the range is on the zero page when
+ * kvb_create_kv_tensors returns — one cuMemMap + cuMemSetAccess per unit, 0.3 s for the contiguous Llama-8B pool
+ * here, ~17 s for its per-layer layout (91 520 units; the reference measures 0.6-2 s on GB10, bench_layout/README.md:75).
+ * Background (kvb_vmm_zero_init_mode(1) or KVB200_VMM_ZERO_INIT=background, before create): create backs unit 0 only
+ * and returns; the group's VMM thread backs the rest in its idle time (while the engine loads weights), pages the
+ * bookkeeping maps meanwhile go straight to their handle.  Unbacked, unmapped units FAULT if touched, so the
+ * reference's "stray accesses never fault" guarantee holds from kvb_vmm_wait_init() on.
+ * kvb_vmm_zero_init_mode: -1 = follow the environment, 0 eager, 1 background; returns the previous mode.
+ * kvb_vmm_init_progress out3 = {units done, units, microseconds spent in init}. */
+int kvb_vmm_zero_init_mode(int mode);
+int kvb_vmm_wait_init(int64_t group_id);
+int kvb_vmm_init_progress(int64_t group_id, int64_t *out3);
 /* kv_tensors_created(group_id) — torch_bindings.cpp:42-46; returns 1/0 */
 int kvb_kv_tensors_created(int64_t group_id);
 

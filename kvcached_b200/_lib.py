@@ -95,6 +95,9 @@ SIGNATURES = {
     "kvb_vmm_set_retain_free_fraction": (C.c_int, [i64, f64, f64]),
     "kvb_vmm_set_retain_max_fraction": (C.c_int, [i64, f64]),
     "kvb_vmm_footprint": (C.c_int, [i64, p_i64]),
+    "kvb_vmm_zero_init_mode": (C.c_int, [C.c_int]),
+    "kvb_vmm_wait_init": (C.c_int, [i64]),
+    "kvb_vmm_init_progress": (C.c_int, [i64, p_i64]),
     "kvb_vmm_pending_unmaps": (i64, [i64]),
     "kvb_vmm_prefetch_config": (C.c_int, [i64, C.c_int]),
     "kvb_vmm_set_prefetch_hints": (C.c_int, [i64, p_i64, i64]),

@@ -136,6 +136,22 @@ int kvb_vmm_set_retain_max_fraction(int64_t group_id, double f) {
   g->set_retain_max_fraction(f);
   return 0;
 }
+int kvb_vmm_zero_init_mode(int mode) {
+  int old = g_zero_init_mode.load();
+  if (mode >= -1 && mode <= 1) g_zero_init_mode.store(mode);
+  return old;
+}
+int kvb_vmm_wait_init(int64_t group_id) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  return g->wait_init();
+}
+int kvb_vmm_init_progress(int64_t group_id, int64_t *out3) {
+  VmmGroup *g = vmm_group(group_id, false);
+  if (!g || !out3) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }
+  g->init_progress(out3);
+  return 0;
+}
 int kvb_vmm_footprint(int64_t group_id, int64_t *out8) {
   VmmGroup *g = vmm_group(group_id, false);
   if (!g || !out8) { set_error("group %ld does not exist", (long)group_id); return KVB_ERR_STATE; }

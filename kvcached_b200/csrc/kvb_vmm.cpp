@@ -91,6 +91,7 @@ static constexpr int KVB_ERR_STATE_ = -3;
 // The reference reserves at 0x1f0_0000_0000 + running offset (ftensor.cpp:26-47, constants.hpp).  We
 // hint at a different window so both libraries can live in one process.
 static constexpr uint64_t kVaHint = 0x2f0000000000ull;
+std::atomic<int> g_zero_init_mode{-1};   // -1 env KVB200_VMM_ZERO_INIT, 0 eager, 1 background
 static std::atomic<size_t> g_va_off{0};
 
 // ------------------------------------------------------------------------------------------ group
@@ -100,7 +101,12 @@ VmmGroup::~VmmGroup() {
   if (!d) return;
   if (!mock::installed) cudaSetDevice(dev_);
   if (va_base_) {
-    d->MemUnmap(va_base_, va_bytes_);      // tolerate stale mappings at teardown (ftensor.cpp:78-98)
+    if (init_next_ >= n_units_ || n_units_ == 0) {
+      d->MemUnmap(va_base_, va_bytes_);      // tolerate stale mappings at teardown (ftensor.cpp:78-98)
+    } else {                                  // background init was cut short: only backed units can be unmapped
+      for (int64_t u = 0; u < n_units_; ++u)
+        if (zero_ok_[(size_t)u]) d->MemUnmap(sub_addr(u / n_sub_, (int)(u % n_sub_)), unit_);
+    }
     d->MemAddressFree(va_base_, va_bytes_);
   }
   for (auto h : handles_)
@@ -171,14 +177,31 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   CU_TRY(d->MemCreate(&zero_, unit_, &prop_, 0));
   have_zero_ = true;
   n_created_++;
-  for (auto &r : ranges_) {
-    for (size_t off = 0; off + unit_ <= r.bytes; off += unit_) {
-      CU_TRY(d->MemMap(r.base + off, unit_, 0, zero_, 0));
-      CU_TRY(d->MemSetAccess(r.base + off, unit_, &access_, 1));
-    }
+  // Eager (default, like the reference): every unit is on the zero page when create returns — one cuMemMap + one
+  // cuMemSetAccess per unit (a range call over many mappings costs MORE per unit on this driver, tools/vmm_stall2.cu).
+  // Background (KVB200_VMM_ZERO_INIT=background / kvb_vmm_zero_init_mode(1)): only unit 0 is mapped here, the VMM
+  // thread backs the rest in its idle time; pages the bookkeeping maps meanwhile go straight to their handle.  The
+  // "stray accesses never fault" guarantee (ftensor.cpp:134) then holds from kvb_vmm_wait_init() on.
+  n_units_ = n_pages_ * n_sub_;
+  zero_ok_.assign((size_t)n_units_, 0);
+  {
+    const char *zi = getenv("KVB200_VMM_ZERO_INIT");
+    int mode = g_zero_init_mode.load();
+    if (mode < 0) mode = (zi && (zi[0] == 'b' || zi[0] == 'B')) ? 1 : 0;
+    bg_init_ = mode == 1;
   }
+  const auto t_init0 = std::chrono::steady_clock::now();
+  const int64_t eager_units = bg_init_ ? 1 : n_units_;
+  for (int64_t u = 0; u < eager_units; ++u) {
+    CUdeviceptr a = sub_addr(u / n_sub_, (int)(u % n_sub_));
+    CU_TRY(d->MemMap(a, unit_, 0, zero_, 0));
+    CU_TRY(d->MemSetAccess(a, unit_, &access_, 1));
+    zero_ok_[(size_t)u] = 1;
+  }
+  init_next_ = eager_units;
+  init_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init0).count();
   // the zero page must read as zeros
-  if (!mock::installed && (cudaMemset((void *)ranges_[0].base, 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
+  if (!mock::installed && (cudaMemset((void *)sub_addr(0, 0), 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
     set_error("zero page memset failed: %s", cudaGetErrorString(cudaGetLastError()));
     return KVB_ERR_CUDA_;
   }
@@ -230,6 +253,17 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     const char *e = getenv("KVB200_VMM_ASYNC");
     async_ = !(e && e[0] == '0');
   }
+  if (init_next_ < n_units_) {   // background init needs the VMM thread
+    if (!async_) {
+      for (int64_t u = init_next_; u < n_units_; ++u) {
+        CUdeviceptr a = sub_addr(u / n_sub_, (int)(u % n_sub_));
+        CU_TRY(d->MemMap(a, unit_, 0, zero_, 0));
+        CU_TRY(d->MemSetAccess(a, unit_, &access_, 1));
+        zero_ok_[(size_t)u] = 1;
+      }
+      init_next_ = n_units_;
+    }
+  }
   if (pool_cap_pages_ < 0) {
     // Physical handles are recycled rather than released per unmap (page.cpp:10-25 creates and releases one per map):
     // the pool cap bounds idle + retained handles; idle ones go back to the device after the retention time
@@ -247,6 +281,10 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
     pool_cap_pages_ = pages;
   }
   created_ = true;
+  if (init_next_ < n_units_) {
+    Lock lk(qmu_);
+    ensure_worker(lk);
+  }
   return (int)ranges_.size();
 }
 
@@ -492,10 +530,10 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   int done = 0;
   for (int s = 0; s < n_sub_ && !rc; ++s) {
     CUdeviceptr a = sub_addr(p, s);
-    CU_TIMED_L(2, g_drv.MemUnmap(a, unit_));
+    if (zero_ok_[(size_t)p * n_sub_ + s]) { CU_TIMED_L(2, g_drv.MemUnmap(a, unit_)); }   // (background init: not backed yet)
     CU_TIMED_L(3, g_drv.MemMap(a, unit_, 0, to_mapped ? hs[(size_t)s] : zero_, 0));
     CU_TIMED_L(4, g_drv.MemSetAccess(a, unit_, &access_, 1));
-    if (!rc) done++;
+    if (!rc) { done++; zero_ok_[(size_t)p * n_sub_ + s] = 1; }
   }
   if (rc && to_mapped) {
     // a map that failed half way (per-layer layout): the units already switched go back to the zero page, so that
@@ -588,10 +626,15 @@ void VmmGroup::worker_main() {
   Lock lk(qmu_);
   while (true) {
     cv_work_.wait_for(lk, std::chrono::milliseconds(50),
-                      [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0 || need_spec_ > 0; });
+                      [&] { return stop_ || need_map_ > 0 || need_unmap_ > 0 || need_spec_ > 0 || init_next_ < n_units_; });
     if (stop_ && need_map_ == 0 && need_unmap_ == 0) break;
     if (now_ms() - mem_t_ms_ > 5.0) poll_meminfo(lk);
     expire(now_ms());
+    if (need_map_ == 0 && need_unmap_ == 0 && need_spec_ == 0 && init_next_ < n_units_ && !stop_) {
+      init_some(lk);      // background zero-page init: a few units, then look for real work again
+      cv_done_.notify_all();
+      continue;
+    }
     if (need_map_ == 0 && need_unmap_ == 0 && need_spec_ == 0) {   // timer wake-up, nothing due
       lk.unlock();
       {
@@ -617,6 +660,46 @@ void VmmGroup::worker_main() {
   }
   worker_running_ = false;
   cv_done_.notify_all();
+}
+
+// Background zero-page init (VMM thread, idle time): up to 16 units per call, lock released around the driver calls.
+// Units the bookkeeping mapped meanwhile are skipped (they hold their handle; their unmap puts them on the zero page).
+void VmmGroup::init_some(Lock &lk) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int k = 0; k < 16 && init_next_ < n_units_ && need_map_ == 0; ++k) {
+    const int64_t u = init_next_;
+    if (!zero_ok_[(size_t)u]) {
+      const CUdeviceptr a = sub_addr(u / n_sub_, (int)(u % n_sub_));
+      lk.unlock();
+      CUresult r = g_drv.MemMap(a, unit_, 0, zero_, 0);
+      if (r == CUDA_SUCCESS) r = g_drv.MemSetAccess(a, unit_, &access_, 1);
+      lk.lock();
+      if (r != CUDA_SUCCESS) {
+        if (!werr_) { werr_ = KVB_ERR_CUDA_; werr_msg_ = std::string("zero-page init failed: ") + cu_str(r); }
+        init_next_ = n_units_;
+        return;
+      }
+      zero_ok_[(size_t)u] = 1;
+    }
+    init_next_ = u + 1;
+  }
+  init_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int VmmGroup::wait_init() {
+  if (!created_) return 0;
+  Lock lk(qmu_);
+  if (init_next_ >= n_units_) return 0;
+  ensure_worker(lk);
+  cv_done_.wait(lk, [&] { return init_next_ >= n_units_ || werr_; });
+  return werr_ ? werr_ : 0;
+}
+
+void VmmGroup::init_progress(int64_t *out3) {
+  Lock lk(qmu_);
+  out3[0] = init_next_;
+  out3[1] = n_units_;
+  out3[2] = (int64_t)(init_ms_ * 1000.0);
 }
 
 void VmmGroup::set_idle_hook(std::function<void()> fn) {

@@ -6,6 +6,8 @@
 
 #include <cuda.h>
 
+#include <atomic>
+
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -106,6 +108,10 @@ class VmmGroup {
   bool async() const { return async_; }
   void set_sync_before_unmap(bool on) { sync_before_unmap_ = on; }
   int64_t pending_unmaps();
+  // Zero-page init (ftensor.cpp:160-176 does it eagerly: 0.6-2 s at start-up, bench_layout/README.md:75).  Background
+  // mode: create() backs unit 0 only, the VMM thread the rest in its idle time; wait_init() = every unit is backed.
+  int wait_init();
+  void init_progress(int64_t *out3);   // {units backed or skipped so far, units, microseconds spent in init}
   // Called by the VMM thread on its timer wake-ups (<= 50 ms apart) with no engine lock held: the block manager hangs
   // the collection of launches that returned before their kernel finished (asynchronous frees) on it.
   // set_idle_hook returns once a hook that is running has finished.
@@ -148,6 +154,7 @@ class VmmGroup {
   void ensure_worker(Lock &lk);
   int drain(Lock &lk, bool maps_only);
   void worker_main();
+  void init_some(Lock &lk);
   void stop_worker();
   CUdeviceptr sub_addr(int64_t p, int sub) const;
 
@@ -167,6 +174,10 @@ class VmmGroup {
   CUmemGenericAllocationHandle zero_ = 0;
   bool have_zero_ = false;
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
+  std::vector<uint8_t> zero_ok_;  // per unit: the VA unit has a mapping (zero page or handle)
+  int64_t n_units_ = 0, init_next_ = 0;
+  bool bg_init_ = false;
+  double init_ms_ = 0;
   std::vector<uint8_t> mapped_;   // physical state
   std::vector<uint8_t> want_;     // state after every event received so far
   std::vector<uint8_t> spec_;     // hinted: map ahead of the event
@@ -206,6 +217,7 @@ class VmmGroup {
   int64_t n_mapped_ = 0, n_created_ = 0, n_released_ = 0, n_map_calls_ = 0, n_unmap_calls_ = 0;
 };
 
+extern std::atomic<int> g_zero_init_mode;
 // process-global registry (FTensorAllocator::init / global_allocator / shutdown, allocator.cpp:72-119)
 int vmm_init(int dev, int64_t page_size, bool contiguous);
 int vmm_shutdown();

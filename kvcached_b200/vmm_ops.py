@@ -133,6 +133,22 @@ def footprint(group_id: int = 0) -> Dict[str, int]:
     return dict(zip(keys, o.tolist()))
 
 
+def zero_init_mode(mode: int) -> int:
+    """-1 follow KVB200_VMM_ZERO_INIT, 0 eager (default), 1 background; call before create_kv_tensors.  Returns the old mode."""
+    return int(_lib.load().kvb_vmm_zero_init_mode(int(mode)))
+
+
+def wait_init(group_id: int = 0) -> None:
+    """Background zero-page init: returns when every unit of the range is backed."""
+    _lib.check(_lib.load().kvb_vmm_wait_init(group_id), "vmm wait_init")
+
+
+def init_progress(group_id: int = 0) -> Dict[str, float]:
+    o = np.zeros(3, dtype=np.int64)
+    _lib.check(_lib.load().kvb_vmm_init_progress(group_id, o.ctypes.data_as(_lib.p_i64)), "vmm init_progress")
+    return {"units_done": int(o[0]), "units": int(o[1]), "init_ms": float(o[2]) / 1e3}
+
+
 def wait_maps(group_id: int = 0) -> None:
     _lib.check(_lib.load().kvb_vmm_wait_maps(group_id), "vmm wait_maps")
 

@@ -61,6 +61,7 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: in
     contiguous = cfg.get("contiguous", True)
     B = cfg["block_size"] * cfg["cell_size"]
     vmm_ops.init_kvcached(device, P, contiguous)
+    t_create0 = time.perf_counter()
     if device == "cpu":
         # CPUPage::map only records the address (csrc/page.cpp:34-37): the virtual
         # tensor can stay tiny whatever the manager's size is.
@@ -73,6 +74,7 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: in
         per_layer = ((cfg["num_blocks"] * B + P - 1) // P) * P * nkv
         vmm_ops.create_kv_tensors(per_layer, 2, device, L, num_kv_buffers=nkv)
 
+    create_s = time.perf_counter() - t_create0      # create_kv_tensors: VA reservation + zero-page init (ftensor.cpp:160-176)
     mgr = KVCacheManager(cfg["num_blocks"], cfg["block_size"], cfg["cell_size"], L,
                          reserve_null_block=cfg.get("reserve_null_block", False),
                          num_kv_buffers=nkv)
@@ -126,7 +128,7 @@ def run(trace: dict, device: str = "cpu", timing_only: bool = False, repeats: in
         elapsed_all.append(elapsed)
     out = {"elapsed_s": elapsed_all[-1], "elapsed_all_s": elapsed_all, "n_calls": n_calls, "n_blocks": n_blocks,
            "null_block": mgr.null_block, "nproc": os.cpu_count(), "device": device,
-           "prealloc": bool(cfg.get("prealloc", False)), "marks": MARKS}
+           "prealloc": bool(cfg.get("prealloc", False)), "marks": MARKS, "create_kv_tensors_s": create_s}
     if not timing_only:
         out["records"] = records
     else:

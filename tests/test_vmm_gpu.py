@@ -430,3 +430,42 @@ def test_kv_scatter_gather_tp_shard_cells_80_layers(cell, T_tokens):
         m.close()
     finally:
         vmm_ops.shutdown_kvcached()
+
+
+def test_background_zero_page_init_on_the_device():
+    """kvb_vmm_zero_init_mode(1): create returns before the range is backed; pages mapped meanwhile hold data; after
+    wait_init() every unmapped unit reads the zero page (ftensor.cpp:160-176's guarantee, reached later)."""
+    import time
+    import torch
+    torch.cuda.init()
+    vmm_ops.zero_init_mode(1)
+    try:
+        vmm_ops.init_kvcached("cuda:0", PAGE, False)           # per-layer: 8 layers x K,V = 16 units per page
+        L, pages = 8, 256
+        t0 = time.perf_counter()
+        tens = vmm_ops.create_kv_tensors(pages * PAGE * 2, 2, "cuda:0", L)
+        t_create = time.perf_counter() - t0
+        pr = vmm_ops.init_progress()
+        assert pr["units"] == pages * 2 * L and pr["units_done"] < pr["units"], (pr, t_create)
+        lib = _lib.load()
+        ids = np.array([200, 201], dtype=np.int64)             # far ahead of the background init
+        assert lib.kvb_map_pages(0, ids.ctypes.data_as(_lib.p_i64), ids.size) == 1, _lib.last_error()
+        per_page = PAGE // 2                                   # int16 elements per page
+        for l in (0, L - 1):
+            k_half = tens[l].view(torch.int16)[: pages * per_page]
+            k_half[200 * per_page: 202 * per_page] = 1234 + l
+        torch.cuda.synchronize()
+        vmm_ops.wait_init()
+        pr = vmm_ops.init_progress()
+        assert pr["units_done"] == pr["units"]
+        for l in (0, L - 1):
+            k_half = tens[l].view(torch.int16)[: pages * per_page]
+            assert bool((k_half[200 * per_page: 202 * per_page] == 1234 + l).all())
+            assert int(k_half[5 * per_page]) == 0 and int(k_half[255 * per_page + 7]) == 0     # zero page
+        assert lib.kvb_unmap_pages(0, ids.ctypes.data_as(_lib.p_i64), ids.size) == 1
+        torch.cuda.synchronize()
+        assert int(tens[0].view(torch.int16)[200 * per_page]) == 0
+        assert vmm_ops.mapped_pages() == []
+    finally:
+        vmm_ops.shutdown_kvcached()
+        vmm_ops.zero_init_mode(-1)

@@ -172,6 +172,46 @@ def case_retention_cap():
     assert e["handles"] == 0 and e["mappings"] == 0
 
 
+def case_background_init():
+    """kvb_vmm_zero_init_mode(1): create backs unit 0 only, the VMM thread the rest; pages mapped meanwhile go straight to
+    their handle (no unmap of an unbacked unit), wait_init() leaves every unit backed, and a group torn down half way
+    through its init unmaps only what it backed."""
+    assert lib.kvb_vmm_mock_driver(64 << 30, 300) == 0          # 300 us per sleeping driver call: init takes a while
+    vmm_ops.zero_init_mode(1)
+    vmm_ops.init_kvcached("cuda:0", PAGE, False)                # per-layer layout: 4 layers x K,V = 8 units per page
+    t0 = time.time()
+    vmm_ops.create_kv_tensors_raw(200 * PAGE * 2, 4, 2)
+    t_create = time.time() - t0
+    st = no_violations()
+    assert st["maps"] < 200 and t_create < 0.2, (st, t_create)  # 1600 units eagerly would take ~0.5 s here
+    events([150, 151, 3], False)                                # long before the init gets there
+    vmm_ops.wait_maps()
+    st = no_violations()
+    assert vmm_ops.mapped_pages() == [3, 150, 151]
+    vmm_ops.wait_init()
+    pr = vmm_ops.init_progress()
+    assert pr["units_done"] == pr["units"] == 1600
+    st = no_violations()
+    assert st["mappings"] == 1600 and st["handles"] == 1 + 3 * 8
+    events([150, 151, 3], True)
+    vmm_ops.fence()
+    st = no_violations()
+    assert st["mappings"] == 1600 and vmm_ops.mapped_pages() == []
+    vmm_ops.shutdown_kvcached()
+    e = no_violations()
+    assert e["handles"] == 0 and e["mappings"] == 0
+    # torn down while the init is still running
+    vmm_ops.init_kvcached("cuda:0", PAGE, False)
+    vmm_ops.create_kv_tensors_raw(200 * PAGE * 2, 4, 2)
+    events([7], False)
+    vmm_ops.wait_maps()
+    assert vmm_ops.init_progress()["units_done"] < 1600
+    vmm_ops.shutdown_kvcached()
+    e = no_violations()
+    assert e["handles"] == 0 and e["mappings"] == 0
+    vmm_ops.zero_init_mode(0)
+
+
 def case_steal_and_reserve():
     """A device of 40 units (+ the zero page): maps beyond the reserve take the page retained LAST; when somebody else
     takes memory, retained pages are handed back until the reserve is whole."""
