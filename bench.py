@@ -367,7 +367,10 @@ def init_and_layout_leg(local_rank: int, cfg: dict, ref_create_s) -> dict:
         return row
 
     try:
+        first = create(True, per_layer_full, False)
+        vmm_ops.shutdown_kvcached()
         out["contiguous_eager"] = create(True, per_layer_full, False)
+        out["contiguous_eager"]["create_s_first_run"] = first["create_s"]   # the driver has slow phases: both runs shown
         vmm_ops.shutdown_kvcached()
         out["contiguous_background"] = create(True, per_layer_full, True)
         vmm_ops.shutdown_kvcached()
@@ -377,8 +380,8 @@ def init_and_layout_leg(local_rank: int, cfg: dict, ref_create_s) -> dict:
         out["per_layer_eager_full_pool_extrapolated_s"] = out["per_layer_eager_eighth_pool"]["create_s"] * per_layer_full / pl
         # page map / unmap in the per-layer layout vs the raw loop (same 64 driver units per page)
         mu = {}
-        for n in (1, 8):
-            iters = 10 if n == 1 else 4
+        for n in (1, 4):
+            iters = 10 if n == 1 else 6
             lib.kvb_vmm_pool_config(0, 64)
             _lib.check(lib.kvb_vmm_pool_prefill(0, n + 2), "pool_prefill")
             ids = np.arange(10, 10 + n, dtype=np.int64)
@@ -483,9 +486,10 @@ def two_model_worker(role: str, d: str, local_rank: int) -> None:
     # ---- phase 2: memory freed by A becomes allocatable by B
     bpp = mgr.stats().blocks_per_page
     if role == "A":
-        want_pages = int(0.55 * torch.cuda.mem_get_info()[1] / vmm_ops.vmm_stats()["page_bytes"])
+        # 80 % of what this process can get right now (B, the parent bench process and both handle pools hold the rest)
+        want_pages = int(0.8 * mgr.available_size()) // bpp
         ids = mgr.alloc_np(want_pages * bpp)
-        assert ids is not None
+        assert ids is not None and want_pages > 16, (want_pages, mgr.available_size())
         vmm_ops.fence()
         out["handover"] = {"held_pages": want_pages, "held_gib": want_pages * vmm_ops.vmm_stats()["page_bytes"] / 2**30}
         open(os.path.join(d, "A_holds"), "w").close()
@@ -926,7 +930,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     # ================= the per-rank scatter at the TP shard shapes, on this GPU (ranks do not interact) ==========
     # Llama-3.3-70B: 80 layers, 8 KV heads sharded over TP ranks -> cell 2048 / 1024 / 512 / 256 B (BASELINE configs[4])
     shard = None
-    init_leg = None
+    init_leg = no_zero = None
     if rank == 0 and world == 1:
         shard = {}
         mgr.close()
@@ -964,6 +968,33 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             ms_.close()
             vmm_ops.shutdown_kvcached()
             torch.cuda.empty_cache()
+        # e2e once more WITHOUT the zero page (opt-in kvb_vmm_zero_init_mode(2)): half the sleeping driver calls per page
+        # transition, unmapped pages fault instead of reading zeros
+        try:
+            vmm_ops.zero_init_mode(2)
+            vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
+            vmm_ops.create_kv_tensors_raw(per_layer, cfg["num_layers"], 2)
+            mgr_nz = R.manager_from_config(cfg, device_index=local_rank)
+            tnz = []
+            vt0 = vmm_ops.vmm_timing()
+            for it in range(1 + K):
+                t0 = time.perf_counter()
+                R.replay_host_steps(mgr_nz, plan, keep_results=False)
+                vmm_ops.fence()
+                tnz.append(time.perf_counter() - t0)
+                if it == 0:
+                    vt0 = vmm_ops.vmm_timing()
+            vt1 = vmm_ops.vmm_timing()
+            no_zero = {"value": n_calls * K / sum(tnz[1:]), "unit": UNIT, "ms_per_step": 1e3 * sum(tnz[1:]) / K,
+                       "driver_ms_per_replay": sum(vt1[k] - vt0[k] for k in ("unmap_ms", "map_ms", "setaccess_ms", "create_ms",
+                                                                             "release_ms")) / K,
+                       "policy": "as e2e, but no zero page behind unmapped pages (they fault if touched)"}
+            mgr_nz.close()
+        except Exception as e:
+            no_zero = {"error": str(e)[:300]}
+        finally:
+            vmm_ops.shutdown_kvcached()
+            vmm_ops.zero_init_mode(-1)
         init_leg = init_and_layout_leg(local_rank, cfg, (cpu_baseline or {}).get("create_kv_tensors_s"))
         # the rest of the bench needs the original group again
         vmm_ops.init_kvcached(f"cuda:{local_rank}", PAGE, True)
@@ -1031,6 +1062,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
         # the two engine processes need the device: this process lets go of its own mappings first
         mgr.trim()
         vmm_ops.settle()
+        lib.kvb_vmm_pool_config(0, 0)          # ... and of the unmapped handles its pool keeps
+        del flush_buf
         torch.cuda.empty_cache()
         two_model = two_model_leg(local_rank)
     if rank == 0:
@@ -1057,6 +1090,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                         "vmm": {"handles_created": vst["handles_created"], "map_calls": vst["map_calls"],
                                 "map_ahead_hits": est["prefetch_hits"], "retention_hits": est["retention_hits"],
                                 "page_bytes": vst["page_bytes"]},
+                        "no_zero_page": no_zero,
                         "tp": tp_stats, "tp_transport": (args.tp_transport if world > 1 else None),
                         "api": "KVCacheManager.run_ops (kvb_mgr_step) per scheduler step, attach_vmm=True: maps are in "
                                "place (on every TP rank) when a step returns, unmaps drain on the VMM thread, "

@@ -86,7 +86,10 @@ int kvb_create_kv_tensors(int64_t group_id, int64_t size_per_layer, int64_t num_
  * and returns; the group's VMM thread backs the rest in its idle time (while the engine loads weights), pages the
  * bookkeeping maps meanwhile go straight to their handle.  Unbacked, unmapped units FAULT if touched, so the
  * reference's "stray accesses never fault" guarantee holds from kvb_vmm_wait_init() on.
- * kvb_vmm_zero_init_mode: -1 = follow the environment, 0 eager, 1 background; returns the previous mode.
+ * None (mode 2, KVB200_VMM_ZERO_INIT=none): no zero page at all — a map is cuMemMap + cuMemSetAccess, an unmap is
+ * cuMemUnmap alone (half the sleeping driver calls of a zero-page cycle); touching an unmapped page faults.  Opt-in,
+ * for engines that never touch blocks they do not hold.
+ * kvb_vmm_zero_init_mode: -1 = follow the environment, 0 eager, 1 background, 2 none; returns the previous mode.
  * kvb_vmm_init_progress out3 = {units done, units, microseconds spent in init}. */
 int kvb_vmm_zero_init_mode(int mode);
 int kvb_vmm_wait_init(int64_t group_id);

@@ -138,7 +138,7 @@ int kvb_vmm_set_retain_max_fraction(int64_t group_id, double f) {
 }
 int kvb_vmm_zero_init_mode(int mode) {
   int old = g_zero_init_mode.load();
-  if (mode >= -1 && mode <= 1) g_zero_init_mode.store(mode);
+  if (mode >= -1 && mode <= 2) g_zero_init_mode.store(mode);
   return old;
 }
 int kvb_vmm_wait_init(int64_t group_id) {

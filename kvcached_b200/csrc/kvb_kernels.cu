@@ -2476,7 +2476,7 @@ static int resident_grid(K kernel, int threads, int *cache_by_dev) {
   return *cache;
 }
 
-int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
+int launch_step_prepare() {
   static bool attr_set[kMaxDev];
   const int dev = cur_dev();
   if (!attr_set[dev]) {
@@ -2485,6 +2485,12 @@ int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
+  return 0;
+}
+
+int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
+  int rc = launch_step_prepare();
+  if (rc) return rc;
   kvb_step_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
   return (int)cudaGetLastError();
 }

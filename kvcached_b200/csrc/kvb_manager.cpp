@@ -116,6 +116,12 @@ struct kvb_mgr {
   Summary *t_sum = nullptr;   // device
   std::vector<int64_t> t_steps;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // resident replay as a CUDA graph: the launch sequence of a step range is captured once and replayed (one kernel
+  // node per scheduler step; what changes between replays lives in device memory, not in the launch arguments)
+  cudaGraphExec_t t_graph = nullptr;
+  int64_t t_graph_key[5] = {-1, -1, -1, -1, -1};   // step_begin, step_end, steps_per_launch, phys_free, resize_target
+  int64_t t_graph_launches = 0;
+  int64_t phys_capture = -1;                       // >= 0: value every launch of a capture uses
   std::unique_ptr<ShmUsage> shm;   // usage publishing + limit (mem_info_tracker.hpp); null = off
   int64_t shm_publishes = 0;
   // single-request fast path: a ring of pinned slots; kvb_mgr_free launches and returns, its summary is collected by
@@ -163,6 +169,7 @@ int ensure_io(kvb_mgr *m, size_t in_bytes, size_t out_bytes) {
 
 // PageAllocator::get_avail_physical_pages, csrc/page_allocator.cpp:442-455
 int64_t phys_free_pages(kvb_mgr *m) {
+  if (m->phys_capture >= 0) return m->phys_capture;
   if (m->phys_override >= 0) return m->phys_override;
   // live like the reference, but at most once per refresh interval; our own map/unmap activity
   // invalidates the cached value (apply_events), other tenants' activity is seen within the interval.
@@ -751,6 +758,7 @@ extern "C" int kvb_mgr_destroy(kvb_mgr *m) {
   if (m->t_res) cudaFree(m->t_res);
   if (m->t_out) cudaFree(m->t_out);
   if (m->t_sum) cudaFree(m->t_sum);
+  if (m->t_graph) cudaGraphExecDestroy(m->t_graph);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -1161,6 +1169,7 @@ extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops
   if (n_ids) CUDA_TRY(cudaMemcpy(m->t_ids, ids, (size_t)n_ids * 8, cudaMemcpyHostToDevice));
   if (n_refs) CUDA_TRY(cudaMemcpy(m->t_refs, refs, (size_t)n_refs * sizeof(kvb_ref), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(m->t_res, 0, (size_t)n_ops * sizeof(kvb_res)));
+  if (m->t_graph) { cudaGraphExecDestroy(m->t_graph); m->t_graph = nullptr; }
   m->t_out_cap = out_capacity;
   m->t_nops = n_ops;
   m->t_steps.assign(step_offsets, step_offsets + n_steps + 1);
@@ -1189,14 +1198,54 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
   if (ensure_device(m->dev)) { set_error("cudaSetDevice(%d) failed", m->dev); return KVB_ERR_CUDA; }
   { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t launches0 = m->launches;
+  auto run_range = [&]() -> int {
+    for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
+      int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
+      int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
+      if (oe == ob) continue;
+      int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0);
+      if (rc) return rc;
+    }
+    return 0;
+  };
+  // Launch-bound loop -> CUDA graph (KVB200_TRACE_GRAPH=0 disables): captured once per (range, physical budget, limit)
+  const bool use_graph = env_i64("KVB200_TRACE_GRAPH", 1) != 0 && (step_end - step_begin) / steps_per_launch >= 8;
+  const int64_t phys_now = phys_free_pages(m);
+  const int64_t rt_now = m->shm ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
+  const int64_t key[5] = {step_begin, step_end, steps_per_launch, phys_now, rt_now};
+  bool have_graph = use_graph && m->t_graph && memcmp(key, m->t_graph_key, sizeof(key)) == 0;
+  if (use_graph && !have_graph) {
+    if (m->t_graph) { cudaGraphExecDestroy(m->t_graph); m->t_graph = nullptr; }
+    launch_step_prepare();
+    cudaGraph_t g = nullptr;
+    m->phys_capture = phys_now;
+    const int64_t l0 = m->launches;
+    if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc = run_range();
+      cudaError_t ce = cudaStreamEndCapture(m->stream, &g);
+      if (rc == 0 && ce == cudaSuccess && g && cudaGraphInstantiate(&m->t_graph, g, 0) == cudaSuccess) {
+        memcpy(m->t_graph_key, key, sizeof(key));
+        m->t_graph_launches = m->launches - l0;
+        have_graph = true;
+      } else {
+        m->t_graph = nullptr;
+      }
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaGetLastError();
+    m->phys_capture = -1;
+    g_total_launches.fetch_sub(m->launches - l0, std::memory_order_relaxed);   // captured, not executed
+    m->launches = l0;
+  }
   // events of the whole range accumulate in the device log
   CUDA_TRY(cudaMemsetAsync(m->st.sc + SC_NEV, 0, 8, m->stream));
   CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
-  for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
-    int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
-    int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
-    if (oe == ob) continue;
-    int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0);
+  if (have_graph) {
+    CUDA_TRY(cudaGraphLaunch(m->t_graph, m->stream));
+    m->launches += m->t_graph_launches;
+    g_total_launches.fetch_add(m->t_graph_launches, std::memory_order_relaxed);
+  } else {
+    int rc = run_range();
     if (rc) return rc;
   }
   CUDA_TRY(cudaEventRecord(m->ev1, m->stream));

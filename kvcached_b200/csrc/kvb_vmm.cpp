@@ -101,9 +101,9 @@ VmmGroup::~VmmGroup() {
   if (!d) return;
   if (!mock::installed) cudaSetDevice(dev_);
   if (va_base_) {
-    if (init_next_ >= n_units_ || n_units_ == 0) {
+    if (zero_page_ && (init_next_ >= n_units_ || n_units_ == 0)) {
       d->MemUnmap(va_base_, va_bytes_);      // tolerate stale mappings at teardown (ftensor.cpp:78-98)
-    } else {                                  // background init was cut short: only backed units can be unmapped
+    } else {                                  // holes (background init cut short / no zero page): only backed units
       for (int64_t u = 0; u < n_units_; ++u)
         if (zero_ok_[(size_t)u]) d->MemUnmap(sub_addr(u / n_sub_, (int)(u % n_sub_)), unit_);
     }
@@ -187,21 +187,26 @@ int VmmGroup::create(int64_t size_per_layer, int64_t num_layers, int64_t num_kv,
   {
     const char *zi = getenv("KVB200_VMM_ZERO_INIT");
     int mode = g_zero_init_mode.load();
-    if (mode < 0) mode = (zi && (zi[0] == 'b' || zi[0] == 'B')) ? 1 : 0;
+    if (mode < 0) mode = (zi && (zi[0] == 'b' || zi[0] == 'B')) ? 1 : ((zi && (zi[0] == 'n' || zi[0] == 'N')) ? 2 : 0);
     bg_init_ = mode == 1;
+    // mode 2 ("none"): NO zero page — an unmapped page has no mapping at all, so a map is cuMemMap + cuMemSetAccess
+    // and an unmap is cuMemUnmap alone (half the sleeping driver calls of the zero-page cycle); a stray access to an
+    // unmapped page FAULTS.  For engines that never touch blocks they do not hold; the reference always keeps the
+    // zero page (ftensor.cpp:134), so this is opt-in.
+    zero_page_ = mode != 2;
   }
   const auto t_init0 = std::chrono::steady_clock::now();
-  const int64_t eager_units = bg_init_ ? 1 : n_units_;
+  const int64_t eager_units = !zero_page_ ? 0 : (bg_init_ ? 1 : n_units_);
   for (int64_t u = 0; u < eager_units; ++u) {
     CUdeviceptr a = sub_addr(u / n_sub_, (int)(u % n_sub_));
     CU_TRY(d->MemMap(a, unit_, 0, zero_, 0));
     CU_TRY(d->MemSetAccess(a, unit_, &access_, 1));
     zero_ok_[(size_t)u] = 1;
   }
-  init_next_ = eager_units;
+  init_next_ = zero_page_ ? eager_units : n_units_;
   init_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_init0).count();
   // the zero page must read as zeros
-  if (!mock::installed && (cudaMemset((void *)sub_addr(0, 0), 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
+  if (zero_page_ && !mock::installed && (cudaMemset((void *)sub_addr(0, 0), 0, unit_) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
     set_error("zero page memset failed: %s", cudaGetErrorString(cudaGetLastError()));
     return KVB_ERR_CUDA_;
   }
@@ -531,9 +536,14 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
   for (int s = 0; s < n_sub_ && !rc; ++s) {
     CUdeviceptr a = sub_addr(p, s);
     if (zero_ok_[(size_t)p * n_sub_ + s]) { CU_TIMED_L(2, g_drv.MemUnmap(a, unit_)); }   // (background init: not backed yet)
-    CU_TIMED_L(3, g_drv.MemMap(a, unit_, 0, to_mapped ? hs[(size_t)s] : zero_, 0));
-    CU_TIMED_L(4, g_drv.MemSetAccess(a, unit_, &access_, 1));
-    if (!rc) { done++; zero_ok_[(size_t)p * n_sub_ + s] = 1; }
+    if (to_mapped || zero_page_) {
+      CU_TIMED_L(3, g_drv.MemMap(a, unit_, 0, to_mapped ? hs[(size_t)s] : zero_, 0));
+      CU_TIMED_L(4, g_drv.MemSetAccess(a, unit_, &access_, 1));
+      if (!rc) zero_ok_[(size_t)p * n_sub_ + s] = 1;
+    } else if (!rc) {
+      zero_ok_[(size_t)p * n_sub_ + s] = 0;      // no zero page: the unit is simply unmapped now
+    }
+    if (!rc) done++;
   }
   if (rc && to_mapped) {
     // a map that failed half way (per-layer layout): the units already switched go back to the zero page, so that
@@ -541,7 +551,8 @@ int VmmGroup::transition(Lock &lk, int64_t p, bool to_mapped) {
     for (int s = 0; s <= done && s < n_sub_; ++s) {
       CUdeviceptr a = sub_addr(p, s);
       g_drv.MemUnmap(a, unit_);
-      if (g_drv.MemMap(a, unit_, 0, zero_, 0) == CUDA_SUCCESS) g_drv.MemSetAccess(a, unit_, &access_, 1);
+      if (zero_page_ && g_drv.MemMap(a, unit_, 0, zero_, 0) == CUDA_SUCCESS) g_drv.MemSetAccess(a, unit_, &access_, 1);
+      else zero_ok_[(size_t)p * n_sub_ + s] = 0;
     }
   }
   lk.lock();

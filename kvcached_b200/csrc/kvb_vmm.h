@@ -176,7 +176,7 @@ class VmmGroup {
   std::vector<CUmemGenericAllocationHandle> handles_;   // [n_pages * n_sub], 0 = zero page mapped
   std::vector<uint8_t> zero_ok_;  // per unit: the VA unit has a mapping (zero page or handle)
   int64_t n_units_ = 0, init_next_ = 0;
-  bool bg_init_ = false;
+  bool bg_init_ = false, zero_page_ = true;
   double init_ms_ = 0;
   std::vector<uint8_t> mapped_;   // physical state
   std::vector<uint8_t> want_;     // state after every event received so far

@@ -134,7 +134,8 @@ def footprint(group_id: int = 0) -> Dict[str, int]:
 
 
 def zero_init_mode(mode: int) -> int:
-    """-1 follow KVB200_VMM_ZERO_INIT, 0 eager (default), 1 background; call before create_kv_tensors.  Returns the old mode."""
+    """-1 follow KVB200_VMM_ZERO_INIT, 0 eager (default), 1 background, 2 none (no zero page: unmapped pages fault);
+    call before create_kv_tensors.  Returns the old mode."""
     return int(_lib.load().kvb_vmm_zero_init_mode(int(mode)))
 
 

@@ -212,3 +212,88 @@ def test_unmodified_reference_sglang_mla_interface(reference_manager_module, mon
         mgr.close()
     finally:
         itf.shutdown_kvcached()
+
+
+@pytest.mark.parametrize("contiguous", [True, False])
+def test_unmodified_reference_mamba_states_hybrid_model(reference_manager_module, monkeypatch, contiguous):
+    """Hybrid models (attention + mamba layers): the reference's `alloc_mamba_states`
+    (sglang/interfaces.py:178-401, unmodified) builds the conv / temporal state views of an elastic MambaPool over its
+    OWN KV-cache group (one mamba slot = one kvcached block of the padded super-cell, one buffer per layer,
+    `unified_pool` in the per-layer layout), next to the attention KV pool of group 0.  Both groups run on our
+    extension and our KVCacheManager: slots allocated by the manager are backed in every mamba layer, states written
+    through the reference's views read back, a freed-and-trimmed slot reads the zero page again, and the two groups'
+    page sets stay independent (ElasticMambaPool, sglang/patches.py:812-1000, does exactly this with group ids >= 1000)."""
+    import math
+    from types import SimpleNamespace
+    import torch
+    import kvcached_b200
+    torch.cuda.init()
+    monkeypatch.setenv("KVCACHED_CONTIGUOUS_LAYOUT", "true" if contiguous else "false")
+    for k in [k for k in sys.modules if k.startswith("kvcached.integration") or k == "kvcached.utils"]:
+        monkeypatch.delitem(sys.modules, k)
+    itf = importlib.import_module("kvcached.integration.sglang.interfaces")
+    monkeypatch.setattr(itf, "KVCacheManager", kvcached_b200.KVCacheManager)
+    itf.init_kvcached(device="cuda:0")
+    try:
+        assert our_vmm_ops_contiguous() == contiguous
+        # ---- group 0: the attention layers' KV pool
+        L_attn, bs, H, D = 4, 16, 8, 128
+        k_views, v_views = itf.alloc_kv_cache((1024 * bs, H, D), torch.float16, "cuda:0", L_attn, page_size=bs)
+        kv_mgr = itf.get_kv_cache_manager(1024, bs, H * D * 2, L_attn)
+        assert kv_mgr._post_init_done.wait(timeout=30.0)
+        # ---- group 1000: the mamba layers' state pool (Mamba2-like shapes)
+        L_mamba, slots = 6, 96
+        params = SimpleNamespace(shape=SimpleNamespace(conv=[(3, 1536)], temporal=(24, 64, 128)),
+                                 dtype=SimpleNamespace(conv=torch.bfloat16, temporal=torch.float32))
+        conv, temporal, info = itf.alloc_mamba_states(num_slots=slots, num_mamba_layers=L_mamba, cache_params=params,
+                                                      device="cuda:0", group_id=1000)
+        cell = info["cell_size"]
+        raw = 3 * 1536 * 2 + 24 * 64 * 128 * 4
+        assert cell >= raw and PAGE % cell == 0 and info["is_contiguous"] == contiguous
+        m_mgr = kvcached_b200.KVCacheManager(slots, 1, cell, L_mamba, num_kv_buffers=1, group_id=1000,
+                                             reserve_null_block=False)
+        assert m_mgr._post_init_done.wait(timeout=30.0)
+        spp = PAGE // cell                                   # slots per page
+        got = m_mgr.alloc(spp + 2)                           # two pages of slots
+        assert got == list(range(spp + 2))
+        assert our_vmm_ops.mapped_pages(1000) == [0, 1] and our_vmm_ops.mapped_pages(0) == []
+
+        def conv_at(layer, slot):
+            return conv[0][layer, slot] if contiguous else conv[0][layer][slot]
+
+        def temp_at(layer, slot):
+            return temporal[layer, slot] if contiguous else temporal[layer][slot]
+
+        for layer in (0, L_mamba - 1):
+            for s in (0, spp - 1, spp + 1):
+                conv_at(layer, s).fill_(float(layer + s))
+                temp_at(layer, s).fill_(float(100 * layer + s))
+        torch.cuda.synchronize()
+        for layer in (0, L_mamba - 1):
+            for s in (0, spp - 1, spp + 1):
+                assert bool((conv_at(layer, s) == float(layer + s)).all())
+                assert bool((temp_at(layer, s) == float(100 * layer + s)).all())
+        assert tuple(conv_at(0, 0).shape) == (3, 1536) and tuple(temp_at(0, 0).shape) == (24, 64, 128)
+        # the attention pool maps its own pages, independently
+        ids = kv_mgr.alloc(70)
+        assert our_vmm_ops.mapped_pages(0) != [] and our_vmm_ops.mapped_pages(1000) == [0, 1]
+        k_views[1][ids[0] * bs] = 3.0
+        torch.cuda.synchronize()
+        assert float(k_views[1][ids[0] * bs].flatten()[0]) == 3.0
+        # a slot beyond what is mapped reads the zero page; freed + trimmed slots go back to it
+        assert float(temp_at(0, 2 * spp + 3).flatten()[0]) == 0.0
+        m_mgr.free(got)
+        m_mgr.trim()
+        torch.cuda.synchronize()
+        assert our_vmm_ops.mapped_pages(1000) == []
+        assert float(temp_at(0, 0).flatten()[0]) == 0.0 and float(conv_at(L_mamba - 1, spp + 1).flatten()[0]) == 0.0
+        kv_mgr.free(ids)
+        m_mgr.close()
+        kv_mgr.close()
+    finally:
+        itf.shutdown_kvcached()
+
+
+def our_vmm_ops_contiguous() -> bool:
+    from kvcached_b200 import _lib
+    return bool(_lib.load().kvb_contiguous_layout())

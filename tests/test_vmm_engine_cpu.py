@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize("case", ["sync", "cancel_and_retention", "steal_and_reserve", "map_ahead", "random_per_layer", "oom", "layouts",
-                                  "quiet_and_contended_reserve", "hints_without_memory", "retention_cap", "background_init"])
+                                  "quiet_and_contended_reserve", "hints_without_memory", "retention_cap", "background_init", "no_zero_page"])
 def test_vmm_engine_against_mock_driver(case):
     env = dict(os.environ)
     for k in ("KVB200_VMM_ASYNC", "KVB200_VMM_PREFETCH", "KVB200_VMM_RETAIN_MS", "KVB200_RETAIN_FREE_FRACTION"):

@@ -212,6 +212,33 @@ def case_background_init():
     vmm_ops.zero_init_mode(0)
 
 
+def case_no_zero_page():
+    """kvb_vmm_zero_init_mode(2): nothing is mapped at create; a map is cuMemMap + cuMemSetAccess, an unmap cuMemUnmap
+    alone — two sleeping driver calls per map/unmap pair instead of four."""
+    assert lib.kvb_vmm_mock_driver(64 << 30, 0) == 0
+    vmm_ops.zero_init_mode(2)
+    vmm_ops.init_kvcached("cuda:0", PAGE, True)
+    vmm_ops.create_kv_tensors_raw(64 * PAGE * 2, 4, 2)
+    vmm_ops.set_prefetch(0)
+    st = no_violations()
+    assert st["maps"] == 0 and st["mappings"] == 0 and st["creates"] == 1
+    events([3, 4, 5], False)
+    vmm_ops.fence()
+    st = no_violations()
+    assert st["maps"] == 3 and st["access"] == 3 and st["unmaps"] == 0 and st["mappings"] == 3
+    events([4], True)
+    vmm_ops.fence()
+    st = no_violations()
+    assert st["unmaps"] == 1 and st["maps"] == 3 and st["mappings"] == 2 and vmm_ops.mapped_pages() == [3, 5]
+    events([4], False)
+    vmm_ops.fence()
+    assert no_violations()["mappings"] == 3
+    vmm_ops.shutdown_kvcached()
+    e = no_violations()
+    assert e["handles"] == 0 and e["mappings"] == 0
+    vmm_ops.zero_init_mode(0)
+
+
 def case_steal_and_reserve():
     """A device of 40 units (+ the zero page): maps beyond the reserve take the page retained LAST; when somebody else
     takes memory, retained pages are handed back until the reserve is whole."""
