@@ -49,7 +49,8 @@ def workload_config(world: int) -> dict:
     if world > 1:
         return {"workload": f"T-decode-4096 under TP={world}: Llama-3.3-70B KV layout (80 layers, 8 KV heads sharded "
                             f"{8 // world} per rank, d=128, bf16, block 16, 2 MiB pages, contiguous layout), 4096 requests, "
-                            "seed 0; rank 0 runs the block manager, one NCCL broadcast of the page list per scheduler step",
+                            "seed 0; rank 0 runs the block manager, its step kernel pushes each step's page list to the other "
+                            "ranks through a shared-memory mailbox (--tp-transport nccl: one NCCL broadcast per step)",
                 "num_blocks": NUM_BLOCKS_TP, "requests": N_REQUESTS, "tp": world,
                 "l2": "scatter inputs exceed L2; a 256 MiB buffer is written between trace replays"}
     return {"workload": "T-decode-4096: Llama-3.1-8B KV layout (32 layers, 8 KV heads, d=128, bf16, block 16, "
@@ -482,7 +483,7 @@ def two_model_worker(role: str, d: str, local_rank: int) -> None:
     _wait_file(os.path.join(d, f"unlimited_{role}"))
     ids = mgr.alloc(1)
     mgr.free(ids)
-    out["limit"]["total_pages_restored"] = int(mgr.stats().num_total_pages)
+    out["limit"]["total_pages_after_raising_to_three_quarters"] = int(mgr.stats().num_total_pages)
     # ---- phase 2: memory freed by A becomes allocatable by B
     bpp = mgr.stats().blocks_per_page
     if role == "A":
@@ -581,7 +582,9 @@ def two_model_leg(local_rank: int) -> dict:
             shm_set_limit(name, total // 4)
             open(os.path.join(d, f"limited_{role}"), "w").close()
             alive_wait(os.path.join(d, f"limit_seen_{role}"))
-            shm_set_limit(name, total)
+            # back up to 3/4: a total EQUAL to the size the pool was created with means "no change" to the reference's
+            # watcher (it compares with the constructor's mem_size_per_layer_, page_allocator.cpp:772-774) and to ours
+            shm_set_limit(name, total // 4 * 3)
             open(os.path.join(d, f"unlimited_{role}"), "w").close()
         for role in ("A", "B"):
             alive_wait(os.path.join(d, f"result_{role}.json"), timeout=300)

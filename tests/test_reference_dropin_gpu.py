@@ -256,7 +256,8 @@ def test_unmodified_reference_mamba_states_hybrid_model(reference_manager_module
         spp = PAGE // cell                                   # slots per page
         got = m_mgr.alloc(spp + 2)                           # two pages of slots
         assert got == list(range(spp + 2))
-        assert our_vmm_ops.mapped_pages(1000) == [0, 1] and our_vmm_ops.mapped_pages(0) == []
+        # (group 0 holds SGLang's null block: its page 0 is mapped and stays so)
+        assert our_vmm_ops.mapped_pages(1000) == [0, 1] and our_vmm_ops.mapped_pages(0) == [0]
 
         def conv_at(layer, slot):
             return conv[0][layer, slot] if contiguous else conv[0][layer][slot]
@@ -276,7 +277,7 @@ def test_unmodified_reference_mamba_states_hybrid_model(reference_manager_module
         assert tuple(conv_at(0, 0).shape) == (3, 1536) and tuple(temp_at(0, 0).shape) == (24, 64, 128)
         # the attention pool maps its own pages, independently
         ids = kv_mgr.alloc(70)
-        assert our_vmm_ops.mapped_pages(0) != [] and our_vmm_ops.mapped_pages(1000) == [0, 1]
+        assert len(our_vmm_ops.mapped_pages(0)) >= 2 and our_vmm_ops.mapped_pages(1000) == [0, 1]
         k_views[1][ids[0] * bs] = 3.0
         torch.cuda.synchronize()
         assert float(k_views[1][ids[0] * bs].flatten()[0]) == 3.0

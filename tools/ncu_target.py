@@ -23,10 +23,21 @@ if which in ("step", "both"):
         ms, nl = R.run_resident(m, ct, steps_per_launch=spl)
     print("step kernel: ops", ct.n_calls, "steps", ct.step_offsets.size - 1, "launches", nl, "ms", ms)
     m.close()
+if which == "single":
+    # the single-request path: alloc(16) (flagged record) / free (publishes nothing) pairs
+    cfg = T.make_config("llama8b", 91520)
+    m = R.manager_from_config(cfg, attach_vmm=False); m.set_phys_free_pages(1 << 40)
+    pin = m.alloc(1)
+    for _ in range(300):
+        m.free(m.alloc(16))
+    m.sync()
+    print("single-request pairs done")
+    m.close()
 if which in ("kv", "both"):
     PAGE = 2 << 20
     vmm_ops.init_kvcached("cuda:0", PAGE, True)
-    L, bs, cell, blocks = 32, 16, 2048, max(4096, int(os.environ.get("NCU_T", "16384")) // 16 + 64)
+    L, bs, cell = int(os.environ.get("NCU_L", "32")), 16, int(os.environ.get("NCU_CELL", "2048"))
+    blocks = max(4096, int(os.environ.get("NCU_T", "16384")) // 16 + 64)
     (rng_,) = vmm_ops.create_kv_tensors_raw(blocks * bs * cell * 2, L, 2)
     mg = KVCacheManager(blocks, bs, cell, L)
     Tn = int(os.environ.get("NCU_T", "16384"))
