@@ -429,7 +429,7 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
 constexpr int HT_WK = 8;
 __device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uint32_t *primes32, const int32_t *keys,
                                                     int D, int nb, int32_t *ord, int32_t *tab_first, int32_t *tab_cnt,
-                                                    int64_t *perm) {
+                                                    int64_t *perm, int placed0 = 0, int slot0 = 0, unsigned key0 = 0u) {
   const int lane = threadIdx.x & 31;
   const unsigned gt = ~((2u << lane) - 1u);   // lanes above mine
   int32_t *suf_at = reinterpret_cast<int32_t *>(perm + 32 * HT_WK);
@@ -441,6 +441,9 @@ __device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uin
     slot[k] = p;
     key[k] = p < D ? (unsigned)keys[p] : 0u;
   }
+  // hand-over from the single-key phases (ht_order_hybrid): positions below placed0 (<= 32) hold the container's
+  // current order, `nb` is the bucket count of the phase about to run
+  if (lane < placed0) { slot[0] = slot0; key[0] = key0; }
   while (true) {
     const int upto = D < nb ? D : nb;        // keys in the container when this bucket count ends
     int b[HT_WK], later[HT_WK];
@@ -507,6 +510,52 @@ __device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uin
 #pragma unroll
   for (int k = 0; k < HT_WK; ++k)
     if (32 * k + lane < D) ord[32 * k + lane] = slot[k];
+}
+
+// 32 < D <= 32 * HT_WK: the first rehash phases hold at most 32 keys (bucket counts 2, 5, 11, 23, ...) and run in the
+// one-key-per-lane form of ht_order_warp (registers and votes only, ~4x cheaper per phase than the multi-key form);
+// the phase that first exceeds 32 keys, and the ones after it, continue in ht_order_warp_multi.
+__device__ __forceinline__ void ht_order_hybrid(const DevState &c, const uint32_t *primes32, const int32_t *keys, int D,
+                                                int nb, int32_t *ord, int32_t *tab_first, int32_t *tab_cnt,
+                                                int64_t *perm) {
+  const int lane = threadIdx.x & 31;
+  const unsigned gt = ~((2u << lane) - 1u);
+  int32_t *scratch64 = reinterpret_cast<int32_t *>(perm);      // 64 words, free until the multi-key form starts
+  int cur_slot = lane;
+  unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
+  int placed = 0;
+  while ((D < nb ? D : nb) <= 32) {
+    const int upto = D < nb ? D : nb;
+    if (lane >= placed && lane < upto) { cur_slot = lane; cur_key = (unsigned)keys[lane]; }
+    const bool in = lane < upto;
+    const unsigned b = in ? cur_key % (unsigned)nb : 0xffffffffu - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    const int gfirst = __ffs(grp) - 1;
+    const int later_in_grp = __popc(grp & gt);
+    int suf = (in && gfirst == lane) ? __popc(grp) : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int y = __shfl_down_sync(0xffffffffu, suf, d);
+      if (lane + d < 32) suf += y;
+    }
+    int before = __shfl_sync(0xffffffffu, suf, (gfirst + 1) & 31);
+    if (gfirst == 31) before = 0;
+    const int newpos = before + later_in_grp;
+    if (in) { scratch64[newpos] = cur_slot; scratch64[32 + newpos] = (int)cur_key; }
+    __syncwarp();
+    if (in) { cur_slot = scratch64[lane]; cur_key = (unsigned)scratch64[32 + lane]; }
+    __syncwarp();
+    placed = upto;
+    if (placed >= D) break;                                  // (cannot happen for D > 32; kept for safety)
+    int64_t want = (int64_t)placed + 2;
+    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+    nb = next_bkt(c, primes32, want);
+  }
+  if (placed >= D) {
+    if (lane < D) ord[lane] = cur_slot;
+    return;
+  }
+  ht_order_warp_multi(c, primes32, keys, D, nb, ord, tab_first, tab_cnt, perm, placed, cur_slot, cur_key);
 }
 
 // bucket count the table ends with (decides shared vs global tables before the replay)
@@ -898,6 +947,171 @@ __device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, i
   return 1;
 }
 
+// alloc_run_fast at WARP scope: runs of at most 32 requests whose blocks come from the reserved blocks, the 32 newest
+// entries of the avail stack and at most 32 fresh pages — a decode step's "one block each" run, a single alloc(n).
+// Same stream rule, same results; warp 0 does all of it with shuffles and votes (the block-wide form pays a dozen
+// block barriers and three block scans for the same few hundred ids), the other warps wait at the one barrier at the
+// end.  Returns 1 if the run was handled, 0 if it needs the wider windows of alloc_run_fast (nothing touched).  Uniform.
+__device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  int64_t *sc = s.sc;
+  const int R = run_end - op0;
+  if (!c.exact || sc[SC_INSHRINK] || R > 32) return 0;
+  if (tid < 32) {
+    const unsigned FULL = 0xffffffffu;
+    const int tail = (int)sc[SC_AP_TAIL];
+    const int rls = (int)sc[SC_RL_SIZE], fls = (int)sc[SC_FL_SIZE];
+    const int n_i = lane < R ? s.ops[op0 - chunk_base + lane].n : 0;
+    // the 32 newest stack entries and the next 32 pages alloc_page() would hand out
+    int e = -1, ecnt = 0, ehead = 0;
+    {
+      const int i = tail - 1 - lane;
+      e = (i >= 0) ? c.ap[i] : -1;
+      if (e >= 0) { ecnt = c.pg_cnt[e]; ehead = c.pg_head[e]; }
+    }
+    int npg = -1;
+    if (lane < rls) npg = c.rl[(int)((sc[SC_RL_HEAD] + lane) & c.q_mask)];
+    else if (lane - rls < fls) npg = c.fl[(int)((sc[SC_FL_HEAD] + (lane - rls)) & c.q_mask)];
+    const bool neg = __any_sync(FULL, n_i < 0 || n_i > (1 << 21));
+    // exclusive scans over the warp
+    int off_i = n_i, cum = e >= 0 ? ecnt : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(FULL, off_i, d), z = __shfl_up_sync(FULL, cum, d);
+      if (lane >= d) { off_i += y; cum += z; }
+    }
+    const int T = __shfl_sync(FULL, off_i, 31), sum_av = __shfl_sync(FULL, cum, 31);
+    off_i -= n_i;
+    cum -= (e >= 0 ? ecnt : 0);
+    const unsigned livem = __ballot_sync(FULL, e >= 0);
+    const int nlive = __popc(livem), li = __popc(livem & ((1u << lane) - 1u));
+    const int64_t A0 = avail_size(c, sc);
+    const int64_t cursor = sc[SC_OUT_CURSOR];
+    const int nrb = (int)sc[SC_NRB];
+    const int take_rb = nrb < T ? nrb : T;
+    const int rem1 = T - take_rb;
+    const int take_av = rem1 < sum_av ? rem1 : sum_av;
+    const int rem2 = rem1 - take_av;                           // blocks that come from fresh pages
+    const int F = (rem2 + c.bpp - 1) / c.bpp;
+    const bool ok = !neg && A0 >= T && cursor + T <= a.out_cap && (rem2 == 0 || tail <= 32) && F <= 32 && F <= rls + fls;
+    if (ok) {
+      if (e >= 0) { s.cpage[li] = e; s.ccnt[li] = ecnt; s.chead[li] = ehead; s.csidx[li] = tail - 1 - lane; s.ccum[li] = cum; }
+      s.newpg[lane] = npg;
+      __syncwarp();
+      const int from_rl = F < rls ? F : rls;                    // alloc_page(): reserved list first, then free list
+      const int from_fl = F - from_rl;
+      const int last_used = F ? rem2 - (F - 1) * c.bpp : 0;
+      const int64_t nev0 = sc[SC_NEV];
+      const int64_t rbh = sc[SC_RB_HEAD];
+      for (int j = lane; j < T; j += 32) {
+        int64_t id;
+        if (j < take_rb) {
+          id = c.rb[(int)((rbh + j) & c.rb_mask)];
+        } else {
+          const int j1 = j - take_rb;
+          if (j1 < take_av) {
+            int lo = 0, hi = nlive - 1;                         // last live entry with ccum <= j1
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s.ccum[mid] <= j1) lo = mid; else hi = mid - 1;
+            }
+            const int pg = s.cpage[lo];
+            int pos = s.chead[lo] + (j1 - s.ccum[lo]);
+            if (pos >= c.bpp) pos -= c.bpp;
+            id = (int64_t)pg * c.bpp + c.ring[(size_t)pg * c.bpp + pos];
+          } else {
+            const int j2 = j1 - take_av;
+            const int q = j2 / c.bpp;
+            id = (int64_t)s.newpg[q] * c.bpp + (j2 - q * c.bpp);
+          }
+          atomicOr(&c.bitmap[id >> 5], 1u << (id & 31));
+        }
+        a.out_ids[cursor + j] = id;
+      }
+      if (lane < R) {
+        kvb_res r{};
+        r.status = KVB_ST_OK;
+        r.n = n_i;
+        r.off = cursor + off_i;
+        r.avail = A0 - off_i - n_i;
+        a.res[op0 + lane] = r;
+      }
+      // consumed / partly consumed avail pages
+      int n_full_av = 0;
+      {
+        int lo = 0, hi = nlive;                                 // first live entry NOT entirely consumed
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s.ccum[mid] + s.ccnt[mid] <= take_av) lo = mid + 1; else hi = mid;
+        }
+        n_full_av = lo;
+      }
+      if (lane < nlive) {
+        const int pg = s.cpage[lane], cn = s.ccnt[lane], cm = s.ccum[lane];
+        if (lane < n_full_av) {
+          const int hh = s.chead[lane] + cn;
+          c.pg_state[pg] = PG_FULL;
+          c.pg_cnt[pg] = 0;
+          c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
+        } else if (cm < take_av) {                               // the one page left partly consumed
+          const int used = take_av - cm;
+          const int hh = s.chead[lane] + used;
+          c.pg_cnt[pg] = cn - used;
+          c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
+        }
+      }
+      // fresh pages
+      for (int q = 0; q < F; ++q) {
+        const int pg = s.newpg[q];
+        const bool partial = (q == F - 1) && last_used < c.bpp;
+        if (lane == 0) {
+          c.pg_state[pg] = partial ? PG_AVAIL : PG_FULL;
+          c.pg_cnt[pg] = partial ? c.bpp - last_used : 0;
+          c.pg_head[pg] = partial ? last_used : 0;
+          if (q >= from_rl) {                                    // came off the free list: needs a mapping
+            const int64_t k = nev0 + (q - from_rl);
+            if (k < c.ev_cap) c.ev[k] = (int64_t)pg * 2;
+            c.pg_mapped[pg] = 1;
+          }
+          if (partial) { c.ap[0] = pg; c.pg_pos[pg] = 0; }       // the stack is empty when fresh pages are taken
+        }
+        if (partial) {                                           // InternalPage::init: FIFO = identity
+          uint32_t *rr = c.ring + (size_t)pg * c.bpp;
+          for (int t = lane; t < c.bpp; t += 32) rr[t] = (uint32_t)t;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const bool fresh_partial = F > 0 && last_used < c.bpp;
+        sc[SC_RB_HEAD] = (rbh + take_rb) & c.rb_mask;
+        sc[SC_NRB] -= take_rb;
+        sc[SC_NAB] += (int64_t)F * c.bpp - rem2 - take_av;
+        sc[SC_NAVAILPG] += (fresh_partial ? 1 : 0) - n_full_av;
+        sc[SC_NFULLPG] += n_full_av + F - (fresh_partial ? 1 : 0);
+        sc[SC_NFREE] -= F;
+        sc[SC_RL_HEAD] = (sc[SC_RL_HEAD] + from_rl) & c.q_mask;
+        sc[SC_RL_SIZE] -= from_rl;
+        sc[SC_FL_HEAD] = (sc[SC_FL_HEAD] + from_fl) & c.q_mask;
+        sc[SC_FL_SIZE] -= from_fl;
+        sc[SC_NEV] += from_fl;
+        sc[SC_NMAPPED] += from_fl;
+        sc[SC_PHYS] -= from_fl;
+        sc[SC_OUT_CURSOR] = cursor + T;
+        int new_tail;
+        if (F > 0) new_tail = fresh_partial ? 1 : 0;
+        else if (n_full_av < nlive) new_tail = s.csidx[n_full_av] + 1;   // newest surviving entry
+        else new_tail = tail > 32 ? tail - 32 : 0;                       // whole window consumed (or empty)
+        sc[SC_AP_TAIL] = new_tail;
+      }
+    }
+    if (lane == 0) s.misc[MI_E] = ok ? 1 : 0;
+  }
+  __syncthreads();
+  const int handled = s.misc[MI_E];
+  __syncthreads();
+  return handled;
+}
+
 // A run of consecutive ALLOC requests [op0, run_end) (all inside the staged chunk), or one
 // TRY_RESERVE request (to_reserved = 1, ids appended to reserved_blocks instead of the output).
 __device__ void alloc_run(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end,
@@ -1083,7 +1297,7 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
       ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);   // registers + warp votes
 #endif
     } else if (multi) {
-      ht_order_warp_multi(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
+      ht_order_hybrid(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
     } else if (!use_g) {
       for (int b = lane; b < nb0; b += 32) s.ht_bkt[b] = -1;
       __syncwarp();
@@ -1256,6 +1470,203 @@ __device__ void free_core(const DevState &c, Smem &s, const LaunchArgs &a, int n
   }
   __syncthreads();
   KVB_PROF(8);
+}
+
+// free(ids) for calls of at most NT ids — one id per thread, the call's scratch in SHARED memory.
+// free_core keeps ids, pages, first-appearance and slot tables in global scratch arrays: every phase boundary is an
+// L2 round trip plus a block barrier (the phase profile charged 12 k cycles to a 16-id free).  Here the only global
+// round trips on the critical path are the bitmap test-and-clear and one parallel load of the touched pages' state:
+//   1. page of my id; distinct pages and their first index through a 1 024-entry shared hash table (atomicCAS claim +
+//      atomicMin of the thread index) -> slots in first-appearance order (ballot/popc rank), page state -> shared;
+//   2. warp 0 replays the unordered_map order of the slots (ht_order_warp / ht_order_hybrid) while warp 1 ranks the
+//      ids inside their pages (__match_any_sync) and appends them to the page FIFOs;
+//   3. per page, in dict order, the same update rule as free_core's F4 with every input in shared memory; F5 as there.
+// Results are free_core's, bit for bit.  Returns 0 (uniform, NO state touched) when the call names more than
+// HS_D_CAP distinct pages: the caller then takes free_core.
+constexpr int HS_D_CAP = 32 * HT_WK;
+__device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n, int64_t my_id) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int64_t *sc = s.sc;
+  int32_t *Hkey = s.ht_bkt, *Hval = s.ht_bkt + 1024, *Hslot = s.ht_bkt + 2048;
+  int32_t *scr = reinterpret_cast<int32_t *>(s.segs);        // alloc-run scratch, idle during a free
+  int32_t *sl = scr, *pst = scr + 512, *pcnt = scr + 1024, *phead = scr + 1536, *ppos = scr + 2048;
+  int64_t *ids64 = reinterpret_cast<int64_t *>(scr + 2560);
+  int32_t *efree = scr + 3584;                               // pages_to_free, dict order (<= HS_D_CAP entries)
+  static_assert(sizeof(s.segs) >= (3584 + 512) * 4 && HT_NB_CAP + 1 >= 3072 && NT <= 512 && HS_D_CAP <= 512, "free_small scratch");
+  if (n <= 0) return 1;
+  ap_compact(c, s);
+  for (int i = tid; i < 1024; i += NT) { Hkey[i] = -1; Hval[i] = INT_MAX; }
+  if (tid == 0) { s.misc[MI_BAD] = 0; s.misc[MI_UNK] = 0; s.acc[0] = 0; s.acc[1] = 0; s.acc[2] = 0; s.acc[3] = 0; }
+  bool part = false;      // my id names a page that takes part in the dict order
+  int p = -1;
+  if (tid < n && my_id >= 0 && my_id < c.num_blocks) {
+    const int64_t p64 = blk_page(c, my_id);
+    if (p64 <= c.max_pages) { p = (int)p64; part = true; }
+  }
+  __syncthreads();
+  unsigned h = 0;
+  if (part) {
+    h = ((unsigned)p * 0x9E3779B1u) >> 22;
+    while (true) {
+      const int prev = atomicCAS(&Hkey[h], -1, p);
+      if (prev == -1 || prev == p) break;
+      h = (h + 1) & 1023u;
+    }
+    atomicMin(&Hval[h], tid);
+  }
+  __syncthreads();
+  const bool first = part && Hval[h] == tid;
+  int D;
+  const int r = block_rank(first, s.wtot, &D);
+  if (D > HS_D_CAP) return 0;
+  KVB_PROF(4);
+  // ---- from here on the state changes
+  bool ok = part;
+  if (ok && !c.exact) {   // a block straddling the page edge is never handed out
+    const int64_t st0 = pg_start(c, p);
+    ok = my_id >= st0 && my_id < st0 + pg_nblk(c, p);
+  }
+  if (ok) {               // a block must be allocated: test-and-clear
+    const uint32_t bit = 1u << (my_id & 31);
+    const uint32_t old = atomicAnd(&c.bitmap[my_id >> 5], ~bit);
+    ok = (old & bit) != 0;
+  }
+  if (first) {
+    Hslot[h] = r;
+    s.ht_key[r] = p;
+    s.ht_cnt[r] = 0;
+    pst[r] = c.pg_state[p];
+    pcnt[r] = c.pg_cnt[p];
+    phead[r] = c.pg_head[p];
+    ppos[r] = c.pg_pos[p];
+  }
+  {
+    const unsigned bm = __ballot_sync(0xffffffffu, tid < n && !ok);
+    if (lane == 0 && bm) atomicAdd(&s.misc[MI_BAD], __popc(bm));
+  }
+  __syncthreads();
+  if (tid < n) { sl[tid] = ok ? Hslot[h] : -1; ids64[tid] = my_id; }
+  __syncthreads();
+  KVB_PROF(5);
+  // ---- dict order (warp 0) || FIFO ranks and ring appends (warp 1); groups.reserve(n / bpp + 1), page_allocator.cpp:477
+  const int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
+  if (w == 0) {
+    if (D <= 32) ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);
+    else ht_order_hybrid(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
+    KVB_PROF(11);
+  } else if (w == 1) {
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const int slot = (j < n) ? sl[j] : -1;
+      const unsigned mask = __match_any_sync(0xffffffffu, slot >= 0 ? slot : -1 - lane);
+      const int rk = __popc(mask & ((1u << lane) - 1u));
+      const int basecnt = slot >= 0 ? s.ht_cnt[slot] : 0;
+      __syncwarp();
+      if (slot >= 0 && rk == 0) s.ht_cnt[slot] = basecnt + __popc(mask);
+      __syncwarp();
+      if (slot >= 0) {
+        const int pp = s.ht_key[slot];
+        int pos = phead[slot] + pcnt[slot] + basecnt + rk;   // InternalPage::free_batch appends (:69-73)
+        pos %= c.bpp;
+        c.ring[(size_t)pp * c.bpp + pos] = (uint32_t)(ids64[j] - pg_start(c, pp));
+      }
+    }
+  }
+  __syncthreads();
+  KVB_PROF(6);
+  // ---- per-page update in dict order (:322-349): free_core's F4 with shared-memory inputs
+  int tail = (int)sc[SC_AP_TAIL];
+  int E = 0;
+  {
+    bool live = false, empty = false;
+    int pp = -1, add = 0, st = PG_NONE, newc = 0, slot = 0;
+    if (tid < D) {
+      slot = s.ht_ord[tid];
+      pp = s.ht_key[slot];
+      add = s.ht_cnt[slot];
+      st = pst[slot];
+      if (st == PG_NONE) {
+        atomicAdd(&s.misc[MI_UNK], 1);   // page not in avail_pages / full_pages: logged and skipped
+      } else if (add > 0) {
+        live = true;
+        newc = pcnt[slot] + add;
+        empty = (newc == pg_nblk(c, pp));   // InternalPage::empty (:75-77)
+      }
+    }
+    int totS, totE;
+    const int rs = block_rank(live && !empty, s.wtot, &totS);
+    const int re = block_rank(live && empty, s.wtot2, &totE);
+    int d_nab = 0, d_av = 0, d_fu = 0;
+    if (live) {
+      if (st == PG_AVAIL) c.ap[ppos[slot]] = -1;   // avail_pages.pop(page_id)
+      long long dnab = add;
+      if (empty) {
+        efree[re] = pp;
+        c.pg_state[pp] = PG_NONE;
+        c.pg_cnt[pp] = 0;
+        dnab -= newc;
+      } else {
+        c.ap[tail + rs] = pp;            // avail_pages[page_id] = page (newest)
+        c.pg_pos[pp] = tail + rs;
+        c.pg_state[pp] = PG_AVAIL;
+        c.pg_cnt[pp] = newc;
+      }
+      d_nab = (int)dnab;
+      d_av = (empty ? 0 : 1) - (st == PG_AVAIL ? 1 : 0);
+      d_fu = -(st == PG_FULL ? 1 : 0);
+    }
+    const int s_nab = __reduce_add_sync(0xffffffffu, d_nab);
+    const int s_av = __reduce_add_sync(0xffffffffu, d_av);
+    const int s_fu = __reduce_add_sync(0xffffffffu, d_fu);
+    if (lane == 0) {
+      if (s_nab) atomicAdd((unsigned long long *)&s.acc[0], (unsigned long long)(long long)s_nab);
+      if (s_av) atomicAdd((unsigned long long *)&s.acc[1], (unsigned long long)(long long)s_av);
+      if (s_fu) atomicAdd((unsigned long long *)&s.acc[2], (unsigned long long)(long long)s_fu);
+    }
+    tail += totS;
+    E = totE;
+  }
+  __syncthreads();
+  KVB_PROF(7);
+  // ---- PageAllocator::free_pages(pages_to_free) (page_allocator.cpp:264-310): free_core's F5
+  const int rl_size = (int)sc[SC_RL_SIZE], fl_size = (int)sc[SC_FL_SIZE];
+  const int room = c.max_reserved - rl_size;
+  const int k = room > 0 ? (room < E ? room : E) : 0;
+  const int64_t nev0 = sc[SC_NEV];
+  for (int i = tid; i < E; i += NT) {
+    const int pp = efree[i];
+    if (i < k) {
+      c.rl[(int)((sc[SC_RL_HEAD] + rl_size + i) & c.q_mask)] = pp;   // stays mapped
+    } else {
+      const int u = i - k;
+      c.fl[(int)((sc[SC_FL_HEAD] + fl_size + u) & c.q_mask)] = pp;
+      if (nev0 + u < c.ev_cap) c.ev[nev0 + u] = (int64_t)pp * 2 + 1;
+      c.pg_mapped[pp] = 0;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    sc[SC_NAB] += s.acc[0];
+    sc[SC_NAVAILPG] += s.acc[1];
+    sc[SC_NFULLPG] += s.acc[2];
+    sc[SC_AP_TAIL] = tail;
+    sc[SC_NFREE] += E;
+    sc[SC_RL_SIZE] += k;
+    sc[SC_FL_SIZE] += E - k;
+    sc[SC_NEV] += E - k;
+    sc[SC_NMAPPED] -= E - k;
+    sc[SC_PHYS] += E - k;
+    sc[SC_BAD_FREES] += s.misc[MI_BAD];
+    sc[SC_UNKNOWN_FREES] += s.misc[MI_UNK];
+    if (sc[SC_INSHRINK] && alloced_blocks(c, sc) <= sc[SC_TARGET]) {   // pending shrink (:354-360)
+      pa_resize(c, sc, sc[SC_TARGET] * c.B, nullptr);
+      sc[SC_INSHRINK] = 0;
+      sc[SC_TARGET] = -1;
+    }
+  }
+  __syncthreads();
+  KVB_PROF(8);
+  return 1;
 }
 
 // Gather the ids of a FREE_REF request into c.fids: concat of result(op)[lo:hi] of earlier requests.
@@ -1713,7 +2124,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           int e = s.misc[MI_K];
           if (e - op > NT) e = op + NT;
           KVB_PROF(0);
-          if (alloc_run_fast(c, s, a, chunk_base, op, e)) {
+          if (alloc_run_warp(c, s, a, chunk_base, op, e) || alloc_run_fast(c, s, a, chunk_base, op, e)) {
             op = e;
             KVB_PROF(1);
           } else {
@@ -1732,10 +2143,19 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         case KVB_OP_FREE_REF:
         case KVB_OP_FREE_RESERVED: {
           int n = 0;
+          bool done = false;
           if (o.kind == KVB_OP_FREE_IDS) {
             n = o.n;
-            if (a.inline_on == 1) { for (int j = tid; j < n; j += NT) c.fids[j] = a.inline_ids[j]; }
-            else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
+            if (n <= NT && n <= c.f_cap) {     // one id per thread, straight from the request: no staging pass
+              int64_t my = -1;
+              if (tid < n) my = (a.inline_on == 1) ? a.inline_ids[tid] : a.ids[o.arg + tid];
+              KVB_PROF(3);
+              done = free_small(c, s, a, n, my) != 0;
+            }
+            if (!done) {
+              if (a.inline_on == 1) { for (int j = tid; j < n; j += NT) c.fids[j] = a.inline_ids[j]; }
+              else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
+            }
           } else if (o.kind == KVB_OP_FREE_REF) {
             n = gather_refs(c, s, a, o.arg, o.n);
           } else {
@@ -1743,9 +2163,10 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
             for (int j = tid; j < n; j += NT) c.fids[j] = c.rb[(int)((sc[SC_RB_HEAD] + j) & c.rb_mask)];
           }
           __syncthreads();
-          KVB_PROF(3);
+          if (!done) KVB_PROF(3);
           const bool too_many = n > c.f_cap;   // more ids than blocks exist: cannot be a valid call
-          if (!too_many) free_core(c, s, a, n, 0);
+          if (!done && !too_many && n <= NT) done = free_small(c, s, a, n, tid < n ? c.fids[tid] : -1) != 0;
+          if (!done && !too_many) free_core(c, s, a, n, 0);
           if (tid == 0) {
             if (o.kind == KVB_OP_FREE_RESERVED) { sc[SC_NRB] = 0; sc[SC_RB_HEAD] = 0; }
             kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
@@ -1988,9 +2409,13 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           const int n = (int)o.arg;
           const bool too_many = n > c.f_cap;
           if (!too_many) {
-            for (int j = tid; j < n; j += NT) c.fids[j] = a.slot_pre[j];
-            __syncthreads();
-            free_core(c, s, a, n, 0);
+            bool done = false;
+            if (n <= NT) done = free_small(c, s, a, n, tid < n ? a.slot_pre[tid] : -1) != 0;
+            if (!done) {
+              for (int j = tid; j < n; j += NT) c.fids[j] = a.slot_pre[j];
+              __syncthreads();
+              free_core(c, s, a, n, 0);
+            }
           }
           if (tid == 0) {
             kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
