@@ -1709,6 +1709,44 @@ __device__ int gather_refs(const DevState &c, Smem &s, const LaunchArgs &a, int6
   return total;
 }
 
+// The same gather for calls that fit one id per thread (at most NT refs naming at most NT ids): thread t takes the
+// t-th id of the concatenation into a REGISTER (binary search of its ref in the shared offset table) — no staging
+// pass through c.fids.  Returns the id count, or -1 (uniform, nothing written) when the call does not fit.
+__device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, int64_t ref_off, int nrefs, int64_t *my_id) {
+  const int tid = threadIdx.x;
+  *my_id = -1;
+  if (nrefs > NT) return -1;
+  int64_t *r_src = s.tmp64;
+  int32_t *r_dst = s.ht_ord;
+  int len = 0;
+  int64_t src = 0;
+  if (tid < nrefs) {
+    kvb_ref rf = a.refs[ref_off + tid];
+    kvb_res rs = a.res[rf.op];
+    int n = rs.status == KVB_ST_OK ? rs.n : 0;
+    int lo = rf.lo < 0 ? (rf.lo + n < 0 ? 0 : rf.lo + n) : (rf.lo > n ? n : rf.lo);
+    int hi = rf.hi < 0 ? (rf.hi + n < 0 ? 0 : rf.hi + n) : (rf.hi > n ? n : rf.hi);
+    len = hi > lo ? hi - lo : 0;
+    src = rs.off + lo;
+  }
+  int tot;
+  const int ex = block_exscan(len, s.wtot, &tot);
+  if (tot > NT) return -1;
+  r_src[tid] = src;
+  r_dst[tid] = tid < nrefs ? ex : INT_MAX;     // offsets are non-decreasing; empty refs share their successor's offset
+  __syncthreads();
+  if (tid < tot) {
+    int lo = 0, hi = nrefs - 1;                // last ref whose first id is at or before position tid
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (r_dst[mid] <= tid) lo = mid; else hi = mid - 1;
+    }
+    *my_id = a.out_ids[r_src[lo] + (tid - r_dst[lo])];
+  }
+  __syncthreads();
+  return tot;
+}
+
 // ==================================================================================== clear
 // KVCacheManager.clear (kv_cache_manager.py:444-489; semantics SURVEY A.7): everything released,
 // reserved pages trimmed, free list sorted ascending, counters zeroed.  The null block is
@@ -2157,7 +2195,13 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
               else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
             }
           } else if (o.kind == KVB_OP_FREE_REF) {
-            n = gather_refs(c, s, a, o.arg, o.n);
+            int64_t my = -1;
+            n = gather_refs_reg(c, s, a, o.arg, o.n, &my);
+            if (n >= 0 && n <= c.f_cap) {
+              KVB_PROF(3);
+              done = free_small(c, s, a, n, my) != 0;
+            }
+            if (!done) n = gather_refs(c, s, a, o.arg, o.n);
           } else {
             n = (int)sc[SC_NRB];
             for (int j = tid; j < n; j += NT) c.fids[j] = c.rb[(int)((sc[SC_RB_HEAD] + j) & c.rb_mask)];
