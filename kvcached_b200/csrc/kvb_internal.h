@@ -160,6 +160,8 @@ constexpr int kStepThreads = KVB_STEP_THREADS;   // 256, 384 or 512 (>= OPS_CHUN
 size_t step_kernel_smem_bytes();
 // launches (host side, defined in kvb_kernels.cu)
 int launch_step(const DevState &st, const LaunchArgs &a, void *stream);
+int launch_one(const DevState &st, const LaunchArgs &a, void *stream);   // single ALLOC / FREE_IDS / AVAIL request (inline_op)
+#define KVB_ST_RETRY (-100)   /* kvb_one_kernel: the request needs the general kernel; nothing was touched */
 int launch_step_prepare();   // per-device function attributes (must not happen inside a stream capture)
 int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream);
 int launch_audit(const DevState &st, int64_t *d_out4, void *stream, bool zero_counters = true);

@@ -956,12 +956,22 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
   const int tid = threadIdx.x, lane = tid & 31;
   int64_t *sc = s.sc;
   const int R = run_end - op0;
-  if (!c.exact || sc[SC_INSHRINK] || R > 32) return 0;
+  constexpr int RQ = 4;     // requests per lane: runs of up to 128 requests
+  if (!c.exact || sc[SC_INSHRINK] || R > 32 * RQ) return 0;
   if (tid < 32) {
     const unsigned FULL = 0xffffffffu;
     const int tail = (int)sc[SC_AP_TAIL];
     const int rls = (int)sc[SC_RL_SIZE], fls = (int)sc[SC_FL_SIZE];
-    const int n_i = lane < R ? s.ops[op0 - chunk_base + lane].n : 0;
+    int n_q[RQ];              // lane l holds requests [RQ * l, RQ * l + RQ) of the run
+    int n_i = 0;
+    bool odd = false;
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const int idx = lane * RQ + q;
+      n_q[q] = idx < R ? s.ops[op0 - chunk_base + idx].n : 0;
+      odd |= n_q[q] < 0 || n_q[q] > (1 << 21);
+      n_i += odd ? 0 : n_q[q];
+    }
     // the 32 newest stack entries and the next 32 pages alloc_page() would hand out
     int e = -1, ecnt = 0, ehead = 0;
     {
@@ -972,7 +982,7 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
     int npg = -1;
     if (lane < rls) npg = c.rl[(int)((sc[SC_RL_HEAD] + lane) & c.q_mask)];
     else if (lane - rls < fls) npg = c.fl[(int)((sc[SC_FL_HEAD] + (lane - rls)) & c.q_mask)];
-    const bool neg = __any_sync(FULL, n_i < 0 || n_i > (1 << 21));
+    const bool neg = __any_sync(FULL, odd);
     // exclusive scans over the warp
     int off_i = n_i, cum = e >= 0 ? ecnt : 0;
 #pragma unroll
@@ -993,7 +1003,8 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
     const int take_av = rem1 < sum_av ? rem1 : sum_av;
     const int rem2 = rem1 - take_av;                           // blocks that come from fresh pages
     const int F = (rem2 + c.bpp - 1) / c.bpp;
-    const bool ok = !neg && A0 >= T && cursor + T <= a.out_cap && (rem2 == 0 || tail <= 32) && F <= 32 && F <= rls + fls;
+    const bool ok = !neg && T <= 2048 && A0 >= T && cursor + T <= a.out_cap && (rem2 == 0 || tail <= 32) && F <= 32 &&
+                    F <= rls + fls;
     if (ok) {
       if (e >= 0) { s.cpage[li] = e; s.ccnt[li] = ecnt; s.chead[li] = ehead; s.csidx[li] = tail - 1 - lane; s.ccum[li] = cum; }
       s.newpg[lane] = npg;
@@ -1028,13 +1039,21 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
         }
         a.out_ids[cursor + j] = id;
       }
-      if (lane < R) {
-        kvb_res r{};
-        r.status = KVB_ST_OK;
-        r.n = n_i;
-        r.off = cursor + off_i;
-        r.avail = A0 - off_i - n_i;
-        a.res[op0 + lane] = r;
+      {
+        int off_q = off_i;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+          const int idx = lane * RQ + q;
+          if (idx < R) {
+            kvb_res r{};
+            r.status = KVB_ST_OK;
+            r.n = n_q[q];
+            r.off = cursor + off_q;
+            r.avail = A0 - off_q - n_q[q];
+            a.res[op0 + idx] = r;
+          }
+          off_q += n_q[q];
+        }
       }
       // consumed / partly consumed avail pages
       int n_full_av = 0;
@@ -2100,6 +2119,45 @@ __device__ int slots_unique_blocks(const DevState &c, Smem &s, const LaunchArgs 
 }  // namespace
 
 // ==================================================================================== the step kernel
+// Flagged publish of a single-request launch: payload and flag travel in the same 8-byte store, so no fence orders
+// them (LlWord in kvb_internal.h).  res and ids were written to device scratch by the request; the caller's block
+// barrier made them visible.
+__device__ __forceinline__ void publish_flagged(const DevState &c, Smem &s, const LaunchArgs &a, int64_t ev_begin,
+                                                int64_t out_begin) {
+  const int tid = threadIdx.x;
+  const int64_t *sc = s.sc;
+  const kvb_res r = a.res[a.op_begin];
+  const int64_t nev = sc[SC_NEV] - ev_begin;
+  const int nids = (r.status == KVB_ST_OK && r.n > 0 && sc[SC_OUT_CURSOR] > out_begin) ? (int)(sc[SC_OUT_CURSOR] - out_begin) : 0;
+  const int nevin = nev < kLlEvents ? (int)nev : kLlEvents;
+  const int total = LL_IDS + nids;
+  const uint64_t flag = (uint64_t)a.ll_flag << 32;
+  const int64_t fls = sc[SC_FL_SIZE];
+  for (int wd = tid; wd < total; wd += NT) {
+    uint32_t v = 0;
+    if (wd == LL_STATUS) v = (uint32_t)r.status;
+    else if (wd == LL_N) v = (uint32_t)r.n;
+    else if (wd < LL_AUX) v = (uint32_t)((uint64_t)r.avail >> (32 * (wd - LL_AVAIL)));
+    else if (wd < LL_NEV) v = (uint32_t)((uint64_t)r.aux >> (32 * (wd - LL_AUX)));
+    else if (wd == LL_NEV) v = (uint32_t)nev;
+    else if (wd == LL_NHINT) v = (uint32_t)(fls < 16 ? fls : 16);
+    else if (wd < LL_SC) {
+      const int h = wd - LL_HINT;
+      v = h < fls ? (uint32_t)c.fl[(int)((sc[SC_FL_HEAD] + h) & c.q_mask)] : 0xffffffffu;
+    } else if (wd < LL_EV) {
+      const int q = wd - LL_SC;
+      v = (uint32_t)((uint64_t)sc[q >> 1] >> (32 * (q & 1)));
+    } else if (wd < LL_IDS) {
+      const int q = wd - LL_EV;
+      v = (q >> 1) < nevin ? (uint32_t)((uint64_t)c.ev[ev_begin + (q >> 1)] >> (32 * (q & 1))) : 0u;
+    } else {
+      v = (uint32_t)a.out_ids[out_begin + (wd - LL_IDS)];     // block ids are < 2^31
+    }
+    a.ll[wd] = flag | v;
+  }
+}
+
+// ==================================================================================== the step kernel
 __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &s = *reinterpret_cast<Smem *>(smem_raw);
@@ -2495,39 +2553,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   __syncthreads();
   KVB_PROF(9);
   if (tid < SC_COUNT) c.sc[tid] = sc[tid];
-  if (a.ll) {
-    // Single request, flagged publish: payload and flag travel in the same 8-byte store, so no fence orders them.
-    // (res and ids were written to device scratch by the request; the block barrier above made them visible.)
-    const kvb_res r = a.res[a.op_begin];
-    const int64_t nev = sc[SC_NEV] - ev_begin;
-    const int nids = (r.status == KVB_ST_OK && r.n > 0 && sc[SC_OUT_CURSOR] > out_begin) ? (int)(sc[SC_OUT_CURSOR] - out_begin) : 0;
-    const int nevin = nev < kLlEvents ? (int)nev : kLlEvents;
-    const int total = LL_IDS + nids;
-    const uint64_t flag = (uint64_t)a.ll_flag << 32;
-    const int64_t fls = sc[SC_FL_SIZE];
-    for (int wd = tid; wd < total; wd += NT) {
-      uint32_t v = 0;
-      if (wd == LL_STATUS) v = (uint32_t)r.status;
-      else if (wd == LL_N) v = (uint32_t)r.n;
-      else if (wd < LL_AUX) v = (uint32_t)((uint64_t)r.avail >> (32 * (wd - LL_AVAIL)));
-      else if (wd < LL_NEV) v = (uint32_t)((uint64_t)r.aux >> (32 * (wd - LL_AUX)));
-      else if (wd == LL_NEV) v = (uint32_t)nev;
-      else if (wd == LL_NHINT) v = (uint32_t)(fls < 16 ? fls : 16);
-      else if (wd < LL_SC) {
-        const int h = wd - LL_HINT;
-        v = h < fls ? (uint32_t)c.fl[(int)((sc[SC_FL_HEAD] + h) & c.q_mask)] : 0xffffffffu;
-      } else if (wd < LL_EV) {
-        const int q = wd - LL_SC;
-        v = (uint32_t)((uint64_t)sc[q >> 1] >> (32 * (q & 1)));
-      } else if (wd < LL_IDS) {
-        const int q = wd - LL_EV;
-        v = (q >> 1) < nevin ? (uint32_t)((uint64_t)c.ev[ev_begin + (q >> 1)] >> (32 * (q & 1))) : 0u;
-      } else {
-        v = (uint32_t)a.out_ids[out_begin + (wd - LL_IDS)];     // block ids are < 2^31
-      }
-      a.ll[wd] = flag | v;
-    }
-  }
+  if (a.ll) publish_flagged(c, s, a, ev_begin, out_begin);
   Summary *sm = a.summary;
   if (sm) {
     int64_t nev = sc[SC_NEV] - ev_begin;
@@ -2591,6 +2617,65 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
       *reinterpret_cast<volatile int64_t *>(&sm->seq) = a.seq;        // written last: the host polls it
     }
   }
+  KVB_PROF(10);
+}
+
+// ==================================================================================== single requests
+// kvb_mgr_alloc / kvb_mgr_free launch THIS kernel: the same device functions (alloc_run_warp, free_small, the flagged
+// publish) without the other twenty request kinds around them.  kvb_step_kernel is 1.3 MB of SASS and a launch
+// executes a few thousand instructions of it exactly once: ncu charged 66 % of the issue stalls of a single-request
+// launch to instruction fetch (profiles/r2_step_single_rules.csv).  Requests this kernel cannot serve with those two
+// paths (shrink mode, blocks straddling page edges, windows too small, > 256 distinct pages) are answered with
+// KVB_ST_RETRY — nothing touched — and the host sends them through kvb_step_kernel.
+__global__ void __launch_bounds__(NT, 1) kvb_one_kernel(DevState c, LaunchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  int64_t *sc = s.sc;
+  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
+  if (tid < 16) s.misc[tid] = 0;
+  if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
+  if (tid == 0) s.ops[0] = a.inline_op;
+  __syncthreads();
+  if (tid == 0) {
+    sc[SC_PHYS] = a.phys_free;
+    sc[SC_LAUNCHES] += 1;
+    sc[SC_OUT_CURSOR] = 0;
+    if (!a.keep_events) sc[SC_NEV] = 0;
+  }
+  __syncthreads();
+  const int64_t ev_begin = a.keep_events ? 0 : sc[SC_NEV];
+#ifdef KVB_PROFILE
+  if (tid == 0) s.prof_t = clock64();
+#endif
+  const kvb_op o = s.ops[0];
+  int retry = 0;
+  if (o.kind == KVB_OP_ALLOC) {
+    if (a.resize_target > 0) {            // _alloc() first applies a limit change (kv_cache_manager.py:258-260)
+      if (tid == 0) mgr_resize(c, sc, a.resize_target);
+      __syncthreads();
+    }
+    retry = !alloc_run_warp(c, s, a, 0, 0, 1);
+  } else if (o.kind == KVB_OP_FREE_IDS) {
+    int64_t my = -1;
+    if (tid < o.n) my = (a.inline_on == 1) ? a.inline_ids[tid] : a.ids[tid];
+    retry = (o.n > NT) || !free_small(c, s, a, o.n, my);
+    if (!retry && tid == 0) {
+      kvb_res r{}; r.status = KVB_ST_OK; r.n = o.n; r.off = 0; r.avail = avail_size(c, sc);
+      a.res[0] = r;
+    }
+  } else if (tid == 0) {                  // KVB_OP_AVAIL: the flush of frees that published nothing
+    kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+    a.res[0] = r;
+  }
+  if (retry && tid == 0) {
+    kvb_res r{}; r.status = KVB_ST_RETRY; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+    a.res[0] = r;
+  }
+  __syncthreads();
+  KVB_PROF(9);
+  if (tid < SC_COUNT) c.sc[tid] = sc[tid];
+  if (a.ll) publish_flagged(c, s, a, ev_begin, 0);
   KVB_PROF(10);
 }
 
@@ -2961,6 +3046,18 @@ int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
   int rc = launch_step_prepare();
   if (rc) return rc;
   kvb_step_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
+  return (int)cudaGetLastError();
+}
+
+int launch_one(const DevState &st, const LaunchArgs &a, void *stream) {
+  static bool attr_set[kMaxDev];
+  const int dev = cur_dev();
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kvb_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  kvb_one_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
   return (int)cudaGetLastError();
 }
 

@@ -450,7 +450,8 @@ int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_
     a.ll = sl->ll;
     a.ll_flag = flag;
   }
-  int lrc = launch_step(m->st, a, m->stream);
+  // the compact single-request kernel; a free whose ids do not fit the parameters goes through the general one
+  int lrc = big_free ? launch_step(m->st, a, m->stream) : launch_one(m->st, a, m->stream);
   if (lrc != 0) { set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); return KVB_ERR_CUDA; }
   m->launches++;
   m->n_fast++;
@@ -915,6 +916,11 @@ extern "C" int64_t kvb_mgr_alloc(kvb_mgr *m, int64_t n, int64_t *out, int64_t ca
   if (n <= kFastOut && fast_ok(m)) {   // one request in the kernel parameters, result straight into a pinned slot
     std::lock_guard<std::mutex> lk(m->mu);
     rc = fast_op(m, KVB_OP_ALLOC, (int32_t)n, nullptr, true, &r, out, cap);
+    if (rc == 0 && r.status == KVB_ST_RETRY) {   // not a case for the compact kernel: nothing was touched
+      kvb_op o{KVB_OP_ALLOC, (int32_t)n, 0};
+      int64_t rs = step_locked(m, &o, 1, nullptr, 0, nullptr, 0, &r, out, cap);
+      rc = rs < 0 ? (int)rs : 0;
+    }
   } else {
     rc = one_op(m, KVB_OP_ALLOC, (int32_t)n, 0, nullptr, 0, &r, out, cap);
   }
@@ -930,7 +936,13 @@ extern "C" int kvb_mgr_free(kvb_mgr *m, const int64_t *ids, int64_t n) {
     // free() returns nothing, so it does not wait for its kernel (stream order keeps the sequence); the launch's
     // summary — counters, page unmaps — is consumed by the next call on this manager, or by the VMM thread when idle
     std::lock_guard<std::mutex> lk(m->mu);
-    return fast_op(m, KVB_OP_FREE_IDS, (int32_t)n, ids, !m->async_free, &r, nullptr, 0);
+    int rc = fast_op(m, KVB_OP_FREE_IDS, (int32_t)n, ids, !m->async_free, &r, nullptr, 0);
+    if (rc == 0 && r.status == KVB_ST_RETRY) {   // (only a waiting free can be told to retry)
+      kvb_op o{KVB_OP_FREE_IDS, (int32_t)n, 0};
+      int64_t rs = step_locked(m, &o, 1, ids, n, nullptr, 0, &r, nullptr, 0);
+      rc = rs < 0 ? (int)rs : 0;
+    }
+    return rc;
   }
   return one_op(m, KVB_OP_FREE_IDS, (int32_t)n, 0, ids, n, &r, nullptr, 0);
 }
