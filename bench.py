@@ -41,8 +41,9 @@ N_REQUESTS = 4096
 PAGE = 2 << 20
 SCATTER_T = 65536           # tokens per fused all-layer scatter launch (16 GiB of traffic > L2)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE kvb_kv_copy_kernel<scatter> launch at exactly this shape
-# (T = 65 536 tokens, 32 layers, cell 2048 B), ncu --set full, profiles/r1_kv_copy_T65536_full.csv
-SCATTER_TRAFFIC_NCU = 8_592_656_000 + 8_543_728_000
+# (T = 65 536 tokens, 32 layers, cell 2048 B), ncu --set full, profiles/r2_kv_copy_cell2048.csv (round 1 measured
+# 17.136 GB with the previous kernel: profiles/r1_kv_copy_T65536_full.csv)
+SCATTER_TRAFFIC_NCU = 8_593_535_000 + 8_547_023_000
 
 
 def workload_config(world: int) -> dict:
@@ -1052,7 +1053,7 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "bound": "hbm", "achieved": kv["scatter"]["gbs_per_gpu"], "peak": peak, "unit": "GB/s",
                 "frac": kv["scatter"]["gbs_per_gpu"] / peak,
                 "traffic": SCATTER_TRAFFIC_NCU if (world == 1 and Tn == SCATTER_T) else None,
-                "traffic_source": "ncu --set full dram bytes of one launch at this shape (profiles/r1_kv_copy_T65536_full.csv)",
+                "traffic_source": "ncu --set full dram bytes of one launch at this shape (profiles/r2_kv_copy_cell2048.csv)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "step_kernel": {"us_per_scheduler_step": 1e3 * res_ms_total / K / n_sched_steps,
