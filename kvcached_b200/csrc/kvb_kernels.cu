@@ -515,12 +515,15 @@ __device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uin
 // 32 < D <= 32 * HT_WK: the first rehash phases hold at most 32 keys (bucket counts 2, 5, 11, 23, ...) and run in the
 // one-key-per-lane form of ht_order_warp (registers and votes only, ~4x cheaper per phase than the multi-key form);
 // the phase that first exceeds 32 keys, and the ones after it, continue in ht_order_warp_multi.
-__device__ __forceinline__ void ht_order_hybrid(const DevState &c, const uint32_t *primes32, const int32_t *keys, int D,
-                                                int nb, int32_t *ord, int32_t *tab_first, int32_t *tab_cnt,
-                                                int64_t *perm) {
+// The single-key phases of a replay with D > 32 keys: runs rehash phases in the one-key-per-lane form while they hold
+// at most 32 keys.  On return *nb is the bucket count of the NEXT phase, *placed the keys placed so far (<= 32), and
+// lane l < *placed holds the element at position l of the container's order (cur_slot / cur_key).
+__device__ __forceinline__ void ht_order_prefix(const DevState &c, const uint32_t *primes32, const int32_t *keys, int D,
+                                                int *nb_io, int *placed_out, int *slot_out, unsigned *key_out,
+                                                int32_t *scratch64) {
   const int lane = threadIdx.x & 31;
   const unsigned gt = ~((2u << lane) - 1u);
-  int32_t *scratch64 = reinterpret_cast<int32_t *>(perm);      // 64 words, free until the multi-key form starts
+  int nb = *nb_io;
   int cur_slot = lane;
   unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
   int placed = 0;
@@ -551,11 +554,104 @@ __device__ __forceinline__ void ht_order_hybrid(const DevState &c, const uint32_
     if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
     nb = next_bkt(c, primes32, want);
   }
+  *nb_io = nb;
+  *placed_out = placed;
+  *slot_out = cur_slot;
+  *key_out = cur_key;
+}
+
+// 32 < D <= 32 * HT_WK on ONE warp: the first rehash phases hold at most 32 keys (bucket counts 2, 5, 11, 23, ...) and run
+// in the one-key-per-lane form (registers and votes only); the phase that first exceeds 32 keys, and the ones after
+// it, continue in ht_order_warp_multi.
+__device__ __forceinline__ void ht_order_hybrid(const DevState &c, const uint32_t *primes32, const int32_t *keys, int D,
+                                                int nb, int32_t *ord, int32_t *tab_first, int32_t *tab_cnt,
+                                                int64_t *perm) {
+  const int lane = threadIdx.x & 31;
+  int placed, cur_slot;
+  unsigned cur_key;
+  ht_order_prefix(c, primes32, keys, D, &nb, &placed, &cur_slot, &cur_key, reinterpret_cast<int32_t *>(perm));
   if (placed >= D) {
     if (lane < D) ord[lane] = cur_slot;
     return;
   }
   ht_order_warp_multi(c, primes32, keys, D, nb, ord, tab_first, tab_cnt, perm, placed, cur_slot, cur_key);
+}
+
+// The later phases BLOCK-wide (all NT threads call; D <= 256): thread t holds the element at position t of the
+// container's order, warp c = t / 32 is chunk c.  Per phase, with S = current order ++ newly inserted keys:
+//   first position of my bucket in S         atomicMin into a shared table (one atomic per bucket and chunk);
+//   keys of my bucket at later positions     inside my chunk: __match_any_sync; in later chunks: the per-(bucket,
+//                                            chunk) counts are PACKED into one shared 64-bit word per bucket (8 chunks x
+//                                            8 bits), so one read gives them all — no chunk-by-chunk walk;
+//   keys of buckets that first appear later  suffix sum, over positions, of the bucket sizes held by bucket leaders;
+//   new position = the two sums; the permutation goes through shared memory in place.
+// Five block barriers per phase whatever the key count; the one-warp form walks its 8 chunks twice per phase.
+__device__ void ht_order_block(const DevState &c, Smem &s, const int32_t *keys, int D, int nb, int placed, int32_t *ord) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned gt = ~((2u << lane) - 1u), lt = (1u << lane) - 1u;
+  int32_t *tab_first = s.ht_bkt;                  // [nb <= 1024]
+  int32_t *suf = s.ht_bkt + 1024;                 // [256]
+  int32_t *cur_slot = s.ht_bkt + 1280;            // [256] element at position t
+  int32_t *cur_key = s.ht_bkt + 1536;
+  unsigned long long *packed = reinterpret_cast<unsigned long long *>(s.tmp64);   // [nb <= NT]
+  while (true) {
+    const int upto = D < nb ? D : nb;
+    const bool in = t < upto;
+    int slot = 0;
+    unsigned key = 0;
+    if (in) {
+      if (t >= placed) { slot = t; key = (unsigned)keys[t]; }
+      else { slot = cur_slot[t]; key = (unsigned)cur_key[t]; }
+    }
+    const int b = in ? (int)(key % (unsigned)nb) : -1;
+    if (in) { tab_first[b] = INT_MAX; packed[b] = 0ull; }
+    __syncthreads();
+    const unsigned m = __match_any_sync(0xffffffffu, in ? b : -1 - lane);
+    const int intra_later = __popc(m & gt);
+    if (in && (m & lt) == 0) {                     // lowest lane of my bucket inside this chunk
+      atomicMin(&tab_first[b], t);
+      atomicAdd(&packed[b], (unsigned long long)__popc(m) << (8 * w));
+    }
+    __syncthreads();
+    int gfirst = 0, cnt = 0, later = intra_later;
+    if (in) {
+      gfirst = tab_first[b];
+      const unsigned long long pk = packed[b];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ck = (int)((pk >> (8 * k)) & 0xffull);
+        cnt += ck;
+        if (k > w) later += ck;
+      }
+    }
+    int v = (in && gfirst == t) ? cnt : 0;         // inclusive suffix sum over positions
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_down_sync(0xffffffffu, v, d);
+      if (lane + d < 32) v += y;
+    }
+    if (lane == 0) s.wtot[w] = v;
+    __syncthreads();
+    if (in) {
+      int base = 0;
+      for (int i = w + 1; i < 8; ++i) base += s.wtot[i];
+      suf[t] = v + base;
+    }
+    __syncthreads();
+    if (in) {
+      const int newpos = suf[gfirst] - cnt + later;
+      cur_slot[newpos] = slot;
+      cur_key[newpos] = (int)key;
+    }
+    __syncthreads();
+    placed = upto;
+    if (upto >= D) break;
+    int64_t want = (int64_t)upto + 2;              // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb))
+    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
+    nb = next_bkt(c, s.primes32, want);
+  }
+  if (t < D) ord[t] = cur_slot[t];
+  __syncthreads();
 }
 
 // bucket count the table ends with (decides shared vs global tables before the replay)
@@ -1569,9 +1665,22 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   KVB_PROF(5);
   // ---- dict order (warp 0) || FIFO ranks and ring appends (warp 1); groups.reserve(n / bpp + 1), page_allocator.cpp:477
   const int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
+  // block-wide later phases: bucket counts stay <= 503 (D <= 256 and a rehash at most doubles a count below D), which
+  // is what the packed per-bucket words have room for
+  const bool blockwide = D > 32 && nb0 <= 512;
   if (w == 0) {
-    if (D <= 32) ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);
-    else ht_order_hybrid(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
+    if (D <= 32) {
+      ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);
+    } else if (!blockwide) {
+      ht_order_hybrid(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_bkt, s.ht_next, s.tmp64);
+    } else {
+      // the phases that hold <= 32 keys here, on one warp; the rest block-wide after the barrier below
+      int nb1 = nb0, placed1, cs;
+      unsigned ck;
+      ht_order_prefix(c, s.primes32, s.ht_key, D, &nb1, &placed1, &cs, &ck, s.ht_next);
+      if (lane < placed1) { s.ht_bkt[1280 + lane] = cs; s.ht_bkt[1536 + lane] = (int)ck; }
+      if (lane == 0) { s.misc[MI_NB0] = nb1; s.misc[MI_K] = placed1; }
+    }
     KVB_PROF(11);
   } else if (w == 1) {
     for (int j0 = 0; j0 < n; j0 += 32) {
@@ -1592,6 +1701,7 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
     }
   }
   __syncthreads();
+  if (blockwide) ht_order_block(c, s, s.ht_key, D, s.misc[MI_NB0], s.misc[MI_K], s.ht_ord);
   KVB_PROF(6);
   // ---- per-page update in dict order (:322-349): free_core's F4 with shared-memory inputs
   int tail = (int)sc[SC_AP_TAIL];
