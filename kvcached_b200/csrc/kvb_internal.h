@@ -138,6 +138,10 @@ struct LaunchArgs {
   // keep_events: the page event log continues from the previous launch (it published nothing: a free() whose summary
   // is left to the next launch) and this launch reports the log from its start.
   int32_t keep_events;
+  int32_t safe_before;    // resident traces: results of requests below this index come from launches older than this
+                          // launch's predecessor in the stream / graph (0 = unknown: nothing may be read early)
+  int32_t tune;           // tuning switches (KVB200_TUNE): bit 0 = many-page frees replay the dict order on one warp,
+                          // bit 1 = launches without programmatic stream serialization, bit 2 = no early ref gather
   // Flagged publish of a single-request launch: every 64-bit word of `ll` carries 32 bits of payload and the launch's
   // 32-bit flag, so the host validates each word on its own and the kernel needs NO system-scope fence between
   // payload and sequence word (8-byte stores are single-copy atomic over PCIe).  Layout: LlWord below.

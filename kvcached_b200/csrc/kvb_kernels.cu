@@ -1667,7 +1667,7 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   const int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
   // block-wide later phases: bucket counts stay <= 503 (D <= 256 and a rehash at most doubles a count below D), which
   // is what the packed per-bucket words have room for
-  const bool blockwide = D > 32 && nb0 <= 512;
+  const bool blockwide = D > 32 && nb0 <= 512 && !(a.tune & 1);
   if (w == 0) {
     if (D <= 32) {
       ht_order_warp(c, s.primes32, s.ht_key, D, nb0, s.ht_ord, s.ht_next);
@@ -1841,7 +1841,13 @@ __device__ int gather_refs(const DevState &c, Smem &s, const LaunchArgs &a, int6
 // The same gather for calls that fit one id per thread (at most NT refs naming at most NT ids): thread t takes the
 // t-th id of the concatenation into a REGISTER (binary search of its ref in the shared offset table) — no staging
 // pass through c.fids.  Returns the id count, or -1 (uniform, nothing written) when the call does not fit.
-__device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, int64_t ref_off, int nrefs, int64_t *my_id) {
+// EARLY = the call is made before pdl_enter(), while the predecessor launch may still be running: results of requests
+// below `safe_before` come from launches that had completed before this one could start (a launch lets its successor
+// in only after its own wait), anything at or above it makes the call return -1.  Those loads bypass L1 (ld.cg): a
+// line that also holds a result the predecessor is still writing must not stay cached on this SM.
+template <bool EARLY>
+__device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, int64_t ref_off, int nrefs, int64_t *my_id,
+                               int safe_before = 0) {
   const int tid = threadIdx.x;
   *my_id = -1;
   if (nrefs > NT) return -1;
@@ -1849,18 +1855,30 @@ __device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, 
   int32_t *r_dst = s.ht_ord;
   int len = 0;
   int64_t src = 0;
+  bool late = false;
   if (tid < nrefs) {
     kvb_ref rf = a.refs[ref_off + tid];
-    kvb_res rs = a.res[rf.op];
+    kvb_res rs;
+    if (EARLY) {
+      late = rf.op >= safe_before;
+      const int4 *q = reinterpret_cast<const int4 *>(a.res + (late ? 0 : rf.op));
+      static_assert(sizeof(kvb_res) == 32, "kvb_res is read as two 16-byte words");
+      const int4 lo4 = __ldcg(q), hi4 = __ldcg(q + 1);
+      memcpy(&rs, &lo4, 16);
+      memcpy(reinterpret_cast<char *>(&rs) + 16, &hi4, 16);
+    } else {
+      rs = a.res[rf.op];
+    }
     int n = rs.status == KVB_ST_OK ? rs.n : 0;
     int lo = rf.lo < 0 ? (rf.lo + n < 0 ? 0 : rf.lo + n) : (rf.lo > n ? n : rf.lo);
     int hi = rf.hi < 0 ? (rf.hi + n < 0 ? 0 : rf.hi + n) : (rf.hi > n ? n : rf.hi);
     len = hi > lo ? hi - lo : 0;
     src = rs.off + lo;
   }
+  if (EARLY && __syncthreads_or(late)) return -1;
   int tot;
   const int ex = block_exscan(len, s.wtot, &tot);
-  if (tot > NT) return -1;
+  if (tot > NT) { __syncthreads(); return -1; }
   r_src[tid] = src;
   r_dst[tid] = tid < nrefs ? ex : INT_MAX;     // offsets are non-decreasing; empty refs share their successor's offset
   __syncthreads();
@@ -1870,7 +1888,8 @@ __device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, 
       const int mid = (lo + hi + 1) >> 1;
       if (r_dst[mid] <= tid) lo = mid; else hi = mid - 1;
     }
-    *my_id = a.out_ids[r_src[lo] + (tid - r_dst[lo])];
+    const int64_t *src_id = a.out_ids + r_src[lo] + (tid - r_dst[lo]);
+    *my_id = EARLY ? __ldcg(src_id) : *src_id;
   }
   __syncthreads();
   return tot;
@@ -2228,6 +2247,16 @@ __device__ int slots_unique_blocks(const DevState &c, Smem &s, const LaunchArgs 
 
 }  // namespace
 
+// Programmatic dependent launch (sm_90+): a launch made with cudaLaunchAttributeProgrammaticStreamSerialization becomes
+// resident while its predecessor in the stream / graph is still running and parks here until that grid has completed
+// and its memory is visible; it then lets ITS successor start the same way.  The launch gap between the kernels of
+// consecutive scheduler steps (CTA scheduling, parameter and shared-memory set-up) disappears behind the running kernel.
+// Without the attribute both instructions do nothing.  Nothing of the device state may be read before pdl_enter().
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ==================================================================================== the step kernel
 // Flagged publish of a single-request launch: payload and flag travel in the same 8-byte store, so no fence orders
 // them (LlWord in kvb_internal.h).  res and ids were written to device scratch by the request; the caller's block
@@ -2274,9 +2303,34 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   const int tid = threadIdx.x;
   int64_t *sc = s.sc;
 
-  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
+  // Before pdl_enter(): only what no kernel writes — launch parameters, the prime table, the caller's request arrays.
+  // The first chunk of requests is staged and the ref lists of its FREE_REF requests are pulled into L2 (the trace is
+  // read once per replay, i.e. from DRAM) while the predecessor kernel is still running.
+  {
+    const int n_first = (a.op_end - a.op_begin) < OPS_CHUNK ? (a.op_end - a.op_begin) : OPS_CHUNK;
+    if (tid < n_first) {
+      const kvb_op o = a.inline_on ? a.inline_op : a.ops[a.op_begin + tid];
+      s.ops[tid] = o;
+      if (o.kind == KVB_OP_FREE_REF && a.refs && o.n > 0) {
+        const char *r0 = reinterpret_cast<const char *>(a.refs + o.arg);
+        const int bytes = (o.n < 1024 ? o.n : 1024) * (int)sizeof(kvb_ref);
+        for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + b));
+      }
+    }
+  }
   if (tid < 16) s.misc[tid] = 0;
   if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
+  // A resident trace opens most steps with the free() of a request that finished one step earlier; its ids are
+  // results of launches older than the predecessor (a.safe_before, set by kvb_mgr_trace_run) unless its last block
+  // was allocated in the step just before — so the whole gather (refs -> results -> ids in registers) can run here too.
+  int64_t early_id = -1;
+  int early_n = -1;
+  if (a.safe_before > 0 && !a.inline_on) {
+    const kvb_op o0 = a.ops[a.op_begin];
+    if (o0.kind == KVB_OP_FREE_REF) early_n = gather_refs_reg<true>(c, s, a, o0.arg, o0.n, &early_id, a.safe_before);
+  }
+  pdl_enter();
+  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
   __syncthreads();
   if (tid == 0) {
     sc[SC_PHYS] = a.phys_free;
@@ -2295,8 +2349,10 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   while (op < a.op_end && !s.misc[MI_STOP]) {
     const int chunk_base = op;
     const int chunk_n = (a.op_end - op) < OPS_CHUNK ? (a.op_end - op) : OPS_CHUNK;
-    if (tid < chunk_n) s.ops[tid] = a.inline_on ? a.inline_op : a.ops[chunk_base + tid];
-    __syncthreads();
+    if (chunk_base != a.op_begin) {      // the first chunk was staged before pdl_enter()
+      if (tid < chunk_n) s.ops[tid] = a.inline_on ? a.inline_op : a.ops[chunk_base + tid];
+      __syncthreads();
+    }
     while (op < chunk_base + chunk_n && !s.misc[MI_STOP]) {
       const kvb_op o = s.ops[op - chunk_base];
       if (a.arena_mode != 1 && sc[SC_NEV] + 2 * (int64_t)c.max_pages + 8 > c.ev_cap) {   // event log nearly full: hand back to the host
@@ -2330,9 +2386,12 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           int e = s.misc[MI_K];
           if (e - op > NT) e = op + NT;
           KVB_PROF(0);
-          if (alloc_run_warp(c, s, a, chunk_base, op, e) || alloc_run_fast(c, s, a, chunk_base, op, e)) {
+          if (alloc_run_warp(c, s, a, chunk_base, op, e)) {
             op = e;
             KVB_PROF(1);
+          } else if (alloc_run_fast(c, s, a, chunk_base, op, e)) {
+            op = e;
+            KVB_PROF(12);
           } else {
             alloc_run(c, s, a, chunk_base, op, e, 0);
             op = s.sim.op;   // == e unless the output buffer ran out
@@ -2363,8 +2422,8 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
               else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
             }
           } else if (o.kind == KVB_OP_FREE_REF) {
-            int64_t my = -1;
-            n = gather_refs_reg(c, s, a, o.arg, o.n, &my);
+            int64_t my = early_id;
+            n = (op == a.op_begin && early_n >= 0) ? early_n : gather_refs_reg<false>(c, s, a, o.arg, o.n, &my);
             if (n >= 0 && n <= c.f_cap) {
               KVB_PROF(3);
               done = free_small(c, s, a, n, my) != 0;
@@ -2742,10 +2801,11 @@ __global__ void __launch_bounds__(NT, 1) kvb_one_kernel(DevState c, LaunchArgs a
   Smem &s = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
   int64_t *sc = s.sc;
-  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
   if (tid < 16) s.misc[tid] = 0;
   if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
   if (tid == 0) s.ops[0] = a.inline_op;
+  pdl_enter();                           // nothing of the device state is read above this line
+  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
   __syncthreads();
   if (tid == 0) {
     sc[SC_PHYS] = a.phys_free;
@@ -3140,6 +3200,22 @@ static int resident_grid(K kernel, int threads, int *cache_by_dev) {
   return *cache;
 }
 
+// One CTA of NT threads; with programmatic stream serialization unless KVB200_PDL=0 (pdl_enter() above).
+static int launch_bookkeeping(void (*kernel)(DevState, LaunchArgs), const DevState &st, const LaunchArgs &a, void *stream) {
+  static const bool pdl = []() { const char *e = getenv("KVB200_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = sizeof(Smem);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && !(a.tune & 2)) ? 1 : 0;     // KVB200_TUNE bit 1: same-process A/B of the attribute
+  return (int)cudaLaunchKernelEx(&cfg, kernel, st, a);
+}
+
 int launch_step_prepare() {
   static bool attr_set[kMaxDev];
   const int dev = cur_dev();
@@ -3155,8 +3231,7 @@ int launch_step_prepare() {
 int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
   int rc = launch_step_prepare();
   if (rc) return rc;
-  kvb_step_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
-  return (int)cudaGetLastError();
+  return launch_bookkeeping(kvb_step_kernel, st, a, stream);
 }
 
 int launch_one(const DevState &st, const LaunchArgs &a, void *stream) {
@@ -3167,8 +3242,7 @@ int launch_one(const DevState &st, const LaunchArgs &a, void *stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
-  kvb_one_kernel<<<1, NT, sizeof(Smem), (cudaStream_t)stream>>>(st, a);
-  return (int)cudaGetLastError();
+  return launch_bookkeeping(kvb_one_kernel, st, a, stream);
 }
 
 int launch_init_state(const DevState &st, int64_t num_total_pages, void *stream) {

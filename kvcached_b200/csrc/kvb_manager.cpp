@@ -137,6 +137,8 @@ struct kvb_mgr {
   bool fast_on = true;                     // KVB200_FAST_PATH=0 disables
   bool async_free = true;                  // KVB200_ASYNC_FREE=0: kvb_mgr_free waits for its kernel
   int64_t n_fast = 0, n_async_free = 0;
+  int tune = 0;                            // KVB200_TUNE: kernel tuning switches (LaunchArgs.tune)
+  int safe_before_next = 0;                // LaunchArgs.safe_before of the next launch (kvb_mgr_trace_run sets it per launch)
   bool in_hook = false;                    // collect_pending runs on the VMM thread (idle hook)
   bool tp_on = false;              // kvb_tp_init attached this manager (rank 0) to the group's TP mailbox
   int tp_flags_next = 0;           // flags of the record the next launch may push (kTpFlagSettle)
@@ -292,6 +294,13 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
   a.host_res = host_res;
   a.host_out = host_out;
   a.resize_target = (m->shm && !group_only) ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
+  a.tune = m->tune;
+  // The kernel stages its requests BEFORE it waits for its predecessor (programmatic dependent launch): allowed only
+  // where the request array is final at launch time — the resident trace, or pinned host memory the host has filled.
+  // A request array that an async copy on the stream is still filling takes the plain, fully serialised launch.
+  if (group_only || (arena_mode != 1 && !m->zero_copy)) a.tune |= 2;
+  a.safe_before = (arena_mode == 1 && !(a.tune & 4)) ? m->safe_before_next : 0;
+  m->safe_before_next = 0;
   if (m->tp_on && !group_only && arena_mode != 1 && d_sum) {
     // tensor parallel: the kernel pushes this launch's page list into the mailbox itself (kvb_tp.h); the ring
     // must have a free slot before the launch, the host learns from the summary whether it was used
@@ -440,6 +449,7 @@ int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_
   a.seq = ++m->seq;
   a.arena_mode = 0;
   a.keep_events = m->log_open ? 1 : 0;
+  a.tune = m->tune;
   a.resize_target = m->shm ? m->shm->resize_target(m->mem_size, m->cfg.num_layers, m->cfg.num_kv_buffers) : -1;
   const uint32_t flag = (uint32_t)(a.seq & 0x7fffffff) | 0x80000000u;
   if (big_free) {
@@ -698,6 +708,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
     }
   }
 
+  m->tune = (int)env_i64("KVB200_TUNE", 0);
   m->fast_on = env_i64("KVB200_FAST_PATH", 1) != 0;
   m->async_free = env_i64("KVB200_ASYNC_FREE", 1) != 0;
   if (c.attach_vmm && vmm_initialized()) {
@@ -1211,12 +1222,18 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
   { int rc0 = collect_pending(m); if (rc0) return rc0; }
   int64_t launches0 = m->launches;
   auto run_range = [&]() -> int {
+    // Results of requests below the PREVIOUS launch's first request are complete when a launch becomes resident (its
+    // predecessor lets it in only after having waited for its own predecessor); the first launch of the range follows
+    // a memset / a synchronised stream, so everything before it is complete.
+    int64_t prev_ob = -1;
     for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
       int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
       int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
       if (oe == ob) continue;
+      m->safe_before_next = (int)(prev_ob < 0 ? ob : prev_ob);
       int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0);
       if (rc) return rc;
+      prev_ob = ob;
     }
     return 0;
   };

@@ -210,3 +210,49 @@ def test_over_allocation_returns_none_and_config_error():
     m.close()
     with pytest.raises(KVCachedConfigError):
         KVCacheManager(16, 16, (4 << 20) // 16, 2, attach_vmm=False)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_free_of_many_pages_per_call_vs_oracle(seed):
+    """free() calls of <= 512 ids that name 33 .. 256 distinct pages: the shared-memory free path with the block-wide
+    replay of libstdc++'s unordered_map order (ht_order_prefix + ht_order_block).  The avail_pages order after every
+    call IS that order, so the snapshot comparison pins it; ids per page vary so that some pages empty out."""
+    cfg = T.make_config("llama8b", 64 * 300)          # 300 pages of 64 blocks
+    rng = np.random.default_rng(seed)
+    om = oracle.manager_from_config(cfg)
+    m = _mgr(cfg)
+    held = om.alloc(64 * 280)
+    assert m.alloc(64 * 280) == held
+    held = np.array(held, dtype=np.int64)
+    alive = np.ones(held.size, dtype=bool)
+    for it, D in enumerate([33, 34, 47, 48, 64, 97, 100, 128, 199, 200, 255, 256, 40, 250]):
+        pages = rng.choice(280, size=D, replace=False)
+        ids = []
+        for p in pages:
+            cand = np.nonzero(alive[p * 64:(p + 1) * 64])[0]
+            if cand.size == 0:
+                continue
+            k = min(cand.size, int(rng.integers(1, 3)) if D > 200 else int(rng.integers(1, 6)))
+            take = rng.choice(cand, size=k, replace=False) + p * 64
+            ids.extend(int(x) for x in take)
+        ids = [int(held[i]) for i in rng.permutation(ids)][:512]
+        for i in ids:
+            alive[np.nonzero(held == i)[0][0]] = False
+        om.free(ids)
+        m.free(ids)
+        got, want = m.snapshot(), om.snapshot()
+        bad = diff_record({"r": None, **got}, {"r": None, **want})
+        assert not bad, f"call {it} (D={D}, n={len(ids)}) differs in {bad}: got { {k: got[k] for k in bad} } want { {k: want[k] for k in bad} }"
+        # and the allocation that follows consumes the pages in that order
+        n = int(rng.integers(1, 40))
+        a, b = m.alloc(n), om.alloc(n)
+        assert a == b
+        for i in a:
+            j = np.nonzero(held == i)[0]
+            if j.size:
+                alive[j[0]] = True
+            else:
+                held = np.append(held, i)
+                alive = np.append(alive, True)
+    assert m.audit()[3] == 0
+    m.close()

@@ -9,12 +9,12 @@ import torch
 from kvcached_b200 import _lib, replay as R, trace as T
 torch.cuda.init()
 lib = _lib.load()
-NAMES = ["pre-alloc/idle", "alloc fast", "alloc general", "free: stage ids", "F0 classify", "F1+F2 distinct pages", "F3 dict order + ranks",
-         "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work", "w32: phase head", "w32: match_any", "w32: suffix scan", "w32: permute"]
+NAMES = ["pre-alloc/idle", "alloc run, warp path", "alloc general", "free: stage ids", "F0 classify", "F1+F2 distinct pages", "F3 dict order + ranks",
+         "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work", "alloc run, block-wide (w32: phase head in free_core)", "w32: match_any", "w32: suffix scan", "w32: permute"]
 def show(m, title, launches):
     prof = np.zeros(32, dtype=np.int64)
     lib.kvb_mgr_profile(m._h, prof.ctypes.data_as(_lib.p_i64), 1)
-    tot = prof[:11].sum()
+    tot = prof[:11].sum() + prof[12]
     print(f"== {title}: {tot/launches:.0f} cycles per launch in marked phases ({tot/launches/1.9:.0f} ns at 1.9 GHz)")
     for i, n in enumerate(NAMES):
         if prof[16 + i]:
