@@ -65,6 +65,7 @@ constexpr int NEWPG_W = 64;      // prefetched window of upcoming fresh page ids
 constexpr int HT_D_CAP = 2048;   // distinct pages per free() handled in shared memory
 constexpr int HT_NB_CAP = 4099;  // hash buckets handled in shared memory
 constexpr int EV_INLINE = 256;
+constexpr int EARLY_K = 4;        // leading free() requests of a resident step whose ids are gathered before the wait
 constexpr int PRIMES_SM = 128;   // __prime_list[0..127] reaches 2^17; larger bucket counts read the global table
 
 enum : int { SEG_RB = 0, SEG_RING = 1, SEG_FRESH = 2 };
@@ -114,6 +115,8 @@ struct Smem {
   int32_t wtot[NW], wtot2[NW];
   int32_t misc[16];
   int64_t tmp64[NT];
+  int32_t early_ids[EARLY_K][NT];   // ids of the launch's leading FREE_REF requests, gathered before pdl_enter()
+  int32_t early_n[EARLY_K];         // their id counts, -1 = gather it after the wait
   AllocSim sim;
   long long prof_t;
 };
@@ -2323,11 +2326,17 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   // A resident trace opens most steps with the free() of a request that finished one step earlier; its ids are
   // results of launches older than the predecessor (a.safe_before, set by kvb_mgr_trace_run) unless its last block
   // was allocated in the step just before — so the whole gather (refs -> results -> ids in registers) can run here too.
-  int64_t early_id = -1;
-  int early_n = -1;
-  if (a.safe_before > 0 && !a.inline_on) {
-    const kvb_op o0 = a.ops[a.op_begin];
-    if (o0.kind == KVB_OP_FREE_REF) early_n = gather_refs_reg<true>(c, s, a, o0.arg, o0.n, &early_id, a.safe_before);
+  // A scheduler step lists its frees first (trace.py), so this covers up to EARLY_K of them.
+  if (tid < EARLY_K) s.early_n[tid] = -1;
+  if (a.safe_before > 0 && !a.inline_on && c.num_blocks < (1ll << 31)) {
+    for (int k = 0; k < EARLY_K && a.op_begin + k < a.op_end; ++k) {
+      const kvb_op ok = a.ops[a.op_begin + k];
+      if (ok.kind != KVB_OP_FREE_REF) break;
+      int64_t id = -1;
+      const int nk = gather_refs_reg<true>(c, s, a, ok.arg, ok.n, &id, a.safe_before);   // ends with a block barrier
+      s.early_ids[k][tid] = (int32_t)id;                                                // block ids are < 2^31, -1 = none
+      if (tid == 0) s.early_n[k] = nk;
+    }
   }
   pdl_enter();
   if (tid < SC_COUNT) sc[tid] = c.sc[tid];
@@ -2422,8 +2431,10 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
               else { for (int j = tid; j < n; j += NT) c.fids[j] = a.ids[o.arg + j]; }
             }
           } else if (o.kind == KVB_OP_FREE_REF) {
-            int64_t my = early_id;
-            n = (op == a.op_begin && early_n >= 0) ? early_n : gather_refs_reg<false>(c, s, a, o.arg, o.n, &my);
+            int64_t my = -1;
+            const int ek = op - a.op_begin;
+            if (ek < EARLY_K && s.early_n[ek] >= 0) { n = s.early_n[ek]; my = s.early_ids[ek][tid]; }
+            else n = gather_refs_reg<false>(c, s, a, o.arg, o.n, &my);
             if (n >= 0 && n <= c.f_cap) {
               KVB_PROF(3);
               done = free_small(c, s, a, n, my) != 0;
