@@ -65,6 +65,8 @@ constexpr int NEWPG_W = 64;      // prefetched window of upcoming fresh page ids
 constexpr int HT_D_CAP = 2048;   // distinct pages per free() handled in shared memory
 constexpr int HT_NB_CAP = 4099;  // hash buckets handled in shared memory
 constexpr int EV_INLINE = 256;
+// call sites of the one-barrier scans: each owns its row of Smem::wsite
+enum : int { WS_GATHER = 0, WS_FS_D, WS_FS_F4, WS_AF0, WS_AF1, WS_AF2, WS_AF3, WS_COUNT };
 constexpr int EARLY_K = 4;        // leading free() requests of a resident step whose ids are gathered before the wait
 constexpr int PRIMES_SM = 128;   // __prime_list[0..127] reaches 2^17; larger bucket counts read the global table
 
@@ -100,6 +102,11 @@ struct AllocSim {
   int64_t round_base;  // output position where this round started
 };
 
+struct WarpPlan {
+  int32_t T, take_rb, take_av, rem2, nlive, F, from_rl, last_used, tail, pad;
+  int64_t cursor, A0, nev0, rbh;
+};
+
 struct Smem {
   int64_t sc[SC_COUNT];
   int64_t acc[8];
@@ -113,10 +120,13 @@ struct Smem {
   int32_t ht_key[HT_D_CAP], ht_next[HT_D_CAP], ht_ord[HT_D_CAP], ht_cnt[HT_D_CAP];
   int32_t ht_bkt[HT_NB_CAP + 1];
   int32_t wtot[NW], wtot2[NW];
+  int32_t wsite[WS_COUNT][NW];   // per-call-site buffers of the one-barrier scans (block_*_1b)
   int32_t misc[16];
   int64_t tmp64[NT];
   int32_t early_ids[EARLY_K][NT];   // ids of the launch's leading FREE_REF requests, gathered before pdl_enter()
   int32_t early_n[EARLY_K];         // their id counts, -1 = gather it after the wait
+  WarpPlan wplan;                   // alloc_run_warp: warp 0's plan for the CTA
+  int32_t wroff[128];               // ... and the id-stream offset of each request of the run
   AllocSim sim;
   long long prof_t;
 };
@@ -245,19 +255,24 @@ __device__ void pa_trim(const DevState &c, int64_t *sc) {
 // ------------------------------------------------------------------------------------ block-wide scans
 // Ordered exclusive prefix of a per-thread flag over the CTA: __ballot_sync + __popc inside a warp,
 // warp totals through shared memory.  Returns the exclusive rank; *total receives the CTA total.
+// Second stage of both scans: lane i holds warp i's total, two warp reductions (REDUX.SUM) give the sum over the warps
+// below mine and the CTA total.  The kernel is issue-bound (one CTA = four warps per scheduler, every warp runs the
+// uniform code): a 16-iteration loop over wtot cost ~80 issue slots per warp and call, this costs ~8
+// (profiles/r2_step_instruction_counts.md).
+__device__ __forceinline__ void warp_totals(const int32_t *wtot, int lane, int w, int *base, int *tot) {
+  static_assert(NW <= 32, "one lane per warp total");
+  const int t = lane < NW ? wtot[lane] : 0;
+  *tot = __reduce_add_sync(0xffffffffu, t);
+  *base = __reduce_add_sync(0xffffffffu, lane < w ? t : 0);
+}
 __device__ __forceinline__ int block_rank(bool flag, int32_t *wtot, int *total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned m = __ballot_sync(0xffffffffu, flag);
   int r = __popc(m & ((1u << lane) - 1u));
   if (lane == 0) wtot[w] = __popc(m);
   __syncthreads();
-  int base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    int t = wtot[i];
-    if (i < w) base += t;
-    tot += t;
-  }
+  int base, tot;
+  warp_totals(wtot, lane, w, &base, &tot);
   __syncthreads();
   *total = tot;
   return base + r;
@@ -273,16 +288,81 @@ __device__ __forceinline__ int block_exscan(int v, int32_t *wtot, int *total) {
   }
   if (lane == 31) wtot[w] = x;
   __syncthreads();
-  int base = 0, tot = 0;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    int t = wtot[i];
-    if (i < w) base += t;
-    tot += t;
-  }
+  int base, tot;
+  warp_totals(wtot, lane, w, &base, &tot);
   __syncthreads();
   *total = tot;
   return base + x - v;
+}
+
+// One-barrier forms.  The trailing barrier of block_rank / block_exscan only protects `wtot` against the NEXT scan that
+// writes it; a scan whose buffer belongs to one call site alone does not need it, provided every thread passes some
+// other block barrier between reading the totals here and the next execution of the same site (true of every site
+// below: each is followed by barriers of its own function before that function can run again).
+__device__ __forceinline__ int block_rank_1b(bool flag, int32_t *site, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) site[w] = __popc(m);
+  __syncthreads();
+  int base, tot;
+  warp_totals(site, lane, w, &base, &tot);
+  *total = tot;
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ int block_exscan_1b(int v, int32_t *site, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) site[w] = x;
+  __syncthreads();
+  int base, tot;
+  warp_totals(site, lane, w, &base, &tot);
+  *total = tot;
+  return base + x - v;
+}
+// Two ranks in one pass: both counts are <= NT < 2^16, so the warp totals travel packed in one word.
+__device__ __forceinline__ void block_rank2_1b(bool fa, bool fb, int32_t *site, int *ra, int *ta, int *rb, int *tb) {
+  static_assert(NT < (1 << 16), "packed totals");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+  if (lane == 0) site[w] = __popc(ma) | (__popc(mb) << 16);
+  __syncthreads();
+  int base, tot;
+  warp_totals(site, lane, w, &base, &tot);
+  const unsigned lt = (1u << lane) - 1u;
+  *ra = (base & 0xffff) + __popc(ma & lt);
+  *ta = tot & 0xffff;
+  *rb = (int)((unsigned)base >> 16) + __popc(mb & lt);
+  *tb = (int)((unsigned)tot >> 16);
+}
+// alloc_run_fast's three scans (exclusive sum, rank, exclusive sum) and its vote in one pass: rows 0..3 of `site`.
+__device__ __forceinline__ void block_scan3_1b(int v0, bool f1, int v2, bool bad, int32_t (*site)[NW], int *x0, int *t0,
+                                               int *x1, int *t1, int *x2, int *t2, bool *any_bad) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int a = v0, b = v2;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int ya = __shfl_up_sync(0xffffffffu, a, d), yb = __shfl_up_sync(0xffffffffu, b, d);
+    if (lane >= d) { a += ya; b += yb; }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, f1);
+  const bool wbad = __any_sync(0xffffffffu, bad);
+  if (lane == 31) { site[0][w] = a; site[2][w] = b; }
+  if (lane == 0) { site[1][w] = __popc(m); site[3][w] = wbad ? 1 : 0; }
+  __syncthreads();
+  int base, tot;
+  warp_totals(site[0], lane, w, &base, &tot);
+  *x0 = base + a - v0; *t0 = tot;
+  warp_totals(site[1], lane, w, &base, &tot);
+  *x1 = base + __popc(m & ((1u << lane) - 1u)); *t1 = tot;
+  warp_totals(site[2], lane, w, &base, &tot);
+  *x2 = base + b - v2; *t2 = tot;
+  warp_totals(site[3], lane, w, &base, &tot);
+  *any_bad = tot != 0;
 }
 
 // ------------------------------------------------------------------------------------ libstdc++ policy
@@ -305,6 +385,25 @@ __device__ int next_bkt(const DevState &c, const uint32_t *primes32, int64_t n) 
     if (c.primes[mid] < (uint64_t)n) lo = mid + 1; else hi = mid;
   }
   return (int)c.primes[lo];
+}
+
+// The same for the bucket counts a free() of at most NT ids can reach (n <= __prime_list[PRIMES_SM - 1], 32-bit
+// arithmetic, branch-free lower_bound over the shared copy of the table): ~30 instructions instead of ~170, and every
+// warp of the CTA runs it.
+__device__ __forceinline__ int next_bkt_small(const uint32_t *primes32, int n) {
+  if (n < 14) return n <= 0 ? 1 : (int)((0x22235577BBBBDDull >> (4 * (13 - n))) & 15);
+  int lo = 6;
+#pragma unroll
+  for (int len = PRIMES_SM - 6; len > 1;) {       // first index in [lo, lo + len) whose prime is >= n
+    const int half = len >> 1;
+    if (primes32[lo + half - 1] < (uint32_t)n) lo += half;
+    len -= half;
+  }
+  return (int)primes32[lo];
+}
+__device__ __forceinline__ int next_bkt_grow(const uint32_t *primes32, int placed, int nb) {   // _M_need_rehash's request
+  const int want = placed + 2 > 2 * nb ? placed + 2 : 2 * nb;
+  return next_bkt_small(primes32, want);
 }
 
 // Replays std::unordered_map<int64_t, ...>::operator[] for keys[0..D) (distinct, first-appearance
@@ -416,9 +515,7 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
     placed = upto;
     KVB_PROF_W(15);
     if (placed >= D) break;
-    int64_t want = (int64_t)placed + 2;                 // _M_need_rehash -> _M_next_bkt(max(n+1+1, 2*nb))
-    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-    nb = next_bkt(c, primes32, want);
+    nb = next_bkt_grow(primes32, placed, nb);           // _M_need_rehash -> _M_next_bkt(max(n+1+1, 2*nb)); nb < D <= 32 here
   }
   if (lane < D) ord[lane] = cur_slot;
 }
@@ -506,9 +603,7 @@ __device__ __forceinline__ void ht_order_warp_multi(const DevState &c, const uin
       }
     __syncwarp();
     if (upto >= D) break;
-    int64_t want = (int64_t)upto + 2;         // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb))
-    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-    nb = next_bkt(c, primes32, want);
+    nb = next_bkt_grow(primes32, upto, nb);   // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb)); nb < D <= 256 here
   }
 #pragma unroll
   for (int k = 0; k < HT_WK; ++k)
@@ -553,9 +648,7 @@ __device__ __forceinline__ void ht_order_prefix(const DevState &c, const uint32_
     __syncwarp();
     placed = upto;
     if (placed >= D) break;                                  // (cannot happen for D > 32; kept for safety)
-    int64_t want = (int64_t)placed + 2;
-    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-    nb = next_bkt(c, primes32, want);
+    nb = next_bkt_grow(primes32, placed, nb);                // placed <= 32, nb <= 32 here
   }
   *nb_io = nb;
   *placed_out = placed;
@@ -588,7 +681,7 @@ __device__ __forceinline__ void ht_order_hybrid(const DevState &c, const uint32_
 //                                            8 bits), so one read gives them all — no chunk-by-chunk walk;
 //   keys of buckets that first appear later  suffix sum, over positions, of the bucket sizes held by bucket leaders;
 //   new position = the two sums; the permutation goes through shared memory in place.
-// Five block barriers per phase whatever the key count; the one-warp form walks its 8 chunks twice per phase.
+// Four block barriers per phase whatever the key count; the one-warp form walks its 8 chunks twice per phase.
 __device__ void ht_order_block(const DevState &c, Smem &s, const int32_t *keys, int D, int nb, int placed, int32_t *ord) {
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned gt = ~((2u << lane) - 1u), lt = (1u << lane) - 1u;
@@ -634,24 +727,21 @@ __device__ void ht_order_block(const DevState &c, Smem &s, const int32_t *keys, 
       if (lane + d < 32) v += y;
     }
     if (lane == 0) s.wtot[w] = v;
+    if (in) suf[t] = v;                            // suffix inside my chunk; the chunks above are added by the reader
     __syncthreads();
+    int above = (lane < 8 && lane < NW) ? s.wtot[lane] : 0;   // lane i: keys held by chunks i, i + 1, ... (D <= 256: 8 chunks)
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) above += __shfl_down_sync(0xffffffffu, above, d);   // lanes >= 8 hold 0
+    above = __shfl_sync(0xffffffffu, above, ((in ? gfirst : 0) >> 5) + 1);           // chunks above my bucket's first key
     if (in) {
-      int base = 0;
-      for (int i = w + 1; i < 8; ++i) base += s.wtot[i];
-      suf[t] = v + base;
-    }
-    __syncthreads();
-    if (in) {
-      const int newpos = suf[gfirst] - cnt + later;
+      const int newpos = suf[gfirst] + above - cnt + later;
       cur_slot[newpos] = slot;
       cur_key[newpos] = (int)key;
     }
     __syncthreads();
     placed = upto;
     if (upto >= D) break;
-    int64_t want = (int64_t)upto + 2;              // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb))
-    if (want < 2 * (int64_t)nb) want = 2 * (int64_t)nb;
-    nb = next_bkt(c, s.primes32, want);
+    nb = next_bkt_grow(s.primes32, upto, nb);      // _M_need_rehash -> _M_next_bkt(max(n + 1 + 1, 2 * nb)); nb < D <= 256
   }
   if (t < D) ord[t] = cur_slot[t];
   __syncthreads();
@@ -909,13 +999,14 @@ __device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, i
     else if (j - rls < fls) v = c.fl[(int)((sc[SC_FL_HEAD] + (j - rls)) & c.q_mask)];
     s.newpg[j] = v;
   }
-  const bool neg = __syncthreads_or(n_i < 0 || n_i > (1 << 21));   // odd sizes take the general walk
-  int T;
-  const int off_i = block_exscan(n_i, s.wtot, &T);
-  int nlive;
-  const int li = block_rank(e >= 0, s.wtot2, &nlive);        // position among live entries, newest first
-  int sum_av;
-  const int cum = block_exscan(e >= 0 ? ecnt : 0, s.wtot, &sum_av);
+  // one pass, one barrier: request offsets, position among live entries (newest first), cumulative free blocks, and
+  // the vote on odd sizes (they take the general walk)
+  bool neg;
+  int T, off_i, nlive, li, sum_av, cum;
+  {
+    const bool odd = n_i < 0 || n_i > (1 << 21);
+    block_scan3_1b(odd ? 0 : n_i, e >= 0, e >= 0 ? ecnt : 0, odd, &s.wsite[WS_AF0], &off_i, &T, &li, &nlive, &cum, &sum_av, &neg);
+  }
   if (e >= 0) {
     s.cpage[li] = e;
     s.ccnt[li] = ecnt;
@@ -1046,17 +1137,21 @@ __device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, i
   return 1;
 }
 
-// alloc_run_fast at WARP scope: runs of at most 32 requests whose blocks come from the reserved blocks, the 32 newest
-// entries of the avail stack and at most 32 fresh pages — a decode step's "one block each" run, a single alloc(n).
-// Same stream rule, same results; warp 0 does all of it with shuffles and votes (the block-wide form pays a dozen
-// block barriers and three block scans for the same few hundred ids), the other warps wait at the one barrier at the
-// end.  Returns 1 if the run was handled, 0 if it needs the wider windows of alloc_run_fast (nothing touched).  Uniform.
+// alloc_run_fast planned at WARP scope: runs of at most 128 requests whose blocks come from the reserved blocks, the 32
+// newest entries of the avail stack and at most 32 fresh pages — a decode step's "one block each" run, a single
+// alloc(n).  Same stream rule, same results.  Warp 0 PLANS with shuffles and votes (the block-wide form pays three
+// block scans for it) and leaves the plan in shared memory; after ONE barrier the whole CTA carries it out: all NT
+// threads emit ids and results, warp 1 retires the consumed avail pages, the warps share the fresh pages, thread 0
+// updates the counters.  (The first version also emitted on warp 0: T / 32 dependent passes over the id stream, 64
+// of them for alloc(2048).)  Returns 1 if the run was handled, 0 if it needs the wider windows of alloc_run_fast
+// (nothing touched).  Uniform.
 __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int64_t *sc = s.sc;
   const int R = run_end - op0;
   constexpr int RQ = 4;     // requests per lane: runs of up to 128 requests
   if (!c.exact || sc[SC_INSHRINK] || R > 32 * RQ) return 0;
+  WarpPlan &pl = s.wplan;
   if (tid < 32) {
     const unsigned FULL = 0xffffffffu;
     const int tail = (int)sc[SC_AP_TAIL];
@@ -1107,128 +1202,135 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
     if (ok) {
       if (e >= 0) { s.cpage[li] = e; s.ccnt[li] = ecnt; s.chead[li] = ehead; s.csidx[li] = tail - 1 - lane; s.ccum[li] = cum; }
       s.newpg[lane] = npg;
-      __syncwarp();
-      const int from_rl = F < rls ? F : rls;                    // alloc_page(): reserved list first, then free list
-      const int from_fl = F - from_rl;
-      const int last_used = F ? rem2 - (F - 1) * c.bpp : 0;
-      const int64_t nev0 = sc[SC_NEV];
-      const int64_t rbh = sc[SC_RB_HEAD];
-      for (int j = lane; j < T; j += 32) {
-        int64_t id;
-        if (j < take_rb) {
-          id = c.rb[(int)((rbh + j) & c.rb_mask)];
-        } else {
-          const int j1 = j - take_rb;
-          if (j1 < take_av) {
-            int lo = 0, hi = nlive - 1;                         // last live entry with ccum <= j1
-            while (lo < hi) {
-              const int mid = (lo + hi + 1) >> 1;
-              if (s.ccum[mid] <= j1) lo = mid; else hi = mid - 1;
-            }
-            const int pg = s.cpage[lo];
-            int pos = s.chead[lo] + (j1 - s.ccum[lo]);
-            if (pos >= c.bpp) pos -= c.bpp;
-            id = (int64_t)pg * c.bpp + c.ring[(size_t)pg * c.bpp + pos];
-          } else {
-            const int j2 = j1 - take_av;
-            const int q = j2 / c.bpp;
-            id = (int64_t)s.newpg[q] * c.bpp + (j2 - q * c.bpp);
-          }
-          atomicOr(&c.bitmap[id >> 5], 1u << (id & 31));
-        }
-        a.out_ids[cursor + j] = id;
-      }
       {
         int off_q = off_i;
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
           const int idx = lane * RQ + q;
-          if (idx < R) {
-            kvb_res r{};
-            r.status = KVB_ST_OK;
-            r.n = n_q[q];
-            r.off = cursor + off_q;
-            r.avail = A0 - off_q - n_q[q];
-            a.res[op0 + idx] = r;
-          }
+          if (idx < R) s.wroff[idx] = off_q;
           off_q += n_q[q];
         }
       }
-      // consumed / partly consumed avail pages
-      int n_full_av = 0;
-      {
-        int lo = 0, hi = nlive;                                 // first live entry NOT entirely consumed
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (s.ccum[mid] + s.ccnt[mid] <= take_av) lo = mid + 1; else hi = mid;
-        }
-        n_full_av = lo;
-      }
-      if (lane < nlive) {
-        const int pg = s.cpage[lane], cn = s.ccnt[lane], cm = s.ccum[lane];
-        if (lane < n_full_av) {
-          const int hh = s.chead[lane] + cn;
-          c.pg_state[pg] = PG_FULL;
-          c.pg_cnt[pg] = 0;
-          c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
-        } else if (cm < take_av) {                               // the one page left partly consumed
-          const int used = take_av - cm;
-          const int hh = s.chead[lane] + used;
-          c.pg_cnt[pg] = cn - used;
-          c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
-        }
-      }
-      // fresh pages
-      for (int q = 0; q < F; ++q) {
-        const int pg = s.newpg[q];
-        const bool partial = (q == F - 1) && last_used < c.bpp;
-        if (lane == 0) {
-          c.pg_state[pg] = partial ? PG_AVAIL : PG_FULL;
-          c.pg_cnt[pg] = partial ? c.bpp - last_used : 0;
-          c.pg_head[pg] = partial ? last_used : 0;
-          if (q >= from_rl) {                                    // came off the free list: needs a mapping
-            const int64_t k = nev0 + (q - from_rl);
-            if (k < c.ev_cap) c.ev[k] = (int64_t)pg * 2;
-            c.pg_mapped[pg] = 1;
-          }
-          if (partial) { c.ap[0] = pg; c.pg_pos[pg] = 0; }       // the stack is empty when fresh pages are taken
-        }
-        if (partial) {                                           // InternalPage::init: FIFO = identity
-          uint32_t *rr = c.ring + (size_t)pg * c.bpp;
-          for (int t = lane; t < c.bpp; t += 32) rr[t] = (uint32_t)t;
-        }
-      }
-      __syncwarp();
       if (lane == 0) {
-        const bool fresh_partial = F > 0 && last_used < c.bpp;
-        sc[SC_RB_HEAD] = (rbh + take_rb) & c.rb_mask;
-        sc[SC_NRB] -= take_rb;
-        sc[SC_NAB] += (int64_t)F * c.bpp - rem2 - take_av;
-        sc[SC_NAVAILPG] += (fresh_partial ? 1 : 0) - n_full_av;
-        sc[SC_NFULLPG] += n_full_av + F - (fresh_partial ? 1 : 0);
-        sc[SC_NFREE] -= F;
-        sc[SC_RL_HEAD] = (sc[SC_RL_HEAD] + from_rl) & c.q_mask;
-        sc[SC_RL_SIZE] -= from_rl;
-        sc[SC_FL_HEAD] = (sc[SC_FL_HEAD] + from_fl) & c.q_mask;
-        sc[SC_FL_SIZE] -= from_fl;
-        sc[SC_NEV] += from_fl;
-        sc[SC_NMAPPED] += from_fl;
-        sc[SC_PHYS] -= from_fl;
-        sc[SC_OUT_CURSOR] = cursor + T;
-        int new_tail;
-        if (F > 0) new_tail = fresh_partial ? 1 : 0;
-        else if (n_full_av < nlive) new_tail = s.csidx[n_full_av] + 1;   // newest surviving entry
-        else new_tail = tail > 32 ? tail - 32 : 0;                       // whole window consumed (or empty)
-        sc[SC_AP_TAIL] = new_tail;
+        pl.T = T; pl.take_rb = take_rb; pl.take_av = take_av; pl.rem2 = rem2; pl.nlive = nlive; pl.F = F;
+        pl.from_rl = F < rls ? F : rls;                          // alloc_page(): reserved list first, then free list
+        pl.last_used = F ? rem2 - (F - 1) * c.bpp : 0;
+        pl.tail = tail;
+        pl.cursor = cursor; pl.A0 = A0; pl.nev0 = sc[SC_NEV]; pl.rbh = sc[SC_RB_HEAD];
       }
     }
     if (lane == 0) s.misc[MI_E] = ok ? 1 : 0;
   }
   __syncthreads();
-  const int handled = s.misc[MI_E];
+  if (!s.misc[MI_E]) { __syncthreads(); return 0; }
+  // ---- the whole CTA carries the plan out; nothing below reads sc except thread 0 at the end
+  const int T = pl.T, take_rb = pl.take_rb, take_av = pl.take_av, rem2 = pl.rem2, nlive = pl.nlive, F = pl.F;
+  const int from_rl = pl.from_rl, from_fl = F - from_rl, last_used = pl.last_used, tail = pl.tail;
+  const int64_t cursor = pl.cursor, A0 = pl.A0, nev0 = pl.nev0, rbh = pl.rbh;
+  for (int j = tid; j < T; j += NT) {
+    int64_t id;
+    if (j < take_rb) {
+      id = c.rb[(int)((rbh + j) & c.rb_mask)];
+    } else {
+      const int j1 = j - take_rb;
+      if (j1 < take_av) {
+        int lo = 0, hi = nlive - 1;                         // last live entry with ccum <= j1
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (s.ccum[mid] <= j1) lo = mid; else hi = mid - 1;
+        }
+        const int pg = s.cpage[lo];
+        int pos = s.chead[lo] + (j1 - s.ccum[lo]);
+        if (pos >= c.bpp) pos -= c.bpp;
+        id = (int64_t)pg * c.bpp + c.ring[(size_t)pg * c.bpp + pos];
+      } else {
+        const int j2 = j1 - take_av;
+        const int q = j2 / c.bpp;
+        id = (int64_t)s.newpg[q] * c.bpp + (j2 - q * c.bpp);
+      }
+      atomicOr(&c.bitmap[id >> 5], 1u << (id & 31));
+    }
+    a.out_ids[cursor + j] = id;
+  }
+  if (tid < R) {
+    const int nq = s.ops[op0 - chunk_base + tid].n, off_q = s.wroff[tid];
+    kvb_res r{};
+    r.status = KVB_ST_OK;
+    r.n = nq;
+    r.off = cursor + off_q;
+    r.avail = A0 - off_q - nq;
+    a.res[op0 + tid] = r;
+  }
+  // consumed / partly consumed avail pages
+  int n_full_av = 0;
+  if (w <= 1) {                                             // needed by the page-update warp and by thread 0
+    int lo = 0, hi = nlive;                                 // first live entry NOT entirely consumed
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s.ccum[mid] + s.ccnt[mid] <= take_av) lo = mid + 1; else hi = mid;
+    }
+    n_full_av = lo;
+  }
+  if (w == (NW > 1 ? 1 : 0) && lane < nlive) {
+    const int pg = s.cpage[lane], cn = s.ccnt[lane], cm = s.ccum[lane];
+    if (lane < n_full_av) {
+      const int hh = s.chead[lane] + cn;
+      c.pg_state[pg] = PG_FULL;
+      c.pg_cnt[pg] = 0;
+      c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
+    } else if (cm < take_av) {                               // the one page left partly consumed
+      const int used = take_av - cm;
+      const int hh = s.chead[lane] + used;
+      c.pg_cnt[pg] = cn - used;
+      c.pg_head[pg] = hh >= c.bpp ? hh - c.bpp : hh;
+    }
+  }
+  // fresh pages: one warp each
+  for (int q = w; q < F; q += NW) {
+    const int pg = s.newpg[q];
+    const bool partial = (q == F - 1) && last_used < c.bpp;
+    if (lane == 0) {
+      c.pg_state[pg] = partial ? PG_AVAIL : PG_FULL;
+      c.pg_cnt[pg] = partial ? c.bpp - last_used : 0;
+      c.pg_head[pg] = partial ? last_used : 0;
+      if (q >= from_rl) {                                    // came off the free list: needs a mapping
+        const int64_t k = nev0 + (q - from_rl);
+        if (k < c.ev_cap) c.ev[k] = (int64_t)pg * 2;
+        c.pg_mapped[pg] = 1;
+      }
+      if (partial) { c.ap[0] = pg; c.pg_pos[pg] = 0; }       // the stack is empty when fresh pages are taken
+    }
+    if (partial) {                                           // InternalPage::init: FIFO = identity
+      uint32_t *rr = c.ring + (size_t)pg * c.bpp;
+      for (int t = lane; t < c.bpp; t += 32) rr[t] = (uint32_t)t;
+    }
+  }
+  if (tid == 0) {
+    const bool fresh_partial = F > 0 && last_used < c.bpp;
+    sc[SC_RB_HEAD] = (rbh + take_rb) & c.rb_mask;
+    sc[SC_NRB] -= take_rb;
+    sc[SC_NAB] += (int64_t)F * c.bpp - rem2 - take_av;
+    sc[SC_NAVAILPG] += (fresh_partial ? 1 : 0) - n_full_av;
+    sc[SC_NFULLPG] += n_full_av + F - (fresh_partial ? 1 : 0);
+    sc[SC_NFREE] -= F;
+    sc[SC_RL_HEAD] = (sc[SC_RL_HEAD] + from_rl) & c.q_mask;
+    sc[SC_RL_SIZE] -= from_rl;
+    sc[SC_FL_HEAD] = (sc[SC_FL_HEAD] + from_fl) & c.q_mask;
+    sc[SC_FL_SIZE] -= from_fl;
+    sc[SC_NEV] += from_fl;
+    sc[SC_NMAPPED] += from_fl;
+    sc[SC_PHYS] -= from_fl;
+    sc[SC_OUT_CURSOR] = cursor + T;
+    int new_tail;
+    if (F > 0) new_tail = fresh_partial ? 1 : 0;
+    else if (n_full_av < nlive) new_tail = s.csidx[n_full_av] + 1;   // newest surviving entry
+    else new_tail = tail > 32 ? tail - 32 : 0;                       // whole window consumed (or empty)
+    sc[SC_AP_TAIL] = new_tail;
+  }
   __syncthreads();
-  return handled;
+  return 1;
 }
+
 
 // A run of consecutive ALLOC requests [op0, run_end) (all inside the staged chunk), or one
 // TRY_RESERVE request (to_reserved = 1, ids appended to reserved_blocks instead of the output).
@@ -1635,8 +1737,8 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   __syncthreads();
   const bool first = part && Hval[h] == tid;
   int D;
-  const int r = block_rank(first, s.wtot, &D);
-  if (D > HS_D_CAP) return 0;
+  const int r = block_rank_1b(first, s.wsite[WS_FS_D], &D);
+  if (D > HS_D_CAP) { __syncthreads(); return 0; }
   KVB_PROF(4);
   // ---- from here on the state changes
   bool ok = part;
@@ -1667,7 +1769,7 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   __syncthreads();
   KVB_PROF(5);
   // ---- dict order (warp 0) || FIFO ranks and ring appends (warp 1); groups.reserve(n / bpp + 1), page_allocator.cpp:477
-  const int nb0 = next_bkt(c, s.primes32, (int64_t)n / c.bpp + 1);
+  const int nb0 = next_bkt_small(s.primes32, n / c.bpp + 1);      // n <= NT
   // block-wide later phases: bucket counts stay <= 503 (D <= 256 and a rehash at most doubles a count below D), which
   // is what the packed per-bucket words have room for
   const bool blockwide = D > 32 && nb0 <= 512 && !(a.tune & 1);
@@ -1725,9 +1827,8 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
         empty = (newc == pg_nblk(c, pp));   // InternalPage::empty (:75-77)
       }
     }
-    int totS, totE;
-    const int rs = block_rank(live && !empty, s.wtot, &totS);
-    const int re = block_rank(live && empty, s.wtot2, &totE);
+    int totS, totE, rs, re;
+    block_rank2_1b(live && !empty, live && empty, s.wsite[WS_FS_F4], &rs, &totS, &re, &totE);
     int d_nab = 0, d_av = 0, d_fu = 0;
     if (live) {
       if (st == PG_AVAIL) c.ap[ppos[slot]] = -1;   // avail_pages.pop(page_id)
@@ -1880,7 +1981,7 @@ __device__ int gather_refs_reg(const DevState &c, Smem &s, const LaunchArgs &a, 
   }
   if (EARLY && __syncthreads_or(late)) return -1;
   int tot;
-  const int ex = block_exscan(len, s.wtot, &tot);
+  const int ex = block_exscan_1b(len, s.wsite[WS_GATHER], &tot);
   if (tot > NT) { __syncthreads(); return -1; }
   r_src[tid] = src;
   r_dst[tid] = tid < nrefs ? ex : INT_MAX;     // offsets are non-decreasing; empty refs share their successor's offset
