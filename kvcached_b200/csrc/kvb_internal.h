@@ -83,8 +83,11 @@ struct DevState {
   int32_t max_cached;           // -1 unlimited, 0 evict on free, > 0 cap
   int64_t *ev;                  // page event log: page*2 + is_unmap
   const uint64_t *primes;       // libstdc++ __prime_list
+  const uint16_t *grow_tab;     // [kGrowTab] bucket count after the rehash of a FULL table of nb buckets (nb < kGrowTab)
   long long *prof;              // -DKVB_PROFILE builds: [0..15] cycles per phase, [16..31] marks (else null)
 };
+
+constexpr int kGrowTab = 1024;
 
 // What one launch publishes for the host (written last; pinned host or device memory).
 struct Summary {
@@ -141,7 +144,8 @@ struct LaunchArgs {
   int32_t safe_before;    // resident traces: results of requests below this index come from launches older than this
                           // launch's predecessor in the stream / graph (0 = unknown: nothing may be read early)
   int32_t tune;           // tuning switches (KVB200_TUNE): bit 0 = many-page frees replay the dict order on one warp,
-                          // bit 1 = launches without programmatic stream serialization, bit 2 = no early ref gather
+                          // bit 1 = launches without programmatic stream serialization, bit 2 = no early ref gather,
+                          // bit 3 = always the general kernel (no kvb_decode_kernel)
   // Flagged publish of a single-request launch: every 64-bit word of `ll` carries 32 bits of payload and the launch's
   // 32-bit flag, so the host validates each word on its own and the kernel needs NO system-scope fence between
   // payload and sequence word (8-byte stores are single-copy atomic over PCIe).  Layout: LlWord below.
@@ -163,7 +167,8 @@ constexpr int kStepThreads = KVB_STEP_THREADS;   // 256, 384 or 512 (>= OPS_CHUN
 
 size_t step_kernel_smem_bytes();
 // launches (host side, defined in kvb_kernels.cu)
-int launch_step(const DevState &st, const LaunchArgs &a, void *stream);
+// alloc_free_only: every request of the launch is ALLOC / FREE_IDS / FREE_REF / FREE_RESERVED / AVAIL -> kvb_decode_kernel
+int launch_step(const DevState &st, const LaunchArgs &a, void *stream, bool alloc_free_only = false);
 int launch_one(const DevState &st, const LaunchArgs &a, void *stream);   // single ALLOC / FREE_IDS / AVAIL request (inline_op)
 #define KVB_ST_RETRY (-100)   /* kvb_one_kernel: the request needs the general kernel; nothing was touched */
 int launch_step_prepare();   // per-device function attributes (must not happen inside a stream capture)

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include <climits>
+#include <cstddef>
 #include <cstdlib>
 #include <cstdint>
 
@@ -117,6 +118,7 @@ struct Smem {
   int32_t newpg[NEWPG_W];
   int32_t cpage[APW], ccnt[APW], chead[APW], csidx[APW], ccum[APW];   // live window entries, newest first
   uint32_t primes32[PRIMES_SM];                                        // head of libstdc++'s __prime_list
+  uint16_t grow16[kGrowTab];                                           // DevState::grow_tab; MUST follow primes32 (next_bkt_grow)
   int32_t ht_key[HT_D_CAP], ht_next[HT_D_CAP], ht_ord[HT_D_CAP], ht_cnt[HT_D_CAP];
   int32_t ht_bkt[HT_NB_CAP + 1];
   int32_t wtot[NW], wtot2[NW];
@@ -130,6 +132,8 @@ struct Smem {
   AllocSim sim;
   long long prof_t;
 };
+
+static_assert(offsetof(Smem, grow16) == offsetof(Smem, primes32) + PRIMES_SM * sizeof(uint32_t), "grow16 follows primes32");
 
 enum : int { MI_D = 0, MI_NB0, MI_E, MI_USE_G, MI_STOP, MI_BASE_A, MI_BASE_B, MI_N, MI_BAD, MI_UNK, MI_K };
 
@@ -188,7 +192,7 @@ __device__ __forceinline__ int dq_pop_back(int32_t *q, int mask, int64_t *sc, in
 }
 
 // PageAllocator::resize, csrc/page_allocator.cpp:312-401 (thread 0; rare)
-__device__ int pa_resize(const DevState &c, int64_t *sc, int64_t new_mem_size, int *capacity_err) {
+__device__ __noinline__ int pa_resize(const DevState &c, int64_t *sc, int64_t new_mem_size, int *capacity_err) {
   int64_t new_pages = new_mem_size / c.P;
   int64_t total = sc[SC_NTOTAL];
   if (new_pages < total - sc[SC_NFREE]) return 0;
@@ -401,7 +405,10 @@ __device__ __forceinline__ int next_bkt_small(const uint32_t *primes32, int n) {
   }
   return (int)primes32[lo];
 }
-__device__ __forceinline__ int next_bkt_grow(const uint32_t *primes32, int placed, int nb) {   // _M_need_rehash's request
+// _M_need_rehash's request when key number placed + 1 arrives at a table of nb buckets.  The replay only asks when the
+// table is full (placed == nb): that answer sits in the table that follows primes32 in shared memory (Smem::grow16).
+__device__ __forceinline__ int next_bkt_grow(const uint32_t *primes32, int placed, int nb) {
+  if (placed == nb && nb < kGrowTab) return reinterpret_cast<const uint16_t *>(primes32 + PRIMES_SM)[nb];
   const int want = placed + 2 > 2 * nb ? placed + 2 : 2 * nb;
   return next_bkt_small(primes32, want);
 }
@@ -1334,7 +1341,7 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
 
 // A run of consecutive ALLOC requests [op0, run_end) (all inside the staged chunk), or one
 // TRY_RESERVE request (to_reserved = 1, ids appended to reserved_blocks instead of the output).
-__device__ void alloc_run(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end,
+__device__ __noinline__ void alloc_run(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end,
                           int to_reserved) {
   const int tid = threadIdx.x;
   int64_t *sc = s.sc;
@@ -2401,7 +2408,12 @@ __device__ __forceinline__ void publish_flagged(const DevState &c, Smem &s, cons
 }
 
 // ==================================================================================== the step kernel
-__global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs a) {
+// COMPACT = the kernel of a scheduler step that holds nothing but alloc(n) / free(ids) requests (kvb_decode_kernel): the
+// twenty other request kinds are not compiled in.  A launch executes a few thousand instructions exactly once, so
+// what it pays for is instruction FETCH (profiles/r2_step_single_rules.csv) — a kernel a third of the size with the
+// hot paths side by side fetches less.  The host picks the kernel per launch (kvb_manager.cpp launch()).
+template <bool COMPACT>
+__device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &s = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -2424,6 +2436,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   }
   if (tid < 16) s.misc[tid] = 0;
   if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
+  for (int i = tid; i < kGrowTab / 2; i += NT) reinterpret_cast<uint32_t *>(s.grow16)[i] = reinterpret_cast<const uint32_t *>(c.grow_tab)[i];
   // A resident trace opens most steps with the free() of a request that finished one step earlier; its ids are
   // results of launches older than the predecessor (a.safe_before, set by kvb_mgr_trace_run) unless its last block
   // was allocated in the step just before — so the whole gather (refs -> results -> ids in registers) can run here too.
@@ -2470,7 +2483,7 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         __syncthreads();
         break;
       }
-      if (a.group_only) {
+      if (!COMPACT && a.group_only) {
         for (int j = tid; j < o.n; j += NT) c.fids[j] = a.ids[o.arg + j];
         __syncthreads();
         free_core(c, s, a, o.n, 1);
@@ -2478,14 +2491,16 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
         op++;
         continue;
       }
-      if (a.resize_target > 0 && (o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_TRY_RESERVE || o.kind == KVB_OP_PIN_NEW || o.kind == KVB_OP_ALLOC_DEV)) {
+      if (!COMPACT && a.resize_target > 0 && (o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_TRY_RESERVE || o.kind == KVB_OP_PIN_NEW || o.kind == KVB_OP_ALLOC_DEV)) {
         // _alloc() first applies a limit change published through the shm segment (kv_cache_manager.py:258-260,
         // page_allocator.cpp:764-782); the result is ignored there too.  Repeating it for the later requests of
         // a run changes nothing, so once per alloc-type request (= once per run) is exact.
         if (tid == 0) mgr_resize(c, sc, a.resize_target);
         __syncthreads();
       }
-      switch (o.kind) {
+      // (COMPACT: the host never sends another kind; one that arrives anyway is answered like an unknown kind)
+      switch (COMPACT && !(o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_FREE_IDS || o.kind == KVB_OP_FREE_REF ||
+                           o.kind == KVB_OP_FREE_RESERVED || o.kind == KVB_OP_AVAIL) ? -1 : o.kind) {
         case KVB_OP_ALLOC: {
           // end of the run of consecutive ALLOC requests inside the staged chunk
           if (tid == 0) s.misc[MI_K] = chunk_base + chunk_n;
@@ -2510,9 +2525,11 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           break;
         }
         case KVB_OP_TRY_RESERVE: {
-          alloc_run(c, s, a, chunk_base, op, op + 1, 1);
-          op++;
-          break;
+          if constexpr (!COMPACT) {
+            alloc_run(c, s, a, chunk_base, op, op + 1, 1);
+            op++;
+            break;
+          }
         }
         case KVB_OP_FREE_IDS:
         case KVB_OP_FREE_REF:
@@ -2560,37 +2577,43 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           break;
         }
         case KVB_OP_RESIZE: {   // KVCacheManager.resize, kv_cache_manager.py:381-401
-          if (tid == 0) {
-            kvb_res r{}; r.n = 0; r.off = 0;
-            r.status = mgr_resize(c, sc, o.arg);
-            r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            if (tid == 0) {
+              kvb_res r{}; r.n = 0; r.off = 0;
+              r.status = mgr_resize(c, sc, o.arg);
+              r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_PA_RESIZE: {
-          if (tid == 0) {
-            kvb_res r{}; r.n = 0; r.off = 0;
-            int cap_err = 0;
-            r.status = pa_resize(c, sc, o.arg, &cap_err) ? KVB_ST_OK : (cap_err ? KVB_ST_CAPACITY : KVB_ST_FALSE);
-            r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            if (tid == 0) {
+              kvb_res r{}; r.n = 0; r.off = 0;
+              int cap_err = 0;
+              r.status = pa_resize(c, sc, o.arg, &cap_err) ? KVB_ST_OK : (cap_err ? KVB_ST_CAPACITY : KVB_ST_FALSE);
+              r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_TRIM: {
-          if (tid == 0) {
-            pa_trim(c, sc);
-            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            if (tid == 0) {
+              pa_trim(c, sc);
+              kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_AVAIL: {
           if (tid == 0) {
@@ -2601,223 +2624,243 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
           break;
         }
         case KVB_OP_CLEAR: {
-          // free_reserved(); free_pages(all); trim(); reset_free_page_order(); counters = 0
-          clear_all(c, s, 0);
-          if (tid == 0) {
-            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            // free_reserved(); free_pages(all); trim(); reset_free_page_order(); counters = 0
+            clear_all(c, s, 0);
+            if (tid == 0) {
+              kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_RESET_ORDER: {
-          clear_all(c, s, 1);
-          if (tid == 0) {
-            kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            clear_all(c, s, 1);
+            if (tid == 0) {
+              kvb_res r{}; r.status = KVB_ST_OK; r.n = 0; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_ALLOC_PAGE: {   // PageAllocator::alloc_page, page_allocator.cpp:161-237
-          if (tid == 0) {
-            kvb_res r{}; r.n = 0; r.off = -1;
-            if (sc[SC_RL_SIZE] > 0) {
-              r.off = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
-              sc[SC_NFREE] -= 1;
-              r.status = KVB_ST_OK;
-            } else if (sc[SC_FL_SIZE] > 0) {
-              int p = dq_pop_front(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE);
-              sc[SC_NFREE] -= 1;
-              ev_push(c, sc, p, 0);
-              r.off = p;
-              r.status = KVB_ST_OK;
-            } else {
-              r.status = KVB_ST_NO_PAGES;
+          if constexpr (!COMPACT) {
+            if (tid == 0) {
+              kvb_res r{}; r.n = 0; r.off = -1;
+              if (sc[SC_RL_SIZE] > 0) {
+                r.off = dq_pop_front(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE);
+                sc[SC_NFREE] -= 1;
+                r.status = KVB_ST_OK;
+              } else if (sc[SC_FL_SIZE] > 0) {
+                int p = dq_pop_front(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE);
+                sc[SC_NFREE] -= 1;
+                ev_push(c, sc, p, 0);
+                r.off = p;
+                r.status = KVB_ST_OK;
+              } else {
+                r.status = KVB_ST_NO_PAGES;
+              }
+              if (r.status == KVB_ST_OK) {   // the page is held by the caller: account it as full
+                c.pg_state[(int)r.off] = PG_FULL;
+                c.pg_cnt[(int)r.off] = 0;
+                sc[SC_NFULLPG] += 1;
+              }
+              r.avail = avail_size(c, sc);
+              a.res[op] = r;
             }
-            if (r.status == KVB_ST_OK) {   // the page is held by the caller: account it as full
-              c.pg_state[(int)r.off] = PG_FULL;
-              c.pg_cnt[(int)r.off] = 0;
-              sc[SC_NFULLPG] += 1;
-            }
-            r.avail = avail_size(c, sc);
-            a.res[op] = r;
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_FREE_PAGES: {   // PageAllocator::free_pages, page_allocator.cpp:264-310
-          if (tid == 0) {
-            int done = 0;
-            for (int i = 0; i < o.n; ++i) {
-              int64_t p64 = a.ids[o.arg + i];
-              if (p64 < 0 || p64 >= c.max_pages) continue;
-              int p = (int)p64;
-              if (c.pg_state[p] == PG_NONE) continue;
-              sc[SC_NFULLPG] -= (c.pg_state[p] == PG_FULL);
-              sc[SC_NAVAILPG] -= (c.pg_state[p] == PG_AVAIL);
-              c.pg_state[p] = PG_NONE;
-              sc[SC_NFREE] += 1;
-              if (sc[SC_RL_SIZE] < c.max_reserved) {
-                dq_push_back(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE, p);
-              } else {
-                ev_push(c, sc, p, 1);
-                dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+          if constexpr (!COMPACT) {
+            if (tid == 0) {
+              int done = 0;
+              for (int i = 0; i < o.n; ++i) {
+                int64_t p64 = a.ids[o.arg + i];
+                if (p64 < 0 || p64 >= c.max_pages) continue;
+                int p = (int)p64;
+                if (c.pg_state[p] == PG_NONE) continue;
+                sc[SC_NFULLPG] -= (c.pg_state[p] == PG_FULL);
+                sc[SC_NAVAILPG] -= (c.pg_state[p] == PG_AVAIL);
+                c.pg_state[p] = PG_NONE;
+                sc[SC_NFREE] += 1;
+                if (sc[SC_RL_SIZE] < c.max_reserved) {
+                  dq_push_back(c.rl, c.q_mask, sc, SC_RL_HEAD, SC_RL_SIZE, p);
+                } else {
+                  ev_push(c, sc, p, 1);
+                  dq_push_back(c.fl, c.q_mask, sc, SC_FL_HEAD, SC_FL_SIZE, p);
+                }
+                done++;
               }
-              done++;
+              kvb_res r{}; r.status = KVB_ST_OK; r.n = done; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
             }
-            kvb_res r{}; r.status = KVB_ST_OK; r.n = done; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_PIN_NEW: {   // get_new_blocks(n), patches.py:483-517
-          const int n = o.n;
-          int64_t evicted = 0;
-          int st = KVB_ST_NONE;
-          if (n >= 0 && (int64_t)n <= avail_size(c, sc) + sc[SC_LRU_COUNT]) {
-            for (int it = 0; it < 2; ++it) {
-              const int64_t A = avail_size(c, sc);
-              if (A < n && sc[SC_LRU_COUNT] > 0) {
-                const int k = (int)((n - A) < sc[SC_LRU_COUNT] ? (n - A) : sc[SC_LRU_COUNT]);
+          if constexpr (!COMPACT) {
+            const int n = o.n;
+            int64_t evicted = 0;
+            int st = KVB_ST_NONE;
+            if (n >= 0 && (int64_t)n <= avail_size(c, sc) + sc[SC_LRU_COUNT]) {
+              for (int it = 0; it < 2; ++it) {
+                const int64_t A = avail_size(c, sc);
+                if (A < n && sc[SC_LRU_COUNT] > 0) {
+                  const int k = (int)((n - A) < sc[SC_LRU_COUNT] ? (n - A) : sc[SC_LRU_COUNT]);
+                  __syncthreads();
+                  lru_pop_oldest(c, s, k, a.out_ids + sc[SC_OUT_CURSOR]);
+                  if (tid == 0) sc[SC_OUT_CURSOR] += k;
+                  __syncthreads();
+                  free_core(c, s, a, k, 0);
+                  evicted += k;
+                }
+                if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
                 __syncthreads();
-                lru_pop_oldest(c, s, k, a.out_ids + sc[SC_OUT_CURSOR]);
-                if (tid == 0) sc[SC_OUT_CURSOR] += k;
-                __syncthreads();
-                free_core(c, s, a, k, 0);
-                evicted += k;
+                st = a.res[op].status;
+                if (st != KVB_ST_NONE) break;   // ids, or RuntimeError("No free pages left") which the pool does not catch
               }
-              if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
-              __syncthreads();
-              st = a.res[op].status;
-              if (st != KVB_ST_NONE) break;   // ids, or RuntimeError("No free pages left") which the pool does not catch
+              if (st == KVB_ST_OK) {
+                const int64_t off = a.res[op].off;
+                for (int t = tid; t < n; t += NT) c.pin_ref[a.out_ids[off + t]] = 1;
+              }
+            } else if (tid == 0) {   // "Cannot get n free blocks from the pool": ValueError, nothing changed
+              kvb_res r{}; r.status = KVB_ST_NONE; r.n = 0; r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); r.aux = 0;
+              a.res[op] = r;
             }
-            if (st == KVB_ST_OK) {
-              const int64_t off = a.res[op].off;
-              for (int t = tid; t < n; t += NT) c.pin_ref[a.out_ids[off + t]] = 1;
-            }
-          } else if (tid == 0) {   // "Cannot get n free blocks from the pool": ValueError, nothing changed
-            kvb_res r{}; r.status = KVB_ST_NONE; r.n = 0; r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); r.aux = 0;
-            a.res[op] = r;
+            __syncthreads();
+            if (tid == 0) a.res[op].aux = evicted;
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          if (tid == 0) a.res[op].aux = evicted;
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_PIN_TOUCH:
         case KVB_OP_PIN_MARK:
         case KVB_OP_PIN_FREE:
         case KVB_OP_PIN_EVICT:
         case KVB_OP_PIN_RESET: {
-          int64_t aux = 0;
-          const int64_t off0 = sc[SC_OUT_CURSOR];
-          const bool too_many = o.n > c.f_cap;
-          if (too_many) {
-          } else if (o.kind == KVB_OP_PIN_TOUCH) {
-            pin_touch(c, s, a, o.arg, o.n);
-          } else if (o.kind == KVB_OP_PIN_MARK) {   // cache_full_blocks: _block_id_to_key[block_id] = key (patches.py:463-465)
-            for (int j = tid; j < o.n; j += NT) {
-              int64_t id = a.ids[o.arg + j];
-              if (id >= 0 && id < c.num_blocks) atomicOr(&c.pin_keyed[id >> 5], 1u << (id & 31));
+          if constexpr (!COMPACT) {
+            int64_t aux = 0;
+            const int64_t off0 = sc[SC_OUT_CURSOR];
+            const bool too_many = o.n > c.f_cap;
+            if (too_many) {
+            } else if (o.kind == KVB_OP_PIN_TOUCH) {
+              pin_touch(c, s, a, o.arg, o.n);
+            } else if (o.kind == KVB_OP_PIN_MARK) {   // cache_full_blocks: _block_id_to_key[block_id] = key (patches.py:463-465)
+              for (int j = tid; j < o.n; j += NT) {
+                int64_t id = a.ids[o.arg + j];
+                if (id >= 0 && id < c.num_blocks) atomicOr(&c.pin_keyed[id >> 5], 1u << (id & 31));
+              }
+            } else if (o.kind == KVB_OP_PIN_FREE) {
+              aux = pin_free(c, s, a, o.arg, o.n, a.out_ids + off0);
+            } else if (o.kind == KVB_OP_PIN_EVICT) {
+              pin_evict(c, s, a, o.arg, o.n);
+            } else {
+              pin_reset(c, s, a);
             }
-          } else if (o.kind == KVB_OP_PIN_FREE) {
-            aux = pin_free(c, s, a, o.arg, o.n, a.out_ids + off0);
-          } else if (o.kind == KVB_OP_PIN_EVICT) {
-            pin_evict(c, s, a, o.arg, o.n);
-          } else {
-            pin_reset(c, s, a);
+            __syncthreads();
+            if (tid == 0) {
+              sc[SC_OUT_CURSOR] = off0 + aux;
+              kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = o.n; r.off = off0; r.avail = avail_size(c, sc); r.aux = aux;
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          if (tid == 0) {
-            sc[SC_OUT_CURSOR] = off0 + aux;
-            kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = o.n; r.off = off0; r.avail = avail_size(c, sc); r.aux = aux;
-            a.res[op] = r;
-          }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_ALLOC_EXTEND:
         case KVB_OP_ALLOC_DECODE: {
-          const int decode = o.kind == KVB_OP_ALLOC_DECODE;
-          int64_t npg, ntok;
-          slots_scan(c, s, a, decode, &npg, &ntok);
-          int st = KVB_ST_OK;
-          if ((decode ? (int64_t)a.slot_bs : ntok) > a.slot_tokens || npg > INT_MAX) {
-            st = KVB_ERR_OVERFLOW;                 // caller's index buffer is too small
-          } else if (npg > 0) {                    // the reference skips alloc() when no page is needed (:217, :258)
+          if constexpr (!COMPACT) {
+            const int decode = o.kind == KVB_OP_ALLOC_DECODE;
+            int64_t npg, ntok;
+            slots_scan(c, s, a, decode, &npg, &ntok);
+            int st = KVB_ST_OK;
+            if ((decode ? (int64_t)a.slot_bs : ntok) > a.slot_tokens || npg > INT_MAX) {
+              st = KVB_ERR_OVERFLOW;                 // caller's index buffer is too small
+            } else if (npg > 0) {                    // the reference skips alloc() when no page is needed (:217, :258)
+              if (tid == 0) {
+                s.ops[op - chunk_base].n = (int32_t)npg;
+                if (a.resize_target > 0) mgr_resize(c, sc, a.resize_target);   // alloc()'s limit check, kv_cache_manager.py:258-260
+              }
+              __syncthreads();
+              if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
+              __syncthreads();
+              st = a.res[op].status;
+            }
+            if (st == KVB_ST_OK) slots_expand(c, a, decode, a.out_ids + (npg > 0 ? a.res[op].off : 0));
+            __syncthreads();
             if (tid == 0) {
-              s.ops[op - chunk_base].n = (int32_t)npg;
-              if (a.resize_target > 0) mgr_resize(c, sc, a.resize_target);   // alloc()'s limit check, kv_cache_manager.py:258-260
+              kvb_res r{};
+              if (npg > 0 && st != KVB_ERR_OVERFLOW) r = a.res[op];
+              else { r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); }
+              r.status = st;
+              r.n = st == KVB_ST_OK ? (int32_t)npg : 0;
+              r.aux = decode ? a.slot_bs : ntok;    // slot indices written
+              a.res[op] = r;
             }
             __syncthreads();
-            if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
-            __syncthreads();
-            st = a.res[op].status;
+            op++;
+            break;
           }
-          if (st == KVB_ST_OK) slots_expand(c, a, decode, a.out_ids + (npg > 0 ? a.res[op].off : 0));
-          __syncthreads();
-          if (tid == 0) {
-            kvb_res r{};
-            if (npg > 0 && st != KVB_ERR_OVERFLOW) r = a.res[op];
-            else { r.off = sc[SC_OUT_CURSOR]; r.avail = avail_size(c, sc); }
-            r.status = st;
-            r.n = st == KVB_ST_OK ? (int32_t)npg : 0;
-            r.aux = decode ? a.slot_bs : ntok;    // slot indices written
-            a.res[op] = r;
-          }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_ALLOC_DEV: {   // alloc(n); ids also land in the caller's device array
-          if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
-          __syncthreads();
-          if (a.res[op].status == KVB_ST_OK) {
-            const int64_t off = a.res[op].off;
-            for (int t = tid; t < o.n; t += NT) a.slot_out[t] = a.out_ids[off + t];
+          if constexpr (!COMPACT) {
+            if (!alloc_run_fast(c, s, a, chunk_base, op, op + 1)) alloc_run(c, s, a, chunk_base, op, op + 1, 0);
+            __syncthreads();
+            if (a.res[op].status == KVB_ST_OK) {
+              const int64_t off = a.res[op].off;
+              for (int t = tid; t < o.n; t += NT) a.slot_out[t] = a.out_ids[off + t];
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_FREE_DEV: {    // free(ids), ids taken in order from the caller's device array
-          const int n = (int)o.arg;
-          const bool too_many = n > c.f_cap;
-          if (!too_many) {
-            bool done = false;
-            if (n <= NT) done = free_small(c, s, a, n, tid < n ? a.slot_pre[tid] : -1) != 0;
-            if (!done) {
-              for (int j = tid; j < n; j += NT) c.fids[j] = a.slot_pre[j];
-              __syncthreads();
-              free_core(c, s, a, n, 0);
+          if constexpr (!COMPACT) {
+            const int n = (int)o.arg;
+            const bool too_many = n > c.f_cap;
+            if (!too_many) {
+              bool done = false;
+              if (n <= NT) done = free_small(c, s, a, n, tid < n ? a.slot_pre[tid] : -1) != 0;
+              if (!done) {
+                for (int j = tid; j < n; j += NT) c.fids[j] = a.slot_pre[j];
+                __syncthreads();
+                free_core(c, s, a, n, 0);
+              }
             }
+            if (tid == 0) {
+              kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          if (tid == 0) {
-            kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
-          }
-          __syncthreads();
-          op++;
-          break;
         }
         case KVB_OP_FREE_SLOTS: {
-          const int nb = slots_unique_blocks(c, s, a, o.arg);
-          if (nb > 0) free_core(c, s, a, nb, 0);
-          if (tid == 0) {
-            kvb_res r{}; r.status = KVB_ST_OK; r.n = nb; r.off = 0; r.avail = avail_size(c, sc);
-            a.res[op] = r;
+          if constexpr (!COMPACT) {
+            const int nb = slots_unique_blocks(c, s, a, o.arg);
+            if (nb > 0) free_core(c, s, a, nb, 0);
+            if (tid == 0) {
+              kvb_res r{}; r.status = KVB_ST_OK; r.n = nb; r.off = 0; r.avail = avail_size(c, sc);
+              a.res[op] = r;
+            }
+            __syncthreads();
+            op++;
+            break;
           }
-          __syncthreads();
-          op++;
-          break;
         }
         default: {
           if (tid == 0) { kvb_res r{}; r.status = KVB_ERR_INVALID; r.n = 0; r.off = 0; r.avail = 0; a.res[op] = r; }
@@ -2901,6 +2944,15 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
   KVB_PROF(10);
 }
 
+// __grid_constant__: the device functions take the parameter structs by reference; without it every thread first
+// copies them (2.7 KB) to its local memory.
+__global__ void __launch_bounds__(NT, 1) kvb_step_kernel(const __grid_constant__ DevState c, const __grid_constant__ LaunchArgs a) {
+  step_body<false>(c, a);
+}
+__global__ void __launch_bounds__(NT, 1) kvb_decode_kernel(const __grid_constant__ DevState c, const __grid_constant__ LaunchArgs a) {
+  step_body<true>(c, a);
+}
+
 // ==================================================================================== single requests
 // kvb_mgr_alloc / kvb_mgr_free launch THIS kernel: the same device functions (alloc_run_warp, free_small, the flagged
 // publish) without the other twenty request kinds around them.  kvb_step_kernel is 1.3 MB of SASS and a launch
@@ -2908,13 +2960,14 @@ __global__ void __launch_bounds__(NT, 1) kvb_step_kernel(DevState c, LaunchArgs 
 // launch to instruction fetch (profiles/r2_step_single_rules.csv).  Requests this kernel cannot serve with those two
 // paths (shrink mode, blocks straddling page edges, windows too small, > 256 distinct pages) are answered with
 // KVB_ST_RETRY — nothing touched — and the host sends them through kvb_step_kernel.
-__global__ void __launch_bounds__(NT, 1) kvb_one_kernel(DevState c, LaunchArgs a) {
+__global__ void __launch_bounds__(NT, 1) kvb_one_kernel(const __grid_constant__ DevState c, const __grid_constant__ LaunchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem &s = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
   int64_t *sc = s.sc;
   if (tid < 16) s.misc[tid] = 0;
   if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
+  for (int i = tid; i < kGrowTab / 2; i += NT) reinterpret_cast<uint32_t *>(s.grow16)[i] = reinterpret_cast<const uint32_t *>(c.grow_tab)[i];
   if (tid == 0) s.ops[0] = a.inline_op;
   pdl_enter();                           // nothing of the device state is read above this line
   if (tid < SC_COUNT) sc[tid] = c.sc[tid];
@@ -3313,7 +3366,7 @@ static int resident_grid(K kernel, int threads, int *cache_by_dev) {
 }
 
 // One CTA of NT threads; with programmatic stream serialization unless KVB200_PDL=0 (pdl_enter() above).
-static int launch_bookkeeping(void (*kernel)(DevState, LaunchArgs), const DevState &st, const LaunchArgs &a, void *stream) {
+static int launch_bookkeeping(void (*kernel)(const DevState, const LaunchArgs), const DevState &st, const LaunchArgs &a, void *stream) {
   static const bool pdl = []() { const char *e = getenv("KVB200_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(1);
@@ -3335,15 +3388,19 @@ int launch_step_prepare() {
     cudaError_t e = cudaFuncSetAttribute(kvb_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(kvb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
   return 0;
 }
 
-int launch_step(const DevState &st, const LaunchArgs &a, void *stream) {
+int launch_step(const DevState &st, const LaunchArgs &a, void *stream, bool alloc_free_only) {
   int rc = launch_step_prepare();
   if (rc) return rc;
-  return launch_bookkeeping(kvb_step_kernel, st, a, stream);
+  static const bool compact_on = []() { const char *e = getenv("KVB200_DECODE_KERNEL"); return !(e && e[0] == '0'); }();
+  const bool compact = alloc_free_only && compact_on && !(a.tune & 8) && !a.group_only && a.resize_target <= 0;
+  return launch_bookkeeping(compact ? kvb_decode_kernel : kvb_step_kernel, st, a, stream);
 }
 
 int launch_one(const DevState &st, const LaunchArgs &a, void *stream) {

@@ -119,6 +119,7 @@ struct kvb_mgr {
   // resident replay as a CUDA graph: the launch sequence of a step range is captured once and replayed (one kernel
   // node per scheduler step; what changes between replays lives in device memory, not in the launch arguments)
   cudaGraphExec_t t_graph = nullptr;
+  std::vector<int32_t> t_other;            // resident trace: prefix count of requests that are not alloc / free
   int64_t t_graph_key[5] = {-1, -1, -1, -1, -1};   // step_begin, step_end, steps_per_launch, phys_free, resize_target
   int64_t t_graph_launches = 0;
   int64_t phys_capture = -1;                       // >= 0: value every launch of a capture uses
@@ -265,11 +266,18 @@ int deliver_events(kvb_mgr *m, const Summary *hs, bool settle) {
   return rc;
 }
 
+// Requests kvb_decode_kernel serves (the rest of the request kinds need kvb_step_kernel).
+static inline bool alloc_free_kind(int kind) {
+  return kind == KVB_OP_ALLOC || kind == KVB_OP_FREE_IDS || kind == KVB_OP_FREE_REF || kind == KVB_OP_FREE_RESERVED ||
+         kind == KVB_OP_AVAIL;
+}
+
 // One launch over requests [op_begin, op_end) of a device-resident request array.
 int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int64_t *d_ids, const kvb_ref *d_refs,
            kvb_res *d_res, int64_t *d_outids, int64_t out_cap, Summary *d_sum, int arena_mode, int group_only,
            int64_t *grp_pages = nullptr, int64_t *grp_counts = nullptr, int64_t *grp_ids = nullptr,
-           kvb_res *host_res = nullptr, int64_t *host_out = nullptr, const LaunchArgs *slots = nullptr) {
+           kvb_res *host_res = nullptr, int64_t *host_out = nullptr, const LaunchArgs *slots = nullptr,
+           bool alloc_free_only = false) {
   LaunchArgs a{};
   if (slots) {
     a.slot_pre = slots->slot_pre; a.slot_seq = slots->slot_seq; a.slot_last = slots->slot_last;
@@ -316,7 +324,7 @@ int launch(kvb_mgr *m, const kvb_op *d_ops, int op_begin, int op_end, const int6
       a.tp_flags = m->tp_flags_next;
     }
   }
-  int rc = launch_step(m->st, a, m->stream);
+  int rc = launch_step(m->st, a, m->stream, alloc_free_only);
   if (rc != 0) {
     set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return KVB_ERR_CUDA;
@@ -461,7 +469,7 @@ int fast_op(kvb_mgr *m, int kind, int32_t n, const int64_t *ids, bool wait, kvb_
     a.ll_flag = flag;
   }
   // the compact single-request kernel; a free whose ids do not fit the parameters goes through the general one
-  int lrc = big_free ? launch_step(m->st, a, m->stream) : launch_one(m->st, a, m->stream);
+  int lrc = big_free ? launch_step(m->st, a, m->stream, true) : launch_one(m->st, a, m->stream);
   if (lrc != 0) { set_error("step kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); return KVB_ERR_CUDA; }
   m->launches++;
   m->n_fast++;
@@ -645,6 +653,7 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   size_t o_tbits = carve((size_t)(nwords + 8) * 4);
   size_t o_ev = carve((size_t)s.ev_cap * 8);
   size_t o_pr = carve((size_t)kNumPrimes * 8);
+  size_t o_gt = carve((size_t)kGrowTab * 2);
   m->d_block_bytes = off;
   if (cudaMalloc((void **)&m->d_block, off) != cudaSuccess) return fail("cudaMalloc(state)");
   unsigned char *b = m->d_block;
@@ -683,6 +692,20 @@ extern "C" kvb_mgr *kvb_mgr_create(const kvb_mgr_config *cfg) {
   static_assert(sizeof(unsigned long) == sizeof(uint64_t), "LP64 expected");
   if (cudaMemcpy((void *)s.primes, std::__detail::__prime_list, kNumPrimes * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     return fail("cudaMemcpy(primes)");
+  {
+    // What libstdc++ itself answers when a table of nb buckets holding nb keys takes one more (_M_need_rehash:
+    // _M_next_bkt(max(n_elt + n_ins, growth_factor * n_bkt)) at load factor 1) — asked of the real policy object, so
+    // the kernels' rehash chain 2 -> 5 -> 11 -> 23 -> 47 -> ... is one table read per phase instead of a binary search.
+    std::vector<uint16_t> gt((size_t)kGrowTab);
+    for (int nb = 0; nb < kGrowTab; ++nb) {
+      std::__detail::_Prime_rehash_policy pol;
+      const size_t want = std::max<size_t>((size_t)nb + 2, (size_t)2 * nb);
+      gt[(size_t)nb] = (uint16_t)pol._M_next_bkt(want);
+    }
+    s.grow_tab = (const uint16_t *)(b + o_gt);
+    if (cudaMemcpy((void *)s.grow_tab, gt.data(), gt.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail("cudaMemcpy(grow table)");
+  }
   if (cudaMalloc((void **)&m->d_scratch, 64 * 8) != cudaSuccess) return fail("cudaMalloc(scratch)");
   if (cudaMemset(m->d_scratch, 0, 64 * 8) != cudaSuccess) return fail("cudaMemset(scratch)");
 #ifdef KVB_PROFILE
@@ -806,10 +829,12 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     }
   }
   // trim / clear / resize hand memory back on purpose: their unmaps settle before the call returns
-  bool settle = false;
-  for (int64_t i = 0; i < n_ops; ++i)
+  bool settle = false, af_only = true;
+  for (int64_t i = 0; i < n_ops; ++i) {
     settle |= ops[i].kind == KVB_OP_TRIM || ops[i].kind == KVB_OP_CLEAR || ops[i].kind == KVB_OP_RESIZE ||
               ops[i].kind == KVB_OP_PA_RESIZE;
+    af_only &= alloc_free_kind(ops[i].kind);
+  }
   if (need_out > out_cap) { set_error("out_ids capacity %ld < %ld ids requested (alloc n, get_new_blocks 2n, free_blocks n)", (long)out_cap, (long)need_out); return KVB_ERR_OVERFLOW; }
   size_t b_ops = (size_t)n_ops * sizeof(kvb_op), b_ids = (size_t)n_ids * 8, b_refs = align_up((size_t)n_refs * sizeof(kvb_ref), 8);
   size_t in_bytes = b_ops + b_ids + b_refs;
@@ -844,7 +869,7 @@ static int64_t step_locked(kvb_mgr *m, const kvb_op *ops, int64_t n_ops, const i
     volatile int64_t *vseq = &((Summary *)m->h_out)->seq;
     if (zc) *vseq = 0;
     rc = launch(m, d_ops, (int)done, (int)n_ops, d_ids, d_refs, d_res, d_outids, need_out, d_sum, first ? 0 : 2, 0,
-                nullptr, nullptr, nullptr, zc ? h_res : nullptr, zc ? h_outids : nullptr);
+                nullptr, nullptr, nullptr, zc ? h_res : nullptr, zc ? h_outids : nullptr, nullptr, af_only);
     if (rc) return rc;
     if (zc) {
       const int64_t want = m->seq;
@@ -1196,6 +1221,8 @@ extern "C" int kvb_mgr_trace_upload(kvb_mgr *m, const kvb_op *ops, int64_t n_ops
   m->t_out_cap = out_capacity;
   m->t_nops = n_ops;
   m->t_steps.assign(step_offsets, step_offsets + n_steps + 1);
+  m->t_other.assign((size_t)n_ops + 1, 0);     // prefix count of requests kvb_decode_kernel does not serve
+  for (int64_t i = 0; i < n_ops; ++i) m->t_other[(size_t)i + 1] = m->t_other[(size_t)i] + (alloc_free_kind(ops[i].kind) ? 0 : 1);
   if (m->t_steps.front() != 0 || m->t_steps.back() != n_ops) { set_error("trace_upload: step_offsets must span [0, n_ops]"); return KVB_ERR_INVALID; }
   return 0;
 }
@@ -1231,7 +1258,9 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
       int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
       if (oe == ob) continue;
       m->safe_before_next = (int)(prev_ob < 0 ? ob : prev_ob);
-      int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0);
+      const bool af_only = m->t_other[(size_t)oe] == m->t_other[(size_t)ob];
+      int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, af_only);
       if (rc) return rc;
       prev_ob = ob;
     }

@@ -8,8 +8,9 @@ import torch
 from kvcached_b200 import _lib, replay as R, trace as T
 torch.cuda.init()
 lib = _lib.load()
-NAMES = {0: "default (PDL + early ref gather + block-wide dict-order replay)", 1: "one-warp dict-order replay",
-         2: "no programmatic dependent launch", 4: "no early ref gather", 6: "no PDL, no early gather (round-2 session-12 kernel)"}
+NAMES = {0: "default (PDL, early ref gather, kvb_decode_kernel)", 1: "one-warp dict-order replay",
+         2: "no programmatic dependent launch", 4: "no early ref gather", 6: "no PDL, no early gather",
+         8: "general kernel for every step (no kvb_decode_kernel)"}
 variants = [int(x) for x in sys.argv[1:]] or [0, 2, 4, 6, 1]
 cfg = T.make_config("llama8b", 91520)
 ct = R.compile_trace(T.decode_trace(cfg, 4096, seed=0))
