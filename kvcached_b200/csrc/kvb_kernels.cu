@@ -127,6 +127,7 @@ struct Smem {
   int64_t tmp64[NT];
   int32_t early_ids[EARLY_K][NT];   // ids of the launch's leading FREE_REF requests, gathered before pdl_enter()
   int32_t early_n[EARLY_K];         // their id counts, -1 = gather it after the wait
+  uint32_t namask[OPS_CHUNK / 32];  // staged chunk: bit = this request is not an ALLOC (or lies past the chunk's end)
   WarpPlan wplan;                   // alloc_run_warp: warp 0's plan for the CTA
   int32_t wroff[128];               // ... and the id-stream offset of each request of the run
   AllocSim sim;
@@ -1730,6 +1731,19 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
     const int64_t p64 = blk_page(c, my_id);
     if (p64 <= c.max_pages) { p = (int)p64; part = true; }
   }
+  // Issued now, consumed after the classification below: the bitmap test-and-clear (a block must be allocated) and the
+  // state of my id's page travel to L2 and back while the CTA builds its hash table.  (A call that turns out to name
+  // too many pages for this path puts its bits back, so "nothing touched" still holds for the caller.)
+  bool ok = part;
+  if (ok && !c.exact) {   // a block straddling the page edge is never handed out
+    const int64_t st0 = pg_start(c, p);
+    ok = my_id >= st0 && my_id < st0 + pg_nblk(c, p);
+  }
+  const uint32_t bit = ok ? 1u << (my_id & 31) : 0u;
+  uint32_t old_word = 0;
+  if (ok) old_word = atomicAnd(&c.bitmap[my_id >> 5], ~bit);
+  int e_st = 0, e_cnt = 0, e_head = 0, e_pos = 0;
+  if (part) { e_st = c.pg_state[p]; e_cnt = c.pg_cnt[p]; e_head = c.pg_head[p]; e_pos = c.pg_pos[p]; }
   __syncthreads();
   unsigned h = 0;
   if (part) {
@@ -1745,27 +1759,22 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   const bool first = part && Hval[h] == tid;
   int D;
   const int r = block_rank_1b(first, s.wsite[WS_FS_D], &D);
-  if (D > HS_D_CAP) { __syncthreads(); return 0; }
+  if (D > HS_D_CAP) {
+    if (ok && (old_word & bit)) atomicOr(&c.bitmap[my_id >> 5], bit);
+    __syncthreads();
+    return 0;
+  }
   KVB_PROF(4);
   // ---- from here on the state changes
-  bool ok = part;
-  if (ok && !c.exact) {   // a block straddling the page edge is never handed out
-    const int64_t st0 = pg_start(c, p);
-    ok = my_id >= st0 && my_id < st0 + pg_nblk(c, p);
-  }
-  if (ok) {               // a block must be allocated: test-and-clear
-    const uint32_t bit = 1u << (my_id & 31);
-    const uint32_t old = atomicAnd(&c.bitmap[my_id >> 5], ~bit);
-    ok = (old & bit) != 0;
-  }
+  ok = ok && (old_word & bit) != 0;
   if (first) {
     Hslot[h] = r;
     s.ht_key[r] = p;
     s.ht_cnt[r] = 0;
-    pst[r] = c.pg_state[p];
-    pcnt[r] = c.pg_cnt[p];
-    phead[r] = c.pg_head[p];
-    ppos[r] = c.pg_pos[p];
+    pst[r] = e_st;
+    pcnt[r] = e_cnt;
+    phead[r] = e_head;
+    ppos[r] = e_pos;
   }
   {
     const unsigned bm = __ballot_sync(0xffffffffu, tid < n && !ok);
@@ -2408,6 +2417,16 @@ __device__ __forceinline__ void publish_flagged(const DevState &c, Smem &s, cons
 }
 
 // ==================================================================================== the step kernel
+// Every thread of the CTA calls this when a chunk of requests is staged (kind = its request's kind, -1 past the end):
+// one vote per warp leaves, per 32 requests, the mask of those that are NOT an ALLOC — the end of an alloc run is then a
+// find-first-set for every thread on its own, no barrier and no shared atomics at the start of each run.
+__device__ __forceinline__ void stage_run_masks(Smem &s, int kind) {
+  static_assert(NT >= OPS_CHUNK, "one thread per staged request");
+  const unsigned na = __ballot_sync(0xffffffffu, kind != KVB_OP_ALLOC);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && w < OPS_CHUNK / 32) s.namask[w] = na;
+}
+
 // COMPACT = the kernel of a scheduler step that holds nothing but alloc(n) / free(ids) requests (kvb_decode_kernel): the
 // twenty other request kinds are not compiled in.  A launch executes a few thousand instructions exactly once, so
 // what it pays for is instruction FETCH (profiles/r2_step_single_rules.csv) — a kernel a third of the size with the
@@ -2424,15 +2443,18 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
   // read once per replay, i.e. from DRAM) while the predecessor kernel is still running.
   {
     const int n_first = (a.op_end - a.op_begin) < OPS_CHUNK ? (a.op_end - a.op_begin) : OPS_CHUNK;
+    int kind0 = -1;
     if (tid < n_first) {
       const kvb_op o = a.inline_on ? a.inline_op : a.ops[a.op_begin + tid];
       s.ops[tid] = o;
+      kind0 = o.kind;
       if (o.kind == KVB_OP_FREE_REF && a.refs && o.n > 0) {
         const char *r0 = reinterpret_cast<const char *>(a.refs + o.arg);
         const int bytes = (o.n < 1024 ? o.n : 1024) * (int)sizeof(kvb_ref);
         for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + b));
       }
     }
+    stage_run_masks(s, kind0);
   }
   if (tid < 16) s.misc[tid] = 0;
   if (tid >= 64 && tid < 64 + PRIMES_SM) s.primes32[tid - 64] = (uint32_t)c.primes[tid - 64];
@@ -2473,7 +2495,9 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
     const int chunk_base = op;
     const int chunk_n = (a.op_end - op) < OPS_CHUNK ? (a.op_end - op) : OPS_CHUNK;
     if (chunk_base != a.op_begin) {      // the first chunk was staged before pdl_enter()
-      if (tid < chunk_n) s.ops[tid] = a.inline_on ? a.inline_op : a.ops[chunk_base + tid];
+      int kind_q = -1;
+      if (tid < chunk_n) { const kvb_op oq = a.inline_on ? a.inline_op : a.ops[chunk_base + tid]; s.ops[tid] = oq; kind_q = oq.kind; }
+      stage_run_masks(s, kind_q);
       __syncthreads();
     }
     while (op < chunk_base + chunk_n && !s.misc[MI_STOP]) {
@@ -2502,13 +2526,16 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
       switch (COMPACT && !(o.kind == KVB_OP_ALLOC || o.kind == KVB_OP_FREE_IDS || o.kind == KVB_OP_FREE_REF ||
                            o.kind == KVB_OP_FREE_RESERVED || o.kind == KVB_OP_AVAIL) ? -1 : o.kind) {
         case KVB_OP_ALLOC: {
-          // end of the run of consecutive ALLOC requests inside the staged chunk
-          if (tid == 0) s.misc[MI_K] = chunk_base + chunk_n;
-          __syncthreads();
-          for (int q = op + 1 + tid; q < chunk_base + chunk_n; q += NT)
-            if (s.ops[q - chunk_base].kind != KVB_OP_ALLOC) { atomicMin(&s.misc[MI_K], q); break; }
-          __syncthreads();
-          int e = s.misc[MI_K];
+          // end of the run of consecutive ALLOC requests inside the staged chunk: first "not an ALLOC" bit after op
+          int e = chunk_base + chunk_n;
+          {
+            const int r = op + 1 - chunk_base;
+            for (int wd = r >> 5; wd < OPS_CHUNK / 32; ++wd) {
+              unsigned mk = s.namask[wd];
+              if (wd == (r >> 5)) mk &= 0xffffffffu << (r & 31);
+              if (mk) { e = chunk_base + wd * 32 + __ffs(mk) - 1; break; }
+            }
+          }
           if (e - op > NT) e = op + NT;
           KVB_PROF(0);
           if (alloc_run_warp(c, s, a, chunk_base, op, e)) {

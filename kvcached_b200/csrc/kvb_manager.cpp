@@ -1253,13 +1253,21 @@ extern "C" int kvb_mgr_trace_run(kvb_mgr *m, int64_t step_begin, int64_t step_en
     // predecessor lets it in only after having waited for its own predecessor); the first launch of the range follows
     // a memset / a synchronised stream, so everything before it is complete.
     int64_t prev_ob = -1;
+    // The summary (counters, event count) is the range's closing report: only its last launch writes one — the earlier
+    // ones would be overwritten unread.  Per-request results and ids are written by every launch.
+    int64_t last_s = -1;
+    for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
+      int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
+      if (m->t_steps[(size_t)e] != m->t_steps[(size_t)s]) last_s = s;
+    }
     for (int64_t s = step_begin; s < step_end; s += steps_per_launch) {
       int64_t e = std::min<int64_t>(s + steps_per_launch, step_end);
       int64_t ob = m->t_steps[(size_t)s], oe = m->t_steps[(size_t)e];
       if (oe == ob) continue;
       m->safe_before_next = (int)(prev_ob < 0 ? ob : prev_ob);
       const bool af_only = m->t_other[(size_t)oe] == m->t_other[(size_t)ob];
-      int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap, m->t_sum, 1, 0,
+      int rc = launch(m, m->t_ops, (int)ob, (int)oe, m->t_ids, m->t_refs, m->t_res, m->t_out, m->t_out_cap,
+                      s == last_s ? m->t_sum : nullptr, 1, 0,
                       nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, af_only);
       if (rc) return rc;
       prev_ob = ob;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session 16: kvb_decode_kernel (alloc/free-only steps), __grid_constant__ parameters, rehash growth table
+# round 2, session 16+: decode kernel, early-issued bitmap test, staged run masks, closing summary only
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/tests_gpu.log
 timeout 300 python tools/probe_ab.py 0 8 2 > gpurun_out/probe_ab.log 2>&1; echo "probe_ab rc=$?"; cat gpurun_out/probe_ab.log
