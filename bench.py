@@ -158,28 +158,42 @@ def oracle_port_ops_per_s(trace: dict) -> dict:
             "sample": f"one replay of the full trace through oracle/kv_oracle.cpp ({n} calls, {dt:.3f} s, incl. Python glue)"}
 
 
+REF_SAMPLE_DIV = {1: 4}     # N -> the reference replays 1 / div of the workload per step (default 8)
+
+
 def reference_sample_trace(world: int):
-    """N > 1: the reference cannot create the 70B geometry's contiguous tensors (ftensor.cpp:161 asserts that its fixed
-    base address is a multiple of the 320 MiB compound page), so it runs its per-layer layout — 160 driver map loops
-    per page event — on a bounded sample of the workload: the same generator and distributions with 512 requests on
-    a pool 1/8 the size (same page events per call), so that K + W replays end within minutes."""
+    """The reference's step is a BOUNDED SAMPLE of the workload: the same generator and distributions with 1 / div of
+    the requests on a pool 1 / div the size, i.e. the same page events and the same list lengths per call, so ops/s is
+    comparable with the full trace while K + W steps end within minutes on the slowest boxes of the pool (a full replay
+    through the reference takes 9 - 45 s here, the driver asks for 25 of them).  N = 1: 1024 requests, contiguous
+    layout.  N > 1: 512 requests; the reference cannot create the 70B geometry's contiguous tensors (ftensor.cpp:161
+    asserts that its fixed base address is a multiple of the 320 MiB compound page), so it runs its per-layer layout —
+    160 driver map loops per page event."""
     from kvcached_b200 import trace as T
-    cfg = T.make_config(f"llama70b_tp{world}", NUM_BLOCKS_TP // 8)
-    return cfg, T.decode_trace(cfg, N_REQUESTS // 8, seed=0)
+    div = REF_SAMPLE_DIV.get(world, 8)
+    if world == 1:
+        cfg = T.make_config("llama8b", NUM_BLOCKS // div)
+    else:
+        cfg = T.make_config(f"llama70b_tp{world}", NUM_BLOCKS_TP // div)
+    return cfg, T.decode_trace(cfg, N_REQUESTS // div, seed=0)
+
+
+def reference_sample_note(world: int) -> str:
+    div = REF_SAMPLE_DIV.get(world, 8)
+    nb = (NUM_BLOCKS if world == 1 else NUM_BLOCKS_TP) // div
+    return (f"replays of a bounded sample of the workload ({N_REQUESTS // div} requests, pool {nb} blocks: same generator, "
+            "distributions and page events per call as the full trace)")
 
 
 def reference_main(args, rank: int, world: int):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    sample = "full replays of the trace"
+    cfg, tr = reference_sample_trace(world)
+    sample = reference_sample_note(world)
     if world == 1:
-        cfg, tr = build_trace(world)
         attempts = [("cuda:0", True, True, "cuda:0, contiguous layout, prealloc thread on (shipping default)")]
     else:
-        cfg, tr = reference_sample_trace(world)
-        sample = (f"replays of a bounded sample ({N_REQUESTS // 8} requests, pool {NUM_BLOCKS_TP // 8} blocks: same "
-                  "generator, distributions and page events per call as the full trace)")
         attempts = [("cuda:0", True, False, "cuda:0, per-layer layout (the contiguous 70B geometry trips the reference's "
                                             "own alignment assert, ftensor.cpp:161), prealloc thread on")]
     attempts.append(("cpu", False, True, "cpu device (bookkeeping only: map/unmap are no-ops)"))
@@ -632,22 +646,24 @@ def ours_main(args, rank: int, world: int, local_rank: int):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            out = run_reference(tr, repeats=1 + args.ref_replays, device="cuda:0", prealloc=True, timeout=900)
+            _scfg, str_ = reference_sample_trace(1)
+            s_calls = str_["meta"]["n_ops"]
+            out = run_reference(str_, repeats=1 + args.ref_replays, device="cuda:0", prealloc=True, timeout=900)
             el = out["elapsed_all_s"][1:]
-            cpu_baseline = {"value": n_calls * len(el) / sum(el), "unit": UNIT, "cores": 2, "kind": "reference",
+            cpu_baseline = {"value": s_calls * len(el) / sum(el), "unit": UNIT, "cores": 2, "kind": "reference",
                             "replays_s": el, "create_kv_tensors_s": out.get("create_kv_tensors_s"),
-                            "sample": f"1 warm-up + {len(el)} timed full replays ({n_calls} calls each) through the "
-                                      f"unmodified reference KVCacheManager on cuda:0 (real cuMemMap work, prealloc "
-                                      f"thread on = shipping default), {out.get('pinned')}; host has {os.cpu_count()} "
-                                      f"cores, the scheduler path is single-threaded"}
+                            "sample": f"1 warm-up + {len(el)} timed {reference_sample_note(1)} ({s_calls} calls each) "
+                                      f"through the unmodified reference KVCacheManager on cuda:0 (real cuMemMap work, "
+                                      f"prealloc thread on = shipping default), {out.get('pinned')}; host has "
+                                      f"{os.cpu_count()} cores, the scheduler path is single-threaded"}
             try:   # prealloc off = the deterministic parity mode
-                o3 = run_reference(tr, repeats=1, device="cuda:0", prealloc=False, timeout=600)
-                cpu_baseline["prealloc_off_value"] = n_calls / o3["elapsed_all_s"][-1]
+                o3 = run_reference(str_, repeats=1, device="cuda:0", prealloc=False, timeout=600)
+                cpu_baseline["prealloc_off_value"] = s_calls / o3["elapsed_all_s"][-1]
             except Exception as e:
                 cpu_baseline["prealloc_off_value"] = f"failed: {e}"[:200]
             try:   # "cpu" device: map/unmap are no-ops, i.e. the reference's bookkeeping alone
-                o2 = run_reference(tr, repeats=2, device="cpu", prealloc=False, timeout=600)
-                cpu_baseline["bookkeeping_only_value"] = n_calls / o2["elapsed_all_s"][-1]
+                o2 = run_reference(str_, repeats=2, device="cpu", prealloc=False, timeout=600)
+                cpu_baseline["bookkeeping_only_value"] = s_calls / o2["elapsed_all_s"][-1]
             except Exception:
                 pass
         except Exception as e:
@@ -733,7 +749,12 @@ def ours_main(args, rank: int, world: int, local_rank: int):
         if rank != 0:
             tp.fence()
 
+    # The e2e legs replay the whole trace through the driver (0.3 - 7 s per replay on this pool): at most 6 timed
+    # replays after at most 3 warm-up ones, whatever K and W ask of the device-timed value.
+    Ke, We = min(K, 6), min(W, 3)
+
     def e2e_leg(strict: bool) -> dict:
+        K, W = Ke, We
         vmm_ops.set_retention(0.0 if strict else 2000.0)
         pooled_peak = 0
         vmm_ops.settle()
@@ -782,7 +803,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                "physical_overshoot_pages_peak_mean": sum(over_peak) / len(over_peak),
                "physical_overshoot_gib_peak_max": max(over_peak) * page_gib,
                "retained_pages_peak_max": max(ret_peak),
-               "pooled_unmapped_handles_pages_after_fence_max": pooled_peak, "pool_cap_pages": fp["pool_cap_pages"]}
+               "pooled_unmapped_handles_pages_after_fence_max": pooled_peak, "pool_cap_pages": fp["pool_cap_pages"],
+               "steps": K, "warmup": W}
         # the PHYSICAL mapping (everything mapped, not only what is wanted) against the bookkeeping
         mapped_now = vmm_ops.mapped_pages()
         phys_now = vmm_ops.vmm_stats()["mapped_pages"]
@@ -981,7 +1003,8 @@ def ours_main(args, rank: int, world: int, local_rank: int):
             mgr_nz = R.manager_from_config(cfg, device_index=local_rank)
             tnz = []
             vt0 = vmm_ops.vmm_timing()
-            for it in range(1 + K):
+            Knz = min(K, 4)
+            for it in range(1 + Knz):
                 t0 = time.perf_counter()
                 R.replay_host_steps(mgr_nz, plan, keep_results=False)
                 vmm_ops.fence()
@@ -989,9 +1012,10 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 if it == 0:
                     vt0 = vmm_ops.vmm_timing()
             vt1 = vmm_ops.vmm_timing()
-            no_zero = {"value": n_calls * K / sum(tnz[1:]), "unit": UNIT, "ms_per_step": 1e3 * sum(tnz[1:]) / K,
+            no_zero = {"value": n_calls * Knz / sum(tnz[1:]), "unit": UNIT, "ms_per_step": 1e3 * sum(tnz[1:]) / Knz,
+                       "steps": Knz,
                        "driver_ms_per_replay": sum(vt1[k] - vt0[k] for k in ("unmap_ms", "map_ms", "setaccess_ms", "create_ms",
-                                                                             "release_ms")) / K,
+                                                                             "release_ms")) / Knz,
                        "policy": "as e2e, but no zero page behind unmapped pages (they fault if touched)"}
             mgr_nz.close()
         except Exception as e:
@@ -1057,8 +1081,9 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "step_kernel": {"us_per_scheduler_step": 1e3 * res_ms_total / K / n_sched_steps,
-                                "note": "kvb_step_kernel is one latency-bound CTA over L2-resident state "
-                                        "(11 KB bitmap, 366 KB rings at this size): no HBM roofline applies"}}
+                                "note": "kvb_decode_kernel / kvb_step_kernel: one latency-bound CTA per scheduler step over "
+                                        "L2-resident state (11 KB bitmap, 366 KB rings at this size), launched with "
+                                        "programmatic stream serialization inside a CUDA graph: no HBM roofline applies"}}
     total_launches = lib.kvb_total_launches() - launches0
 
     two_model = None
