@@ -479,6 +479,17 @@ __device__ __forceinline__ void ht_order_seq(const DevState &c, const uint32_t *
 // first — i.e. S sorted by (first position of my bucket in S, my position in S), both descending.  A rehash
 // re-places the current list front to back under the new nb, which is the same rule applied to S = current
 // order; keys inserted afterwards simply extend S.  Lane l holds the key at position l of S.
+// Keys of the runs whose leader (first key of a bucket in S) sits at a lane above g.  Leaders hold their run's size
+// (<= 32): six votes slice the sizes by bit, every lane sums the bits above its own g — independent instructions,
+// where a suffix scan over the lanes is a chain of five dependent shuffles plus a sixth to fetch the leader's value.
+__device__ __forceinline__ int keys_of_later_runs(bool leader, int size, int g) {
+  const unsigned above = ~((2u << g) - 1u);       // g = 31: no lane above
+  int r = 0;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) r += __popc(__ballot_sync(0xffffffffu, leader && ((size >> b) & 1)) & above) << b;
+  return r;
+}
+
 #ifdef KVB_PROFILE
 #define KVB_PROF_W(slot) do { if (threadIdx.x == 0) { long long t_ = clock64(); c.prof[slot] += t_ - *pt; c.prof[16 + (slot)] += 1; *pt = t_; } } while (0)
 #else
@@ -505,14 +516,7 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
     const int gfirst = __ffs(grp) - 1;                  // first position of my bucket in S
     const int later_in_grp = __popc(grp & gt);
     // keys whose bucket first appears after mine come before me: suffix sum of run sizes over run leaders
-    int suf = (in && gfirst == lane) ? __popc(grp) : 0;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int y = __shfl_down_sync(0xffffffffu, suf, d);
-      if (lane + d < 32) suf += y;
-    }
-    int before = __shfl_sync(0xffffffffu, suf, (gfirst + 1) & 31);
-    if (gfirst == 31) before = 0;
+    const int before = keys_of_later_runs(in && gfirst == lane, __popc(grp), gfirst);
     const int newpos = before + later_in_grp;
     KVB_PROF_W(14);
     // permute through shared memory: position p takes the element whose newpos == p
@@ -641,14 +645,7 @@ __device__ __forceinline__ void ht_order_prefix(const DevState &c, const uint32_
     const unsigned grp = __match_any_sync(0xffffffffu, b);
     const int gfirst = __ffs(grp) - 1;
     const int later_in_grp = __popc(grp & gt);
-    int suf = (in && gfirst == lane) ? __popc(grp) : 0;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int y = __shfl_down_sync(0xffffffffu, suf, d);
-      if (lane + d < 32) suf += y;
-    }
-    int before = __shfl_sync(0xffffffffu, suf, (gfirst + 1) & 31);
-    if (gfirst == 31) before = 0;
+    const int before = keys_of_later_runs(in && gfirst == lane, __popc(grp), gfirst);
     const int newpos = before + later_in_grp;
     if (in) { scratch64[newpos] = cur_slot; scratch64[32 + newpos] = (int)cur_key; }
     __syncwarp();
@@ -2475,13 +2472,13 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
     }
   }
   pdl_enter();
-  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
-  __syncthreads();
-  if (tid == 0) {
-    sc[SC_PHYS] = a.phys_free;
-    sc[SC_LAUNCHES] += 1;
-    if (a.arena_mode == 0) sc[SC_OUT_CURSOR] = 0;
-    if (a.arena_mode != 1 && !a.keep_events) sc[SC_NEV] = 0;
+  if (tid < SC_COUNT) {      // the launch's own adjustments ride on the load: one barrier instead of two
+    int64_t v = c.sc[tid];
+    if (tid == SC_PHYS) v = a.phys_free;
+    if (tid == SC_LAUNCHES) v += 1;
+    if (tid == SC_OUT_CURSOR && a.arena_mode == 0) v = 0;
+    if (tid == SC_NEV && a.arena_mode != 1 && !a.keep_events) v = 0;
+    sc[tid] = v;
   }
   __syncthreads();
   const int64_t ev_begin = a.keep_events ? 0 : sc[SC_NEV];
@@ -2997,13 +2994,13 @@ __global__ void __launch_bounds__(NT, 1) kvb_one_kernel(const __grid_constant__ 
   for (int i = tid; i < kGrowTab / 2; i += NT) reinterpret_cast<uint32_t *>(s.grow16)[i] = reinterpret_cast<const uint32_t *>(c.grow_tab)[i];
   if (tid == 0) s.ops[0] = a.inline_op;
   pdl_enter();                           // nothing of the device state is read above this line
-  if (tid < SC_COUNT) sc[tid] = c.sc[tid];
-  __syncthreads();
-  if (tid == 0) {
-    sc[SC_PHYS] = a.phys_free;
-    sc[SC_LAUNCHES] += 1;
-    sc[SC_OUT_CURSOR] = 0;
-    if (!a.keep_events) sc[SC_NEV] = 0;
+  if (tid < SC_COUNT) {
+    int64_t v = c.sc[tid];
+    if (tid == SC_PHYS) v = a.phys_free;
+    if (tid == SC_LAUNCHES) v += 1;
+    if (tid == SC_OUT_CURSOR) v = 0;
+    if (tid == SC_NEV && !a.keep_events) v = 0;
+    sc[tid] = v;
   }
   __syncthreads();
   const int64_t ev_begin = a.keep_events ? 0 : sc[SC_NEV];
