@@ -503,6 +503,14 @@ __device__ __forceinline__ void ht_order_warp(const DevState &c, const uint32_t 
   int cur_slot = lane;
   unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
   int placed = 0;   // keys already in the container
+  if (nb == 2 && D > 2) {
+    // Two keys under two buckets always end as [key 1, key 0] — same bucket: the later key joins the front of the run;
+    // different buckets: the later key becomes the list head — so the first phase of the commonest case (a free() of
+    // fewer than 2 * blocks-per-page ids reserves 2 buckets) is a swap of lanes 0 and 1.
+    placed = 2;
+    if (lane < 2) { cur_slot = 1 - lane; cur_key = (unsigned)keys[1 - lane]; }
+    nb = next_bkt_grow(primes32, 2, 2);
+  }
   while (true) {
     // keys inserted under this bucket count: until the container holds nb keys (the next insert rehashes)
     const int upto = D < nb ? D : nb;
@@ -637,6 +645,11 @@ __device__ __forceinline__ void ht_order_prefix(const DevState &c, const uint32_
   int cur_slot = lane;
   unsigned cur_key = lane < D ? (unsigned)keys[lane] : 0u;
   int placed = 0;
+  if (nb == 2 && D > 2) {          // first phase = swap of lanes 0 and 1 (see ht_order_warp)
+    placed = 2;
+    if (lane < 2) { cur_slot = 1 - lane; cur_key = (unsigned)keys[1 - lane]; }
+    nb = next_bkt_grow(primes32, 2, 2);
+  }
   while ((D < nb ? D : nb) <= 32) {
     const int upto = D < nb ? D : nb;
     if (lane >= placed && lane < upto) { cur_slot = lane; cur_key = (unsigned)keys[lane]; }
@@ -1742,6 +1755,7 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
   int e_st = 0, e_cnt = 0, e_head = 0, e_pos = 0;
   if (part) { e_st = c.pg_state[p]; e_cnt = c.pg_cnt[p]; e_head = c.pg_head[p]; e_pos = c.pg_pos[p]; }
   __syncthreads();
+  KVB_PROF(14);
   unsigned h = 0;
   if (part) {
     h = ((unsigned)p * 0x9E3779B1u) >> 22;
@@ -1753,6 +1767,7 @@ __device__ int free_small(const DevState &c, Smem &s, const LaunchArgs &a, int n
     atomicMin(&Hval[h], tid);
   }
   __syncthreads();
+  KVB_PROF(15);
   const bool first = part && Hval[h] == tid;
   int D;
   const int r = block_rank_1b(first, s.wsite[WS_FS_D], &D);
@@ -2560,6 +2575,7 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
         case KVB_OP_FREE_RESERVED: {
           int n = 0;
           bool done = false;
+          KVB_PROF(13);
           if (o.kind == KVB_OP_FREE_IDS) {
             n = o.n;
             if (n <= NT && n <= c.f_cap) {     // one id per thread, straight from the request: no staging pass

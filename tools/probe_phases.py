@@ -10,11 +10,11 @@ from kvcached_b200 import _lib, replay as R, trace as T
 torch.cuda.init()
 lib = _lib.load()
 NAMES = ["pre-alloc/idle", "alloc run, warp path", "alloc general", "free: stage ids", "F0 classify", "F1+F2 distinct pages", "F3 dict order + ranks",
-         "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work", "alloc run, block-wide (w32: phase head in free_core)", "w32: match_any", "w32: suffix scan", "w32: permute"]
+         "F4 page updates", "F5 free_pages", "loop->publish", "publish", "F3 warp0 own work", "alloc run, block-wide (w32: phase head in free_core)", "free: request loop up to the free case", "F0a: early loads issued, table cleared", "F0b: hash insert"]
 def show(m, title, launches):
     prof = np.zeros(32, dtype=np.int64)
     lib.kvb_mgr_profile(m._h, prof.ctypes.data_as(_lib.p_i64), 1)
-    tot = prof[:11].sum() + prof[12]
+    tot = prof[:11].sum() + prof[12:16].sum()
     print(f"== {title}: {tot/launches:.0f} cycles per launch in marked phases ({tot/launches/1.9:.0f} ns at 1.9 GHz)")
     for i, n in enumerate(NAMES):
         if prof[16 + i]:
