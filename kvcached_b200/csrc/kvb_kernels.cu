@@ -1281,7 +1281,7 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
   }
   // consumed / partly consumed avail pages
   int n_full_av = 0;
-  if (w <= 1) {                                             // needed by the page-update warp and by thread 0
+  if (w == 1 || w == NW - 1) {                              // needed by the page-update warp and by the counter thread
     int lo = 0, hi = nlive;                                 // first live entry NOT entirely consumed
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -1323,7 +1323,7 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
       for (int t = lane; t < c.bpp; t += 32) rr[t] = (uint32_t)t;
     }
   }
-  if (tid == 0) {
+  if (tid == NT - 32) {        // the counters: lane 0 of the last warp, which has no ids to emit unless T > NT - 32
     const bool fresh_partial = F > 0 && last_used < c.bpp;
     sc[SC_RB_HEAD] = (rbh + take_rb) & c.rb_mask;
     sc[SC_NRB] -= take_rb;
@@ -2602,8 +2602,10 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
             n = (int)sc[SC_NRB];
             for (int j = tid; j < n; j += NT) c.fids[j] = c.rb[(int)((sc[SC_RB_HEAD] + j) & c.rb_mask)];
           }
-          __syncthreads();
-          if (!done) KVB_PROF(3);
+          if (!done) {           // ids were staged in c.fids (uniform; a call free_small served ended with a barrier)
+            __syncthreads();
+            KVB_PROF(3);
+          }
           const bool too_many = n > c.f_cap;   // more ids than blocks exist: cannot be a valid call
           if (!done && !too_many && n <= NT) done = free_small(c, s, a, n, tid < n ? c.fids[tid] : -1) != 0;
           if (!done && !too_many) free_core(c, s, a, n, 0);
@@ -2612,8 +2614,7 @@ __device__ __forceinline__ void step_body(const DevState &c, const LaunchArgs &a
             kvb_res r{}; r.status = too_many ? KVB_ERR_OVERFLOW : KVB_ST_OK; r.n = n; r.off = 0; r.avail = avail_size(c, sc);
             a.res[op] = r;
           }
-          __syncthreads();
-          op++;
+          op++;                  // (the barrier that closes every request follows the switch)
           break;
         }
         case KVB_OP_RESIZE: {   // KVCacheManager.resize, kv_cache_manager.py:381-401
