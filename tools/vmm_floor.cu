@@ -4,7 +4,8 @@
 // statistics.  A measurement tool (not part of the product); build:
 //   nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tools/vmm_floor tools/vmm_floor.cu -lcuda
 // usage: vmm_floor <events.txt> <variant> [reps=3] [unit_mib=128]
-//   variants: zero | nozero | zero_kernel | zero_ondemand | zero_thr2 | zero_bgkernel | zero_sync
+//   variants: zero | nozero | zero_kernel | zero_ondemand | zero_thr2 | zero_bgkernel | zero_sync | zero_multi<K>
+//   (zero_multi<K>: K zero handles, page p is backed by zero handle p % K — how much of the unmap tail is the ALIAS count?)
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -101,10 +102,14 @@ int main(int argc, char **argv) {
   CUdeviceptr base = 0;
   CK(cuMemAddressReserve(&base, unit * (size_t)N, 2u << 20, 0x4f0000000000ull, 0));
   CUmemGenericAllocationHandle zero = 0;
+  int nzero = 1;
+  if (variant.rfind("zero_multi", 0) == 0) nzero = std::max(1, atoi(variant.c_str() + 10));
+  std::vector<CUmemGenericAllocationHandle> zeros;
   if (zero_design) {
-    CK(cuMemCreate(&zero, unit, &prop, 0));
+    for (int k = 0; k < nzero; ++k) { CUmemGenericAllocationHandle z; CK(cuMemCreate(&z, unit, &prop, 0)); zeros.push_back(z); }
+    zero = zeros[0];
     for (long p = 0; p < N; ++p) {
-      CK(cuMemMap(base + (size_t)p * unit, unit, 0, zero, 0));
+      CK(cuMemMap(base + (size_t)p * unit, unit, 0, zeros[(size_t)(p % nzero)], 0));
       CK(cuMemSetAccess(base + (size_t)p * unit, unit, &acc, 1));
     }
   }
@@ -136,7 +141,7 @@ int main(int argc, char **argv) {
     });
   }
 
-  Stat s_unmap, s_map, s_acc, s_create, s_step;
+  Stat s_unmap, s_map, s_acc, s_create, s_step, s_unmap_zero;
   auto do_event = [&](long e, Stat &su, Stat &sm, Stat &sa, Stat &sc) {
     long p = e >> 1;
     bool un = e & 1;
@@ -151,7 +156,7 @@ int main(int argc, char **argv) {
       if (zero_design) {
         auto t0 = clk::now();
         CK(cuMemUnmap(a, unit));
-        su.add(us(t0, clk::now()));
+        s_unmap_zero.add(us(t0, clk::now()));
       }
       auto t1 = clk::now();
       CK(cuMemMap(a, unit, 0, h, 0));
@@ -167,7 +172,7 @@ int main(int argc, char **argv) {
       auto t1 = clk::now();
       su.add(us(t0, t1));
       if (zero_design) {
-        CK(cuMemMap(a, unit, 0, zero, 0));
+        CK(cuMemMap(a, unit, 0, zeros[(size_t)(p % nzero)], 0));
         auto t2 = clk::now();
         CK(cuMemSetAccess(a, unit, &acc, 1));
         auto t3 = clk::now();
@@ -180,7 +185,7 @@ int main(int argc, char **argv) {
   };
 
   for (int rep = 0; rep < reps; ++rep) {
-    s_unmap.clear(); s_map.clear(); s_acc.clear(); s_create.clear(); s_step.clear();
+    s_unmap.clear(); s_map.clear(); s_acc.clear(); s_create.clear(); s_step.clear(); s_unmap_zero.clear();
     auto T0 = clk::now();
     for (auto &st : steps) {
       if (kern) { tiny<<<1, 32>>>(flag); cudaStreamSynchronize(0); }
@@ -227,6 +232,7 @@ int main(int argc, char **argv) {
     printf("  replay %d: %.1f ms total, %.1f us per page event\n", rep, us(T0, T1) / 1e3, us(T0, T1) / n_ev);
     s_create.print("cuMemCreate");
     s_unmap.print("cuMemUnmap");
+    s_unmap_zero.print("Unmap(zero)");
     s_map.print("cuMemMap");
     s_acc.print("SetAccess");
     s_step.print("step");
@@ -235,7 +241,7 @@ int main(int argc, char **argv) {
       if (held[(size_t)p]) {
         CUdeviceptr a = base + (size_t)p * unit;
         CK(cuMemUnmap(a, unit));
-        if (zero_design) { CK(cuMemMap(a, unit, 0, zero, 0)); CK(cuMemSetAccess(a, unit, &acc, 1)); }
+        if (zero_design) { CK(cuMemMap(a, unit, 0, zeros[(size_t)(p % nzero)], 0)); CK(cuMemSetAccess(a, unit, &acc, 1)); }
         pool.push_back(held[(size_t)p]);
         held[(size_t)p] = 0;
       }
