@@ -1159,8 +1159,8 @@ __device__ int alloc_run_fast(const DevState &c, Smem &s, const LaunchArgs &a, i
 // newest entries of the avail stack and at most 32 fresh pages — a decode step's "one block each" run, a single
 // alloc(n).  Same stream rule, same results.  Warp 0 PLANS with shuffles and votes (the block-wide form pays three
 // block scans for it) and leaves the plan in shared memory; after ONE barrier the whole CTA carries it out: all NT
-// threads emit ids and results, warp 1 retires the consumed avail pages, the warps share the fresh pages, thread 0
-// updates the counters.  (The first version also emitted on warp 0: T / 32 dependent passes over the id stream, 64
+// threads emit ids and results, warp 1 retires the consumed avail pages, the warps share the fresh pages, lane 0
+// of the last warp updates the counters.  (The first version also emitted on warp 0: T / 32 dependent passes over the id stream, 64
 // of them for alloc(2048).)  Returns 1 if the run was handled, 0 if it needs the wider windows of alloc_run_fast
 // (nothing touched).  Uniform.
 __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, int chunk_base, int op0, int run_end) {
@@ -1241,7 +1241,7 @@ __device__ int alloc_run_warp(const DevState &c, Smem &s, const LaunchArgs &a, i
   }
   __syncthreads();
   if (!s.misc[MI_E]) { __syncthreads(); return 0; }
-  // ---- the whole CTA carries the plan out; nothing below reads sc except thread 0 at the end
+  // ---- the whole CTA carries the plan out; nothing below reads sc except the counter thread at the end
   const int T = pl.T, take_rb = pl.take_rb, take_av = pl.take_av, rem2 = pl.rem2, nlive = pl.nlive, F = pl.F;
   const int from_rl = pl.from_rl, from_fl = F - from_rl, last_used = pl.last_used, tail = pl.tail;
   const int64_t cursor = pl.cursor, A0 = pl.A0, nev0 = pl.nev0, rbh = pl.rbh;
