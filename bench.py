@@ -947,6 +947,10 @@ def ours_main(args, rank: int, world: int, local_rank: int):
                                       "h2d_bytes": h2d_b, "d2h_bytes": 8,
                                       "note": "bound by the host->device copy (PCIe), not by the scatter kernel"}
     del kd, vd, sd
+    # every rank is done with the pages before rank 0 gives them back: without this barrier a follower that is still in
+    # its loop above scatters into pages its own VMM thread is switching to the zero page (unmapped for the ~250 us of a
+    # transition) — an illegal address on the followers, seen once at N=4 (session 23)
+    barrier()
     if rank == 0:
         mgr.free(ids)
     tp_fence()
